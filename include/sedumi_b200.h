@@ -1,0 +1,159 @@
+/* sedumi_b200.h -- C-ABI of libsedumi_b200.so: the B200 (sm_100a) implementation of
+ * SeDuMi's per-iteration normal-equations hot path.
+ *
+ * Boundary contract.  The reference's FFI for this path is the MEX plugin interface:
+ * one `mexFunction(nlhs, plhs, nrhs, prhs)` per target (install_sedumi.m:70-110).  The
+ * MEX stubs in sedumi_b200/mex/<target>.cpp keep those names and mxArray signatures and
+ * do nothing but unpack mxArrays into the plain pointers below.  Every entry point cites
+ * the reference mexFunction it stands behind.
+ *
+ * Conventions
+ *   - all matrices column-major IEEE double; sparse matrices CSC with 0-based int64 jc/ir
+ *     (bit-compatible with MATLAB's mwIndex on 64-bit platforms);
+ *   - index vectors that MATLAB passes as 1-based doubles (perm, xsuper, blkstart...) are
+ *     converted by the stub to 0-based int64 before they get here;
+ *   - functions return 0 on success, nonzero on failure (sb200_last_error() has the text);
+ *     nothing in this library calls exit()/abort() on CUDA failure;
+ *   - `*_dev` variants take DEVICE pointers (inputs already resident in HBM) and enqueue
+ *     on the library stream without synchronising; host variants copy in, run, copy out;
+ *   - plans hold iteration-invariant structure on the device (symbolic factor, patterns).
+ *     Host entry points look plans up in a content-addressed cache, so every call stays a
+ *     pure function of its arguments (SURVEY.md section 8b "Threading / re-entrancy").
+ */
+#ifndef SEDUMI_B200_H
+#define SEDUMI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t sb_idx;
+
+/* ------------------------------------------------------------------ context */
+int         sb200_init(int device);              /* idempotent; selects device, creates stream */
+void        sb200_shutdown(void);
+const char *sb200_last_error(void);
+int         sb200_device_count(void);
+int         sb200_sync(void);                     /* cudaStreamSynchronize(library stream) */
+void       *sb200_stream(void);                   /* cudaStream_t of the library */
+int64_t     sb200_kernel_launches(void);          /* kernels launched by this library so far */
+int         sb200_dev_alloc(void **p, int64_t bytes);
+int         sb200_dev_free(void *p);
+int         sb200_h2d(void *dst, const void *src, int64_t bytes);
+int         sb200_d2h(void *dst, const void *src, int64_t bytes);
+
+/* ------------------------------------------------------------------ supernodal LDL'
+ * blkchol.c:239-440 (mexFunction), blkchol2.c:96-167 (cholonBlk), :346-420 (precorrect),
+ * :464-563 (blkLDL); fwblkslv.c:77-134,193-320; bwblkslv.c:73-125,182-298.             */
+typedef struct sb200_chol_plan sb200_chol_plan;
+
+/* Symbolic structure: L.L pattern (Ljc/Lir expanded per column, ascending, diagonal
+ * first, nested inside supernodes), L.xsuper, L.perm (all 0-based) and the CSC pattern
+ * of the matrix X=ADA to be factored (full symmetric pattern). */
+int sb200_chol_plan_create(sb200_chol_plan **plan, sb_idx m, sb_idx nsuper,
+                           const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                           const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir);
+void sb200_chol_plan_destroy(sb200_chol_plan *plan);
+sb_idx sb200_chol_plan_nnzL(const sb200_chol_plan *plan);
+sb_idx sb200_chol_plan_rect_size(const sb200_chol_plan *plan);   /* doubles in internal layout */
+
+typedef struct {
+  double abstol;     /* pars.chol.abstol    (blkchol.c:292-306)  */
+  double canceltol;  /* pars.chol.canceltol                        */
+  double maxu;       /* pars.chol.maxu                             */
+} sb200_chol_pars;
+
+/* Numeric factorisation, device-resident.  Xpr_dev: values of X in its CSC pattern.
+ * absd_dev may be NULL (then lb uses diag(X), blkchol.c:374-379).
+ * Outputs (device): Lrect_dev  internal rectangular supernode panels (plan_rect_size),
+ *                   d_dev[m], flag_dev[m] (0 none,1 skipped,2 diag-add), sval_dev[m]
+ *                   (skip: pivot value when skipped; add: amount added). */
+int sb200_blkchol_dev(sb200_chol_plan *plan, const double *Xpr_dev, const double *absd_dev,
+                      sb200_chol_pars pars, double *Lrect_dev, double *d_dev,
+                      int *flag_dev, double *sval_dev);
+/* internal panels -> L.L values in the CSC pattern given at plan creation (unit diagonal,
+ * skipped columns = e_i, blkchol.c:409-414) */
+int sb200_chol_rect_to_csc_dev(sb200_chol_plan *plan, const double *Lrect_dev,
+                               const int *flag_dev, double *Lpr_dev);
+int sb200_chol_csc_to_rect_dev(sb200_chol_plan *plan, const double *Lpr_dev, double *Lrect_dev);
+
+/* Host-pointer entry = what mex/blkchol.cpp calls.  skip/add index outputs are 0-based,
+ * ascending; arrays must have room for m entries. */
+int sb200_blkchol(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
+                  const sb_idx *Lir, const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir,
+                  const double *Xpr, const double *absd, sb200_chol_pars pars,
+                  double *Lpr_out, double *d_out, sb_idx *skip_idx, double *skip_val,
+                  sb_idx *nskip, sb_idx *add_idx, double *add_val, sb_idx *nadd);
+
+/* y = L \ b(perm,:)  and  y(perm,:) = L' \ b   (dense right-hand sides, m x nrhs).
+ * *_dev: Lrect_dev in internal layout; b_dev/y_dev column-major m x nrhs.  */
+int sb200_fwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
+                       double *y_dev, sb_idx nrhs);
+int sb200_bwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
+                       double *y_dev, sb_idx nrhs);
+int sb200_fwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
+                   const sb_idx *Lir, const double *Lpr, const sb_idx *perm,
+                   const double *b, double *y, sb_idx nrhs);
+int sb200_bwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
+                   const sb_idx *Lir, const double *Lpr, const sb_idx *perm,
+                   const double *b, double *y, sb_idx nrhs);
+/* Sparse right-hand side (fwblkslv.c:150-183): b CSC m x nrhs, y has the pattern
+ * (yjc, yir) produced by symbfwblk; only ypr is written.  (bwblkslv's sparse branch,
+ * bwblkslv.c:141-172, is never reached from SeDuMi: sparbwslv.m:48 passes full b.) */
+int sb200_fwblkslv_sparse(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
+                          const sb_idx *Lir, const double *Lpr, const sb_idx *perm,
+                          sb_idx nrhs, const sb_idx *bjc, const sb_idx *bir, const double *bpr,
+                          const sb_idx *yjc, const sb_idx *yir, double *ypr);
+
+/* ------------------------------------------------------------------ PSD block algebra
+ * invcholfac.c:59-168 (y = invcholfac(u,K[,perm])) and psdscale.m:45-119
+ * (y = psdscale(ud,x,K[,transp]); the reference has no MEX for it -- a MEX of that name
+ * shadows the .m).  A psd plan depends only on the list of real PSD block orders K.s.   */
+typedef struct sb200_psd_plan sb200_psd_plan;
+int    sb200_psd_plan_get(sb200_psd_plan **plan, sb_idx nblk, const sb_idx *n);   /* cached */
+sb_idx sb200_psd_plan_lenud(const sb200_psd_plan *plan);
+sb_idx sb200_psd_plan_sumn(const sb200_psd_plan *plan);
+/* perm_dev: int32, 0-based inside each block, concatenated (sum n_k), or NULL */
+int sb200_invcholfac_dev(sb200_psd_plan *plan, const double *u_dev, const int *perm_dev, double *y_dev);
+int sb200_psdscale_dev(sb200_psd_plan *plan, const double *u_dev, const int *perm_dev,
+                       const double *x_dev, int transp, double *y_dev);
+/* host entries: u, x, y are the lenud-long PSD parts; perm 0-based inside each block or NULL */
+int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm, double *y);
+int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm,
+                   const double *x, int transp, double *y);
+
+/* ------------------------------------------------------------------ Schur complement ADA'
+ * getada1.c:161-261, getada2.c:126-214, getada3.c:370-569.  The plan holds the patterns of
+ * At and ADA, the PSD block layout and the per-(constraint, block) work lists.
+ *   Ajc1[j]   absolute offset into At.ir of the first PSD nonzero of column j (Ablkjc(:,3));
+ *             it is also the end of the LP/Lorentz part of that column
+ *   lpN=K.l, nq=|K.q|, qstart[0..nq] = 0-based first norm-bound row of each Lorentz cone (+end)
+ *   blkstart[k], blkn[k] = 0-based first row and order of real PSD block k                    */
+typedef struct sb200_ada_plan sb200_ada_plan;
+int sb200_ada_plan_get(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
+                       const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk,
+                       const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair);
+sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *plan);
+int sb200_ada_set_At_values(sb200_ada_plan *plan, const double *Atpr);
+/* device-resident variants: invperm_dev = inverse of the ordering (int32) or NULL = natural */
+int sb200_getada1_dev(sb200_ada_plan *plan, const double *dl_dev, const double *ddet_dev,
+                      const int *invperm_dev, double *ada_out_dev);
+int sb200_getada2_dev(sb200_ada_plan *plan, const long long *Qjc_dev, const int *Qir_dev,
+                      const double *Qpr_dev, const int *invperm_dev, const double *ada_in_dev,
+                      double *ada_out_dev);
+int sb200_getada3_dev(sb200_ada_plan *plan, const double *udsqr_dev, const int *invperm_dev,
+                      sb_idx first, double *ada_dev, double *absd_dev, int symmetrise);
+/* host entries; perm = 0-based Aord.lqperm / qperm / sperm (NULL = natural order) */
+int sb200_getada1(sb200_ada_plan *plan, const double *Atpr, const sb_idx *perm, const double *dl,
+                  const double *ddet, double *ada_out);
+int sb200_getada2(sb200_ada_plan *plan, sb_idx nq, const sb_idx *Qjc, const sb_idx *Qir, const double *Qpr,
+                  const sb_idx *perm, const double *ada_in, double *ada_out);
+int sb200_getada3(sb200_ada_plan *plan, const double *Atpr, const double *udsqr, sb_idx lenud,
+                  const sb_idx *perm, sb_idx first, const double *ada_in, double *ada_out, double *absd_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDUMI_B200_H */

@@ -1,0 +1,122 @@
+"""CPU restatement ("port") of the M-code pieces of SeDuMi's hot path -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product path (sedumi_b200/) never does.
+
+The C pieces of the path are NOT restated: the oracle for those is the reference's own C,
+compiled unmodified into oracle/_ref by oracle/Makefile.  What is restated here (numpy/scipy)
+is the MATLAB glue that has no C source and cannot run without MATLAB/Octave:
+
+  psdscale.m:45-119   -> psdscale        getada.m:14-40     -> getada_m
+  getDAtm.m:39-47     -> getDAtm         deninfac.m:57-93   -> deninfac
+  Amul.m:42-56        -> Amul            asmDxq.m:40-68     -> asmDxq
+  wrapPcg.m:42-94     -> wrapPcg_onepass (the part before PCG refinement)
+
+Parity status: these follow the M source line by line; MATLAB itself is not available here,
+so they are pinned only through the reference MEX functions they call (oracle/_ref) and
+through algebraic identities checked in tests/test_oracle.py -- "parity unpinned" in the
+sense of the task statement for the pure-M arithmetic (dense products, sparse products).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def psdscale(ud, x, K, transp=False):
+    """y = psdscale(ud,x,K,transp)  (psdscale.m:45-119), real blocks."""
+    Ks = np.asarray(K["s"], dtype=np.int64).ravel()
+    if Ks.size == 0:
+        return np.zeros(0)
+    perm = None
+    if isinstance(ud, dict):
+        p = np.asarray(ud.get("perm", np.zeros(0))).ravel()
+        perm = p.astype(np.int64) - 1 if p.size else None
+        u = np.asarray(ud["u"], dtype=float).ravel()
+    else:
+        u = np.asarray(ud, dtype=float).ravel()
+    x = np.asarray(x, dtype=float).ravel()
+    N = int((Ks ** 2).sum())
+    xi = x.size - N
+    y = np.zeros(N)
+    ui = yi = pi = 0
+    for n in Ks:
+        n = int(n)
+        q = n * n
+        TT = u[ui:ui + q].reshape(n, n, order="F")
+        ui += q
+        TT = np.triu(TT) if transp else np.tril(TT)
+        XX = x[xi:xi + q].reshape(n, n, order="F")
+        xi += q
+        if perm is not None and not transp:
+            PP = perm[pi:pi + n]
+            pi += n
+            XX = XX[np.ix_(PP, PP)]
+        XX = TT.T @ XX @ TT
+        if perm is not None and transp:
+            PP = perm[pi:pi + n]
+            pi += n
+            Z = np.empty_like(XX)
+            Z[np.ix_(PP, PP)] = XX
+            XX = Z
+        y[yi:yi + q] = XX.ravel(order="F")
+        yi += q
+    return y
+
+
+def invcholfac_dense(u, K, perm=None):
+    """Independent dense formula for invcholfac (used to cross-check oracle/_ref/invcholfac.so)."""
+    Ks = np.asarray(K["s"], dtype=np.int64).ravel()
+    u = np.asarray(u, dtype=float).ravel()
+    out, ui, pi = [], 0, 0
+    perm = None if perm is None or np.size(perm) == 0 else np.asarray(perm).ravel().astype(np.int64) - 1
+    for n in Ks:
+        n = int(n)
+        U = np.triu(u[ui:ui + n * n].reshape(n, n, order="F"))
+        ui += n * n
+        Z = U.T @ U
+        if perm is not None:
+            PP = perm[pi:pi + n]
+            pi += n
+            Y = np.empty_like(Z)
+            Y[np.ix_(PP, PP)] = Z
+            Z = Y
+        out.append(Z.ravel(order="F"))
+    return np.concatenate(out) if out else np.zeros(0)
+
+
+def ada_dense_formula(At, K, d, udsqr):
+    """Independent dense evaluation of ADA = A*D(d^2)*A' (all cones) for cross-checks:
+    LP: d.l ; Lorentz: det*(J) + (Dq a)(Dq a)' handled via getada1/2 definitions ; PSD: <A_i, D A_j D>."""
+    At = sp.csc_matrix(At)
+    N, m = At.shape
+    A = At.toarray()
+    lpN = int(K["l"])
+    q = np.asarray(K["q"], dtype=np.int64)
+    s = np.asarray(K["s"], dtype=np.int64)
+    nq = len(q)
+    ADA = (A[:lpN].T * d["l"]) @ A[:lpN]
+    r = lpN + nq
+    for k in range(nq):
+        nk = int(q[k])
+        x1 = A[lpN + k]                        # trace row
+        x2 = A[r:r + nk - 1]
+        det = d["det"][k]
+        ADA += det * (x2.T @ x2 - np.outer(x1, x1))
+        dq = d["q1"][k] * x1 + d["q2"][r - lpN - nq: r - lpN - nq + nk - 1] @ x2
+        ADA += np.outer(dq, dq)
+        r += nk - 1
+    off = 0
+    for n in s:
+        n = int(n)
+        D = np.asarray(udsqr[off:off + n * n]).reshape(n, n, order="F")
+        V = A[r:r + n * n]                     # folded lower-triangular coefficients
+        W = np.empty_like(V)
+        for j in range(m):
+            X = V[:, j].reshape(n, n, order="F")
+            X = (X + X.T) / 2
+            W[:, j] = (D @ X @ D).ravel(order="F")
+        ADA += V.T @ W
+        r += n * n
+        off += n * n
+    return ADA

@@ -1,0 +1,504 @@
+// ada.cu -- assembly of the Schur complement ADA' = A D(d^2) A' (getada1 / getada2 / getada3).
+//
+// Reference semantics:
+//   getada1.c:89-152   LP + Lorentz-det part: ada(i,j) = sum_r a_ri dsqr_r a_rj over rows < start of
+//                      PSD, dsqr = [d.l; -d.det; det_k on the norm-bound rows of cone k]; written only
+//                      where invperm[i] <= invperm[j] ("upper triangle in perm order"), zero elsewhere,
+//                      and only for columns that have LP/Lorentz nonzeros
+//   getada2.c:74-118   ada += DAt.q' * DAt.q on the entries that are upper in Aord.qperm order
+//   getada3.c:253-361  PSD part: ada(i,j) += <A_i, D A_j D> on entries upper in Aord.sperm order,
+//                      absd(j) = ada_in(j,j) + sum |a_j .* vec(D A_j D)| (0 for the leading constraints
+//                      of sperm that have no PSD nonzeros, :282-284), then ADA := ADA+ADA'-diag (:151-180)
+//
+// GPU design for the PSD part.  The reference walks constraints in a greedy order and evaluates
+// vec(D A_j D) only on an incrementally growing pattern with BLAS-1 dots (spscale.c:249-305).  That
+// is a scalar algorithm.  Here each (constraint j, PSD block k) pair with nonzeros becomes one dense
+// product   W_jk = D_k * sym(A_jk) * D_k = D_k(:,R) * [sym(A_jk)(R,:) D_k]   (R = nonzero rows of
+// sym(A_jk)), run as a batched DMMA tile GEMM over ALL pairs of a batch in one launch (gemm.cuh),
+// followed by one warp per ADA entry that dots the sparse A_ik against W_jk over the blocks i and j
+// share.  One writer per entry: deterministic, no atomics.  absd and the symmetrisation ride along.
+#include <algorithm>
+#include <map>
+#include "gemm.cuh"
+#include "sb_internal.h"
+
+namespace sb {
+
+struct AdaPair {      // one (constraint, PSD block) with nonzeros
+  int j, k;           // constraint, block
+  int e0, e1;         // entries [e0,e1) in ent_*
+  int r0, r;          // rows R: Rlist[r0 .. r0+r)
+  long long tt_off;   // offset of Tt (n x r) in the batch workspace
+  long long w_off;    // offset of W (n x n) in the batch workspace
+};
+
+// --------------------------------------------------------------------- sparse A'WA on a pattern
+// One CTA per ADA column c; one warp per stored entry (i,c).  B is CSC with per-column row ranges
+// [lo[col], hi[col]).  out = (accumulate ? in : 0) + sum_r B(r,i) w(r) B(r,c)  where pred holds;
+// elsewhere out = accumulate ? in : 0.  Columns with an empty range are skipped when skip_empty.
+__global__ void __launch_bounds__(256)
+ata_pattern_kernel(int m, const long long *adajc, const int *adair, const long long *lo, const long long *hi,
+                   const int *Bir, const double *Bpr, const double *w, const int *invperm,
+                   const double *in, double *out, int accumulate, int skip_empty) {
+  const int c = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const long long clo = lo[c], chi = hi[c];
+  const int ipc = invperm[c];
+  const bool empty_c = skip_empty && (clo >= chi);
+  for (long long inz = adajc[c] + warp; inz < adajc[c + 1]; inz += nw) {
+    const int i = adair[inz];
+    double base = accumulate ? in[inz] : 0.0;
+    if (empty_c || invperm[i] > ipc) { if (lane == 0) out[inz] = base; continue; }
+    long long alo = lo[i], ahi = hi[i], blo = clo, bhi = chi;
+    if (ahi - alo > bhi - blo) { long long t = alo; alo = blo; blo = t; t = ahi; ahi = bhi; bhi = t; }
+    double acc = 0.0;
+    for (long long p = alo + lane; p < ahi; p += 32) {
+      int r = Bir[p];
+      long long l = blo, h = bhi;
+      while (l < h) { long long mid = (l + h) >> 1; if (Bir[mid] < r) l = mid + 1; else h = mid; }
+      if (l < bhi && Bir[l] == r) acc += Bpr[p] * (w ? w[r] : 1.0) * Bpr[l];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[inz] = base + acc;
+  }
+}
+
+// dsqr = [d.l ; -d.det ; det_k repeated over the norm-bound rows of Lorentz cone k]   (getada1.c:110-119)
+__global__ void dsqr_kernel(int lpN, int nq, const long long *qstart, const double *dl, const double *ddet, double *dsqr) {
+  // qstart[k], k=0..nq: 0-based first norm-bound row of cone k (qstart[0] = lpN + nq)
+  long long tot = nq ? qstart[nq] : lpN;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < tot; r += (long long)gridDim.x * blockDim.x) {
+    double v;
+    if (r < lpN) v = dl[r];
+    else if (r < lpN + nq) v = -ddet[r - lpN];
+    else {
+      int l = 0, h = nq;                          // last k with qstart[k] <= r
+      while (h - l > 1) { int mid = (l + h) >> 1; if (qstart[mid] <= r) l = mid; else h = mid; }
+      v = ddet[l];
+    }
+    dsqr[r] = v;
+  }
+}
+
+// --------------------------------------------------------------------- getada3 kernels
+// Tt_p(c, rho) = (D_k * sym(A_jk))(c, R[rho]);   one CTA per pair, thread per row c.
+__global__ void __launch_bounds__(256)
+build_tt_kernel(const AdaPair *pairs, int p0, const int *blk_n, const long long *blk_off,
+                const int *ent_p, const int *ent_q, const int *ent_rp, const int *ent_rq, const int *ent_src,
+                const double *Atpr, const double *udsqr, double *ws) {
+  const AdaPair P = pairs[p0 + blockIdx.x];
+  const int n = blk_n[P.k];
+  const double *D = udsqr + blk_off[P.k];
+  double *Tt = ws + P.tt_off;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    for (int rho = 0; rho < P.r; rho++) Tt[c + (long long)rho * n] = 0.0;
+    for (int e = P.e0; e < P.e1; e++) {
+      const int p = ent_p[e], q = ent_q[e];
+      const double a = Atpr[ent_src[e]];
+      if (p == q) Tt[c + (long long)ent_rp[e] * n] += a * D[c + (long long)p * n];
+      else {
+        const double h = 0.5 * a;                 // sym(X) = (X+X')/2   (spscale.c:227-229)
+        Tt[c + (long long)ent_rq[e] * n] += h * D[c + (long long)p * n];   // column q of sym(A) gets row p
+        Tt[c + (long long)ent_rp[e] * n] += h * D[c + (long long)q * n];
+      }
+    }
+  }
+}
+
+// One CTA per ADA column c (a constraint of the batch); warp per stored entry (i,c).
+__global__ void __launch_bounds__(256)
+ada3_dots_kernel(int c0, const long long *adajc, const int *adair, const int *invperm, int first,
+                 const int *cpair_beg, const AdaPair *pairs, const int *blk_n,
+                 const int *ent_p, const int *ent_q, const int *ent_src, const double *Atpr,
+                 const double *ws, double *ada, double *absd) {
+  const int c = c0 + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int ipc = invperm[c];
+  const int pcb = cpair_beg[c], pce = cpair_beg[c + 1];
+  for (long long inz = adajc[c] + warp; inz < adajc[c + 1]; inz += nw) {
+    const int i = adair[inz];
+    const int ipi = invperm[i];
+    if (ipi > ipc) continue;
+    const bool diag = (i == c);
+    if (!diag && pcb == pce) continue;
+    double acc = 0.0, aabs = 0.0;
+    int pi = cpair_beg[i], pie = cpair_beg[i + 1], pc = pcb;
+    while (pi < pie && pc < pce) {                 // merge the two block lists (sorted by block)
+      const int ki = pairs[pi].k, kc = pairs[pc].k;
+      if (ki < kc) pi++;
+      else if (ki > kc) pc++;
+      else {
+        const int n = blk_n[ki];
+        const double *W = ws + pairs[pc].w_off;
+        for (int e = pairs[pi].e0 + lane; e < pairs[pi].e1; e += 32) {
+          int p = ent_p[e], q = ent_q[e];
+          if (p < q) { int t = p; p = q; q = t; }
+          double term = Atpr[ent_src[e]] * W[p + (long long)q * n];
+          acc += term;
+          aabs += fabs(term);
+        }
+        pi++; pc++;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_down_sync(0xffffffffu, acc, o);
+      aabs += __shfl_down_sync(0xffffffffu, aabs, o);
+    }
+    if (lane == 0) {
+      double base = ada[inz];
+      if (diag && ipc >= first) absd[c] = base + aabs;
+      ada[inz] = base + acc;
+    }
+  }
+}
+
+// absd for constraints without any pair (no kernel column above touches them): diag or 0.
+__global__ void absd_nopsd_kernel(int m, const long long *adajc, const int *adair, const int *invperm, int first,
+                                  const int *cpair_beg, const double *ada, double *absd, int all_diag) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  if (!all_diag && cpair_beg[c] < cpair_beg[c + 1]) return;      // handled by ada3_dots_kernel
+  double v = 0.0;
+  if (all_diag || invperm[c] >= first) {
+    long long l = adajc[c], h = adajc[c + 1];
+    while (l < h) { long long mid = (l + h) >> 1; if (adair[mid] < c) l = mid + 1; else h = mid; }
+    if (l < adajc[c + 1] && adair[l] == c) v = ada[l];
+  }
+  absd[c] = v;
+}
+
+// X := X + X' - diag(X) on a full symmetric pattern (spmakesym, getada3.c:151-180).
+__global__ void makesym_kernel(int m, const long long *jc, const int *ir, double *x) {
+  const int c = blockIdx.x;
+  for (long long inz = jc[c] + threadIdx.x; inz < jc[c + 1]; inz += blockDim.x) {
+    const int i = ir[inz];
+    if (i <= c) continue;                            // the strictly-lower entry owns the pair
+    long long l = jc[i], h = jc[i + 1];
+    while (l < h) { long long mid = (l + h) >> 1; if (ir[mid] < c) l = mid + 1; else h = mid; }
+    if (l < jc[i + 1] && ir[l] == c) { double s = x[inz] + x[l]; x[inz] = s; x[l] = s; }
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+struct sb200_ada_plan {
+  int m = 0;
+  long long N = 0, nnzA = 0, nnzADA = 0;
+  int lpN = 0, nq = 0, nblk = 0;
+  long long lq_rows = 0;          // rows before the PSD part covered by dsqr
+  std::vector<int> blk_n; std::vector<long long> blk_off, blk_start;
+  std::vector<AdaPair> pairs;
+  std::vector<int> cpair_beg;
+  struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; };
+  std::vector<Batch> batches;
+  long long ws_max = 0;
+  uint64_t key = 0, val_hash = 0;
+  bool have_vals = false;
+  // device
+  DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
+  DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_p, d_ent_q, d_ent_rp, d_ent_rq, d_ent_src, d_Rlist;
+  DevBuf<AdaPair> d_pairs;
+  DevBuf<GemmDesc> d_descs;
+  DevBuf<GemmTile> d_tiles;
+  DevBuf<double> d_Atpr, d_dsqr, d_ws;
+  DevBuf<int> d_invperm, d_ident;
+};
+
+static std::map<uint64_t, sb200_ada_plan *> g_ada_plans;
+
+static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air, const sb_idx *Ajc1,
+                     sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, const sb_idx *blkstart, const sb_idx *blkn,
+                     const sb_idx *adajc, const sb_idx *adair) {
+  pl->m = (int)m; pl->N = N; pl->nnzA = Ajc[m]; pl->nnzADA = adajc[m];
+  pl->lpN = (int)lpN; pl->nq = (int)nq; pl->nblk = (int)nblk;
+  SB_CHECK(pl->nnzA < 2147483647LL, "At has too many nonzeros for 32-bit entry indices");
+  long long off = 0;
+  for (sb_idx k = 0; k < nblk; k++) {
+    pl->blk_n.push_back((int)blkn[k]); pl->blk_off.push_back(off); pl->blk_start.push_back(blkstart[k]);
+    off += blkn[k] * blkn[k];
+  }
+  const long long psd0 = nblk ? blkstart[0] : N;
+  pl->lq_rows = nq ? qstart[nq] : lpN;
+  // ---- pairs
+  std::vector<int> ent_p, ent_q, ent_rp, ent_rq, ent_src, Rlist;
+  pl->cpair_beg.assign(m + 1, 0);
+  std::vector<int> tmpR;
+  for (sb_idx j = 0; j < m; j++) {
+    pl->cpair_beg[j] = (int)pl->pairs.size();
+    sb_idx inz = nblk ? Ajc1[j] : Ajc[j + 1];       // no PSD cone: nothing beyond the LP/Lorentz part matters
+    SB_CHECK(Ajc1[j] >= Ajc[j] && Ajc1[j] <= Ajc[j + 1] && inz >= Ajc[j] && inz <= Ajc[j + 1], "getada3: Ajc1(%lld) outside its column", (long long)j);
+    while (inz < Ajc[j + 1]) {
+      sb_idx row = Air[inz];
+      SB_CHECK(row >= psd0 && row < N, "getada3: row %lld of At is not in the PSD part", (long long)row);
+      int k = (int)(std::upper_bound(pl->blk_start.begin(), pl->blk_start.end(), (long long)row) - pl->blk_start.begin()) - 1;
+      const long long bs = pl->blk_start[k]; const int n = pl->blk_n[k];
+      SB_CHECK(row < bs + (long long)n * n, "getada3: row %lld beyond PSD block %d (Hermitian blocks unsupported)", (long long)row, k);
+      AdaPair P{}; P.j = (int)j; P.k = k; P.e0 = (int)ent_p.size();
+      tmpR.clear();
+      while (inz < Ajc[j + 1] && Air[inz] < bs + (long long)n * n) {
+        long long idx = Air[inz] - bs;
+        int p = (int)(idx % n), q = (int)(idx / n);
+        ent_p.push_back(p); ent_q.push_back(q); ent_src.push_back((int)inz);
+        tmpR.push_back(p); tmpR.push_back(q);
+        inz++;
+      }
+      P.e1 = (int)ent_p.size();
+      std::sort(tmpR.begin(), tmpR.end());
+      tmpR.erase(std::unique(tmpR.begin(), tmpR.end()), tmpR.end());
+      P.r0 = (int)Rlist.size(); P.r = (int)tmpR.size();
+      for (int v : tmpR) Rlist.push_back(v);
+      for (int e = P.e0; e < P.e1; e++) {
+        ent_rp.push_back((int)(std::lower_bound(tmpR.begin(), tmpR.end(), ent_p[e]) - tmpR.begin()));
+        ent_rq.push_back((int)(std::lower_bound(tmpR.begin(), tmpR.end(), ent_q[e]) - tmpR.begin()));
+      }
+      pl->pairs.push_back(P);
+    }
+  }
+  pl->cpair_beg[m] = (int)pl->pairs.size();
+  // ---- batches of whole constraints, workspace bounded
+  const long long BUDGET = (long long)96 << 20;     // doubles (768 MB)
+  std::vector<GemmDesc> descs(pl->pairs.size());
+  std::vector<GemmTile> tiles;
+  int c = 0;
+  while (c < m) {
+    sb200_ada_plan::Batch B{}; B.c0 = c; B.p0 = pl->cpair_beg[c]; B.tile0 = (int)tiles.size();
+    long long ws = 0;
+    while (c < m) {
+      long long need = 0;
+      for (int p = pl->cpair_beg[c]; p < pl->cpair_beg[c + 1]; p++) {
+        long long n = pl->blk_n[pl->pairs[p].k];
+        need += n * n + n * pl->pairs[p].r;
+      }
+      if (ws > 0 && ws + need > BUDGET) break;
+      for (int p = pl->cpair_beg[c]; p < pl->cpair_beg[c + 1]; p++) {
+        AdaPair &P = pl->pairs[p];
+        long long n = pl->blk_n[P.k];
+        P.tt_off = ws; ws += n * P.r;
+        P.w_off = ws; ws += n * n;
+        GemmDesc g{};
+        g.offA = pl->blk_off[P.k]; g.gatherOff = P.r0; g.lda = (int)n; g.a_tri = TRI_NONE;
+        g.offB = P.tt_off; g.ldb = (int)n; g.b_tri = TRI_NONE;
+        g.offC = P.w_off; g.ldc = (int)n; g.M = g.N = (int)n; g.K = P.r; g.lower = 1; g.accumulate = 0; g.alpha = 1.0;
+        descs[p] = g;
+        gemm_add_tiles(tiles, p, (int)n, (int)n, true);
+      }
+      c++;
+    }
+    B.c1 = c; B.p1 = pl->cpair_beg[c]; B.ws = ws; B.ntiles = (int)tiles.size() - B.tile0;
+    pl->ws_max = std::max(pl->ws_max, ws);
+    pl->batches.push_back(B);
+  }
+  // ---- upload
+  std::vector<long long> v64;
+  auto up64 = [&](DevBuf<long long> &d, const sb_idx *p, size_t n) { v64.assign(p, p + n); return d.upload(v64); };
+  std::vector<int> v32;
+  SB_TRY(up64(pl->d_Ajc, Ajc, m + 1));
+  SB_TRY(up64(pl->d_Ajc1, Ajc1, m));
+  SB_TRY(up64(pl->d_Ajcend, Ajc + 1, m));
+  SB_TRY(up64(pl->d_adajc, adajc, m + 1));
+  if (nq) SB_TRY(up64(pl->d_qstart, qstart, nq + 1)); else SB_TRY(pl->d_qstart.alloc(1));
+  SB_TRY(to_i32(Air, (size_t)Ajc[m], v32, "At.ir")); SB_TRY(pl->d_Air.upload(v32));
+  SB_TRY(to_i32(adair, (size_t)adajc[m], v32, "ADA.ir")); SB_TRY(pl->d_adair.upload(v32));
+  SB_TRY(pl->d_blk_n.upload(pl->blk_n)); SB_TRY(pl->d_blk_off.upload(pl->blk_off));
+  SB_TRY(pl->d_cpair_beg.upload(pl->cpair_beg));
+  SB_TRY(pl->d_ent_p.upload(ent_p)); SB_TRY(pl->d_ent_q.upload(ent_q));
+  SB_TRY(pl->d_ent_rp.upload(ent_rp)); SB_TRY(pl->d_ent_rq.upload(ent_rq)); SB_TRY(pl->d_ent_src.upload(ent_src));
+  SB_TRY(pl->d_Rlist.upload(Rlist));
+  SB_TRY(pl->d_pairs.upload(pl->pairs));
+  SB_TRY(pl->d_descs.upload(descs)); SB_TRY(pl->d_tiles.upload(tiles));
+  SB_TRY(pl->d_Atpr.alloc((size_t)std::max<long long>(pl->nnzA, 1)));
+  SB_TRY(pl->d_dsqr.alloc((size_t)std::max<long long>(pl->lq_rows, 1)));
+  SB_TRY(pl->d_ws.alloc((size_t)std::max<long long>(pl->ws_max, 1)));
+  SB_TRY(pl->d_invperm.alloc((size_t)std::max(pl->m, 1)));
+  v32.resize(m); for (int i = 0; i < m; i++) v32[i] = i;
+  SB_TRY(pl->d_ident.upload(v32));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+extern "C" {
+
+// Structure of the constraint matrix and of ADA.  All index arrays 0-based.
+//   Ajc1[j]      absolute offset in At.ir of the first PSD nonzero of column j (= Ablkjc(:,3)),
+//                which is also the end of its LP/Lorentz part
+//   lpN          K.l ; nq = |K.q| ; qstart[0..nq]: first norm-bound row of each Lorentz cone (+ end)
+//   blkstart/blkn first row and order of each (real) PSD block
+int sb200_ada_plan_get(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
+                       const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk,
+                       const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair) {
+  SB_TRY(ensure_init());
+  uint64_t h = fnv1a(&N, sizeof N); h = fnv1a(&m, sizeof m, h);
+  h = fnv1a(Ajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(Air, sizeof(sb_idx) * Ajc[m], h);
+  h = fnv1a(Ajc1, sizeof(sb_idx) * m, h); h = fnv1a(&lpN, sizeof lpN, h); h = fnv1a(&nq, sizeof nq, h);
+  if (nq) h = fnv1a(qstart, sizeof(sb_idx) * (nq + 1), h);
+  h = fnv1a(&nblk, sizeof nblk, h);
+  if (nblk) { h = fnv1a(blkstart, sizeof(sb_idx) * nblk, h); h = fnv1a(blkn, sizeof(sb_idx) * nblk, h); }
+  h = fnv1a(adajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(adair, sizeof(sb_idx) * adajc[m], h);
+  auto it = g_ada_plans.find(h);
+  if (it != g_ada_plans.end()) { *plan = it->second; return 0; }
+  sb200_ada_plan *pl = new sb200_ada_plan();
+  int rc = ada_build(pl, N, m, Ajc, Air, Ajc1, lpN, nq, qstart, nblk, blkstart, blkn, adajc, adair);
+  if (rc) { delete pl; return rc; }
+  pl->key = h;
+  if (g_ada_plans.size() >= 8) { for (auto &kv : g_ada_plans) delete kv.second; g_ada_plans.clear(); }
+  g_ada_plans[h] = pl;
+  *plan = pl;
+  return 0;
+}
+
+// Values of At (host) -> device copy held by the plan (skipped when unchanged).
+int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
+  uint64_t h = fnv1a(Atpr, sizeof(double) * pl->nnzA);
+  if (pl->have_vals && h == pl->val_hash) return 0;
+  SB_CUDA(cudaMemcpyAsync(pl->d_Atpr.p, Atpr, sizeof(double) * pl->nnzA, cudaMemcpyHostToDevice, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  pl->val_hash = h; pl->have_vals = true;
+  return 0;
+}
+sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *pl) { return pl->nnzADA; }
+
+static int set_invperm(sb200_ada_plan *pl, const sb_idx *perm, const int **out) {
+  if (!perm) { *out = pl->d_ident.p; return 0; }
+  std::vector<int> inv(pl->m);
+  for (int i = 0; i < pl->m; i++) {
+    SB_CHECK(perm[i] >= 0 && perm[i] < pl->m, "ordering permutation out of range");
+    inv[perm[i]] = i;
+  }
+  SB_CUDA(cudaMemcpyAsync(pl->d_invperm.p, inv.data(), sizeof(int) * pl->m, cudaMemcpyHostToDevice, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = pl->d_invperm.p;
+  return 0;
+}
+
+// getada1 on device values.  invperm_dev NULL = natural order (entries with i <= j).
+int sb200_getada1_dev(sb200_ada_plan *pl, const double *dl_dev, const double *ddet_dev, const int *invperm_dev,
+                      double *ada_out_dev) {
+  SB_TRY(ensure_init());
+  if (pl->m == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  if (pl->lq_rows > 0) {
+    dsqr_kernel<<<(unsigned)std::min<long long>((pl->lq_rows + 255) / 256, 2048), 256, 0, st>>>(
+        pl->lpN, pl->nq, pl->d_qstart.p, dl_dev, ddet_dev, pl->d_dsqr.p);
+    SB_LAUNCH_CHECK();
+  }
+  ata_pattern_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, pl->d_Ajc.p, pl->d_Ajc1.p, pl->d_Air.p,
+                                            pl->d_Atpr.p, pl->d_dsqr.p, invperm_dev ? invperm_dev : pl->d_ident.p,
+                                            nullptr, ada_out_dev, 0, 1);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// getada2 on device values: ada_out = ada_in + Q'Q (upper in perm order), Q = DAt.q as device CSC.
+int sb200_getada2_dev(sb200_ada_plan *pl, const long long *Qjc_dev, const int *Qir_dev, const double *Qpr_dev,
+                      const int *invperm_dev, const double *ada_in_dev, double *ada_out_dev) {
+  SB_TRY(ensure_init());
+  if (pl->m == 0) return 0;
+  ata_pattern_kernel<<<pl->m, 256, 0, ctx().stream>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, Qjc_dev, Qjc_dev + 1, Qir_dev,
+                                                       Qpr_dev, nullptr, invperm_dev ? invperm_dev : pl->d_ident.p,
+                                                       ada_in_dev, ada_out_dev, 1, 1);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// getada3 on device values, in place on ada_dev.  first = number of leading constraints (in the
+// order given by invperm) whose absd stays 0 (getada3.c:282-284); symmetrise = apply spmakesym.
+int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *invperm_dev, sb_idx first,
+                      double *ada_dev, double *absd_dev, int symmetrise) {
+  SB_TRY(ensure_init());
+  if (pl->m == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  const int *ip = invperm_dev ? invperm_dev : pl->d_ident.p;
+  // absd of the constraints with no PSD pair (diag(ADA) if there is no PSD cone at all, getada3.c:549-552)
+  absd_nopsd_kernel<<<(pl->m + 255) / 256, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
+                                                         pl->d_cpair_beg.p, ada_dev, absd_dev, pl->nblk == 0);
+  SB_LAUNCH_CHECK();
+  for (auto &B : pl->batches) {
+    if (B.p1 == B.p0) continue;
+    build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_ent_p.p, pl->d_ent_q.p,
+                                                 pl->d_ent_rp.p, pl->d_ent_rq.p, pl->d_ent_src.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
+    SB_LAUNCH_CHECK();
+    gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
+    SB_LAUNCH_CHECK();
+    ada3_dots_kernel<<<B.c1 - B.c0, 256, 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, pl->d_pairs.p,
+                                                  pl->d_blk_n.p, pl->d_ent_p.p, pl->d_ent_q.p, pl->d_ent_src.p, pl->d_Atpr.p,
+                                                  pl->d_ws.p, ada_dev, absd_dev);
+    SB_LAUNCH_CHECK();
+  }
+  if (symmetrise) {
+    makesym_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ada_dev);
+    SB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- host-pointer entries (what the MEX stubs call).  perm: 0-based ordering (Aord.*perm).
+int sb200_getada1(sb200_ada_plan *pl, const double *Atpr, const sb_idx *perm, const double *dl, const double *ddet,
+                  double *ada_out) {
+  SB_TRY(sb200_ada_set_At_values(pl, Atpr));
+  arena_reset();
+  const int *ip;
+  SB_TRY(set_invperm(pl, perm, &ip));
+  double *d_dl = arena<double>((size_t)std::max(pl->lpN, 1)), *d_det = arena<double>((size_t)std::max(pl->nq, 1));
+  double *d_out = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  SB_CHECK(d_dl && d_det && d_out, "getada1: out of device memory");
+  cudaStream_t st = ctx().stream;
+  if (pl->lpN) SB_CUDA(cudaMemcpyAsync(d_dl, dl, sizeof(double) * pl->lpN, cudaMemcpyHostToDevice, st));
+  if (pl->nq) SB_CUDA(cudaMemcpyAsync(d_det, ddet, sizeof(double) * pl->nq, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_getada1_dev(pl, d_dl, d_det, ip, d_out));
+  SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sb200_getada2(sb200_ada_plan *pl, sb_idx nq, const sb_idx *Qjc, const sb_idx *Qir, const double *Qpr,
+                  const sb_idx *perm, const double *ada_in, double *ada_out) {
+  arena_reset();
+  const int *ip;
+  SB_TRY(set_invperm(pl, perm, &ip));
+  const int m = pl->m;
+  const long long nnzQ = Qjc[m];
+  std::vector<long long> jc(Qjc, Qjc + m + 1);
+  std::vector<int> ir32;
+  SB_TRY(to_i32(Qir, (size_t)nnzQ, ir32, "DAt.q.ir"));
+  long long *d_jc = arena<long long>(m + 1);
+  int *d_ir = arena<int>((size_t)std::max<long long>(nnzQ, 1));
+  double *d_pr = arena<double>((size_t)std::max<long long>(nnzQ, 1));
+  double *d_in = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1)), *d_out = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  SB_CHECK(d_jc && d_ir && d_pr && d_in && d_out, "getada2: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(d_jc, jc.data(), sizeof(long long) * (m + 1), cudaMemcpyHostToDevice, st));
+  if (nnzQ) {
+    SB_CUDA(cudaMemcpyAsync(d_ir, ir32.data(), sizeof(int) * nnzQ, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_pr, Qpr, sizeof(double) * nnzQ, cudaMemcpyHostToDevice, st));
+  }
+  SB_CUDA(cudaMemcpyAsync(d_in, ada_in, sizeof(double) * pl->nnzADA, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_getada2_dev(pl, d_jc, d_ir, d_pr, ip, d_in, d_out));
+  SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  (void)nq;
+  return 0;
+}
+
+int sb200_getada3(sb200_ada_plan *pl, const double *Atpr, const double *udsqr, sb_idx lenud, const sb_idx *perm,
+                  sb_idx first, const double *ada_in, double *ada_out, double *absd_out) {
+  SB_TRY(sb200_ada_set_At_values(pl, Atpr));
+  arena_reset();
+  const int *ip;
+  SB_TRY(set_invperm(pl, perm, &ip));
+  double *d_ud = arena<double>((size_t)std::max<long long>(lenud, 1));
+  double *d_ada = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  double *d_absd = arena<double>((size_t)std::max(pl->m, 1));
+  SB_CHECK(d_ud && d_ada && d_absd, "getada3: out of device memory");
+  cudaStream_t st = ctx().stream;
+  if (lenud) SB_CUDA(cudaMemcpyAsync(d_ud, udsqr, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(d_ada, ada_in, sizeof(double) * pl->nnzADA, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_getada3_dev(pl, d_ud, ip, first, d_ada, d_absd, 1));
+  SB_CUDA(cudaMemcpyAsync(ada_out, d_ada, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(absd_out, d_absd, sizeof(double) * pl->m, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

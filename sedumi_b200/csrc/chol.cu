@@ -1,0 +1,955 @@
+// chol.cu -- supernodal sparse LDL' on B200: numeric factorisation with SeDuMi's pivot
+// safeguards, and the forward/backward block solves.
+//
+// Reference semantics reproduced (not its code structure):
+//   blkchol.c:95-120   permuteP   L := tril(X(perm,perm)) on the symbolic pattern
+//   blkchol.c:157-231  spchol     ub = max diag / maxu^2, lb = max(abstol, canceltol*absd(perm))
+//   blkchol2.c:96-167  cholonBlk  skip pivot if x_kk <= lb_k (d_k = 0, column left alone);
+//                                 if x_kk < ub, compare with a sub-column magnitude / maxu
+//                                 and raise the pivot to it ("diag add")
+//   blkchol2.c:346-420 precorrect updates from earlier supernodes, skipped columns excluded
+//   fwblkslv.c:77-134 / bwblkslv.c:73-125  dense-RHS block solves
+//
+// GPU design.  The reference is a sequential left-looking supernodal code driven by linked
+// lists.  Here the symbolic structure is compiled once into a *plan*: supernode panels in a
+// rectangular column-major layout, the list of (descendant K -> ancestor J) update pairs
+// with precomputed relative row positions, and a level schedule of the supernodal
+// elimination tree.  Numeric work per level = one batched "pull" update kernel (each CTA owns
+// a tile of an ancestor panel and subtracts the contributions of all its descendants in a
+// fixed order -> deterministic, no atomics) + factor kernels.  Supernodes up to SMALL_N
+// columns are factored by one CTA each (batched across the level); wider ones use a blocked
+// right-looking scheme (diag-block CTA with the pivot rules, row-parallel triangular solve,
+// tiled FP64 trailing update).
+//
+// A note on the "diag add" threshold: the reference evaluates
+//     ubk = fabs(x[idamax(...)]) / maxu                       (blkchol2.c:66-70,122)
+// with a Fortran (1-based) idamax used as a C index, so the magnitude actually read is the
+// element FOLLOWING the first maximum of the sub-column (for a maximum in the last row: the
+// first element of the next packed column, i.e. the next pivot's current diagonal).  That
+// is what every build of the reference against a conforming BLAS computes, so it is what
+// we reproduce (see next_after_first_max below); DESIGN.md discusses it.
+#include <algorithm>
+#include <map>
+#include <math.h>
+#include "sb_internal.h"
+
+namespace sb {
+
+static const int SMALL_N = 128;   // supernodes up to this many columns: one CTA each
+static const int NB = 32;         // panel width of the blocked path
+static const int UT_R = 64, UT_C = 32;   // update-kernel tile of an ancestor panel
+
+struct Sn {        // one supernode
+  int first, n, m; // first column, #columns, #rows of first column (incl. diagonal)
+  int lindx;       // offset of its row list in lindx[]
+  long long poff;  // offset of its m x n panel in the rect layout (ld = m)
+  long long coff;  // offset of its first column in the packed CSC value array (= Ljc[first])
+};
+struct Pair {      // update of ancestor J by descendant K
+  int K, J;
+  int koff;        // first row (index into K's row list) that lies in J's columns
+  int mk;          // rows of K from koff to the end
+  int ncolup;      // how many of those lie inside J's columns
+  int rel;         // offset into rel[]: position of each of those mk rows inside J's row list
+};
+struct UTile { int J, r0, c0; };
+
+}  // namespace sb
+
+struct sb200_chol_plan {
+  int m = 0, nsuper = 0, nlevels = 0;
+  long long nnzL = 0, rect = 0;
+  uint64_t key = 0;
+  std::vector<sb::Sn> sn;
+  std::vector<int> snode, level_of;
+  std::vector<std::vector<int>> level_small, level_big;      // supernodes per level
+  std::vector<int> level_small_off;                          // offsets into d_level_list
+  std::vector<std::vector<sb::UTile>> level_tiles;
+  std::vector<int> level_tile_off;
+  std::vector<int> pair_beg;                                  // per J: range in pairs[]
+  std::vector<std::vector<int>> level_all;                   // all supernodes per level (solves)
+  std::vector<int> level_all_off;
+  int max_sn_n = 0, max_sn_m = 0;
+  // device
+  sb::DevBuf<sb::Sn> d_sn;
+  sb::DevBuf<sb::Pair> d_pairs;
+  sb::DevBuf<int> d_pair_beg, d_rel, d_lindx, d_snode, d_perm, d_Xjc, d_Xir, d_level_list, d_level_all;
+  sb::DevBuf<sb::UTile> d_tiles;
+  sb::DevBuf<long long> d_Ljc;
+  // numeric scratch
+  sb::DevBuf<double> d_diagX, d_lb, d_scal, d_vscratch, d_y;
+};
+
+namespace sb {
+
+// ======================================================================= device helpers
+struct ArgMax { double v; int i; };
+__device__ __forceinline__ ArgMax am_better(ArgMax a, ArgMax b) {
+  // first element of maximum magnitude (idamax semantics: ties -> smallest index)
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax *sh) {
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax y; y.v = __shfl_down_sync(0xffffffffu, x.v, o); y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+    x = am_better(x, y);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    x = (l < nw) ? sh[l] : ArgMax{-1.0, 0x7fffffff};
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax y; y.v = __shfl_down_sync(0xffffffffu, x.v, o); y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+      x = am_better(x, y);
+    }
+    if (l == 0) sh[0] = x;
+  }
+  __syncthreads();
+  x = sh[0];
+  __syncthreads();
+  return x;
+}
+
+// ======================================================================= permuteP
+// One CTA per column j of L: gathers X(perm(rows), perm(j)) into the rect panel.
+__global__ void permuteP_kernel(const Sn *sn, const int *snode, const int *lindx, const int *perm,
+                                const int *Xjc, const int *Xir, const double *Xpr,
+                                double *rect, double *diagX) {
+  int j = blockIdx.x;
+  Sn s = sn[snode[j]];
+  int c = j - s.first;
+  const int *rows = lindx + s.lindx;
+  double *col = rect + s.poff + (long long)c * s.m;
+  int pj = perm[j];
+  int b0 = Xjc[pj], b1 = Xjc[pj + 1];
+  bool dense = (b1 - b0) == (int)gridDim.x;       // full column: row r sits at b0 + r
+  for (int t = threadIdx.x; t < s.m; t += blockDim.x) {
+    double v = 0.0;
+    if (t >= c) {
+      int pi = perm[rows[t]];
+      if (dense) v = Xpr[b0 + pi];
+      else {
+        int lo = b0, hi = b1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (Xir[mid] < pi) lo = mid + 1; else hi = mid; }
+        if (lo < b1 && Xir[lo] == pi) v = Xpr[lo];
+      }
+      if (t == c) diagX[j] = v;
+    }
+    col[t] = v;
+  }
+}
+
+// scal[0] = ub = max(diag)/maxu^2 ; lb[j] = max(abstol, canceltol * (absd ? absd[perm[j]] : diag[j]))
+__global__ void bounds_kernel(int m, const double *diagX, const double *absd, const int *perm,
+                              double abstol, double canceltol, double maxu, double *lb, double *scal) {
+  __shared__ double sh[32];
+  double mx = 0.0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    double dj = diagX[j];
+    if (dj > mx) mx = dj;
+    double o = canceltol * (absd ? absd[perm[j]] : dj);
+    lb[j] = (o > abstol) ? o : abstol;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) scal[0] = mx / (maxu * maxu);
+  }
+}
+
+// ======================================================================= update (pull)
+// CTA = one UT_R x UT_C tile of ancestor panel J; loops over J's descendants in order.
+__global__ void __launch_bounds__(256)
+update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pair_beg,
+              const int *rel, const double *d, double *rect) {
+  UTile tl = tiles[blockIdx.x];
+  Sn sj = sn[tl.J];
+  double *PJ = rect + sj.poff;
+  int r0 = tl.r0, r1 = min(tl.r0 + UT_R, sj.m), c0 = tl.c0, c1 = min(tl.c0 + UT_C, sj.n);
+  __shared__ int s_rng[4];
+  for (int e = pair_beg[tl.J]; e < pair_beg[tl.J + 1]; e++) {
+    Pair p = pairs[e];
+    const int *rl = rel + p.rel;
+    if (threadIdx.x == 0) {
+      // rows t1 in [a,b): rel in [r0,r1) ; cols t2 in [cA,cB) (t2 < ncolup): rel in [c0,c1)
+      int lo = 0, hi = p.mk;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r0) lo = mid + 1; else hi = mid; }
+      s_rng[0] = lo; hi = p.mk;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r1) lo = mid + 1; else hi = mid; }
+      s_rng[1] = lo;
+      lo = 0; hi = p.ncolup;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c0) lo = mid + 1; else hi = mid; }
+      s_rng[2] = lo; hi = p.ncolup;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c1) lo = mid + 1; else hi = mid; }
+      s_rng[3] = lo;
+    }
+    __syncthreads();
+    int a = s_rng[0], b = s_rng[1], cA = s_rng[2], cB = s_rng[3];
+    __syncthreads();
+    int nr = b - a, nc = cB - cA;
+    if (nr <= 0 || nc <= 0) continue;
+    Sn sk = sn[p.K];
+    const double *PK = rect + sk.poff + p.koff;       // row koff of K's panel
+    const double *dk = d + sk.first;
+    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+      int t1 = a + idx % nr, t2 = cA + idx / nr;
+      if (t1 < t2) continue;                           // strictly above the diagonal of J
+      double acc = 0.0;
+      const double *x1 = PK + t1, *x2 = PK + t2;
+      for (int kk = 0; kk < sk.n; kk++) {
+        double dkk = dk[kk];
+        acc += x1[(long long)kk * sk.m] * (dkk * x2[(long long)kk * sk.m]);
+      }
+      PJ[rl[t1] + (long long)rl[t2] * sj.m] -= acc;
+    }
+  }
+}
+
+// ======================================================================= small supernodes
+// One CTA factors one whole supernode panel (m x n, in global/L2), column by column.
+__global__ void __launch_bounds__(512)
+factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, const double *lb,
+                    const double *scal, double maxu, int *flag, double *sval,
+                    const double *diagX, int mtot) {
+  Sn s = sn[list[blockIdx.x]];
+  double *P = rect + s.poff;
+  const int ld = s.m, n = s.n, m = s.m;
+  const double ub = scal[0];
+  __shared__ ArgMax sh_am[32];
+  __shared__ double s_x;
+  for (int k = 0; k < n; k++) {
+    const int gk = s.first + k;
+    double *ck = P + (long long)k * ld;
+    double xkk = ck[k];
+    double lbk = lb[gk];
+    bool skip = !(xkk > lbk);
+    bool trig = !skip && (m - k > 1) && (xkk < ub);      // uniform across the CTA
+    if (trig) {
+      ArgMax am{-1.0, 0x7fffffff};
+      for (int t = k + 1 + threadIdx.x; t < m; t += blockDim.x) am = am_better(am, ArgMax{fabs(ck[t]), t});
+      am = block_argmax(am, sh_am);
+      if (threadIdx.x == 0) {
+        int t = am.i + 1;                                // element following the first maximum
+        double v;
+        if (t < m) v = ck[t];
+        else if (k + 1 < n) v = P[(long long)(k + 1) * ld + (k + 1)];
+        else v = (gk + 1 < mtot) ? diagX[gk + 1] : 0.0;
+        double ubk = fabs(v) / maxu;
+        if (xkk < ubk) { flag[gk] = 2; sval[gk] = ubk - xkk; xkk = ubk; }
+        s_x = xkk;
+      }
+      __syncthreads();
+      xkk = s_x;
+      __syncthreads();
+    }
+    if (skip) {
+      if (threadIdx.x == 0) { d[gk] = 0.0; flag[gk] = 1; sval[gk] = xkk; }
+      continue;                                          // column untouched, excluded from updates
+    }
+    // right-looking update of the remaining columns of the supernode with the UNDIVIDED column
+    const int ncol = n - k - 1;
+    if (ncol > 0) {
+      // warp per column c, lanes over rows
+      int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      for (int c = k + 1 + warp; c < n; c += nw) {
+        double lck = ck[c] / xkk;
+        double *cc = P + (long long)c * ld;
+        for (int r = c + lane; r < m; r += 32) cc[r] -= lck * ck[r];
+      }
+    }
+    __syncthreads();
+    for (int r = k + 1 + threadIdx.x; r < m; r += blockDim.x) ck[r] /= xkk;
+    if (threadIdx.x == 0) { d[gk] = xkk; ck[k] = 1.0; }
+    __syncthreads();
+  }
+}
+
+// ======================================================================= blocked path
+// diag kernel: factor the w x w diagonal block at panel offset p0 of supernode S.
+// Tail rows (below the block) are only needed when the stability test fires.
+__global__ void __launch_bounds__(256)
+diag_kernel(Sn s, int p0, int w, double *rect, double *d, const double *lb, const double *scal,
+            double maxu, int *flag, double *sval, const double *diagX, int mtot, double *vscratch) {
+  __shared__ double A[NB][NB + 1];
+  __shared__ double z[NB], dloc[NB];
+  __shared__ int skipped[NB];
+  __shared__ ArgMax sh_am[32];
+  __shared__ double s_x;
+  double *P = rect + s.poff;
+  const int ld = s.m, m = s.m, n = s.n;
+  const double ub = scal[0];
+  for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+    int r = idx % w, c = idx / w;
+    A[r][c] = (r >= c) ? P[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+  }
+  if (threadIdx.x < NB) { skipped[threadIdx.x] = 0; dloc[threadIdx.x] = 0.0; }
+  __syncthreads();
+  for (int k = 0; k < w; k++) {
+    const int gk = s.first + p0 + k;
+    double xkk = A[k][k];
+    double lbk = lb[gk];
+    bool skip = !(xkk > lbk);
+    const int collen = m - (p0 + k);                     // remaining length incl. diagonal
+    bool trig = !skip && (collen > 1) && (xkk < ub);
+    if (trig) {
+      // z: last column of (I+S)^-1, so that  v_tail = P[tail, p0:p0+k] * z   
+      if (threadIdx.x == 0) {
+        z[k] = 1.0;
+        for (int i = k - 1; i >= 0; i--) {
+          double acc = 0.0;
+          if (!skipped[i]) for (int j = i + 1; j <= k; j++) acc += A[j][i] * z[j];
+          z[i] = -acc;
+        }
+      }
+      __syncthreads();
+      ArgMax am{-1.0, 0x7fffffff};
+      // sub-diagonal rows inside the block come first (index = position in the sub-column)
+      for (int r = k + 1 + threadIdx.x; r < w; r += blockDim.x) am = am_better(am, ArgMax{fabs(A[r][k]), r - (k + 1)});
+      for (int r = p0 + w + threadIdx.x; r < m; r += blockDim.x) {
+        double v = 0.0;
+        for (int j = 0; j <= k; j++) v += P[(long long)(p0 + j) * ld + r] * z[j];
+        vscratch[r] = v;
+        am = am_better(am, ArgMax{fabs(v), r - (p0 + k + 1)});
+      }
+      am = block_argmax(am, sh_am);
+      if (threadIdx.x == 0) {
+        int t = am.i + 1;                                // position in the sub-column
+        int sublen = collen - 1;
+        double v;
+        if (t < sublen) {
+          int r = p0 + k + 1 + t;                        // row inside the panel
+          v = (r < p0 + w) ? A[r - p0][k] : vscratch[r];
+        } else if (k + 1 < w) {
+          v = A[k + 1][k + 1];
+        } else if (p0 + w < n) {
+          // diagonal of the next panel's first column as the reference would hold it now:
+          // updated by the columns 0..k-1 of this panel (column k not applied yet)
+          int r = p0 + w;
+          double u[NB];
+          double x = P[(long long)r * ld + r];
+          for (int j = 0; j < k; j++) {
+            double uj = P[(long long)(p0 + j) * ld + r];
+            for (int i = 0; i < j; i++) if (!skipped[i]) uj -= u[i] * A[j][i];
+            u[j] = uj;
+            if (!skipped[j]) x -= uj * uj / dloc[j];
+          }
+          v = x;
+        } else {
+          v = (gk + 1 < mtot) ? diagX[gk + 1] : 0.0;
+        }
+        double ubk = fabs(v) / maxu;
+        if (xkk < ubk) { flag[gk] = 2; sval[gk] = ubk - xkk; xkk = ubk; }
+        s_x = xkk;
+      }
+      __syncthreads();
+      xkk = s_x;
+      __syncthreads();
+    }
+    if (skip) {
+      if (threadIdx.x == 0) { d[gk] = 0.0; flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
+      __syncthreads();
+      continue;
+    }
+    // rank-1 update inside the block with the undivided column
+    for (int idx = threadIdx.x; idx < (w - k - 1) * (w - k - 1); idx += blockDim.x) {
+      int r = k + 1 + idx % (w - k - 1), c = k + 1 + idx / (w - k - 1);
+      if (r >= c) A[r][c] -= (A[c][k] / xkk) * A[r][k];
+    }
+    __syncthreads();
+    for (int r = k + 1 + threadIdx.x; r < w; r += blockDim.x) A[r][k] /= xkk;
+    if (threadIdx.x == 0) { d[gk] = xkk; dloc[k] = xkk; A[k][k] = 1.0; }
+    __syncthreads();
+  }
+  // write L11 back; skipped columns: zero below the diagonal (excluded from everything later)
+  for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+    int r = idx % w, c = idx / w;
+    if (r >= c) P[(long long)(p0 + c) * ld + p0 + r] = (skipped[c] && r > c) ? 0.0 : A[r][c];
+  }
+}
+
+// trsm kernel: rows below the diagonal block:  L21 = A21 * L11^-T * D^-1  (one thread per row)
+__global__ void __launch_bounds__(128)
+trsm_kernel(Sn s, int p0, int w, double *rect, const double *d) {
+  __shared__ double L11[NB][NB + 1];
+  __shared__ double dl[NB];
+  double *P = rect + s.poff;
+  const int ld = s.m;
+  for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+    int r = idx % w, c = idx / w;
+    L11[r][c] = (r > c) ? P[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+  }
+  if (threadIdx.x < w) dl[threadIdx.x] = d[s.first + p0 + threadIdx.x];
+  __syncthreads();
+  int r = p0 + w + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= s.m) return;
+  double a[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) a[j] = (j < w) ? P[(long long)(p0 + j) * ld + r] : 0.0;
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    if (j < w) {
+      double dj = dl[j];
+      double xj = a[j];                                   // undivided, fully updated
+      if (dj > 0.0) {
+#pragma unroll
+        for (int j2 = j + 1; j2 < NB; j2++) if (j2 < w) a[j2] -= xj * L11[j2][j];
+        a[j] = xj / dj;
+      } else a[j] = 0.0;                                  // skipped pivot: column excluded
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; j++) if (j < w) P[(long long)(p0 + j) * ld + r] = a[j];
+}
+
+// trailing update:  C[r,c] -= sum_j L21[r,j] d_j L21[c,j]   (r >= c), 64x64 tiles, 4x4 per thread
+__global__ void __launch_bounds__(256)
+trail_kernel(Sn s, int p0, int w, double *rect, const double *d) {
+  const int base = p0 + w;
+  const int r0 = base + blockIdx.x * 64, c0 = base + blockIdx.y * 64;
+  if (r0 + 63 < c0 || c0 >= s.n || r0 >= s.m) return;     // tile entirely above the diagonal / outside
+  __shared__ double As[NB][64 + 1], Bs[NB][64 + 1];
+  double *P = rect + s.poff;
+  const int ld = s.m;
+  for (int idx = threadIdx.x; idx < 64 * w; idx += blockDim.x) {
+    int i = idx % 64, j = idx / 64;
+    int r = r0 + i, c = c0 + i;
+    As[j][i] = (r < s.m) ? P[(long long)(p0 + j) * ld + r] : 0.0;
+    Bs[j][i] = (c < s.n) ? P[(long long)(p0 + j) * ld + c] * d[s.first + p0 + j] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4] = {};
+  for (int j = 0; j < w; j++) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { av[i] = As[j][tx + 16 * i]; bv[i] = Bs[j][ty + 16 * i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[i][q] += av[i] * bv[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int c = c0 + ty + 16 * q;
+    if (c >= s.n) continue;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int r = r0 + tx + 16 * i;
+      if (r < s.m && r >= c) P[(long long)c * ld + r] -= acc[i][q];
+    }
+  }
+}
+
+// ======================================================================= layout conversion
+__global__ void rect_to_csc_kernel(const Sn *sn, const int *snode, const long long *Ljc,
+                                   const double *rect, const int *flag, double *Lpr) {
+  int j = blockIdx.x;
+  Sn s = sn[snode[j]];
+  int c = j - s.first;
+  const double *col = rect + s.poff + (long long)c * s.m;
+  double *out = Lpr + Ljc[j];
+  bool sk = flag && flag[j] == 1;
+  for (int t = c + threadIdx.x; t < s.m; t += blockDim.x)
+    out[t - c] = (t == c) ? 1.0 : (sk ? 0.0 : col[t]);
+}
+__global__ void csc_to_rect_kernel(const Sn *sn, const int *snode, const long long *Ljc,
+                                   const double *Lpr, double *rect) {
+  int j = blockIdx.x;
+  Sn s = sn[snode[j]];
+  int c = j - s.first;
+  double *col = rect + s.poff + (long long)c * s.m;
+  const double *in = Lpr + Ljc[j];
+  for (int t = threadIdx.x; t < s.m; t += blockDim.x) col[t] = (t >= c) ? in[t - c] : 0.0;
+}
+
+// ======================================================================= solves
+// Forward: one CTA per (supernode of the level, rhs).  y has length m per rhs, already = b(perm).
+__global__ void __launch_bounds__(512)
+fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair_beg, const int *rel,
+               const double *rect, double *y, int m) {
+  extern __shared__ double sm[];             // s[n]
+  Sn sj = sn[list[blockIdx.x]];
+  double *yy = y + (long long)blockIdx.y * m;
+  const int n = sj.n;
+  double *s = sm;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) s[c] = yy[sj.first + c];
+  __syncthreads();
+  // pull contributions of descendants:  s[col] -= L_K[row, :] * y_K
+  for (int e = pair_beg[list[blockIdx.x]]; e < pair_beg[list[blockIdx.x] + 1]; e++) {
+    Pair p = pairs[e];
+    Sn sk = sn[p.K];
+    const double *PK = rect + sk.poff + p.koff;
+    const double *yk = yy + sk.first;
+    const int *rl = rel + p.rel;
+    for (int t = threadIdx.x; t < p.ncolup; t += blockDim.x) {
+      double acc = 0.0;
+      for (int kk = 0; kk < sk.n; kk++) acc += PK[(long long)kk * sk.m + t] * yk[kk];
+      s[rl[t]] -= acc;                       // rl[t] < n: distinct per t inside one pair
+    }
+    __syncthreads();
+  }
+  // dense unit-lower solve of the n x n diagonal block, 32 columns at a time
+  const double *P = rect + sj.poff;
+  const int ld = sj.m;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    int w = min(32, n - k0);
+    if (threadIdx.x < 32) {
+      int lane = threadIdx.x;
+      double v = (lane < w) ? s[k0 + lane] : 0.0;
+      for (int k = 0; k < w; k++) {
+        double yk = __shfl_sync(0xffffffffu, v, k);
+        if (lane > k && lane < w) v -= P[(long long)(k0 + k) * ld + k0 + lane] * yk;
+      }
+      if (lane < w) s[k0 + lane] = v;
+    }
+    __syncthreads();
+    for (int r = k0 + w + threadIdx.x; r < n; r += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < w; k++) acc += P[(long long)(k0 + k) * ld + r] * s[k0 + k];
+      s[r] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < n; c += blockDim.x) yy[sj.first + c] = s[c];
+}
+
+// Backward: z = L'^-1 b in permuted order, levels descending.
+__global__ void __launch_bounds__(512)
+bwsolve_kernel(const int *list, const Sn *sn, const int *lindx, const double *rect, double *z, int m) {
+  extern __shared__ double sm[];
+  Sn sj = sn[list[blockIdx.x]];
+  double *zz = z + (long long)blockIdx.y * m;
+  const int n = sj.n, ld = sj.m;
+  const double *P = rect + sj.poff;
+  const int *rows = lindx + sj.lindx;
+  double *s = sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // s[c] = b[c] - sum_{t>=n} L[t,c] * z[rows[t]]
+  for (int c = warp; c < n; c += nw) {
+    const double *col = P + (long long)c * ld;
+    double acc = 0.0;
+    for (int t = n + lane; t < sj.m; t += 32) acc += col[t] * zz[rows[t]];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) s[c] = zz[sj.first + c] - acc;
+  }
+  __syncthreads();
+  for (int k1 = n; k1 > 0; k1 -= 32) {
+    int k0 = max(0, k1 - 32), w = k1 - k0;
+    if (threadIdx.x < 32) {
+      double v = (lane < w) ? s[k0 + lane] : 0.0;
+      for (int k = w - 1; k >= 0; k--) {
+        double zk = __shfl_sync(0xffffffffu, v, k);
+        // z_c -= L[k, c] * z_k for c < k
+        if (lane < k) v -= P[(long long)(k0 + lane) * ld + k0 + k] * zk;
+      }
+      if (lane < w) s[k0 + lane] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < k0; c += blockDim.x) {
+      const double *col = P + (long long)c * ld + k0;
+      double acc = 0.0;
+      for (int k = 0; k < w; k++) acc += col[k] * s[k0 + k];
+      s[c] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < n; c += blockDim.x) zz[sj.first + c] = s[c];
+}
+
+__global__ void gather_perm_kernel(int m, int nrhs, const int *perm, const double *b, double *y) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)m * nrhs) return;
+  int k = (int)(i % m); long long col = i / m;
+  y[i] = b[col * m + perm[k]];
+}
+__global__ void scatter_perm_kernel(int m, int nrhs, const int *perm, const double *z, double *y) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)m * nrhs) return;
+  int k = (int)(i % m); long long col = i / m;
+  y[col * m + perm[k]] = z[i];
+}
+
+}  // namespace sb
+
+// =========================================================================== host side
+using namespace sb;
+
+static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb_idx *xsuper,
+                      const sb_idx *Ljc, const sb_idx *Lir, const sb_idx *perm,
+                      const sb_idx *Xjc, const sb_idx *Xir) {
+  SB_CHECK(m64 >= 0 && m64 < 2147483647LL, "blkchol: m out of range");
+  const int m = (int)m64, nsuper = (int)nsuper64;
+  pl->m = m; pl->nsuper = nsuper;
+  pl->nnzL = Ljc[m];
+  SB_CHECK(nsuper >= 0 && nsuper <= m, "blkchol: Size L.xsuper mismatch.");
+  SB_CHECK(xsuper[0] == 0 && xsuper[nsuper] == m, "blkchol: L.xsuper must span 1..m+1");
+  pl->sn.resize(nsuper);
+  pl->snode.assign(m, 0);
+  std::vector<int> lindx;
+  long long poff = 0;
+  for (int s = 0; s < nsuper; s++) {
+    Sn &S = pl->sn[s];
+    S.first = (int)xsuper[s];
+    S.n = (int)(xsuper[s + 1] - xsuper[s]);
+    SB_CHECK(S.n > 0, "blkchol: empty supernode %d", s);
+    S.m = (int)(Ljc[S.first + 1] - Ljc[S.first]);
+    SB_CHECK(S.m >= S.n, "blkchol: supernode %d shorter than its width", s);
+    S.lindx = (int)lindx.size();
+    S.poff = poff;
+    S.coff = Ljc[S.first];
+    poff += (long long)S.m * S.n;
+    for (int t = 0; t < S.m; t++) {
+      sb_idx r = Lir[Ljc[S.first] + t];
+      SB_CHECK(r >= 0 && r < m, "blkchol: L.L row index out of range");
+      if (t < S.n) SB_CHECK(r == S.first + t, "blkchol: L.L is not a supernodal pattern (column %d)", S.first);
+      lindx.push_back((int)r);
+    }
+    for (int c = 0; c < S.n; c++) {
+      pl->snode[S.first + c] = s;
+      SB_CHECK(Ljc[S.first + c + 1] - Ljc[S.first + c] == S.m - c, "blkchol: column %d breaks the nested supernode pattern", S.first + c);
+    }
+    pl->max_sn_n = std::max(pl->max_sn_n, S.n);
+    pl->max_sn_m = std::max(pl->max_sn_m, S.m);
+  }
+  pl->rect = poff;
+  // update pairs
+  std::vector<std::vector<Pair>> byJ(nsuper);
+  std::vector<int> rel;
+  pl->level_of.assign(nsuper, 0);
+  for (int K = 0; K < nsuper; K++) {
+    const Sn &SK = pl->sn[K];
+    const int *rk = lindx.data() + SK.lindx;
+    int t = SK.n;
+    while (t < SK.m) {
+      int J = pl->snode[rk[t]];
+      SB_CHECK(J > K, "blkchol: row structure of supernode %d is not ascending", K);
+      int t0 = t;
+      while (t < SK.m && pl->snode[rk[t]] == J) t++;
+      Pair p; p.K = K; p.J = J; p.koff = t0; p.mk = SK.m - t0; p.ncolup = t - t0; p.rel = (int)rel.size();
+      const Sn &SJ = pl->sn[J];
+      const int *rj = lindx.data() + SJ.lindx;
+      int pos = 0;
+      for (int tt = t0; tt < SK.m; tt++) {
+        while (pos < SJ.m && rj[pos] < rk[tt]) pos++;
+        SB_CHECK(pos < SJ.m && rj[pos] == rk[tt], "blkchol: structure of supernode %d not contained in ancestor %d", K, J);
+        rel.push_back(pos);
+      }
+      byJ[J].push_back(p);
+      pl->level_of[J] = std::max(pl->level_of[J], pl->level_of[K] + 1);
+    }
+  }
+  std::vector<Pair> pairs;
+  pl->pair_beg.assign(nsuper + 1, 0);
+  for (int J = 0; J < nsuper; J++) {
+    pl->pair_beg[J] = (int)pairs.size();
+    for (auto &p : byJ[J]) pairs.push_back(p);
+  }
+  pl->pair_beg[nsuper] = (int)pairs.size();
+  int nlev = 0;
+  for (int s = 0; s < nsuper; s++) nlev = std::max(nlev, pl->level_of[s] + 1);
+  pl->nlevels = nlev;
+  pl->level_small.assign(nlev, {}); pl->level_big.assign(nlev, {}); pl->level_tiles.assign(nlev, {});
+  pl->level_all.assign(nlev, {});
+  for (int s = 0; s < nsuper; s++) {
+    int lv = pl->level_of[s];
+    (pl->sn[s].n <= SMALL_N ? pl->level_small : pl->level_big)[lv].push_back(s);
+    pl->level_all[lv].push_back(s);
+    if (pl->pair_beg[s + 1] > pl->pair_beg[s]) {
+      const Sn &S = pl->sn[s];
+      for (int c0 = 0; c0 < S.n; c0 += UT_C)
+        for (int r0 = (c0 / UT_R) * UT_R; r0 < S.m; r0 += UT_R) pl->level_tiles[lv].push_back(UTile{s, r0, c0});
+    }
+  }
+  std::vector<int> small_list, all_list; std::vector<UTile> tiles;
+  for (int lv = 0; lv < nlev; lv++) {
+    pl->level_small_off.push_back((int)small_list.size());
+    pl->level_tile_off.push_back((int)tiles.size());
+    pl->level_all_off.push_back((int)all_list.size());
+    for (int s : pl->level_small[lv]) small_list.push_back(s);
+    for (int s : pl->level_all[lv]) all_list.push_back(s);
+    for (auto &t : pl->level_tiles[lv]) tiles.push_back(t);
+  }
+  std::vector<int> perm32, Xjc32, Xir32;
+  SB_TRY(to_i32(perm, m, perm32, "L.perm"));
+  SB_TRY(to_i32(Xjc, m + 1, Xjc32, "X.jc"));
+  SB_TRY(to_i32(Xir, (size_t)Xjc[m], Xir32, "X.ir"));
+  for (int i = 0; i < m; i++) SB_CHECK(perm32[i] < m, "blkchol: perm out of range");
+  std::vector<long long> Ljc64(Ljc, Ljc + m + 1);
+  SB_TRY(pl->d_sn.upload(pl->sn));
+  SB_TRY(pl->d_pairs.upload(pairs));
+  SB_TRY(pl->d_pair_beg.upload(pl->pair_beg));
+  SB_TRY(pl->d_rel.upload(rel));
+  SB_TRY(pl->d_lindx.upload(lindx));
+  SB_TRY(pl->d_snode.upload(pl->snode));
+  SB_TRY(pl->d_perm.upload(perm32));
+  SB_TRY(pl->d_Xjc.upload(Xjc32));
+  SB_TRY(pl->d_Xir.upload(Xir32));
+  SB_TRY(pl->d_level_list.upload(small_list));
+  SB_TRY(pl->d_level_all.upload(all_list));
+  SB_TRY(pl->d_tiles.upload(tiles));
+  SB_TRY(pl->d_Ljc.upload(Ljc64));
+  SB_TRY(pl->d_diagX.alloc(m));
+  SB_TRY(pl->d_lb.alloc(m));
+  SB_TRY(pl->d_scal.alloc(8));
+  SB_TRY(pl->d_vscratch.alloc(std::max(pl->max_sn_m, 1)));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));       // host vectors go out of scope
+  return 0;
+}
+
+extern "C" {
+
+int sb200_chol_plan_create(sb200_chol_plan **plan, sb_idx m, sb_idx nsuper, const sb_idx *xsuper,
+                           const sb_idx *Ljc, const sb_idx *Lir, const sb_idx *perm,
+                           const sb_idx *Xjc, const sb_idx *Xir) {
+  SB_TRY(ensure_init());
+  sb200_chol_plan *pl = new sb200_chol_plan();
+  int rc = build_plan(pl, m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir);
+  if (rc) { delete pl; return rc; }
+  *plan = pl;
+  return 0;
+}
+void sb200_chol_plan_destroy(sb200_chol_plan *plan) { delete plan; }
+sb_idx sb200_chol_plan_nnzL(const sb200_chol_plan *plan) { return plan->nnzL; }
+sb_idx sb200_chol_plan_rect_size(const sb200_chol_plan *plan) { return plan->rect; }
+
+int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd,
+                      sb200_chol_pars pars, double *rect, double *d, int *flag, double *sval) {
+  SB_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  if (m == 0) return 0;
+  SB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * m, st));
+  SB_CUDA(cudaMemsetAsync(sval, 0, sizeof(double) * m, st));
+  permuteP_kernel<<<m, 256, 0, st>>>(pl->d_sn.p, pl->d_snode.p, pl->d_lindx.p, pl->d_perm.p,
+                                      pl->d_Xjc.p, pl->d_Xir.p, Xpr, rect, pl->d_diagX.p);
+  SB_LAUNCH_CHECK();
+  bounds_kernel<<<1, 1024, 0, st>>>(m, pl->d_diagX.p, absd, pl->d_perm.p, pars.abstol, pars.canceltol,
+                                     pars.maxu, pl->d_lb.p, pl->d_scal.p);
+  SB_LAUNCH_CHECK();
+  for (int lv = 0; lv < pl->nlevels; lv++) {
+    int ntile = (int)pl->level_tiles[lv].size();
+    if (ntile) {
+      update_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_pairs.p,
+                                            pl->d_pair_beg.p, pl->d_rel.p, d, rect);
+      SB_LAUNCH_CHECK();
+    }
+    int nsmall = (int)pl->level_small[lv].size();
+    if (nsmall) {
+      factor_small_kernel<<<nsmall, 512, 0, st>>>(pl->d_level_list.p + pl->level_small_off[lv], pl->d_sn.p, rect, d,
+                                                   pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m);
+      SB_LAUNCH_CHECK();
+    }
+    for (int s : pl->level_big[lv]) {
+      const Sn &S = pl->sn[s];
+      for (int p0 = 0; p0 < S.n; p0 += NB) {
+        int w = std::min(NB, S.n - p0);
+        diag_kernel<<<1, 256, 0, st>>>(S, p0, w, rect, d, pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval,
+                                        pl->d_diagX.p, m, pl->d_vscratch.p);
+        SB_LAUNCH_CHECK();
+        int nrow = S.m - (p0 + w);
+        if (nrow > 0) {
+          trsm_kernel<<<(nrow + 127) / 128, 128, 0, st>>>(S, p0, w, rect, d);
+          SB_LAUNCH_CHECK();
+          int ncol = S.n - (p0 + w);
+          if (ncol > 0) {
+            dim3 g((nrow + 63) / 64, (ncol + 63) / 64);
+            trail_kernel<<<g, 256, 0, st>>>(S, p0, w, rect, d);
+            SB_LAUNCH_CHECK();
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+int sb200_chol_rect_to_csc_dev(sb200_chol_plan *pl, const double *rect, const int *flag, double *Lpr) {
+  SB_TRY(ensure_init());
+  if (pl->m == 0) return 0;
+  rect_to_csc_kernel<<<pl->m, 128, 0, ctx().stream>>>(pl->d_sn.p, pl->d_snode.p, pl->d_Ljc.p, rect, flag, Lpr);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+int sb200_chol_csc_to_rect_dev(sb200_chol_plan *pl, const double *Lpr, double *rect) {
+  SB_TRY(ensure_init());
+  if (pl->m == 0) return 0;
+  csc_to_rect_kernel<<<pl->m, 128, 0, ctx().stream>>>(pl->d_sn.p, pl->d_snode.p, pl->d_Ljc.p, Lpr, rect);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  if (m == 0 || nrhs == 0) return 0;
+  long long tot = (long long)m * nrhs;
+  gather_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, b, y);
+  SB_LAUNCH_CHECK();
+  size_t shm = sizeof(double) * (size_t)pl->max_sn_n;
+  SB_CHECK(shm <= 200 * 1024, "fwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
+  if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(fwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  for (int lv = 0; lv < pl->nlevels; lv++) {
+    dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
+    fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pairs.p,
+                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m);
+    SB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  if (m == 0 || nrhs == 0) return 0;
+  long long tot = (long long)m * nrhs;
+  SB_TRY(pl->d_y.n >= (size_t)tot ? 0 : pl->d_y.alloc((size_t)tot));
+  SB_CUDA(cudaMemcpyAsync(pl->d_y.p, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
+  size_t shm = sizeof(double) * (size_t)pl->max_sn_n;
+  SB_CHECK(shm <= 200 * 1024, "bwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
+  if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(bwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  for (int lv = pl->nlevels - 1; lv >= 0; lv--) {
+    dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
+    bwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_lindx.p,
+                                         rect, pl->d_y.p, m);
+    SB_LAUNCH_CHECK();
+  }
+  scatter_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, pl->d_y.p, y);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------- plan cache
+namespace sb {
+struct PlanCache {
+  std::map<uint64_t, sb200_chol_plan *> plans;
+  ~PlanCache() { /* plans leak at process exit on purpose: the CUDA context may be gone */ }
+};
+static PlanCache g_cache;
+
+static uint64_t structure_key(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                              const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir) {
+  uint64_t h = fnv1a(&m, sizeof m);
+  h = fnv1a(&nsuper, sizeof nsuper, h);
+  h = fnv1a(xsuper, sizeof(sb_idx) * (nsuper + 1), h);
+  h = fnv1a(Ljc, sizeof(sb_idx) * (m + 1), h);
+  h = fnv1a(Lir, sizeof(sb_idx) * Ljc[m], h);
+  h = fnv1a(perm, sizeof(sb_idx) * m, h);
+  if (Xjc) { h = fnv1a(Xjc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(Xir, sizeof(sb_idx) * Xjc[m], h); }
+  return h;
+}
+
+// Find or build the plan for this symbolic structure.  For the solves X's pattern is not
+// needed; a plan created without it (Xjc == NULL) gets an empty X pattern.
+int get_plan(sb200_chol_plan **out, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
+             const sb_idx *Lir, const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir) {
+  SB_TRY(ensure_init());
+  uint64_t key = structure_key(m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir);
+  auto it = g_cache.plans.find(key);
+  if (it != g_cache.plans.end()) { *out = it->second; return 0; }
+  std::vector<sb_idx> zjc;
+  if (!Xjc) { zjc.assign(m + 1, 0); Xjc = zjc.data(); Xir = zjc.data(); }
+  sb200_chol_plan *pl = nullptr;
+  SB_TRY(sb200_chol_plan_create(&pl, m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir));
+  pl->key = key;
+  if (g_cache.plans.size() >= 16) {            // bounded: drop everything, rebuild on demand
+    for (auto &kv : g_cache.plans) sb200_chol_plan_destroy(kv.second);
+    g_cache.plans.clear();
+  }
+  g_cache.plans[key] = pl;
+  *out = pl;
+  return 0;
+}
+}  // namespace sb
+
+extern "C" {
+
+int sb200_blkchol(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                  const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir, const double *Xpr,
+                  const double *absd, sb200_chol_pars pars, double *Lpr_out, double *d_out,
+                  sb_idx *skip_idx, double *skip_val, sb_idx *nskip, sb_idx *add_idx, double *add_val,
+                  sb_idx *nadd) {
+  sb200_chol_plan *pl = nullptr;
+  SB_TRY(get_plan(&pl, m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir));
+  *nskip = 0; *nadd = 0;
+  if (m == 0) return 0;
+  DevBuf<double> dX, dabsd, drect, dd, dsval, dL;
+  DevBuf<int> dflag;
+  SB_TRY(dX.upload(Xpr, (size_t)Xjc[m]));
+  if (absd) SB_TRY(dabsd.upload(absd, (size_t)m));
+  SB_TRY(drect.alloc((size_t)pl->rect));
+  SB_TRY(dd.alloc(m)); SB_TRY(dsval.alloc(m)); SB_TRY(dflag.alloc(m));
+  SB_TRY(dL.alloc((size_t)pl->nnzL));
+  SB_TRY(sb200_blkchol_dev(pl, dX.p, absd ? dabsd.p : nullptr, pars, drect.p, dd.p, dflag.p, dsval.p));
+  SB_TRY(sb200_chol_rect_to_csc_dev(pl, drect.p, dflag.p, dL.p));
+  std::vector<int> flag(m);
+  std::vector<double> sval(m);
+  SB_TRY(dL.download(Lpr_out, (size_t)pl->nnzL));
+  SB_TRY(dd.download(d_out, m));
+  SB_TRY(dflag.download(flag.data(), m));
+  SB_TRY(dsval.download(sval.data(), m));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (int j = 0; j < m; j++) {
+    if (flag[j] == 1) { skip_idx[*nskip] = j; skip_val[*nskip] = sval[j]; (*nskip)++; }
+    else if (flag[j] == 2) { add_idx[*nadd] = j; add_val[*nadd] = sval[j]; (*nadd)++; }
+  }
+  return 0;
+}
+
+static int solve_host(bool fw, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                      const double *Lpr, const sb_idx *perm, const double *b, double *y, sb_idx nrhs) {
+  sb200_chol_plan *pl = nullptr;
+  SB_TRY(get_plan(&pl, m, nsuper, xsuper, Ljc, Lir, perm, nullptr, nullptr));
+  if (m == 0 || nrhs == 0) return 0;
+  DevBuf<double> dL, drect, db, dy;
+  SB_TRY(dL.upload(Lpr, (size_t)pl->nnzL));
+  SB_TRY(db.upload(b, (size_t)(m * nrhs)));
+  SB_TRY(drect.alloc((size_t)pl->rect));
+  SB_TRY(dy.alloc((size_t)(m * nrhs)));
+  SB_TRY(sb200_chol_csc_to_rect_dev(pl, dL.p, drect.p));
+  if (fw) SB_TRY(sb200_fwblkslv_dev(pl, drect.p, db.p, dy.p, nrhs));
+  else SB_TRY(sb200_bwblkslv_dev(pl, drect.p, db.p, dy.p, nrhs));
+  SB_TRY(dy.download(y, (size_t)(m * nrhs)));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int sb200_fwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                   const double *Lpr, const sb_idx *perm, const double *b, double *y, sb_idx nrhs) {
+  return solve_host(true, m, nsuper, xsuper, Ljc, Lir, Lpr, perm, b, y, nrhs);
+}
+int sb200_bwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                   const double *Lpr, const sb_idx *perm, const double *b, double *y, sb_idx nrhs) {
+  return solve_host(false, m, nsuper, xsuper, Ljc, Lir, Lpr, perm, b, y, nrhs);
+}
+
+// Sparse right-hand sides: densify on the host side of the boundary, solve, and pick the
+// entries of the symbolic pattern (mathematically identical to selfwsolve, which merely skips
+// supernodes that provably stay zero: fwblkslv.c:150-183).
+static int solve_sparse(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                        const double *Lpr, const sb_idx *perm, sb_idx nrhs, const sb_idx *bjc, const sb_idx *bir,
+                        const double *bpr, const sb_idx *yjc, const sb_idx *yir, double *ypr) {
+  std::vector<double> B((size_t)(m * nrhs), 0.0), Y((size_t)(m * nrhs), 0.0);
+  {
+    for (sb_idx j = 0; j < nrhs; j++)
+      for (sb_idx k = bjc[j]; k < bjc[j + 1]; k++) B[(size_t)(j * m + bir[k])] = bpr[k];
+    SB_TRY(solve_host(true, m, nsuper, xsuper, Ljc, Lir, Lpr, perm, B.data(), Y.data(), nrhs));
+    for (sb_idx j = 0; j < nrhs; j++)
+      for (sb_idx k = yjc[j]; k < yjc[j + 1]; k++) ypr[k] = Y[(size_t)(j * m + yir[k])];
+  }
+  return 0;
+}
+int sb200_fwblkslv_sparse(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+                          const double *Lpr, const sb_idx *perm, sb_idx nrhs, const sb_idx *bjc, const sb_idx *bir,
+                          const double *bpr, const sb_idx *yjc, const sb_idx *yir, double *ypr) {
+  return solve_sparse(m, nsuper, xsuper, Ljc, Lir, Lpr, perm, nrhs, bjc, bir, bpr, yjc, yir, ypr);
+}
+}  // extern "C"

@@ -1,0 +1,121 @@
+// context.cu -- library context: device selection, stream, error text, raw memory helpers.
+#include <stdarg.h>
+#include "sb_internal.h"
+
+namespace sb {
+
+static Context g_ctx;
+static thread_local char g_err[1024] = "";
+
+Context &ctx() { return g_ctx; }
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+void arena_reset() {
+  Context &c = g_ctx;
+  // Work enqueued earlier may still be reading old scratch: drain the stream first.  Calls
+  // are coarse (one MEX-level operation each), so this costs nothing measurable.
+  if (c.stream && (c.arena_off || c.arena_cur)) cudaStreamSynchronize(c.stream);
+  if (c.arena_chunks.size() > 1) {      // coalesce into one chunk big enough for last call
+    size_t tot = 0;
+    for (auto &ch : c.arena_chunks) { tot += ch.second; cudaFree(ch.first); }
+    c.arena_chunks.clear();
+    char *p = nullptr;
+    if (cudaMalloc((void **)&p, tot) == cudaSuccess) c.arena_chunks.push_back({p, tot});
+    else cudaGetLastError();
+  }
+  c.arena_cur = 0; c.arena_off = 0;
+}
+
+void *arena_alloc(size_t bytes) {
+  Context &c = g_ctx;
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  while (c.arena_cur < c.arena_chunks.size()) {
+    auto &ch = c.arena_chunks[c.arena_cur];
+    if (c.arena_off + bytes <= ch.second) { void *p = ch.first + c.arena_off; c.arena_off += bytes; return p; }
+    c.arena_cur++; c.arena_off = 0;
+  }
+  size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+  char *p = nullptr;
+  if (cudaMalloc((void **)&p, cap) != cudaSuccess) { cudaGetLastError(); set_error("arena: cudaMalloc(%zu) failed", cap); return nullptr; }
+  c.arena_chunks.push_back({p, cap});
+  c.arena_cur = c.arena_chunks.size() - 1;
+  c.arena_off = bytes;
+  return p;
+}
+
+int ensure_init() {
+  if (g_ctx.inited) return 0;
+  return sb200_init(0);
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int sb200_init(int device) {
+  sb::Context &c = sb::ctx();
+  if (c.inited && c.device == device) return 0;
+  int n = sb200_device_count();
+  if (n <= 0) { sb::set_error("sb200_init: no CUDA device visible (the B200 path has no CPU fallback)"); return 1; }
+  if (device < 0 || device >= n) { sb::set_error("sb200_init: device %d out of range (%d visible)", device, n); return 1; }
+  SB_CUDA(cudaSetDevice(device));
+  if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
+  SB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.sm_count = prop.multiProcessorCount;
+  c.device = device;
+  c.inited = true;
+  return 0;
+}
+
+void sb200_shutdown(void) {
+  sb::Context &c = sb::ctx();
+  if (c.stream) cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+  c.inited = false;
+}
+
+const char *sb200_last_error(void) { return sb::g_err; }
+
+int sb200_sync(void) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
+  return 0;
+}
+
+void *sb200_stream(void) { return sb::ensure_init() ? nullptr : (void *)sb::ctx().stream; }
+int64_t sb200_kernel_launches(void) { return sb::ctx().launches; }
+
+int sb200_dev_alloc(void **p, int64_t bytes) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaMalloc(p, bytes > 0 ? (size_t)bytes : 1));
+  return 0;
+}
+int sb200_dev_free(void *p) { SB_CUDA(cudaFree(p)); return 0; }
+int sb200_h2d(void *dst, const void *src, int64_t bytes) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, sb::ctx().stream));
+  return 0;
+}
+int sb200_d2h(void *dst, const void *src, int64_t bytes) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, sb::ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
+  return 0;
+}
+
+}  // extern "C"

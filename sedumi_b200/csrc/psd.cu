@@ -1,0 +1,251 @@
+// psd.cu -- per-PSD-block dense algebra: invcholfac (D = U'U) and psdscale (Y = T'XT).
+//
+// Reference semantics:
+//   invcholfac.c:122-141  per block: Z = triu(U)'*triu(U) (utmulx, triuaux.c:175-186),
+//                         symmetrised, then Y(perm,perm) = Z (invmatperm, triuaux.c:61-72)
+//   psdscale.m:76-110     per block: T = tril(U) (transp=0) or triu(U) (transp=1) of the
+//                         stored n x n array, X optionally X(perm,perm) before (transp=0)
+//                         or the result scattered to (perm,perm) after (transp=1); Y = T'*X*T
+//
+// GPU design: every block is a set of 64x64 tiles in ONE batched launch of the DMMA tile
+// GEMM (gemm.cuh).  Both operations are written as "NT" products over Tt = T' so that all
+// tile loads are contiguous:
+//   invcholfac:  Z(i,j)  = sum_k Tt(i,k) Tt(j,k)            (Tt = triu(U)', lower triangular)
+//   psdscale:    Wt(c,i) = sum_k Tt(c,k) X(i,k);  Y(i,c) = sum_k Tt(i,k) Wt(c,k)
+// and the triangular k-ranges are skipped per tile.  Descriptors and tile lists depend only
+// on K.s, so they live in a cached plan; per call only the block data moves.
+#include <map>
+#include "gemm.cuh"
+#include "sb_internal.h"
+
+struct sb200_psd_plan {
+  int nblk = 0;
+  long long lenud = 0, sumn = 0;
+  int maxn = 0;
+  std::vector<int> n;
+  std::vector<long long> off;      // offset of block k in a lenud vector
+  std::vector<int> poff;           // offset of block k in a perm vector
+  // device
+  sb::DevBuf<int> d_n, d_poff;
+  sb::DevBuf<long long> d_off;
+  sb::DevBuf<sb::GemmDesc> d_desc_ichol, d_desc_s1_lo, d_desc_s1_up, d_desc_s2_lo, d_desc_s2_up;
+  sb::DevBuf<sb::GemmTile> d_tiles_full, d_tiles_lower;
+  int ntiles_full = 0, ntiles_lower = 0;
+  // workspaces (lenud doubles each)
+  sb::DevBuf<double> d_Tt, d_Wt, d_Xp, d_Y;
+  sb::DevBuf<int> d_perm;
+};
+
+namespace sb {
+
+// blockIdx.y = PSD block; Tt(c,k) = mask ? U[k + c*n] : 0 with mask (k<=c) for upper=1, (k>=c) for upper=0
+__global__ void tri_transpose_kernel(const int *ns, const long long *offs, const double *u, double *Tt, int upper) {
+  const int n = ns[blockIdx.y];
+  const double *U = u + offs[blockIdx.y];
+  double *T = Tt + offs[blockIdx.y];
+  __shared__ double tile[32][33];
+  const int tilesPerDim = (n + 31) / 32;
+  for (int t = blockIdx.x; t < tilesPerDim * tilesPerDim; t += gridDim.x) {
+    int k0 = (t % tilesPerDim) * 32, c0 = (t / tilesPerDim) * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      int k = k0 + threadIdx.x, c = c0 + j;
+      tile[j][threadIdx.x] = (k < n && c < n) ? U[k + (long long)c * n] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      int c = c0 + threadIdx.x, k = k0 + j;
+      if (c < n && k < n) {
+        bool keep = upper ? (k <= c) : (k >= c);
+        T[c + (long long)k * n] = keep ? tile[threadIdx.x][j] : 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// out(i,j) = in(p[i], p[j])  (gather=1)   or   out(p[i], p[j]) = in(i,j)  (gather=0); sym=1 reads in(max,min)
+__global__ void perm_block_kernel(const int *ns, const long long *offs, const int *poffs, const int *perm,
+                                  const double *in, double *out, int gather, int sym) {
+  const int n = ns[blockIdx.y];
+  const long long off = offs[blockIdx.y];
+  const int *p = perm ? perm + poffs[blockIdx.y] : nullptr;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % n), j = (int)(idx / n);
+    int pi = p ? p[i] : i, pj = p ? p[j] : j;
+    if (gather) out[off + idx] = in[off + pi + (long long)pj * n];
+    else {
+      double v = sym ? in[off + max(i, j) + (long long)min(i, j) * n] : in[off + idx];
+      out[off + pi + (long long)pj * n] = v;
+    }
+  }
+}
+
+static std::map<uint64_t, sb200_psd_plan *> g_psd_plans;
+
+}  // namespace sb
+
+using namespace sb;
+
+static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
+  pl->nblk = (int)nblk;
+  long long off = 0; int po = 0;
+  for (sb_idx k = 0; k < nblk; k++) {
+    SB_CHECK(n[k] >= 1 && n[k] < 46340, "PSD block order %lld out of range", (long long)n[k]);
+    pl->n.push_back((int)n[k]); pl->off.push_back(off); pl->poff.push_back(po);
+    off += n[k] * n[k]; po += (int)n[k];
+    pl->maxn = std::max(pl->maxn, (int)n[k]);
+  }
+  pl->lenud = off; pl->sumn = po;
+  std::vector<GemmDesc> ichol, s1lo, s1up, s2lo, s2up;
+  std::vector<GemmTile> tfull, tlower;
+  for (int k = 0; k < pl->nblk; k++) {
+    int nk = pl->n[k]; long long o = pl->off[k];
+    GemmDesc g{};
+    g.gatherOff = -1; g.lda = g.ldb = g.ldc = nk; g.M = g.N = g.K = nk; g.alpha = 1.0; g.accumulate = 0;
+    g.offA = g.offB = g.offC = o;
+    // invcholfac: A = B = Tt (k <= row), lower only
+    GemmDesc a = g; a.a_tri = TRI_K_LE_ROW; a.b_tri = TRI_K_LE_ROW; a.lower = 1; ichol.push_back(a);
+    // psdscale stage 1: Wt = Tt * X'   (A = Tt, B = X)
+    GemmDesc b = g; b.lower = 0; b.b_tri = TRI_NONE;
+    b.a_tri = TRI_K_GE_ROW; s1lo.push_back(b);          // T = tril(U): Tt(c,k) nonzero for k >= c
+    b.a_tri = TRI_K_LE_ROW; s1up.push_back(b);          // T = triu(U)
+    // stage 2: Y = Tt * Wt'
+    b.a_tri = TRI_K_GE_ROW; s2lo.push_back(b);
+    b.a_tri = TRI_K_LE_ROW; s2up.push_back(b);
+    gemm_add_tiles(tfull, k, nk, nk, false);
+    gemm_add_tiles(tlower, k, nk, nk, true);
+  }
+  pl->ntiles_full = (int)tfull.size(); pl->ntiles_lower = (int)tlower.size();
+  SB_TRY(pl->d_n.upload(pl->n)); SB_TRY(pl->d_off.upload(pl->off)); SB_TRY(pl->d_poff.upload(pl->poff));
+  SB_TRY(pl->d_desc_ichol.upload(ichol));
+  SB_TRY(pl->d_desc_s1_lo.upload(s1lo)); SB_TRY(pl->d_desc_s1_up.upload(s1up));
+  SB_TRY(pl->d_desc_s2_lo.upload(s2lo)); SB_TRY(pl->d_desc_s2_up.upload(s2up));
+  SB_TRY(pl->d_tiles_full.upload(tfull)); SB_TRY(pl->d_tiles_lower.upload(tlower));
+  SB_TRY(pl->d_Tt.alloc((size_t)pl->lenud)); SB_TRY(pl->d_Wt.alloc((size_t)pl->lenud));
+  SB_TRY(pl->d_Xp.alloc((size_t)pl->lenud)); SB_TRY(pl->d_Y.alloc((size_t)pl->lenud));
+  SB_TRY(pl->d_perm.alloc((size_t)std::max<long long>(pl->sumn, 1)));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+extern "C" {
+
+int sb200_psd_plan_get(sb200_psd_plan **plan, sb_idx nblk, const sb_idx *n) {
+  SB_TRY(ensure_init());
+  uint64_t key = fnv1a(n, sizeof(sb_idx) * nblk, fnv1a(&nblk, sizeof nblk));
+  auto it = g_psd_plans.find(key);
+  if (it != g_psd_plans.end()) { *plan = it->second; return 0; }
+  sb200_psd_plan *pl = new sb200_psd_plan();
+  int rc = psd_build(pl, nblk, n);
+  if (rc) { delete pl; return rc; }
+  g_psd_plans[key] = pl;
+  *plan = pl;
+  return 0;
+}
+sb_idx sb200_psd_plan_lenud(const sb200_psd_plan *pl) { return pl->lenud; }
+sb_idx sb200_psd_plan_sumn(const sb200_psd_plan *pl) { return pl->sumn; }
+
+static dim3 blk_grid(const sb200_psd_plan *pl, int per) {
+  long long t = (long long)pl->maxn * pl->maxn;
+  int gx = (int)std::min<long long>((t + per - 1) / per, 1024);
+  return dim3(std::max(gx, 1), pl->nblk);
+}
+
+// y = invcholfac(u, K, perm): perm_dev is int32 0-based (length sum n_k) or NULL.
+int sb200_invcholfac_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_dev, double *y_dev) {
+  SB_TRY(ensure_init());
+  if (pl->nblk == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
+      pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, 1);
+  SB_LAUNCH_CHECK();
+  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_ichol.p, pl->d_tiles_lower.p, pl->d_Tt.p, pl->d_Tt.p,
+                                                   pl->d_Wt.p, nullptr);
+  SB_LAUNCH_CHECK();
+  perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, pl->d_Wt.p, y_dev, 0, 1);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = psdscale(ud, x, K, transp): x_dev/y_dev are the PSD parts (lenud).  perm_dev as above
+// (NULL when ud.perm is empty or ud is a plain vector).
+int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_dev, const double *x_dev,
+                       int transp, double *y_dev) {
+  SB_TRY(ensure_init());
+  if (pl->nblk == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
+      pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, transp ? 1 : 0);
+  SB_LAUNCH_CHECK();
+  const double *xs = x_dev;
+  if (perm_dev && !transp) {          // prep: X(perm,perm)   (psdscale.m:94-99)
+    perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, x_dev, pl->d_Xp.p, 1, 0);
+    SB_LAUNCH_CHECK();
+    xs = pl->d_Xp.p;
+  }
+  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s1_up : pl->d_desc_s1_lo).p, pl->d_tiles_full.p,
+                                                  pl->d_Tt.p, xs, pl->d_Wt.p, nullptr);
+  SB_LAUNCH_CHECK();
+  bool postp = perm_dev && transp;
+  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s2_up : pl->d_desc_s2_lo).p, pl->d_tiles_full.p,
+                                                  pl->d_Tt.p, pl->d_Wt.p, postp ? pl->d_Y.p : y_dev, nullptr);
+  SB_LAUNCH_CHECK();
+  if (postp) {                         // XX(PP,PP) = XX   (psdscale.m:104-109)
+    perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, pl->d_Y.p, y_dev, 0, 0);
+    SB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int upload_perm(sb200_psd_plan *pl, const sb_idx *perm, const int **out) {
+  *out = nullptr;
+  if (!perm) return 0;
+  std::vector<int> p32((size_t)pl->sumn);
+  for (int k = 0; k < pl->nblk; k++)
+    for (int i = 0; i < pl->n[k]; i++) {
+      sb_idx v = perm[pl->poff[k] + i];
+      SB_CHECK(v >= 0 && v < pl->n[k], "perm entry out of range in PSD block %d", k);
+      p32[pl->poff[k] + i] = (int)v;
+    }
+  SB_CUDA(cudaMemcpyAsync(pl->d_perm.p, p32.data(), sizeof(int) * p32.size(), cudaMemcpyHostToDevice, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = pl->d_perm.p;
+  return 0;
+}
+
+// Host entries.  perm: 0-based within each block (NULL = none).
+int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm, double *y) {
+  sb200_psd_plan *pl = nullptr;
+  SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
+  if (pl->lenud == 0) return 0;
+  arena_reset();
+  double *du = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud);
+  SB_CHECK(du && dy, "invcholfac: out of device memory");
+  const int *dperm;
+  SB_TRY(upload_perm(pl, perm, &dperm));
+  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
+  SB_TRY(sb200_invcholfac_dev(pl, du, dperm, dy));
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm, const double *x, int transp, double *y) {
+  sb200_psd_plan *pl = nullptr;
+  SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
+  if (pl->lenud == 0) return 0;
+  arena_reset();
+  double *du = arena<double>((size_t)pl->lenud), *dx = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud);
+  SB_CHECK(du && dx && dy, "psdscale: out of device memory");
+  const int *dperm;
+  SB_TRY(upload_perm(pl, perm, &dperm));
+  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
+  SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
+  SB_TRY(sb200_psdscale_dev(pl, du, dperm, dx, transp, dy));
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// y = psdscale(ud,x,K[,transp])   per PSD block Y = T'*X*T, T = tril(U) or triu(U)
+// The reference implements this in M (psdscale.m:45-119); a MEX of the same name in the
+// same directory takes precedence, so this plugin is a drop-in for the .m file.
+#include "mex_common.h"
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+  MEX_REQUIRE(nrhs >= 3, "psdscale requires at least 3 input arguments.");
+  MEX_REQUIRE(nlhs <= 1, "psdscale generates 1 output argument.");
+  ConeK K;
+  read_cone(prhs[2], K);
+  if (K.sdpN == 0) { plhs[0] = mxCreateDoubleMatrix(0, 0, mxREAL); return; }      // y = [] (psdscale.m:47-50)
+  if (K.rsdpN != K.sdpN) mexErrMsgTxt("psdscale: Hermitian PSD blocks are not supported by the B200 plugin yet.");
+  bool transp = nrhs >= 4 && numel(prhs[3]) > 0 && mxGetScalar(prhs[3]) != 0.0;
+  const mxArray *UD = prhs[0], *ufield = UD, *pfield = NULL;
+  if (mxIsStruct(UD)) {
+    ufield = need_field(UD, "u", "Missing field ud.u.");
+    pfield = mxGetField(UD, 0, "perm");
+  }
+  sb_idx N = K.rDim;
+  MEX_REQUIRE(numel(ufield) >= (mwSize)N, "ud.u size mismatch");
+  MEX_REQUIRE(numel(prhs[1]) >= (mwSize)N, "x size mismatch");
+  MEX_REQUIRE(!mxIsSparse(prhs[1]), "x must be full");
+  std::vector<sb_idx> perm;
+  bool isperm = pfield && numel(pfield) > 0;
+  if (isperm) {
+    MEX_REQUIRE(numel(pfield) >= (mwSize)K.rLen, "ud.perm size mismatch");
+    idx_from_double(pfield, perm, 1, "ud.perm");
+  }
+  const double *x = mxGetPr(prhs[1]) + (numel(prhs[1]) - (mwSize)N);     // PSD part is the tail (psdscale.m:58)
+  plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
+  int rc = sb200_psdscale(K.sdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]));
+  if (rc) { mxDestroyArray(plhs[0]); plhs[0] = NULL; sb_check(rc, "psdscale"); }
+}
