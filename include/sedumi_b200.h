@@ -153,6 +153,22 @@ int sb200_getada2(sb200_ada_plan *plan, sb_idx nq, const sb_idx *Qjc, const sb_i
 int sb200_getada3(sb200_ada_plan *plan, const double *Atpr, const double *udsqr, sb_idx lenud,
                   const sb_idx *perm, sb_idx first, const double *ada_in, double *ada_out, double *absd_out);
 
+/* ------------------------------------------------------------------ Lorentz streams
+ * ddot.c:165-308, qblkmul.c:57-116, quadadd.c:89-130.
+ * Dense ddot / qblkmul: bs[0..nblk] are block starts relative to the first norm-bound row. */
+int sb200_ddot_dense_dev(sb_idx nblk, const long long *bs_dev, const double *d_dev, const double *X_dev,
+                         sb_idx ldx, sb_idx ncol, double *y_dev);
+int sb200_qblkmul_dev(sb_idx nblk, const long long *bs_dev, sb_idx qdim, const double *mu_dev,
+                      const double *d_dev, double *y_dev);
+int sb200_quadadd_dev(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo);
+int sb200_ddot_dense(sb_idx nblk, const sb_idx *bs, const double *d, const double *X, sb_idx ldx,
+                     sb_idx ncol, double *y);
+int sb200_ddot_sparse(sb_idx nblk, const sb_idx *bs_abs, const double *d, sb_idx m, const sb_idx *xlo,
+                      const sb_idx *xhi, const sb_idx *xir, const double *xpr, sb_idx *yjc, sb_idx *yir,
+                      double *ypr, sb_idx *nnz_out);
+int sb200_qblkmul(sb_idx nblk, const sb_idx *bs, const double *mu, const double *d, double *y);
+int sb200_quadadd(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,217 @@
+// lorentz.cu -- streaming Lorentz-cone kernels: ddot, qblkmul, quadadd.
+//
+// Reference semantics:
+//   ddot.c:69-76      dense:  y(k,col) = d[k]' * x[k,col] for every Lorentz block k
+//   ddot.c:95-155     sparse: y(k,j) for every block k in which column j of X has nonzeros
+//   qblkmul.c:110-115 y[k] = mu(k) * d[k]
+//   quadadd.c:58-81   error-free (double-double) accumulation (zhi,zlo) = (xhi,xlo) + y
+// All three are pure HBM streams: one pass, coalesced, grid-stride.
+#include <algorithm>
+#include "sb_internal.h"
+
+namespace sb {
+
+// one warp per (block, column): dot over the block's rows
+__global__ void ddot_dense_kernel(int nblk, const long long *bs, const double *d, const double *X, long long ldx,
+                                  long long ncol, double *y) {
+  const int lane = threadIdx.x & 31;
+  long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (; w < (long long)nblk * ncol; w += nw) {
+    const int k = (int)(w % nblk);
+    const long long col = w / nblk;
+    const double *x = X + col * ldx;
+    double acc = 0.0;
+    for (long long i = bs[k] + lane; i < bs[k + 1]; i += 32) acc += d[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[w] = acc;
+  }
+}
+
+// one thread per output entry: segment [seg[e], seg[e+1]) of X's nonzeros, all inside one block
+__global__ void ddot_sparse_kernel(long long nout, const long long *seg_lo, const long long *seg_hi, const int *xir,
+                                   const double *xpr, const double *d, long long d_shift, double *y) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nout; e += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (long long p = seg_lo[e]; p < seg_hi[e]; p++) acc += d[xir[p] - d_shift] * xpr[p];
+    y[e] = acc;
+  }
+}
+
+__global__ void qblkmul_kernel(int nblk, const long long *bs, const double *mu, const double *d, double *y) {
+  // bs relative to bs[0] = 0
+  const long long tot = bs[nblk];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    int l = 0, h = nblk;
+    while (h - l > 1) { int mid = (l + h) >> 1; if (bs[mid] <= i) l = mid; else h = mid; }
+    y[i] = mu[l] * d[i];
+  }
+}
+
+// Branch-exact restatement of rquaddadd (quadadd.c:58-81); explicit _rn intrinsics so the
+// compiler can neither contract nor reassociate the error-free transformation.
+__global__ void quadadd_kernel(long long n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double a = xhi[i], b = xlo[i], c = y[i], hi, lo;
+    if (fabs(c) > fabs(a)) {
+      hi = __dadd_rn(c, a);
+      a = __dsub_rn(a, __dsub_rn(hi, c));
+      lo = __dadd_rn(b, a);
+    } else {
+      double t = __dadd_rn(b, c);
+      b = __dsub_rn(b, __dsub_rn(t, c));
+      hi = __dadd_rn(a, t);
+      t = __dsub_rn(t, __dsub_rn(hi, a));
+      lo = __dadd_rn(b, t);
+    }
+    zhi[i] = hi; zlo[i] = lo;
+  }
+}
+
+static inline unsigned grid_for(long long n, int per = 256) {
+  long long g = (n + per - 1) / per;
+  long long cap = (long long)ctx().sm_count * 16;
+  return (unsigned)std::max<long long>(1, std::min(g, cap));
+}
+
+}  // namespace sb
+using namespace sb;
+
+extern "C" {
+
+// ---- device-resident variants
+int sb200_ddot_dense_dev(sb_idx nblk, const long long *bs_dev, const double *d_dev, const double *X_dev, sb_idx ldx,
+                         sb_idx ncol, double *y_dev) {
+  SB_TRY(ensure_init());
+  if (nblk == 0 || ncol == 0) return 0;
+  ddot_dense_kernel<<<grid_for(nblk * ncol * 32), 256, 0, ctx().stream>>>((int)nblk, bs_dev, d_dev, X_dev, ldx, ncol, y_dev);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+int sb200_qblkmul_dev(sb_idx nblk, const long long *bs_dev, sb_idx qdim, const double *mu_dev, const double *d_dev, double *y_dev) {
+  SB_TRY(ensure_init());
+  if (qdim == 0) return 0;
+  qblkmul_kernel<<<grid_for(qdim), 256, 0, ctx().stream>>>((int)nblk, bs_dev, mu_dev, d_dev, y_dev);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+int sb200_quadadd_dev(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo) {
+  SB_TRY(ensure_init());
+  if (n == 0) return 0;
+  quadadd_kernel<<<grid_for(n), 256, 0, ctx().stream>>>(n, xhi, xlo, y, zhi, zlo);
+  SB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- host entries
+// bs[0..nblk]: 0-based block starts RELATIVE to the first norm-bound row (bs[0]=0).
+// d: qdim values; X: first norm-bound row of column 0, leading dimension ldx.
+int sb200_ddot_dense(sb_idx nblk, const sb_idx *bs, const double *d, const double *X, sb_idx ldx, sb_idx ncol, double *y) {
+  SB_TRY(ensure_init());
+  if (nblk == 0 || ncol == 0) return 0;
+  arena_reset();
+  const sb_idx qdim = bs[nblk];
+  std::vector<long long> b64(bs, bs + nblk + 1);
+  long long *dbs = arena<long long>(nblk + 1);
+  double *dd = arena<double>((size_t)qdim), *dX = arena<double>((size_t)(qdim * ncol)), *dy = arena<double>((size_t)(nblk * ncol));
+  SB_CHECK(dbs && dd && dX && dy, "ddot: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dbs, b64.data(), sizeof(long long) * (nblk + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dd, d, sizeof(double) * qdim, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpy2DAsync(dX, sizeof(double) * qdim, X, sizeof(double) * ldx, sizeof(double) * qdim, (size_t)ncol, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_ddot_dense_dev(nblk, dbs, dd, dX, qdim, ncol, dy));
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * nblk * ncol, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Sparse X (CSC, m columns): per column j the nonzeros in [xlo[j], xhi[j]) lie in the Lorentz
+// norm-bound rows [bs_abs[0], bs_abs[nblk]).  Output pattern (yjc, yir) and values ypr are written;
+// yir/ypr need room for sum(xhi-xlo) entries.  Returns the number of entries in *nnz_out.
+int sb200_ddot_sparse(sb_idx nblk, const sb_idx *bs_abs, const double *d, sb_idx m, const sb_idx *xlo, const sb_idx *xhi,
+                      const sb_idx *xir, const double *xpr, sb_idx *yjc, sb_idx *yir, double *ypr, sb_idx *nnz_out) {
+  SB_TRY(ensure_init());
+  // structural pass on the host: one output entry per (column, touched block)
+  std::vector<long long> seg_lo, seg_hi;
+  sb_idx knz = 0;
+  sb_idx pmin = -1, pmax = 0;
+  const sb_idx lend = bs_abs[nblk];
+  for (sb_idx j = 0; j < m; j++) {
+    yjc[j] = knz;
+    sb_idx p = xlo[j];
+    while (p < xhi[j] && xir[p] < lend) {
+      sb_idx i = xir[p];
+      SB_CHECK(i >= bs_abs[0], "ddot: X nonzero below the Lorentz norm-bound rows");
+      sb_idx k = (sb_idx)(std::upper_bound(bs_abs, bs_abs + nblk + 1, i) - bs_abs) - 1;
+      sb_idx p0 = p;
+      while (p < xhi[j] && xir[p] < bs_abs[k + 1]) p++;
+      seg_lo.push_back(p0); seg_hi.push_back(p);
+      yir[knz++] = k;
+      if (pmin < 0) pmin = p0;
+      pmax = p;
+    }
+  }
+  yjc[m] = knz;
+  *nnz_out = knz;
+  if (knz == 0) return 0;
+  arena_reset();
+  const sb_idx span = pmax - pmin;
+  for (auto &v : seg_lo) v -= pmin;
+  for (auto &v : seg_hi) v -= pmin;
+  std::vector<int> ir32((size_t)span);
+  for (sb_idx p = 0; p < span; p++) ir32[p] = (int)xir[pmin + p];
+  const sb_idx qdim = bs_abs[nblk] - bs_abs[0];
+  long long *dlo = arena<long long>(knz), *dhi = arena<long long>(knz);
+  int *dir = arena<int>(span);
+  double *dpr = arena<double>(span), *dd = arena<double>(qdim), *dy = arena<double>(knz);
+  SB_CHECK(dlo && dhi && dir && dpr && dd && dy, "ddot: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dlo, seg_lo.data(), sizeof(long long) * knz, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dhi, seg_hi.data(), sizeof(long long) * knz, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dir, ir32.data(), sizeof(int) * span, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dpr, xpr + pmin, sizeof(double) * span, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dd, d, sizeof(double) * qdim, cudaMemcpyHostToDevice, st));
+  ddot_sparse_kernel<<<grid_for(knz), 256, 0, st>>>(knz, dlo, dhi, dir, dpr, dd, bs_abs[0], dy);
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaMemcpyAsync(ypr, dy, sizeof(double) * knz, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sb200_qblkmul(sb_idx nblk, const sb_idx *bs, const double *mu, const double *d, double *y) {
+  SB_TRY(ensure_init());
+  const sb_idx qdim = bs[nblk];
+  if (qdim == 0) return 0;
+  arena_reset();
+  std::vector<long long> b64(bs, bs + nblk + 1);
+  long long *dbs = arena<long long>(nblk + 1);
+  double *dmu = arena<double>(nblk), *dd = arena<double>(qdim), *dy = arena<double>(qdim);
+  SB_CHECK(dbs && dmu && dd && dy, "qblkmul: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dbs, b64.data(), sizeof(long long) * (nblk + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dmu, mu, sizeof(double) * nblk, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dd, d, sizeof(double) * qdim, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_qblkmul_dev(nblk, dbs, qdim, dmu, dd, dy));
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * qdim, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sb200_quadadd(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo) {
+  SB_TRY(ensure_init());
+  if (n == 0) return 0;
+  arena_reset();
+  double *a = arena<double>(n), *b = arena<double>(n), *c = arena<double>(n), *h = arena<double>(n), *l = arena<double>(n);
+  SB_CHECK(a && b && c && h && l, "quadadd: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(a, xhi, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(b, xlo, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(c, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_quadadd_dev(n, a, b, c, h, l));
+  SB_CUDA(cudaMemcpyAsync(zhi, h, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(zlo, l, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"
