@@ -39,6 +39,10 @@ int         sb200_device_count(void);
 int         sb200_sync(void);                     /* cudaStreamSynchronize(library stream) */
 void       *sb200_stream(void);                   /* cudaStream_t of the library */
 int64_t     sb200_kernel_launches(void);          /* kernels launched by this library so far */
+/* per-kernel timing with CUDA events on the library stream: begin, run, end -> text report
+ * "kernel_name launches total_ms" per line */
+int         sb200_prof_begin(void);
+int         sb200_prof_end(char *buf, int64_t buflen);
 int         sb200_dev_alloc(void **p, int64_t bytes);
 int         sb200_dev_free(void *p);
 int         sb200_h2d(void *dst, const void *src, int64_t bytes);
@@ -93,6 +97,10 @@ int sb200_fwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const dou
                        double *y_dev, sb_idx nrhs);
 int sb200_bwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
                        double *y_dev, sb_idx nrhs);
+/* y = L' \ ((L \ b(perm)) ./ d): wrapPcg.m:56-59 for a problem without dense columns; skipped
+ * pivots get d=1 like deninfac.m:88-93 when flag_dev is given.  w_dev: m*nrhs scratch. */
+int sb200_ldl_solve_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev,
+                        const int *flag_dev, const double *b_dev, double *w_dev, double *y_dev, sb_idx nrhs);
 int sb200_fwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
                    const sb_idx *Lir, const double *Lpr, const sb_idx *perm,
                    const double *b, double *y, sb_idx nrhs);
@@ -119,6 +127,21 @@ sb_idx sb200_psd_plan_sumn(const sb200_psd_plan *plan);
 int sb200_invcholfac_dev(sb200_psd_plan *plan, const double *u_dev, const int *perm_dev, double *y_dev);
 int sb200_psdscale_dev(sb200_psd_plan *plan, const double *u_dev, const int *perm_dev,
                        const double *x_dev, int transp, double *y_dev);
+/* psdframeit.c:65-99  X_k = Qb' diag(lab_k) Qb ; psdinvjmul.c:101-157  X Z + Z X = 2 Y.
+ * frms: per block n x n, column c = Householder vector c (rows c..n-1), last column = beta. */
+int sb200_psdframeit_dev(sb200_psd_plan *plan, const double *lab_dev, const double *frms_dev, double *x_dev);
+int sb200_psdinvjmul_dev(sb200_psd_plan *plan, const double *xlab_dev, const double *frms_dev,
+                         const double *y_dev, double *z_dev);
+int sb200_psdframeit(sb_idx nblk, const sb_idx *n, const double *lab, const double *frms, double *x);
+int sb200_psdinvjmul(sb_idx nblk, const sb_idx *n, const double *xlab, const double *frms,
+                     const double *y, double *z);
+/* urotorder.c:312-490 / givensrot.c:93-168.  perm_out 0-based inside each block; gjc_out n_k entries
+ * per block (0-based rotation offsets, last = count); g in the worst-case layout n_k(n_k-1) doubles
+ * per block for urotorder, packed back to back for givensrot (as the MEX interface carries it). */
+int sb200_urotorder(sb_idx nblk, const sb_idx *n, const double *u, double maxu, double *u_out,
+                    sb_idx *perm_out, sb_idx *gjc_out, double *g_out);
+int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen,
+                    const double *x, double *y);
 /* host entries: u, x, y are the lenud-long PSD parts; perm 0-based inside each block or NULL */
 int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm, double *y);
 int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm,

@@ -1,0 +1,93 @@
+"""The reference's per-iteration hot path, replayed on the CPU -- TEST INFRASTRUCTURE.
+
+Drives the UNMODIFIED reference MEX targets compiled into oracle/_ref (oracle/Makefile) plus the
+numpy restatement of the M-only glue (oracle/restate.py) through the call sequence of
+sedumi.m:442-466 and wrapPcg.m:56-59.  Used by tests (parity oracle), by __graft_entry__.smoke()
+and by bench.py's cpu_baseline / --impl reference legs -- never by the product path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+for _p in (_ROOT, _HERE):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import restate  # noqa: E402
+from sedumi_b200.host import setup as hsetup  # noqa: E402
+from sedumi_b200.mx import MexDir  # noqa: E402
+
+CHOL_PARS = {"canceltol": 1e-12, "maxu": 5e5, "abstol": 1e-20}      # checkpars.m:150-170
+
+
+def ref_dir(debug=False) -> MexDir:
+    return MexDir(os.path.join(_HERE, "_ref", "dbg") if debug else os.path.join(_HERE, "_ref"))
+
+
+class RefHotPath:
+    """Reference call sequence on one problem (S = sedumi_b200.host.setup.HotPathSetup)."""
+
+    def __init__(self, S, chol_pars=None, debug=False):
+        self.S = S
+        self.mex = ref_dir(debug)
+        self.Km = S.Kmex()
+        self.pars = dict(CHOL_PARS, **(chol_pars or {}))
+        self.ADA0 = sp.csc_matrix((np.zeros(S.ADA.nnz), S.ADA.indices, S.ADA.indptr), shape=S.ADA.shape)
+
+    def DAtq(self, d):
+        """getDAtm.m:40-43 (no dense Lorentz blocks)."""
+        S, K = self.S, self.S.K
+        tr = hsetup.extractA(S.At, S.Ablkjc, 1, 2, int(K["mainblks"][0]), int(K["mainblks"][1]))
+        if len(K["q"]) == 0:
+            return tr
+        return sp.csc_matrix(sp.diags(d["q1"]) @ tr +
+                             self.mex.ddot(d["q2"], S.At, K["qblkstart"].reshape(1, -1), S.Ablkjc))
+
+    def assemble(self, d):
+        """sedumi.m:450-452: returns (udsqr, ADA, absd)."""
+        S, mex = self.S, self.mex
+        udsqr = mex.invcholfac(d["u"], self.Km, d["perm"])
+        A1 = mex.getada1(self.ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], {"l": d["l"], "det": d["det"]},
+                         S.K["qblkstart"].reshape(1, -1))
+        A2 = mex.getada2(A1, {"q": self.DAtq(d)}, S.Aord, self.Km)
+        ADA, absd = mex.getada3(A2, S.At, S.Ablkjc[:, 2], S.Aord, udsqr, self.Km, nlhs=2)
+        return udsqr, ADA, absd
+
+    def factor(self, ADA, absd):
+        """sedumi.m:458 + deninfac.m:81-93 (no dense columns)."""
+        L = dict(self.S.L)
+        LL, Ld, skip, add = self.mex.blkchol(hsetup.L_for_mex(L), ADA, self.pars, absd, nlhs=4)
+        L.update(L=LL, d=Ld.ravel().copy(), skip=skip, add=add)
+        sk = skip.indices
+        if sk.size:
+            dtol = np.maximum(self.pars["canceltol"] * absd.ravel()[L["perm"].ravel().astype(int)[sk] - 1], self.pars["abstol"])
+            fix = L["d"][sk] <= dtol
+            L["d"][sk[fix]] = 1.0
+        return L
+
+    def solve(self, L, r):
+        """wrapPcg.m:56-59 without dense columns."""
+        Lm = hsetup.L_for_mex({k: L[k] for k in ("perm", "L", "xsuper", "tmpsiz")})
+        p = self.mex.fwblkslv(Lm, r)
+        y = p / L["d"].reshape(-1, 1)
+        return self.mex.bwblkslv(Lm, y)
+
+    def psdscale(self, d, x, transp):
+        return restate.psdscale({"u": d["u"], "perm": d["perm"]}, x, self.S.K, transp)
+
+    def iteration(self, d, rhs, psd_x, nsolve=4, npsdscale=12):
+        udsqr, ADA, absd = self.assemble(d)
+        L = self.factor(ADA, absd)
+        y = None
+        for _ in range(nsolve):
+            y = self.solve(L, rhs)
+        ps = None
+        for i in range(npsdscale):
+            ps = self.psdscale(d, psd_x, i & 1)
+        return dict(udsqr=udsqr, ADA=ADA, absd=absd, L=L, y=y, psd=ps)

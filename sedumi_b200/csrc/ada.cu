@@ -381,12 +381,12 @@ int sb200_getada1_dev(sb200_ada_plan *pl, const double *dl_dev, const double *dd
   if (pl->lq_rows > 0) {
     dsqr_kernel<<<(unsigned)std::min<long long>((pl->lq_rows + 255) / 256, 2048), 256, 0, st>>>(
         pl->lpN, pl->nq, pl->d_qstart.p, dl_dev, ddet_dev, pl->d_dsqr.p);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("dsqr_kernel");
   }
   ata_pattern_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, pl->d_Ajc.p, pl->d_Ajc1.p, pl->d_Air.p,
                                             pl->d_Atpr.p, pl->d_dsqr.p, invperm_dev ? invperm_dev : pl->d_ident.p,
                                             nullptr, ada_out_dev, 0, 1);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("ata_pattern_kernel");
   return 0;
 }
 
@@ -398,7 +398,7 @@ int sb200_getada2_dev(sb200_ada_plan *pl, const long long *Qjc_dev, const int *Q
   ata_pattern_kernel<<<pl->m, 256, 0, ctx().stream>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, Qjc_dev, Qjc_dev + 1, Qir_dev,
                                                        Qpr_dev, nullptr, invperm_dev ? invperm_dev : pl->d_ident.p,
                                                        ada_in_dev, ada_out_dev, 1, 1);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("ata_pattern_kernel");
   return 0;
 }
 
@@ -413,22 +413,22 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
   // absd of the constraints with no PSD pair (diag(ADA) if there is no PSD cone at all, getada3.c:549-552)
   absd_nopsd_kernel<<<(pl->m + 255) / 256, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
                                                          pl->d_cpair_beg.p, ada_dev, absd_dev, pl->nblk == 0);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("absd_nopsd_kernel");
   for (auto &B : pl->batches) {
     if (B.p1 == B.p0) continue;
     build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_ent_p.p, pl->d_ent_q.p,
                                                  pl->d_ent_rp.p, pl->d_ent_rq.p, pl->d_ent_src.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("build_tt_kernel");
     gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("gemm_nt_kernel");
     ada3_dots_kernel<<<B.c1 - B.c0, 256, 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, pl->d_pairs.p,
                                                   pl->d_blk_n.p, pl->d_ent_p.p, pl->d_ent_q.p, pl->d_ent_src.p, pl->d_Atpr.p,
                                                   pl->d_ws.p, ada_dev, absd_dev);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("ada3_dots_kernel");
   }
   if (symmetrise) {
     makesym_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ada_dev);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("makesym_kernel");
   }
   return 0;
 }

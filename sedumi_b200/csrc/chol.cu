@@ -561,6 +561,17 @@ bwsolve_kernel(const int *list, const Sn *sn, const int *lindx, const double *re
   for (int c = threadIdx.x; c < n; c += blockDim.x) zz[sj.first + c] = s[c];
 }
 
+// w(i,col) /= d_i with deninfac's repair of skipped pivots (deninfac.m:88-93): a skipped pivot
+// (flag==1) whose d is <= max(abstol, canceltol*absd(perm_i)) (= lb_i) is replaced by 1.
+__global__ void scale_by_d_kernel(int m, int nrhs, const double *d, const int *flag, const double *lb, double *w) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)m * nrhs) return;
+  int k = (int)(i % m);
+  double dk = d[k];
+  if (flag && flag[k] == 1 && dk <= lb[k]) dk = 1.0;
+  w[i] /= dk;
+}
+
 __global__ void gather_perm_kernel(int m, int nrhs, const int *perm, const double *b, double *y) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)m * nrhs) return;
@@ -727,22 +738,22 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
   SB_CUDA(cudaMemsetAsync(sval, 0, sizeof(double) * m, st));
   permuteP_kernel<<<m, 256, 0, st>>>(pl->d_sn.p, pl->d_snode.p, pl->d_lindx.p, pl->d_perm.p,
                                       pl->d_Xjc.p, pl->d_Xir.p, Xpr, rect, pl->d_diagX.p);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("permuteP_kernel");
   bounds_kernel<<<1, 1024, 0, st>>>(m, pl->d_diagX.p, absd, pl->d_perm.p, pars.abstol, pars.canceltol,
                                      pars.maxu, pl->d_lb.p, pl->d_scal.p);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("bounds_kernel");
   for (int lv = 0; lv < pl->nlevels; lv++) {
     int ntile = (int)pl->level_tiles[lv].size();
     if (ntile) {
       update_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_pairs.p,
                                             pl->d_pair_beg.p, pl->d_rel.p, d, rect);
-      SB_LAUNCH_CHECK();
+      SB_LAUNCH_CHECK_N("update_kernel");
     }
     int nsmall = (int)pl->level_small[lv].size();
     if (nsmall) {
       factor_small_kernel<<<nsmall, 512, 0, st>>>(pl->d_level_list.p + pl->level_small_off[lv], pl->d_sn.p, rect, d,
                                                    pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m);
-      SB_LAUNCH_CHECK();
+      SB_LAUNCH_CHECK_N("factor_small_kernel");
     }
     for (int s : pl->level_big[lv]) {
       const Sn &S = pl->sn[s];
@@ -750,16 +761,16 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
         int w = std::min(NB, S.n - p0);
         diag_kernel<<<1, 256, 0, st>>>(S, p0, w, rect, d, pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval,
                                         pl->d_diagX.p, m, pl->d_vscratch.p);
-        SB_LAUNCH_CHECK();
+        SB_LAUNCH_CHECK_N("diag_kernel");
         int nrow = S.m - (p0 + w);
         if (nrow > 0) {
           trsm_kernel<<<(nrow + 127) / 128, 128, 0, st>>>(S, p0, w, rect, d);
-          SB_LAUNCH_CHECK();
+          SB_LAUNCH_CHECK_N("trsm_kernel");
           int ncol = S.n - (p0 + w);
           if (ncol > 0) {
             dim3 g((nrow + 63) / 64, (ncol + 63) / 64);
             trail_kernel<<<g, 256, 0, st>>>(S, p0, w, rect, d);
-            SB_LAUNCH_CHECK();
+            SB_LAUNCH_CHECK_N("trail_kernel");
           }
         }
       }
@@ -772,14 +783,14 @@ int sb200_chol_rect_to_csc_dev(sb200_chol_plan *pl, const double *rect, const in
   SB_TRY(ensure_init());
   if (pl->m == 0) return 0;
   rect_to_csc_kernel<<<pl->m, 128, 0, ctx().stream>>>(pl->d_sn.p, pl->d_snode.p, pl->d_Ljc.p, rect, flag, Lpr);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("rect_to_csc_kernel");
   return 0;
 }
 int sb200_chol_csc_to_rect_dev(sb200_chol_plan *pl, const double *Lpr, double *rect) {
   SB_TRY(ensure_init());
   if (pl->m == 0) return 0;
   csc_to_rect_kernel<<<pl->m, 128, 0, ctx().stream>>>(pl->d_sn.p, pl->d_snode.p, pl->d_Ljc.p, Lpr, rect);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("csc_to_rect_kernel");
   return 0;
 }
 
@@ -790,7 +801,7 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   if (m == 0 || nrhs == 0) return 0;
   long long tot = (long long)m * nrhs;
   gather_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, b, y);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("gather_perm_kernel");
   size_t shm = sizeof(double) * (size_t)pl->max_sn_n;
   SB_CHECK(shm <= 200 * 1024, "fwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
   if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(fwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -798,9 +809,25 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
     dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
     fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pairs.p,
                                          pl->d_pair_beg.p, pl->d_rel.p, rect, y, m);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
+}
+
+int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs);
+// y = L' \ ((L \ b(perm)) ./ d)  -- the preconditioner application of wrapPcg.m:56-59 for a problem
+// without dense columns (fwdpr1/bwdpr1 are identities then, fwdpr1.c:132-135).  w: m*nrhs scratch.
+// flag_dev/NULL: when given, skipped pivots get d=1 as deninfac.m:88-93 does (uses the plan's lb
+// from the last sb200_blkchol_dev call).
+int sb200_ldl_solve_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag,
+                        const double *b, double *w, double *y, sb_idx nrhs) {
+  SB_TRY(sb200_fwblkslv_dev(pl, rect, b, w, nrhs));
+  long long tot = (long long)pl->m * nrhs;
+  if (tot > 0) {
+    scale_by_d_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx().stream>>>(pl->m, (int)nrhs, d, flag, pl->d_lb.p, w);
+    SB_LAUNCH_CHECK_N("scale_by_d_kernel");
+  }
+  return sb200_bwblkslv_dev(pl, rect, w, y, nrhs);
 }
 
 int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs) {
@@ -818,10 +845,10 @@ int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
     dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
     bwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_lindx.p,
                                          rect, pl->d_y.p, m);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("bwsolve_kernel");
   }
   scatter_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, pl->d_y.p, y);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("scatter_perm_kernel");
   return 0;
 }
 

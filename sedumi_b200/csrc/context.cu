@@ -50,6 +50,27 @@ void *arena_alloc(size_t bytes) {
   return p;
 }
 
+// ---- optional per-launch timing: an event after every launch; the interval between consecutive
+// events on the (serial) library stream is attributed to the kernel that was just launched.
+struct ProfState {
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char *> names;
+  size_t used = 0;
+};
+static ProfState g_prof;
+void prof_mark(const char *name) {
+  if (g_prof.used >= g_prof.ev.size()) {
+    size_t n = g_prof.ev.size() ? g_prof.ev.size() * 2 : 4096;
+    size_t old = g_prof.ev.size();
+    g_prof.ev.resize(n);
+    for (size_t i = old; i < n; i++) cudaEventCreate(&g_prof.ev[i]);
+    g_prof.names.resize(n);
+  }
+  cudaEventRecord(g_prof.ev[g_prof.used], g_ctx.stream);
+  g_prof.names[g_prof.used] = name;
+  g_prof.used++;
+}
+
 int ensure_init() {
   if (g_ctx.inited) return 0;
   return sb200_init(0);
@@ -99,6 +120,39 @@ int sb200_sync(void) {
 
 void *sb200_stream(void) { return sb::ensure_init() ? nullptr : (void *)sb::ctx().stream; }
 int64_t sb200_kernel_launches(void) { return sb::ctx().launches; }
+
+// Profiling: sb200_prof_begin() starts recording (drains the stream first); sb200_prof_end() stops,
+// synchronises and writes one line per kernel name into `buf`: "name count total_ms\n".
+int sb200_prof_begin(void) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
+  sb::g_prof.used = 0;
+  sb::ctx().profiling = true;
+  sb::prof_mark("__begin__");
+  return 0;
+}
+int sb200_prof_end(char *buf, int64_t buflen) {
+  sb::ctx().profiling = false;
+  SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
+  std::vector<std::pair<const char *, std::pair<long long, double>>> agg;
+  for (size_t i = 1; i < sb::g_prof.used; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sb::g_prof.ev[i - 1], sb::g_prof.ev[i]);
+    const char *nm = sb::g_prof.names[i];
+    size_t j = 0;
+    for (; j < agg.size(); j++) if (agg[j].first == nm || !strcmp(agg[j].first, nm)) break;
+    if (j == agg.size()) agg.push_back({nm, {0, 0.0}});
+    agg[j].second.first++; agg[j].second.second += ms;
+  }
+  int64_t off = 0;
+  if (buflen > 0) buf[0] = 0;
+  for (auto &a : agg) {
+    int n = snprintf(buf + off, (size_t)(buflen - off), "%s %lld %.6f\n", a.first, a.second.first, a.second.second);
+    if (n < 0 || off + n >= buflen) break;
+    off += n;
+  }
+  return 0;
+}
 
 int sb200_dev_alloc(void **p, int64_t bytes) {
   SB_TRY(sb::ensure_init());

@@ -1,0 +1,275 @@
+// givens.cu -- urotorder (stable column re-ordering of the triangular PSD scaling factor by Givens
+// rotations) and givensrot (apply a stored rotation list to every column of Q).
+//
+// Reference semantics:
+//   urotorder.c:79-180   rotorder: at step k, if max_j u_kj^2 > maxu^2 d_k, bring the column with the
+//                        largest remaining norm to position k with Givens rotations (bottom-up),
+//                        apply them to the later columns, maintain d by downdating
+//   auxgivens.c:43-61    givensrot, :114-140 givensrotuj
+//   givensrot.c:60-68    matgivens: for every column, steps k=0..n-2 apply rotations gjc[k]..gjc[k+1]-1
+//
+// The pivot choices are discrete outputs (perm), so the arithmetic that feeds the comparisons is
+// reproduced operation by operation with explicit round-to-nearest intrinsics (no FMA contraction,
+// the reference's left-to-right summation order).  Given bit-identical input the outputs are then
+// bit-identical to the reference built without FMA (gcc -O2 on x86-64).  Parallelism: one CTA per
+// PSD block; inside a step, columns are independent (one thread per column).
+#include <algorithm>
+#include "sb_internal.h"
+
+namespace sb {
+
+#define DRELTOL 1E-10
+
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
+
+// auxgivens.c:43-61
+__device__ void d_givensrot(double *z, const double *g, int n) {
+  double z2 = z[n];
+  for (int i = n; i > 0; i--) {
+    const double gx = g[2 * (i - 1)], gy = g[2 * (i - 1) + 1];
+    const double z1 = z[i - 1];
+    z[i] = sub_(mul_(gy, z1), mul_(gx, z2));
+    z2 = add_(mul_(gx, z1), mul_(gy, z2));
+  }
+  z[0] = z2;
+}
+// auxgivens.c:114-140
+__device__ void d_givensrotuj(double *z, const double *g, int n) {
+  if (n < 1) return;
+  double z2 = z[n - 1];
+  z[n] = mul_(z2, g[2 * (n - 1) + 1]);
+  z2 = mul_(z2, g[2 * (n - 1)]);
+  for (int i = n - 1; i > 0; i--) {
+    const double gx = g[2 * (i - 1)], gy = g[2 * (i - 1) + 1];
+    const double z1 = z[i - 1];
+    z[i] = sub_(mul_(gy, z1), mul_(gx, z2));
+    z2 = add_(mul_(gx, z1), mul_(gy, z2));
+  }
+  z[0] = z2;
+}
+
+struct UrotBlk { int n; long long uoff; int poff; long long goff; };   // goff: in doubles, worst-case layout
+
+__global__ void __launch_bounds__(256)
+urotorder_kernel(const UrotBlk *blks, double *W, int *perm_all, int *gjc_all, double *g_all, double *d_all,
+                 double maxusqr) {
+  const UrotBlk B = blks[blockIdx.x];
+  const int n = B.n;
+  double *u = W + B.uoff;
+  int *perm = perm_all + B.poff, *gjc = gjc_all + B.poff;
+  double *d = d_all + B.poff;
+  double *g = g_all + B.goff;
+  __shared__ double s_h, s_red[32];
+  __shared__ int s_flag, s_pivk, s_inz, s_redi[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int j = tid; j < n; j += blockDim.x) perm[j] = j;
+  if (tid == 0) { d[0] = 0.0; s_h = 1.0; s_pivk = 0; s_inz = 0; }
+  __syncthreads();
+  for (int k = 0; k < n - 1; k++) {
+    double *rowuk = u + k;
+    __syncthreads();                                 // everyone is done with last step's flags
+    if (tid == 0) { gjc[k] = s_inz; s_flag = (d[perm[k]] <= s_h); }
+    __syncthreads();
+    if (s_flag) {                                    // d(i) = sum(u(k:j,i).^2) from scratch
+      for (int j = k + tid; j < n; j += blockDim.x) {
+        const int i = perm[j];
+        const double *x = rowuk + (long long)i * n;
+        double s = 0.0;
+        for (int t = 0; t < j + 1 - k; t++) s = add_(s, mul_(x[t], x[t]));
+        d[i] = s;
+      }
+      __syncthreads();
+      if (tid == 0) s_h = mul_(d[perm[k]], DRELTOL);
+    }
+    // ukmax = max U(k,perm(k+1:n)).^2
+    double mx = 0.0;
+    for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+      double v = rowuk[(long long)perm[j] * n];
+      v = mul_(v, v);
+      mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nw; w++) mx = fmax(mx, s_red[w]);
+      s_flag = (mx > mul_(maxusqr, d[perm[k]]));
+    }
+    __syncthreads();
+    if (!s_flag) continue;                           // uniform
+    // best pivot: first j in k+1..n-1 with the largest d(perm(j)) (strict >, so ties keep the first)
+    double bd = 0.0; int bj = 0x7fffffff;
+    for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+      double v = d[perm[j]];
+      if (v > bd || (v == bd && v > 0.0 && j < bj)) { bd = v; bj = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_down_sync(0xffffffffu, bd, o); int oj = __shfl_down_sync(0xffffffffu, bj, o);
+      if (ov > bd || (ov == bd && ov > 0.0 && oj < bj)) { bd = ov; bj = oj; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[warp] = bd; s_redi[warp] = bj; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nw; w++)
+        if (s_red[w] > bd || (s_red[w] == bd && bd > 0.0 && s_redi[w] < bj)) { bd = s_red[w]; bj = s_redi[w]; }
+      if (bd > 0.0) s_pivk = bj;                     // else: keep the previous pivk like the reference
+      const int pivk = s_pivk, m = pivk - k;
+      const int j = perm[pivk];
+      double *uj = rowuk + (long long)j * n;
+      double *gk = g + 2 * (long long)s_inz;
+      double nexty = uj[m];
+      double y = mul_(nexty, nexty);
+      for (int i = m; i > 0; i--) {
+        double gx = uj[i - 1], gy = nexty;
+        y = add_(y, mul_(gx, gx));
+        nexty = sqrt(y);
+        gk[2 * (i - 1)] = gx / nexty;
+        gk[2 * (i - 1) + 1] = gy / nexty;
+      }
+      uj[0] = nexty;
+      for (int t = pivk; t > k; t--) perm[t] = perm[t - 1];
+      perm[k] = j;
+    }
+    __syncthreads();
+    {
+      const int m = s_pivk - k;
+      const double *gk = g + 2 * (long long)s_inz;
+      for (int i = 1 + tid; k + i < n; i += blockDim.x) {
+        double *z = rowuk + (long long)perm[k + i] * n;
+        if (i <= m) d_givensrotuj(z, gk, i);
+        else d_givensrot(z, gk, m);
+      }
+      __syncthreads();
+      for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+        const int i = perm[j];
+        const double x = rowuk[(long long)i * n];
+        d[i] = sub_(d[i], mul_(x, x));
+      }
+      if (tid == 0) s_inz += m;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) gjc[n - 1] = s_inz;
+}
+
+// u_out(i,j) = W(i, perm[j]) for i <= j, mirrored below (uperm + triu2sym, sdmauxTriu.c:90-100,136-145)
+__global__ void uperm_sym_kernel(const UrotBlk *blks, const double *W, const int *perm_all, double *uout) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  const int *perm = perm_all + B.poff;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % n), j = (int)(idx / n);
+    int lo = min(i, j), hi = max(i, j);
+    uout[B.uoff + idx] = W[B.uoff + lo + (long long)perm[hi] * n];
+  }
+}
+
+// givensrot.c:60-68: every column of every block, steps k = 0..n-2
+__global__ void matgivens_kernel(const UrotBlk *blks, const int *gjc_all, const double *g_all, double *y) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  const int *gjc = gjc_all + B.poff;
+  const double *g = g_all + B.goff;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double *col = y + B.uoff + (long long)j * n;
+    for (int k = 0; k < n - 1; k++) {
+      const int m = gjc[k + 1] - gjc[k];
+      if (m > 0) d_givensrot(col + k, g + 2 * (long long)gjc[k], m);
+    }
+  }
+}
+
+}  // namespace sb
+using namespace sb;
+
+static int make_blocks(sb_idx nblk, const sb_idx *n, std::vector<UrotBlk> &blks, long long &lenud, long long &sumn, long long &gtot) {
+  lenud = 0; sumn = 0; gtot = 0;
+  for (sb_idx k = 0; k < nblk; k++) {
+    SB_CHECK(n[k] >= 1 && n[k] < 46340, "PSD block order out of range");
+    UrotBlk b; b.n = (int)n[k]; b.uoff = lenud; b.poff = (int)sumn; b.goff = gtot;
+    blks.push_back(b);
+    lenud += n[k] * n[k]; sumn += n[k]; gtot += n[k] * (n[k] - 1);     // 2 doubles per rotation, n(n-1)/2 rotations
+  }
+  return 0;
+}
+
+extern "C" {
+
+// [u,perm,gjc,g] = urotorder(u,K,maxu): host entry.  perm_out: 0-based inside each block (the stub
+// composes it with permIN); gjc_out: per block n_k entries (gjc[n_k-1] = number of rotations);
+// g_out: rotations of block k start at g_out + goff[k] (worst-case layout n_k(n_k-1) doubles per block).
+int sb200_urotorder(sb_idx nblk, const sb_idx *n, const double *u, double maxu, double *u_out, sb_idx *perm_out,
+                    sb_idx *gjc_out, double *g_out) {
+  SB_TRY(ensure_init());
+  std::vector<UrotBlk> blks;
+  long long lenud, sumn, gtot;
+  SB_TRY(make_blocks(nblk, n, blks, lenud, sumn, gtot));
+  if (lenud == 0) return 0;
+  arena_reset();
+  UrotBlk *db = arena<UrotBlk>(blks.size());
+  double *W = arena<double>(lenud), *uo = arena<double>(lenud), *g = arena<double>(std::max<long long>(gtot, 1)), *d = arena<double>(sumn);
+  int *perm = arena<int>(sumn), *gjc = arena<int>(sumn);
+  SB_CHECK(db && W && uo && g && d && perm && gjc, "urotorder: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(UrotBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(W, u, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * std::max<long long>(gtot, 1), st));
+  SB_CUDA(cudaMemsetAsync(gjc, 0, sizeof(int) * sumn, st));
+  urotorder_kernel<<<(unsigned)nblk, 256, 0, st>>>(db, W, perm, gjc, g, d, maxu * maxu);
+  SB_LAUNCH_CHECK_N("urotorder_kernel");
+  int maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
+  uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, W, perm, uo);
+  SB_LAUNCH_CHECK_N("uperm_sym_kernel");
+  std::vector<int> hp(sumn), hg(sumn);
+  SB_CUDA(cudaMemcpyAsync(u_out, uo, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(hp.data(), perm, sizeof(int) * sumn, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(hg.data(), gjc, sizeof(int) * sumn, cudaMemcpyDeviceToHost, st));
+  if (gtot) SB_CUDA(cudaMemcpyAsync(g_out, g, sizeof(double) * gtot, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  for (long long i = 0; i < sumn; i++) { perm_out[i] = hp[i]; gjc_out[i] = hg[i]; }
+  return 0;
+}
+
+// y = givensrot(gjc,g,x,K): gjc per block (n_k entries, 0-based counts); g packed per block: the
+// rotations of block k start right after those of block k-1 (2 doubles each).
+int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen, const double *x, double *y) {
+  SB_TRY(ensure_init());
+  std::vector<UrotBlk> blks;
+  long long lenud, sumn, gtot;
+  SB_TRY(make_blocks(nblk, n, blks, lenud, sumn, gtot));
+  if (lenud == 0) return 0;
+  long long inz = 0;
+  std::vector<int> g32(sumn);
+  for (auto &b : blks) {
+    b.goff = inz;
+    for (int i = 0; i < b.n; i++) {
+      sb_idx v = gjc[b.poff + i];
+      SB_CHECK(v >= 0 && v <= (sb_idx)b.n * (b.n - 1) / 2 && (i == 0 || v >= gjc[b.poff + i - 1]), "givensrot: gjc is not a valid rotation count list");
+      g32[b.poff + i] = (int)v;
+    }
+    inz += 2 * gjc[b.poff + b.n - 1];
+    SB_CHECK(inz <= glen, "g size mismatch");
+  }
+  arena_reset();
+  UrotBlk *db = arena<UrotBlk>(blks.size());
+  double *dy = arena<double>(lenud), *dg = arena<double>(std::max<long long>(inz, 1));
+  int *dgjc = arena<int>(sumn);
+  SB_CHECK(db && dy && dg && dgjc, "givensrot: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(UrotBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dy, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dgjc, g32.data(), sizeof(int) * sumn, cudaMemcpyHostToDevice, st));
+  if (inz) SB_CUDA(cudaMemcpyAsync(dg, g, sizeof(double) * inz, cudaMemcpyHostToDevice, st));
+  int maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
+  matgivens_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nblk), 128, 0, st>>>(db, dgjc, dg, dy);
+  SB_LAUNCH_CHECK_N("matgivens_kernel");
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -85,21 +85,21 @@ int sb200_ddot_dense_dev(sb_idx nblk, const long long *bs_dev, const double *d_d
   SB_TRY(ensure_init());
   if (nblk == 0 || ncol == 0) return 0;
   ddot_dense_kernel<<<grid_for(nblk * ncol * 32), 256, 0, ctx().stream>>>((int)nblk, bs_dev, d_dev, X_dev, ldx, ncol, y_dev);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("ddot_dense_kernel");
   return 0;
 }
 int sb200_qblkmul_dev(sb_idx nblk, const long long *bs_dev, sb_idx qdim, const double *mu_dev, const double *d_dev, double *y_dev) {
   SB_TRY(ensure_init());
   if (qdim == 0) return 0;
   qblkmul_kernel<<<grid_for(qdim), 256, 0, ctx().stream>>>((int)nblk, bs_dev, mu_dev, d_dev, y_dev);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("qblkmul_kernel");
   return 0;
 }
 int sb200_quadadd_dev(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo) {
   SB_TRY(ensure_init());
   if (n == 0) return 0;
   quadadd_kernel<<<grid_for(n), 256, 0, ctx().stream>>>(n, xhi, xlo, y, zhi, zlo);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("quadadd_kernel");
   return 0;
 }
 
@@ -172,7 +172,7 @@ int sb200_ddot_sparse(sb_idx nblk, const sb_idx *bs_abs, const double *d, sb_idx
   SB_CUDA(cudaMemcpyAsync(dpr, xpr + pmin, sizeof(double) * span, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(dd, d, sizeof(double) * qdim, cudaMemcpyHostToDevice, st));
   ddot_sparse_kernel<<<grid_for(knz), 256, 0, st>>>(knz, dlo, dhi, dir, dpr, dd, bs_abs[0], dy);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("ddot_sparse_kernel");
   SB_CUDA(cudaMemcpyAsync(ypr, dy, sizeof(double) * knz, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -28,7 +28,9 @@ struct sb200_psd_plan {
   // device
   sb::DevBuf<int> d_n, d_poff;
   sb::DevBuf<long long> d_off;
-  sb::DevBuf<sb::GemmDesc> d_desc_ichol, d_desc_s1_lo, d_desc_s1_up, d_desc_s2_lo, d_desc_s2_up;
+  sb::DevBuf<sb::GemmDesc> d_desc_ichol, d_desc_s1_lo, d_desc_s1_up, d_desc_s2_lo, d_desc_s2_up, d_desc_full, d_desc_lower;
+  sb::DevBuf<int> d_qcol_blk, d_qcol_j0;     // column groups for the Householder accumulation
+  int nqgroups = 0;
   sb::DevBuf<sb::GemmTile> d_tiles_full, d_tiles_lower;
   int ntiles_full = 0, ntiles_lower = 0;
   // workspaces (lenud doubles each)
@@ -81,6 +83,79 @@ __global__ void perm_block_kernel(const int *ns, const long long *offs, const in
   }
 }
 
+
+// ---------------------------------------------------------------- Householder frames (psdframeit / psdinvjmul)
+// frms block k: n x n, column c (c < n-1) holds reflector vector c_c in rows c..n-1, last column holds
+// beta_0..beta_{n-2};  H_c = I - c_c c_c'/beta_c ;  Qb = H_0 H_1 ... H_{n-2}   (reflect.c:203-215, qrK.c:86-122).
+// Column j of Qb is H_0...H_{min(j,n-2)} e_j and columns are independent: one warp per column,
+// 8 columns per CTA, the reflectors streamed from L2.  Q is written column-major.
+__global__ void __launch_bounds__(256)
+householder_q_kernel(const int *grp_blk, const int *grp_j0, const int *ns, const long long *offs,
+                     const double *frms, double *Q) {
+  const int k = grp_blk[blockIdx.x];
+  const int n = ns[k];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = grp_j0[blockIdx.x] + warp;
+  if (j >= n) return;
+  const double *F = frms + offs[k];
+  const double *beta = F + (long long)n * n - n;
+  double *q = Q + offs[k] + (long long)j * n;
+  for (int i = lane; i < n; i += 32) q[i] = (i == j) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int c = min(j, n - 2); c >= 0; c--) {
+    const double *v = F + (long long)c * n;           // v[i], i = c..n-1
+    double t = 0.0;
+    for (int i = c + lane; i < n; i += 32) t += v[i] * q[i];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const double a = t / (-beta[c]);                  // elqxq is called with -beta (reflect.c:214)
+    for (int i = c + lane; i < n; i += 32) q[i] += a * v[i];
+    __syncwarp();
+  }
+}
+
+// out = transpose(in) per block, optionally scaling row k of the result's k-index:  out(c,k) = in(k,c) * (lab ? lab[k] : 1)
+__global__ void transpose_scale_kernel(const int *ns, const long long *offs, const int *poffs, const double *in,
+                                       const double *lab, double *out) {
+  const int n = ns[blockIdx.y];
+  const double *A = in + offs[blockIdx.y];
+  double *B = out + offs[blockIdx.y];
+  const double *lb = lab ? lab + poffs[blockIdx.y] : nullptr;
+  __shared__ double tile[32][33];
+  const int tpd = (n + 31) / 32;
+  for (int t = blockIdx.x; t < tpd * tpd; t += gridDim.x) {
+    int k0 = (t % tpd) * 32, c0 = (t / tpd) * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+      int k = k0 + threadIdx.x, c = c0 + jj;
+      tile[jj][threadIdx.x] = (k < n && c < n) ? A[k + (long long)c * n] : 0.0;
+    }
+    __syncthreads();
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+      int c = c0 + threadIdx.x, k = k0 + jj;
+      if (c < n && k < n) B[c + (long long)k * n] = tile[threadIdx.x][jj] * (lb ? lb[k] : 1.0);
+    }
+    __syncthreads();
+  }
+}
+
+// mode 0: mirror the lower triangle up (tril2sym); mode 1: out = symmetric matrix built from tril(in);
+// mode 2: in-place jdiv on the lower triangle then mirror: m(i,j) *= 2/(x_i+x_j), m(j,j) /= x_j (psdinvjmul.c:69-84)
+__global__ void sym_ops_kernel(const int *ns, const long long *offs, const int *poffs, const double *in, double *out,
+                               const double *x, int mode) {
+  const int n = ns[blockIdx.y];
+  const long long off = offs[blockIdx.y];
+  const double *xx = x ? x + poffs[blockIdx.y] : nullptr;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % n), j = (int)(idx / n);
+    if (mode == 1) { out[off + idx] = in[off + max(i, j) + (long long)min(i, j) * n]; continue; }
+    if (i < j) continue;                              // the lower-triangle thread owns the pair (i,j),(j,i)
+    double v = in[off + i + (long long)j * n];
+    if (mode == 2) v = (i == j) ? v / xx[j] : v * (2.0 / (xx[i] + xx[j]));
+    out[off + i + (long long)j * n] = v;
+    if (i != j) out[off + j + (long long)i * n] = v;
+  }
+}
+
 static std::map<uint64_t, sb200_psd_plan *> g_psd_plans;
 
 }  // namespace sb
@@ -97,7 +172,8 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
     pl->maxn = std::max(pl->maxn, (int)n[k]);
   }
   pl->lenud = off; pl->sumn = po;
-  std::vector<GemmDesc> ichol, s1lo, s1up, s2lo, s2up;
+  std::vector<GemmDesc> ichol, s1lo, s1up, s2lo, s2up, dfull, dlower;
+  std::vector<int> qblk, qj0;
   std::vector<GemmTile> tfull, tlower;
   for (int k = 0; k < pl->nblk; k++) {
     int nk = pl->n[k]; long long o = pl->off[k];
@@ -113,6 +189,9 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
     // stage 2: Y = Tt * Wt'
     b.a_tri = TRI_K_GE_ROW; s2lo.push_back(b);
     b.a_tri = TRI_K_LE_ROW; s2up.push_back(b);
+    GemmDesc f = g; f.a_tri = f.b_tri = TRI_NONE; f.lower = 0; dfull.push_back(f);
+    f.lower = 1; dlower.push_back(f);
+    for (int j0 = 0; j0 < nk; j0 += 8) { qblk.push_back(k); qj0.push_back(j0); }
     gemm_add_tiles(tfull, k, nk, nk, false);
     gemm_add_tiles(tlower, k, nk, nk, true);
   }
@@ -121,6 +200,9 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
   SB_TRY(pl->d_desc_ichol.upload(ichol));
   SB_TRY(pl->d_desc_s1_lo.upload(s1lo)); SB_TRY(pl->d_desc_s1_up.upload(s1up));
   SB_TRY(pl->d_desc_s2_lo.upload(s2lo)); SB_TRY(pl->d_desc_s2_up.upload(s2up));
+  SB_TRY(pl->d_desc_full.upload(dfull)); SB_TRY(pl->d_desc_lower.upload(dlower));
+  pl->nqgroups = (int)qblk.size();
+  SB_TRY(pl->d_qcol_blk.upload(qblk)); SB_TRY(pl->d_qcol_j0.upload(qj0));
   SB_TRY(pl->d_tiles_full.upload(tfull)); SB_TRY(pl->d_tiles_lower.upload(tlower));
   SB_TRY(pl->d_Tt.alloc((size_t)pl->lenud)); SB_TRY(pl->d_Wt.alloc((size_t)pl->lenud));
   SB_TRY(pl->d_Xp.alloc((size_t)pl->lenud)); SB_TRY(pl->d_Y.alloc((size_t)pl->lenud));
@@ -159,12 +241,12 @@ int sb200_invcholfac_dev(sb200_psd_plan *pl, const double *u_dev, const int *per
   cudaStream_t st = ctx().stream;
   tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
       pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, 1);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("tri_transpose_kernel");
   gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_ichol.p, pl->d_tiles_lower.p, pl->d_Tt.p, pl->d_Tt.p,
                                                    pl->d_Wt.p, nullptr);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, pl->d_Wt.p, y_dev, 0, 1);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("perm_block_kernel");
   return 0;
 }
 
@@ -177,23 +259,23 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
   cudaStream_t st = ctx().stream;
   tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
       pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, transp ? 1 : 0);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("tri_transpose_kernel");
   const double *xs = x_dev;
   if (perm_dev && !transp) {          // prep: X(perm,perm)   (psdscale.m:94-99)
     perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, x_dev, pl->d_Xp.p, 1, 0);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("perm_block_kernel");
     xs = pl->d_Xp.p;
   }
   gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s1_up : pl->d_desc_s1_lo).p, pl->d_tiles_full.p,
                                                   pl->d_Tt.p, xs, pl->d_Wt.p, nullptr);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   bool postp = perm_dev && transp;
   gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s2_up : pl->d_desc_s2_lo).p, pl->d_tiles_full.p,
                                                   pl->d_Tt.p, pl->d_Wt.p, postp ? pl->d_Y.p : y_dev, nullptr);
-  SB_LAUNCH_CHECK();
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   if (postp) {                         // XX(PP,PP) = XX   (psdscale.m:104-109)
     perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, pl->d_Y.p, y_dev, 0, 0);
-    SB_LAUNCH_CHECK();
+    SB_LAUNCH_CHECK_N("perm_block_kernel");
   }
   return 0;
 }
@@ -245,6 +327,95 @@ int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *
   SB_TRY(sb200_psdscale_dev(pl, du, dperm, dx, transp, dy));
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, ctx().stream));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+// ---- Householder-frame operations.  frms_dev: lenud doubles (real blocks); lab/xlab: sum(n_k) doubles.
+static int build_q(sb200_psd_plan *pl, const double *frms_dev) {   // Q -> d_Tt, Q' -> d_Wt
+  cudaStream_t st = ctx().stream;
+  householder_q_kernel<<<pl->nqgroups, 256, 0, st>>>(pl->d_qcol_blk.p, pl->d_qcol_j0.p, pl->d_n.p, pl->d_off.p, frms_dev, pl->d_Tt.p);
+  SB_LAUNCH_CHECK_N("householder_q_kernel");
+  int tp = (pl->maxn + 31) / 32;
+  transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, nullptr, pl->d_Wt.p);
+  SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+  return 0;
+}
+
+// x = psdframeit(lab, frms, K):  X_k = Qb' diag(lab_k) Qb   (psdframeit.c:65-99)
+int sb200_psdframeit_dev(sb200_psd_plan *pl, const double *lab_dev, const double *frms_dev, double *x_dev) {
+  SB_TRY(ensure_init());
+  if (pl->nblk == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  SB_TRY(build_q(pl, frms_dev));
+  int tp = (pl->maxn + 31) / 32;
+  // B(c,k) = lab_k * Qb(k,c): transpose of Q with the k-index scaled -> d_Xp
+  transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, lab_dev, pl->d_Xp.p);
+  SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Wt.p, pl->d_Xp.p, x_dev, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, x_dev, x_dev, nullptr, 0);
+  SB_LAUNCH_CHECK_N("sym_ops_kernel");
+  return 0;
+}
+
+// z = psdinvjmul(xlab, xfrm, y, K):  solve X Z + Z X = 2 Y in the eigenbasis of X   (psdinvjmul.c:101-157)
+int sb200_psdinvjmul_dev(sb200_psd_plan *pl, const double *xlab_dev, const double *frms_dev, const double *y_dev, double *z_dev) {
+  SB_TRY(ensure_init());
+  if (pl->nblk == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  SB_TRY(build_q(pl, frms_dev));                                      // Q = d_Tt, Q' = d_Wt
+  sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, y_dev, pl->d_Y.p, nullptr, 1);   // Ys from tril(Y)
+  SB_LAUNCH_CHECK_N("sym_ops_kernel");
+  // P = Q Ys           (A = Q, B = Ys symmetric)            -> d_Xp
+  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>(pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  // M = P Q' (lower)   (A = P, B = Q)                       -> d_Y
+  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Tt.p, pl->d_Y.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Y.p, pl->d_Y.p, xlab_dev, 2);
+  SB_LAUNCH_CHECK_N("sym_ops_kernel");
+  // R = Q' M           (A = Q', B = M symmetric)            -> d_Xp
+  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>(pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Wt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  // Z = R Q (lower)    (A = R, B = Q')                      -> z
+  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Wt.p, z_dev, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, z_dev, z_dev, nullptr, 0);
+  SB_LAUNCH_CHECK_N("sym_ops_kernel");
+  return 0;
+}
+
+int sb200_psdframeit(sb_idx nblk, const sb_idx *n, const double *lab, const double *frms, double *x) {
+  sb200_psd_plan *pl = nullptr;
+  SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
+  if (pl->lenud == 0) return 0;
+  arena_reset();
+  double *dl = arena<double>((size_t)pl->sumn), *df = arena<double>((size_t)pl->lenud), *dx = arena<double>((size_t)pl->lenud);
+  SB_CHECK(dl && df && dx, "psdframeit: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dl, lab, sizeof(double) * pl->sumn, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_psdframeit_dev(pl, dl, df, dx));
+  SB_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sb200_psdinvjmul(sb_idx nblk, const sb_idx *n, const double *xlab, const double *frms, const double *y, double *z) {
+  sb200_psd_plan *pl = nullptr;
+  SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
+  if (pl->lenud == 0) return 0;
+  arena_reset();
+  double *dl = arena<double>((size_t)pl->sumn), *df = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud),
+         *dz = arena<double>((size_t)pl->lenud);
+  SB_CHECK(dl && df && dy && dz, "psdinvjmul: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dl, xlab, sizeof(double) * pl->sumn, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_psdinvjmul_dev(pl, dl, df, dy, dz));
+  SB_CUDA(cudaMemcpyAsync(z, dz, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

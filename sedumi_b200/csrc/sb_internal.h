@@ -17,6 +17,7 @@ struct Context {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  bool profiling = false;
   // bump arena for per-call scratch (reset at the start of each public entry point)
   std::vector<std::pair<char *, size_t>> arena_chunks;
   size_t arena_cur = 0, arena_off = 0;
@@ -48,10 +49,12 @@ int  ensure_init();
 #define SB_TRY(expr)                                                                  \
   do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-// Count + check a kernel launch on the library stream.
-#define SB_LAUNCH_CHECK()                                                             \
+// Count + check a kernel launch on the library stream (and time it when profiling is on).
+void prof_mark(const char *name);
+#define SB_LAUNCH_CHECK_N(name)                                                       \
   do {                                                                                \
     sb::ctx().launches++;                                                             \
+    if (sb::ctx().profiling) sb::prof_mark(name);                                     \
     cudaError_t _e = cudaGetLastError();                                              \
     if (_e != cudaSuccess) {                                                          \
       sb::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,          \

@@ -1,0 +1,210 @@
+"""Device-resident hot path: Python binding of libsedumi_b200's `*_dev` entry points.
+
+This is the library's public API for callers that keep the iteration state in HBM (the
+benchmark's `value` leg, and any host that wants to chain the kernels without crossing the
+MEX boundary between them).  torch is used only for device memory and streams -- every
+arithmetic step is one of our CUDA kernels, reached through the C-ABI in
+include/sedumi_b200.h.  There is no CPU fallback: importing works without a GPU (so the
+symbol table can be checked), but any compute call raises when no device is present.
+
+One `HotPath` object = one problem (iteration-invariant structure uploaded once) and runs
+the reference's per-iteration recipe (sedumi.m:442-466 + the solves of wrapPcg.m:56-59):
+
+    invcholfac -> getada1 -> [getada2] -> getada3 -> blkchol -> nsolve x (fwblkslv, ./d, bwblkslv)
+    -> npsdscale x psdscale
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsedumi_b200.so")
+_lib = None
+
+I64 = C.c_int64
+VP = C.c_void_p
+
+
+class SB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libsedumi_b200.so (raises ImportError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} missing: run __graft_entry__.build() (nvcc, sm_100a) first")
+        L = C.CDLL(_LIB_PATH)
+        L.sb200_last_error.restype = C.c_char_p
+        L.sb200_kernel_launches.restype = I64
+        L.sb200_stream.restype = VP
+        L.sb200_chol_plan_nnzL.restype = I64
+        L.sb200_chol_plan_rect_size.restype = I64
+        L.sb200_ada_plan_nnz.restype = I64
+        L.sb200_psd_plan_lenud.restype = I64
+        _lib = L
+    return _lib
+
+
+def check(rc: int, who: str = "sb200") -> None:
+    if rc != 0:
+        raise SB200Error(f"{who}: {lib().sb200_last_error().decode(errors='replace')}")
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a).ravel(), dtype=np.int64)
+
+
+def _p(a):
+    """ctypes pointer of a numpy array or torch tensor (device or host)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(VP)
+    return VP(a.data_ptr())
+
+
+EXPORTS = [
+    "sb200_init", "sb200_shutdown", "sb200_last_error", "sb200_device_count", "sb200_sync", "sb200_stream",
+    "sb200_kernel_launches", "sb200_dev_alloc", "sb200_dev_free", "sb200_h2d", "sb200_d2h",
+    "sb200_chol_plan_create", "sb200_chol_plan_destroy", "sb200_chol_plan_nnzL", "sb200_chol_plan_rect_size",
+    "sb200_blkchol_dev", "sb200_chol_rect_to_csc_dev", "sb200_chol_csc_to_rect_dev", "sb200_blkchol",
+    "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
+    "sb200_psd_plan_get", "sb200_psd_plan_lenud", "sb200_psd_plan_sumn", "sb200_invcholfac_dev", "sb200_psdscale_dev",
+    "sb200_invcholfac", "sb200_psdscale", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
+    "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_prof_begin", "sb200_prof_end",
+    "sb200_ada_plan_get", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
+    "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3",
+    "sb200_ddot_dense_dev", "sb200_qblkmul_dev", "sb200_quadadd_dev", "sb200_ddot_dense", "sb200_ddot_sparse",
+    "sb200_qblkmul", "sb200_quadadd",
+]
+
+
+class _CholPars(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("canceltol", C.c_double), ("maxu", C.c_double)]
+
+
+class HotPath:
+    """Device-resident state + the per-iteration call sequence for one problem."""
+
+    def __init__(self, S, device: int = 0, chol_pars=None):
+        import torch
+        self.torch = torch
+        L = lib()
+        check(L.sb200_init(C.c_int(device)), "init")
+        self.dev = torch.device("cuda", device)
+        self.S = S
+        K = S.K
+        m = self.m = S.m
+        At = S.At
+        self.nq = len(K["q"])
+        s = np.asarray(K["s"], dtype=np.int64)
+        self.s = s
+        self.lenud = int((s ** 2).sum())
+        self.lpN = int(K["l"])
+        pars = dict(abstol=1e-20, canceltol=1e-12, maxu=5e5)
+        pars.update(chol_pars or {})
+        self.pars = _CholPars(pars["abstol"], pars["canceltol"], pars["maxu"])
+        # ---- plans
+        Ajc, Air = _i64(At.indptr), _i64(At.indices)
+        Ajc1 = _i64(S.Ablkjc[:, 2])
+        qstart = _i64(np.asarray(K["qblkstart"]) - 1)
+        bs = _i64(np.asarray(K["sblkstart"])[:len(s)] - 1) if len(s) else _i64([])
+        adajc, adair = _i64(S.ADA.indptr), _i64(S.ADA.indices)
+        self.ada = VP()
+        check(L.sb200_ada_plan_get(C.byref(self.ada), I64(At.shape[0]), I64(m), _p(Ajc), _p(Air), _p(Ajc1),
+                                   I64(self.lpN), I64(self.nq), _p(qstart), I64(len(s)), _p(bs), _p(_i64(s)),
+                                   _p(adajc), _p(adair)), "ada_plan")
+        check(L.sb200_ada_set_At_values(self.ada, _p(np.ascontiguousarray(At.data, dtype=np.float64))), "At values")
+        self.psd = VP()
+        check(L.sb200_psd_plan_get(C.byref(self.psd), I64(len(s)), _p(_i64(s))), "psd_plan")
+        Lst = S.L
+        LL = Lst["L"]
+        self.chol = VP()
+        check(L.sb200_chol_plan_create(C.byref(self.chol), I64(m), I64(len(Lst["xsuper"].ravel()) - 1),
+                                       _p(_i64(Lst["xsuper"].ravel() - 1)), _p(_i64(LL.indptr)), _p(_i64(LL.indices)),
+                                       _p(_i64(Lst["perm"].ravel() - 1)), _p(adajc), _p(adair)), "chol_plan")
+        self.nnzADA = int(S.ADA.nnz)
+        self.rect = int(L.sb200_chol_plan_rect_size(self.chol))
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        z = lambda n: torch.zeros(max(int(n), 1), **f64)
+        self.d_l, self.d_det = z(self.lpN), z(self.nq)
+        self.d_u, self.udsqr = z(self.lenud), z(self.lenud)
+        self.d_perm = torch.zeros(max(int(s.sum()), 1), dtype=torch.int32, device=self.dev)
+        self.has_perm = False
+        self.ADA, self.absd = z(self.nnzADA), z(m)
+        self.Lrect, self.dvec, self.sval = z(self.rect), z(m), z(m)
+        self.flag = torch.zeros(max(m, 1), dtype=torch.int32, device=self.dev)
+        self.psd_x, self.psd_y = z(self.lenud), z(self.lenud)
+        self.rhs = self.y = self.w = None
+
+    # ------------------------------------------------------------------ data movement
+    def set_scaling(self, d: dict, non_blocking=False) -> int:
+        """Host -> device copy of the NT scaling; returns bytes moved."""
+        t = self.torch
+        nbytes = 0
+        for name, dst in (("l", self.d_l), ("det", self.d_det), ("u", self.d_u)):
+            a = np.ascontiguousarray(np.asarray(d[name], dtype=np.float64).ravel())
+            if a.size:
+                dst[:a.size].copy_(t.from_numpy(a), non_blocking=non_blocking)
+                nbytes += a.nbytes
+        p = np.asarray(d.get("perm", np.zeros(0))).ravel()
+        self.has_perm = p.size > 0
+        if self.has_perm:
+            p0 = (p.astype(np.int64) - 1).astype(np.int32)
+            self.d_perm[:p0.size].copy_(t.from_numpy(p0), non_blocking=non_blocking)
+            nbytes += p0.nbytes
+        return nbytes
+
+    def set_rhs(self, r: np.ndarray) -> int:
+        t = self.torch
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.float64).reshape(self.m, -1, order="F").T)   # rows = rhs
+        self.nrhs = r.shape[0]
+        self.rhs = t.from_numpy(r).to(self.dev)
+        self.y = t.empty_like(self.rhs)
+        self.w = t.empty_like(self.rhs)
+        return r.nbytes
+
+    # ------------------------------------------------------------------ kernels
+    def invcholfac(self):
+        check(lib().sb200_invcholfac_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
+                                         _p(self.udsqr)), "invcholfac")
+
+    def getada(self):
+        L = lib()
+        check(L.sb200_getada1_dev(self.ada, _p(self.d_l), _p(self.d_det), None, _p(self.ADA)), "getada1")
+        if self.nq:
+            raise SB200Error("device-resident getada2 needs DAt.q on the device (Lorentz path: next round)")
+        check(L.sb200_getada3_dev(self.ada, _p(self.udsqr), None, I64(0), _p(self.ADA), _p(self.absd), C.c_int(1)), "getada3")
+
+    def blkchol(self):
+        check(lib().sb200_blkchol_dev(self.chol, _p(self.ADA), _p(self.absd), self.pars, _p(self.Lrect), _p(self.dvec),
+                                      _p(self.flag), _p(self.sval)), "blkchol")
+
+    def solve(self):
+        """y = L' \\ ((L \\ r(perm)) ./ d), all right-hand sides (wrapPcg.m:56-59 without dense columns)."""
+        check(lib().sb200_ldl_solve_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.rhs),
+                                        _p(self.w), _p(self.y), I64(self.nrhs)), "ldl_solve")
+
+    def psdscale(self, transp: int):
+        check(lib().sb200_psdscale_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
+                                       _p(self.psd_x), C.c_int(transp), _p(self.psd_y)), "psdscale")
+
+    def iteration(self, nsolve=4, npsdscale=12):
+        self.invcholfac()
+        self.getada()
+        self.blkchol()
+        for _ in range(nsolve):
+            self.solve()
+        for i in range(npsdscale):
+            self.psdscale(i & 1)
+
+    def sync(self):
+        check(lib().sb200_sync(), "sync")
+
+    def stream(self):
+        return self.torch.cuda.ExternalStream(lib().sb200_stream(), device=self.dev)

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Any, Sequence
 
 import numpy as np
@@ -161,6 +162,8 @@ class MexPlugin:
         self.path = path
         self.lib = C.CDLL(path)
         self.fn = C.cast(self.lib.mexFunction, C.c_void_p)
+        self.seconds = 0.0          # time spent inside mexFunction (marshalling excluded)
+        self.calls = 0
 
     def call_raw(self, nlhs: int, prhs: Sequence[int]) -> list[int]:
         """Call with pre-built mxArray inputs; returns raw output handles (caller frees)."""
@@ -168,7 +171,10 @@ class MexPlugin:
         nout = max(nlhs, 1)
         plhs = (C.c_void_p * nout)()
         rhs = (C.c_void_p * max(len(prhs), 1))(*prhs)
+        t0 = time.perf_counter()
         rc = lib.mxshim_call(self.fn, nlhs, plhs, len(prhs), rhs)
+        self.seconds += time.perf_counter() - t0
+        self.calls += 1
         if rc != 0:
             raise MexError(lib.mxshim_last_error().decode(errors="replace"))
         return [plhs[i] for i in range(nout)]
@@ -199,6 +205,10 @@ class MexDir:
         if name not in self._cache:
             self._cache[name] = MexPlugin(os.path.join(self.path, name + ".so"))
         return self._cache[name]
+
+    def mex_seconds(self) -> float:
+        """Total time spent inside the plugins' mexFunction so far."""
+        return sum(p.seconds for p in self._cache.values())
 
     def has(self, name: str) -> bool:
         return os.path.exists(os.path.join(self.path, name + ".so"))
