@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--workload", default="control07")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +198,8 @@ def main():
               if args.workload == "control07" else args.workload,
               "recipe": f"invcholfac,getada1,getada2,getada3,blkchol,{NSOLVE}x(fwblkslv,./d,bwblkslv),{NPSD}xpsdscale",
               "scaling_state": "S1 mid-run NT scaling (SURVEY 8d), seed 20260926", "parallelism": f"replicas x{args.gpus}",
-              "l2": "L2 flushed (256 MiB write) between timed iterations"}
+              "l2": "L2 flushed (256 MiB write) between timed iterations",
+              "launch": "one CUDA graph per iteration" if not args.no_graph else "stream launches"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -242,6 +244,10 @@ def main():
 
         for _ in range(args.warmup):
             hp.iteration(NSOLVE, NPSD)
+        # the iteration is latency-bound at this size: replay it as one CUDA graph
+        run_iter = hp.capture(NSOLVE, NPSD) if not args.no_graph else (lambda: hp.iteration(NSOLVE, NPSD))
+        for _ in range(2):
+            run_iter()
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -251,17 +257,19 @@ def main():
         for k in range(args.steps):
             flush.fill_(k & 255)                      # evict L2 between timed iterations (untimed)
             ev[k][0].record(stream)
-            hp.iteration(NSOLVE, NPSD)
+            run_iter()
             ev[k][1].record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = lib.sb200_kernel_launches() - l0
+        if not args.no_graph:
+            launches = hp.launches_per_iteration * args.steps      # kernels inside the replayed graphs
         ms = sum(a.elapsed_time(b) for a, b in ev)
         # also a back-to-back (no flush) figure for context
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            hp.iteration(NSOLVE, NPSD)
+            run_iter()
         e1.record(stream)
         stream.synchronize()
         ms_warm = e0.elapsed_time(e1)

@@ -43,6 +43,11 @@ int64_t     sb200_kernel_launches(void);          /* kernels launched by this li
  * "kernel_name launches total_ms" per line */
 int         sb200_prof_begin(void);
 int         sb200_prof_end(char *buf, int64_t buflen);
+/* CUDA-graph capture of a sequence of *_dev calls on the library stream, and its replay */
+int         sb200_graph_begin(void);
+int         sb200_graph_end(void **graph_exec);
+int         sb200_graph_launch(void *graph_exec);
+int         sb200_graph_destroy(void *graph_exec);
 int         sb200_dev_alloc(void **p, int64_t bytes);
 int         sb200_dev_free(void *p);
 int         sb200_h2d(void *dst, const void *src, int64_t bytes);
@@ -191,6 +196,17 @@ int sb200_ddot_sparse(sb_idx nblk, const sb_idx *bs_abs, const double *d, sb_idx
                       double *ypr, sb_idx *nnz_out);
 int sb200_qblkmul(sb_idx nblk, const sb_idx *bs, const double *mu, const double *d, double *y);
 int sb200_quadadd(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo);
+
+/* ------------------------------------------------------------------ dense columns (product form)
+ * dpr1fact.c:630-848, fwdpr1.c:99-202, bwdpr1.c:171-275.  Index arrays 0-based; betajc_out 0-based
+ * (the stub adds 1 like the reference), pivperm 0-based ("C-form" in the reference too).          */
+int sb200_dpr1fact(sb_idx m, sb_idx n, const sb_idx *xjc, const sb_idx *xir, const double *xpr, const double *d_in,
+                   const sb_idx *dzjc, const sb_idx *dzir, const sb_idx *colperm, const sb_idx *firstpiv,
+                   const double *smult, double maxu, double *p_out, double *beta_out, sb_idx *betajc_out,
+                   sb_idx *pivperm_out, double *dopiv_out, double *d_out, sb_idx *nbeta, sb_idx *npivperm);
+int sb200_dpr1solve(int backward, sb_idx m, sb_idx nrhs, sb_idx nden, const sb_idx *dzjc, const sb_idx *dzir,
+                    const double *p, const sb_idx *pivperm, sb_idx permnnz, const double *beta,
+                    const sb_idx *betajc, const double *dopiv, double *y);
 
 #ifdef __cplusplus
 }

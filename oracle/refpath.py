@@ -91,3 +91,30 @@ class RefHotPath:
         for i in range(npsdscale):
             ps = self.psdscale(d, psd_x, i & 1)
         return dict(udsqr=udsqr, ADA=ADA, absd=absd, L=L, y=y, psd=ps)
+
+
+class DenseColumnRef:
+    """Dense-column (product-form) part of the reference path for LP dense columns:
+    symbcholden.m:45-55 (symbolic, via the reference's symbfwblk/incorder/finsymbden) and
+    deninfac.m:57-79 (numeric: sparfwslv + dpr1fact)."""
+
+    def __init__(self, S, L, debug=False):
+        self.mex = ref_dir(debug)
+        self.S = S
+        dense = S.dense
+        assert len(dense.q) == 0, "only LP dense columns are exercised here"
+        Lm = hsetup.L_for_mex({k: L[k] for k in ("perm", "L", "xsuper", "tmpsiz")})
+        self.Lm = Lm
+        i1 = dense.l + 1
+        LAD = self.mex.symbfwblk(Lm, sp.csc_matrix(dense.A[:, :i1 - 1]))
+        perm, dz = self.mex.incorder(LAD, nlhs=2)
+        self.sym = self.mex.finsymbden(LAD, perm, dz, float(i1))
+        self.sym["LAD"] = LAD
+
+    def inputs(self, d, Ld):
+        """(LAD values, L.d, symLden, smult, maxu) as deninfac.m hands them to dpr1fact."""
+        dense = self.S.dense
+        Ad = sp.csc_matrix(dense.A)
+        smult = d["l"][dense.cols[:dense.l].astype(int) - 1]
+        LAD = self.mex.fwblkslv(self.Lm, Ad, self.sym["LAD"])
+        return LAD, Ld, self.sym, smult.reshape(-1, 1)

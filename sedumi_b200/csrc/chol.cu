@@ -31,54 +31,11 @@
 #include <algorithm>
 #include <map>
 #include <math.h>
+#include <stdlib.h>
+#include <time.h>
 #include "sb_internal.h"
 
-namespace sb {
-
-static const int SMALL_N = 128;   // supernodes up to this many columns: one CTA each
-static const int NB = 32;         // panel width of the blocked path
-static const int UT_R = 64, UT_C = 32;   // update-kernel tile of an ancestor panel
-
-struct Sn {        // one supernode
-  int first, n, m; // first column, #columns, #rows of first column (incl. diagonal)
-  int lindx;       // offset of its row list in lindx[]
-  long long poff;  // offset of its m x n panel in the rect layout (ld = m)
-  long long coff;  // offset of its first column in the packed CSC value array (= Ljc[first])
-};
-struct Pair {      // update of ancestor J by descendant K
-  int K, J;
-  int koff;        // first row (index into K's row list) that lies in J's columns
-  int mk;          // rows of K from koff to the end
-  int ncolup;      // how many of those lie inside J's columns
-  int rel;         // offset into rel[]: position of each of those mk rows inside J's row list
-};
-struct UTile { int J, r0, c0; };
-
-}  // namespace sb
-
-struct sb200_chol_plan {
-  int m = 0, nsuper = 0, nlevels = 0;
-  long long nnzL = 0, rect = 0;
-  uint64_t key = 0;
-  std::vector<sb::Sn> sn;
-  std::vector<int> snode, level_of;
-  std::vector<std::vector<int>> level_small, level_big;      // supernodes per level
-  std::vector<int> level_small_off;                          // offsets into d_level_list
-  std::vector<std::vector<sb::UTile>> level_tiles;
-  std::vector<int> level_tile_off;
-  std::vector<int> pair_beg;                                  // per J: range in pairs[]
-  std::vector<std::vector<int>> level_all;                   // all supernodes per level (solves)
-  std::vector<int> level_all_off;
-  int max_sn_n = 0, max_sn_m = 0;
-  // device
-  sb::DevBuf<sb::Sn> d_sn;
-  sb::DevBuf<sb::Pair> d_pairs;
-  sb::DevBuf<int> d_pair_beg, d_rel, d_lindx, d_snode, d_perm, d_Xjc, d_Xir, d_level_list, d_level_all;
-  sb::DevBuf<sb::UTile> d_tiles;
-  sb::DevBuf<long long> d_Ljc;
-  // numeric scratch
-  sb::DevBuf<double> d_diagX, d_lb, d_scal, d_vscratch, d_y;
-};
+#include "chol_plan.h"
 
 namespace sb {
 
@@ -708,6 +665,9 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
   SB_TRY(pl->d_lb.alloc(m));
   SB_TRY(pl->d_scal.alloc(8));
   SB_TRY(pl->d_vscratch.alloc(std::max(pl->max_sn_m, 1)));
+  pl->dense_fast = (nsuper == 1 && m >= 1 && pl->sn[0].m == m && pl->sn[0].n == m &&
+                    (size_t)m * 8 + 4096 <= 200 * 1024);
+  if (pl->dense_fast) SB_TRY(dense_factor_prepare(pl));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));       // host vectors go out of scope
   return 0;
 }
@@ -728,6 +688,13 @@ void sb200_chol_plan_destroy(sb200_chol_plan *plan) { delete plan; }
 sb_idx sb200_chol_plan_nnzL(const sb200_chol_plan *plan) { return plan->nnzL; }
 sb_idx sb200_chol_plan_rect_size(const sb200_chol_plan *plan) { return plan->rect; }
 
+static void launch_bounds_cb(sb200_chol_plan *pl, const double *absd, sb200_chol_pars pars) {
+  bounds_kernel<<<1, 1024, 0, ctx().stream>>>(pl->m, pl->d_diagX.p, absd, pl->d_perm.p, pars.abstol, pars.canceltol,
+                                              pars.maxu, pl->d_lb.p, pl->d_scal.p);
+  ctx().launches++;
+  if (ctx().profiling) prof_mark("bounds_kernel");
+}
+
 int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd,
                       sb200_chol_pars pars, double *rect, double *d, int *flag, double *sval) {
   SB_TRY(ensure_init());
@@ -736,6 +703,7 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
   if (m == 0) return 0;
   SB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * m, st));
   SB_CUDA(cudaMemsetAsync(sval, 0, sizeof(double) * m, st));
+  if (pl->dense_fast) return dense_factor(pl, Xpr, absd, pars, rect, d, flag, sval, launch_bounds_cb);
   permuteP_kernel<<<m, 256, 0, st>>>(pl->d_sn.p, pl->d_snode.p, pl->d_lindx.p, pl->d_perm.p,
                                       pl->d_Xjc.p, pl->d_Xir.p, Xpr, rect, pl->d_diagX.p);
   SB_LAUNCH_CHECK_N("permuteP_kernel");
@@ -799,6 +767,7 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   cudaStream_t st = ctx().stream;
   const int m = pl->m;
   if (m == 0 || nrhs == 0) return 0;
+  if (pl->dense_fast) return dense_fwsolve(pl, rect, b, y, (int)nrhs, nullptr, nullptr);
   long long tot = (long long)m * nrhs;
   gather_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, b, y);
   SB_LAUNCH_CHECK_N("gather_perm_kernel");
@@ -821,6 +790,10 @@ int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
 // from the last sb200_blkchol_dev call).
 int sb200_ldl_solve_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag,
                         const double *b, double *w, double *y, sb_idx nrhs) {
+  if (pl->dense_fast) {
+    SB_TRY(dense_fwsolve(pl, rect, b, w, (int)nrhs, d, flag));
+    return dense_bwsolve(pl, rect, w, y, (int)nrhs);
+  }
   SB_TRY(sb200_fwblkslv_dev(pl, rect, b, w, nrhs));
   long long tot = (long long)pl->m * nrhs;
   if (tot > 0) {
@@ -835,6 +808,7 @@ int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   cudaStream_t st = ctx().stream;
   const int m = pl->m;
   if (m == 0 || nrhs == 0) return 0;
+  if (pl->dense_fast) return dense_bwsolve(pl, rect, b, y, (int)nrhs);
   long long tot = (long long)m * nrhs;
   SB_TRY(pl->d_y.n >= (size_t)tot ? 0 : pl->d_y.alloc((size_t)tot));
   SB_CUDA(cudaMemcpyAsync(pl->d_y.p, b, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
@@ -899,35 +873,50 @@ int get_plan(sb200_chol_plan **out, sb_idx m, sb_idx nsuper, const sb_idx *xsupe
 
 extern "C" {
 
+static double now_ms() {
+  struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int sb200_blkchol(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
                   const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir, const double *Xpr,
                   const double *absd, sb200_chol_pars pars, double *Lpr_out, double *d_out,
                   sb_idx *skip_idx, double *skip_val, sb_idx *nskip, sb_idx *add_idx, double *add_val,
                   sb_idx *nadd) {
+  const bool trace = getenv("SB200_TRACE") != nullptr;
+  double t0 = now_ms();
   sb200_chol_plan *pl = nullptr;
   SB_TRY(get_plan(&pl, m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir));
+  double t1 = now_ms();
   *nskip = 0; *nadd = 0;
   if (m == 0) return 0;
-  DevBuf<double> dX, dabsd, drect, dd, dsval, dL;
-  DevBuf<int> dflag;
-  SB_TRY(dX.upload(Xpr, (size_t)Xjc[m]));
-  if (absd) SB_TRY(dabsd.upload(absd, (size_t)m));
-  SB_TRY(drect.alloc((size_t)pl->rect));
-  SB_TRY(dd.alloc(m)); SB_TRY(dsval.alloc(m)); SB_TRY(dflag.alloc(m));
-  SB_TRY(dL.alloc((size_t)pl->nnzL));
-  SB_TRY(sb200_blkchol_dev(pl, dX.p, absd ? dabsd.p : nullptr, pars, drect.p, dd.p, dflag.p, dsval.p));
-  SB_TRY(sb200_chol_rect_to_csc_dev(pl, drect.p, dflag.p, dL.p));
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  const size_t nnzX = (size_t)Xjc[m];
+  double *dX = arena<double>(nnzX), *dabsd = arena<double>((size_t)m), *drect = arena<double>((size_t)pl->rect),
+         *dd = arena<double>((size_t)m), *dsval = arena<double>((size_t)m), *dL = arena<double>((size_t)pl->nnzL);
+  int *dflag = arena<int>((size_t)m);
+  SB_CHECK(dX && dabsd && drect && dd && dsval && dL && dflag, "blkchol: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(dX, Xpr, sizeof(double) * nnzX, cudaMemcpyHostToDevice, st));
+  if (absd) SB_CUDA(cudaMemcpyAsync(dabsd, absd, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+  double t2 = now_ms();
+  SB_TRY(sb200_blkchol_dev(pl, dX, absd ? dabsd : nullptr, pars, drect, dd, dflag, dsval));
+  SB_TRY(sb200_chol_rect_to_csc_dev(pl, drect, dflag, dL));
+  if (trace) cudaStreamSynchronize(st);
+  double t3 = now_ms();
   std::vector<int> flag(m);
   std::vector<double> sval(m);
-  SB_TRY(dL.download(Lpr_out, (size_t)pl->nnzL));
-  SB_TRY(dd.download(d_out, m));
-  SB_TRY(dflag.download(flag.data(), m));
-  SB_TRY(dsval.download(sval.data(), m));
-  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  SB_CUDA(cudaMemcpyAsync(Lpr_out, dL, sizeof(double) * pl->nnzL, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(d_out, dd, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(flag.data(), dflag, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(sval.data(), dsval, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  double t4 = now_ms();
   for (int j = 0; j < m; j++) {
     if (flag[j] == 1) { skip_idx[*nskip] = j; skip_val[*nskip] = sval[j]; (*nskip)++; }
     else if (flag[j] == 2) { add_idx[*nadd] = j; add_val[*nadd] = sval[j]; (*nadd)++; }
   }
+  if (trace) fprintf(stderr, "[sb200_blkchol] plan %.3f ms, h2d %.3f, factor %.3f, d2h %.3f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3);
   return 0;
 }
 
@@ -936,16 +925,19 @@ static int solve_host(bool fw, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, co
   sb200_chol_plan *pl = nullptr;
   SB_TRY(get_plan(&pl, m, nsuper, xsuper, Ljc, Lir, perm, nullptr, nullptr));
   if (m == 0 || nrhs == 0) return 0;
-  DevBuf<double> dL, drect, db, dy;
-  SB_TRY(dL.upload(Lpr, (size_t)pl->nnzL));
-  SB_TRY(db.upload(b, (size_t)(m * nrhs)));
-  SB_TRY(drect.alloc((size_t)pl->rect));
-  SB_TRY(dy.alloc((size_t)(m * nrhs)));
-  SB_TRY(sb200_chol_csc_to_rect_dev(pl, dL.p, drect.p));
-  if (fw) SB_TRY(sb200_fwblkslv_dev(pl, drect.p, db.p, dy.p, nrhs));
-  else SB_TRY(sb200_bwblkslv_dev(pl, drect.p, db.p, dy.p, nrhs));
-  SB_TRY(dy.download(y, (size_t)(m * nrhs)));
-  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  double *dL = arena<double>((size_t)pl->nnzL), *drect = arena<double>((size_t)pl->rect),
+         *db = arena<double>((size_t)(m * nrhs)), *dy = arena<double>((size_t)(m * nrhs));
+  SB_CHECK(dL && drect && db && dy, "solve: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(dL, Lpr, sizeof(double) * pl->nnzL, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(db, b, sizeof(double) * m * nrhs, cudaMemcpyHostToDevice, st));
+  SB_TRY(sb200_chol_csc_to_rect_dev(pl, dL, drect));
+  if (pl->dense_fast) SB_TRY(dense_compute_dinv(pl, drect));
+  if (fw) SB_TRY(sb200_fwblkslv_dev(pl, drect, db, dy, nrhs));
+  else SB_TRY(sb200_bwblkslv_dev(pl, drect, db, dy, nrhs));
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * m * nrhs, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -1,0 +1,508 @@
+// chol_dense.cu -- fast path for a factor that is ONE dense supernode (every shipped SeDuMi example
+// and every dense-ADA problem: symbchol.m:71-78 builds L = tril(ones) with a single supernode).
+//
+// At these sizes (m = 123..5000) the reference's column-serial LDL' is latency-bound, and so is a
+// naive GPU port (one launch per panel step: 3 launches x m/32 panels).  This file restructures it:
+//
+//  * dense_factor: ONE persistent cooperative kernel.  Per 32-column panel: CTA 0 factors the 32x32
+//    diagonal block warp-synchronously in shared memory, applying SeDuMi's pivot rules
+//    (blkchol2.c:96-167; the rare stability test pulls in the whole CTA); one grid barrier; then every
+//    CTA takes 64x64 tiles of the trailing matrix, re-derives the two row slabs of L21 it needs from
+//    the untouched panel columns (row-parallel triangular solve in registers) and applies the
+//    rank-32 update -- no second barrier between "TRSM" and "SYRK".  L is written to a separate
+//    output array, so panel columns are never overwritten while other CTAs still read them.
+//    The inverses of the 32x32 unit-lower diagonal blocks are produced at the end for the solves.
+//
+//  * dense_fwsolve / dense_bwsolve: dataflow triangular solves.  Warp b owns block-row b: it
+//    accumulates L(b, j) * y_j for j < b as the y_j are published (flags), then applies the inverted
+//    diagonal block.  The critical path per 32 rows is two 32x32 mat-vecs and a flag hand-off
+//    instead of a 32-step substitution; the other warps stream the rest of L concurrently.
+//    (fwblkslv.c:77-134 / bwblkslv.c:73-125 semantics: y = L\b(perm), y(perm) = L'\b.)
+#include <cooperative_groups.h>
+#include "chol_plan.h"
+
+namespace sb {
+
+static const int PB = 32;          // panel width
+static const int TS = 64;          // trailing tile edge
+
+struct ArgMaxD { double v; int i; };
+__device__ __forceinline__ ArgMaxD amd_better(ArgMaxD a, ArgMaxD b) {
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMaxD block_argmax_d(ArgMaxD x, ArgMaxD *sh) {
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMaxD y; y.v = __shfl_down_sync(0xffffffffu, x.v, o); y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+    x = amd_better(x, y);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    x = (l < nw) ? sh[l] : ArgMaxD{-1.0, 0x7fffffff};
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMaxD y; y.v = __shfl_down_sync(0xffffffffu, x.v, o); y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+      x = amd_better(x, y);
+    }
+    if (l == 0) sh[0] = x;
+  }
+  __syncthreads();
+  x = sh[0];
+  __syncthreads();
+  return x;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (*((volatile unsigned *)ctr) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// W: working matrix (m x m, ld = m, lower triangle live); Lo: output factor (same layout).
+__global__ void __launch_bounds__(256)
+dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, const double *scal, double maxu,
+                 int *flag, double *sval, const double *diagX, double *vscratch, double *dinv, unsigned *bar) {
+  __shared__ double A[PB][PB + 1];
+  __shared__ double s_lb[PB], z[PB], dloc[PB];
+  __shared__ int skipped[PB];
+  __shared__ ArgMaxD sh_am[32];
+  __shared__ double s_x;
+  __shared__ int s_state;
+  __shared__ double As[PB][TS + 1], Bs[PB][TS + 1];
+  const int ld = m;
+  const double ub = scal[0];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned bar_target = 0;
+  const int npanels = (m + PB - 1) / PB;
+  for (int pi = 0; pi < npanels; pi++) {
+    const int p0 = pi * PB, w = min(PB, m - p0), base = p0 + w;
+    // ------------------------------------------------------------------ phase A: diagonal block (CTA 0)
+    if (blockIdx.x == 0) {
+      for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
+        int r = idx % PB, c = idx / PB;
+        A[r][c] = (r < w && c < w && r >= c) ? W[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+      }
+      if (tid < PB) { skipped[tid] = 0; dloc[tid] = 0.0; }
+      __syncthreads();
+      if (tid < PB) s_lb[tid] = (tid < w) ? lb[p0 + tid] : 0.0;
+      __syncthreads();
+      int k_resume = 0, resolved_k = -1;
+      // warp 0 keeps row `lane` of the block in registers: a[c] = A[lane][c]
+      double a[PB];
+      if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < PB; c++) a[c] = A[lane][c];
+      }
+      while (true) {
+        if (warp == 0) {
+          int kstop = w;
+#pragma unroll
+          for (int k = 0; k < PB; k++) {
+            if (k < k_resume || k >= kstop || k >= w) continue;
+            const int gk = p0 + k;
+            double xkk = __shfl_sync(0xffffffffu, a[k], k);
+            const bool resolved = (k == resolved_k);
+            if (resolved) xkk = s_x;
+            const bool skip = !(xkk > s_lb[k]);
+            if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) { kstop = k; continue; }   // stability test needed
+            if (skip) {
+              if (lane == 0) { d[gk] = 0.0; flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
+              continue;
+            }
+            const double xr = a[k];
+            const double l = (lane > k) ? xr / xkk : 0.0;
+#pragma unroll
+            for (int c = k + 1; c < PB; c++) {
+              const double lc = __shfl_sync(0xffffffffu, l, c);
+              if (lane >= c) a[c] -= lc * xr;
+            }
+            if (lane > k) a[k] = l;
+            if (lane == k) a[k] = 1.0;
+            if (lane == 0) { d[gk] = xkk; dloc[k] = xkk; }
+          }
+#pragma unroll
+          for (int c = 0; c < PB; c++) A[lane][c] = a[c];
+          if (lane == 0) s_state = kstop;
+        }
+        __syncthreads();
+        const int k = s_state;
+        if (k >= w) break;
+        // ---- stability test for column k (rare): the reference compares x_kk with |x[idamax+1]|/maxu
+        // (blkchol2.c:66-70,122); needs the fully updated sub-column, i.e. the tail rows as well.
+        {
+          const int gk = p0 + k;
+          double xkk = A[k][k];
+          const int collen = m - gk;
+          if (tid == 0) {
+            z[k] = 1.0;
+            for (int i = k - 1; i >= 0; i--) {
+              double acc = 0.0;
+              if (!skipped[i]) for (int j = i + 1; j <= k; j++) acc += A[j][i] * z[j];
+              z[i] = -acc;
+            }
+          }
+          __syncthreads();
+          ArgMaxD am{-1.0, 0x7fffffff};
+          for (int r = k + 1 + tid; r < w; r += blockDim.x) am = amd_better(am, ArgMaxD{fabs(A[r][k]), r - (k + 1)});
+          for (int r = base + tid; r < m; r += blockDim.x) {
+            double v = 0.0;
+            for (int j = 0; j <= k; j++) v += W[(long long)(p0 + j) * ld + r] * z[j];
+            vscratch[r] = v;
+            am = amd_better(am, ArgMaxD{fabs(v), r - (gk + 1)});
+          }
+          am = block_argmax_d(am, sh_am);
+          if (tid == 0) {
+            const int t = am.i + 1, sublen = collen - 1;
+            double v;
+            if (t < sublen) {
+              int r = gk + 1 + t;
+              v = (r < base) ? A[r - p0][k] : vscratch[r];
+            } else if (k + 1 < w) {
+              v = A[k + 1][k + 1];
+            } else if (base < m) {
+              // diagonal of the next panel's first column as the reference holds it at this moment
+              const int r = base;
+              double u[PB];
+              double x = W[(long long)r * ld + r];
+              for (int j = 0; j < k; j++) {
+                double uj = W[(long long)(p0 + j) * ld + r];
+                for (int i = 0; i < j; i++) if (!skipped[i]) uj -= u[i] * A[j][i];
+                u[j] = uj;
+                if (!skipped[j]) x -= uj * uj / dloc[j];
+              }
+              v = x;
+            } else v = 0.0;
+            const double ubk = fabs(v) / maxu;
+            if (xkk < ubk) { flag[gk] = 2; sval[gk] = ubk - xkk; xkk = ubk; }
+            s_x = xkk;
+          }
+          __syncthreads();
+          resolved_k = k; k_resume = k;
+        }
+      }
+      // publish L11 (unit lower; skipped columns zeroed) into the output factor
+      for (int idx = tid; idx < w * w; idx += blockDim.x) {
+        int r = idx % w, c = idx / w;
+        if (r >= c) Lo[(long long)(p0 + c) * ld + p0 + r] = (r == c) ? 1.0 : (skipped[c] ? 0.0 : A[r][c]);
+      }
+    }
+    bar_target += gridDim.x;
+    grid_barrier(bar, bar_target);
+    // ------------------------------------------------------------------ phase B: trailing tiles
+    const int nrow = m - base;
+    if (nrow > 0) {
+      const int nslab = (nrow + TS - 1) / TS;
+      const int ntiles = nslab * (nslab + 1) / 2;
+      // L11 (strictly lower) and d of this panel -> shared (A / dloc are reused as scratch by every CTA)
+      for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
+        int r = idx % PB, c = idx / PB;
+        A[r][c] = (r < w && c < w && r > c) ? Lo[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+      }
+      if (tid < PB) {
+        const double dj = (tid < w) ? d[p0 + tid] : 0.0;
+        dloc[tid] = dj;
+        s_lb[tid] = (dj > 0.0) ? 1.0 / dj : 0.0;        // reciprocal pivots (0 marks a skipped pivot)
+      }
+      __syncthreads();
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        const int tj = t - ti * (ti + 1) / 2;
+        if (tid < 2 * TS) {
+          const bool isB = tid >= TS;
+          const int lr = isB ? tid - TS : tid;
+          const int r = base + (isB ? tj : ti) * TS + lr;
+          double a[PB];
+          if (r < m) {
+#pragma unroll
+            for (int j = 0; j < PB; j++) a[j] = (j < w) ? W[(long long)(p0 + j) * ld + r] : 0.0;
+#pragma unroll
+            for (int j = 0; j < PB; j++) {
+              const double rj = s_lb[j];
+              const double xj = a[j];
+              if (rj > 0.0) {
+#pragma unroll
+                for (int j2 = j + 1; j2 < PB; j2++) a[j2] -= xj * A[j2][j];
+                a[j] = xj * rj;
+              } else a[j] = 0.0;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < PB; j++) a[j] = 0.0;
+          }
+          if (!isB) {
+#pragma unroll
+            for (int j = 0; j < PB; j++) As[j][lr] = a[j];
+            if (tj == 0 && r < m) {
+#pragma unroll
+              for (int j = 0; j < PB; j++) if (j < w) Lo[(long long)(p0 + j) * ld + r] = a[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < PB; j++) Bs[j][lr] = a[j] * dloc[j];
+          }
+        }
+        __syncthreads();
+        {
+          const int tx = tid % 16, ty = tid / 16;
+          double acc[4][4] = {};
+#pragma unroll 8
+          for (int j = 0; j < PB; j++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { av[i] = As[j][tx + 16 * i]; bv[i] = Bs[j][ty + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int q = 0; q < 4; q++) acc[i][q] += av[i] * bv[q];
+          }
+          const int r0 = base + ti * TS, c0 = base + tj * TS;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int c = c0 + ty + 16 * q;
+            if (c < m) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int r = r0 + tx + 16 * i;
+                if (r < m && r >= c) W[(long long)c * ld + r] -= acc[i][q];
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    bar_target += gridDim.x;
+    grid_barrier(bar, bar_target);
+  }
+  // ------------------------------------------------------------------ inverses of the diagonal blocks
+  for (int pi = blockIdx.x; pi < npanels; pi += gridDim.x) {
+    const int p0 = pi * PB, w = min(PB, m - p0);
+    for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
+      int r = idx % PB, c = idx / PB;
+      A[r][c] = (r < w && c < w && r > c) ? Lo[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane c: column c of inv(L11) by forward substitution, x kept in registers
+      double x[PB];
+#pragma unroll
+      for (int i = 0; i < PB; i++) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int i = 1; i < PB; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < PB; j++) if (j < i) acc += A[i][j] * x[j];
+        x[i] -= acc;                                   // rows above the diagonal stay 0 since x[j]=0 for j<lane
+      }
+      double *out = dinv + (long long)pi * PB * PB + lane * PB;
+#pragma unroll
+      for (int i = 0; i < PB; i++) out[i] = x[i];      // column-major: column = lane
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------- solves
+// One CTA of 32 warps per right-hand side.  Warp b owns block rows b, b+32, ... (ascending), y and
+// the ready flags live in shared memory when the whole vector fits (m <= 8192), else in global.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(512)
+dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
+                   const double *dscale, const int *flag, const double *lb, int nb) {
+  extern __shared__ double smem[];
+  double *ys = smem;                                    // m doubles
+  volatile int *ready = (volatile int *)(smem + ((m + 1) & ~1));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double *bb = b + (long long)blockIdx.x * m;
+  double *yy = yout + (long long)blockIdx.x * m;
+  const int ld = m;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) ready[i] = 0;
+  __syncthreads();
+  for (int step = warp; step < nb; step += nw) {
+    const int br = BACKWARD ? (nb - 1 - step) : step;
+    const int k0 = br * PB, w = min(PB, m - k0);
+    // inverse of this block row's diagonal block: independent of everything, fetch first
+    const double *Di = dinv + (long long)br * PB * PB;
+    double di[PB];
+#pragma unroll
+    for (int c = 0; c < PB; c++) di[c] = BACKWARD ? Di[lane * PB + c] : Di[c * PB + lane];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    if (lane < w) acc0 = BACKWARD ? bb[k0 + lane] : bb[perm[k0 + lane]];
+    const int jbeg = BACKWARD ? nb - 1 : 0, jend = br, jstep = BACKWARD ? -1 : 1;
+    for (int j = jbeg; j != jend; j += jstep) {
+      double lv[PB];
+      if (lane < w) {
+        if (!BACKWARD) {
+          const double *Lp = L + (long long)(j * PB) * ld + k0 + lane;
+#pragma unroll
+          for (int c = 0; c < PB; c++) lv[c] = Lp[(long long)c * ld];
+        } else {
+          const int wj = min(PB, m - j * PB);
+          const double *Lp = L + (long long)(k0 + lane) * ld + j * PB;    // column k0+lane, rows of block j
+#pragma unroll
+          for (int r = 0; r < PB; r++) lv[r] = (r < wj) ? Lp[r] : 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < PB; c++) lv[c] = 0.0;
+      }
+      while (ready[j] == 0) { __nanosleep(32); }
+      __threadfence_block();
+      const volatile double *yv = ys + j * PB;
+      const int wj = min(PB, m - j * PB);
+#pragma unroll
+      for (int c = 0; c < PB; c += 4) {
+        acc0 -= lv[c] * ((c < wj) ? yv[c] : 0.0);
+        acc1 -= lv[c + 1] * ((c + 1 < wj) ? yv[c + 1] : 0.0);
+        acc2 -= lv[c + 2] * ((c + 2 < wj) ? yv[c + 2] : 0.0);
+        acc3 -= lv[c + 3] * ((c + 3 < wj) ? yv[c + 3] : 0.0);
+      }
+    }
+    const double acc = (acc0 + acc1) + (acc2 + acc3);
+    // diagonal block: y = inv(L11) s  (forward)  or  y = inv(L11)' s  (backward)
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < PB; c += 4) {
+      y0 += di[c] * __shfl_sync(0xffffffffu, acc, c);
+      y1 += di[c + 1] * __shfl_sync(0xffffffffu, acc, c + 1);
+      y2 += di[c + 2] * __shfl_sync(0xffffffffu, acc, c + 2);
+      y3 += di[c + 3] * __shfl_sync(0xffffffffu, acc, c + 3);
+    }
+    const double yv = (y0 + y1) + (y2 + y3);
+    if (lane < w) {
+      ys[k0 + lane] = yv;
+      if (!BACKWARD) {
+        if (dscale) {                                     // ./d with deninfac's repair of skipped pivots
+          double dk = dscale[k0 + lane];
+          if (flag && flag[k0 + lane] == 1 && dk <= lb[k0 + lane]) dk = 1.0;
+          yy[k0 + lane] = yv / dk;
+        } else yy[k0 + lane] = yv;
+      } else yy[perm[k0 + lane]] = yv;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) ready[br] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+static __global__ void dense_permuteP_kernel(int m, const int *perm, const int *Xjc, const int *Xir, const double *Xpr,
+                                             double *W, double *diagX) {
+  const int j = blockIdx.x;
+  const int pj = perm[j];
+  const int b0 = Xjc[pj], b1 = Xjc[pj + 1];
+  const bool dense = (b1 - b0) == m;
+  double *col = W + (long long)j * m;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    double v = 0.0;
+    if (t >= j) {
+      const int pi = perm[t];
+      if (dense) v = Xpr[b0 + pi];
+      else {
+        int lo = b0, hi = b1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (Xir[mid] < pi) lo = mid + 1; else hi = mid; }
+        if (lo < b1 && Xir[lo] == pi) v = Xpr[lo];
+      }
+      if (t == j) diagX[j] = v;
+    }
+    col[t] = v;
+  }
+}
+
+int dense_factor_prepare(sb200_chol_plan *pl) {
+  const int m = pl->m;
+  pl->npanels = (m + PB - 1) / PB;
+  SB_TRY(pl->d_work.alloc((size_t)m * m));
+  SB_TRY(pl->d_dinv.alloc((size_t)pl->npanels * PB * PB));
+  SB_TRY(pl->d_bar.alloc(4));
+  return 0;
+}
+
+// Xpr_dev -> W (plan scratch) is done by the caller through dense_permuteP; here: bounds + factor.
+int dense_factor(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb200_chol_pars pars,
+                 double *rect, double *d, int *flag, double *sval, void (*bounds)(sb200_chol_plan *, const double *, sb200_chol_pars)) {
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  dense_permuteP_kernel<<<m, 256, 0, st>>>(m, pl->d_perm.p, pl->d_Xjc.p, pl->d_Xir.p, Xpr, pl->d_work.p, pl->d_diagX.p);
+  SB_LAUNCH_CHECK_N("dense_permuteP_kernel");
+  bounds(pl, absd, pars);
+  SB_CUDA(cudaMemsetAsync(pl->d_bar.p, 0, sizeof(unsigned) * 4, st));
+  // cooperative launch: every CTA must be resident
+  int per_sm = 0;
+  SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_ldl_kernel, 256, 0));
+  SB_CHECK(per_sm >= 1, "dense_ldl_kernel cannot be resident");
+  const int nslab = (std::max(m - PB, 0) + TS - 1) / TS;
+  int want = std::max(1, nslab * (nslab + 1) / 2);
+  int grid = std::min(want, per_sm * ctx().sm_count);
+  double *W = pl->d_work.p, *dinv = pl->d_dinv.p, *lb = pl->d_lb.p, *scal = pl->d_scal.p, *diagX = pl->d_diagX.p, *vs = pl->d_vscratch.p;
+  unsigned *bar = pl->d_bar.p;
+  int mm = m;
+  double maxu = pars.maxu;
+  void *args[] = {&mm, &W, &rect, &d, &lb, &scal, &maxu, &flag, &sval, &diagX, &vs, &dinv, &bar};
+  SB_CUDA(cudaLaunchCooperativeKernel((void *)dense_ldl_kernel, dim3(grid), dim3(256), args, 0, st));
+  SB_LAUNCH_CHECK_N("dense_ldl_kernel");
+  return 0;
+}
+
+static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs,
+                        const double *dscale, const int *flag) {
+  const int m = pl->m, nb = (m + PB - 1) / PB;
+  size_t shm = sizeof(double) * ((m + 1) & ~1) + sizeof(int) * nb;
+  SB_CHECK(shm <= 200 * 1024, "dense solve: m=%d too large for the shared-memory dataflow kernel", m);
+  cudaStream_t st = ctx().stream;
+  if (backward) {
+    if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    dense_solve_kernel<true><<<nrhs, 512, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+  } else {
+    if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    dense_solve_kernel<false><<<nrhs, 512, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+  }
+  SB_LAUNCH_CHECK_N(backward ? "dense_solve_kernel<bw>" : "dense_solve_kernel<fw>");
+  return 0;
+}
+int dense_fwsolve(sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs, const double *dscale, const int *flag) {
+  return solve_launch(false, pl, rect, b, y, nrhs, dscale, flag);
+}
+int dense_bwsolve(sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs) {
+  return solve_launch(true, pl, rect, b, y, nrhs, nullptr, nullptr);
+}
+
+// inverses of the diagonal blocks from an L that did not come from dense_factor (MEX-level solves)
+static __global__ void dense_dinv_kernel(int m, const double *Lo, double *dinv) {
+  __shared__ double A[PB][PB + 1];
+  const int pi = blockIdx.x, p0 = pi * PB, w = min(PB, m - p0), lane = threadIdx.x;
+  for (int idx = lane; idx < PB * PB; idx += 32) {
+    int r = idx % PB, c = idx / PB;
+    A[r][c] = (r < w && c < w && r > c) ? Lo[(long long)(p0 + c) * m + p0 + r] : 0.0;
+  }
+  __syncwarp();
+  double x[PB];
+#pragma unroll
+  for (int i = 0; i < PB; i++) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int i = 1; i < PB; i++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < PB; j++) if (j < i) acc += A[i][j] * x[j];
+    x[i] -= acc;
+  }
+  double *out = dinv + (long long)pi * PB * PB + lane * PB;
+#pragma unroll
+  for (int i = 0; i < PB; i++) out[i] = x[i];
+}
+int dense_compute_dinv(sb200_chol_plan *pl, const double *rect) {
+  dense_dinv_kernel<<<pl->npanels, 32, 0, ctx().stream>>>(pl->m, rect, pl->d_dinv.p);
+  SB_LAUNCH_CHECK_N("dense_dinv_kernel");
+  return 0;
+}
+
+}  // namespace sb

@@ -1,0 +1,70 @@
+// chol_plan.h -- plan structures shared by chol.cu (general supernodal path) and chol_dense.cu
+// (single dense supernode fast path).
+#pragma once
+#include <vector>
+#include "sb_internal.h"
+
+namespace sb {
+
+static const int SMALL_N = 128;   // supernodes up to this many columns: one CTA each
+static const int NB = 32;         // panel width of the blocked path
+static const int UT_R = 64, UT_C = 32;   // update-kernel tile of an ancestor panel
+
+struct Sn {        // one supernode
+  int first, n, m; // first column, #columns, #rows of first column (incl. diagonal)
+  int lindx;       // offset of its row list in lindx[]
+  long long poff;  // offset of its m x n panel in the rect layout (ld = m)
+  long long coff;  // offset of its first column in the packed CSC value array (= Ljc[first])
+};
+struct Pair {      // update of ancestor J by descendant K
+  int K, J;
+  int koff;        // first row (index into K's row list) that lies in J's columns
+  int mk;          // rows of K from koff to the end
+  int ncolup;      // how many of those lie inside J's columns
+  int rel;         // offset into rel[]: position of each of those mk rows inside J's row list
+};
+struct UTile { int J, r0, c0; };
+
+}  // namespace sb
+
+struct sb200_chol_plan {
+  int m = 0, nsuper = 0, nlevels = 0;
+  long long nnzL = 0, rect = 0;
+  uint64_t key = 0;
+  std::vector<sb::Sn> sn;
+  std::vector<int> snode, level_of;
+  std::vector<std::vector<int>> level_small, level_big;      // supernodes per level
+  std::vector<int> level_small_off;                          // offsets into d_level_list
+  std::vector<std::vector<sb::UTile>> level_tiles;
+  std::vector<int> level_tile_off;
+  std::vector<int> pair_beg;                                  // per J: range in pairs[]
+  std::vector<std::vector<int>> level_all;                   // all supernodes per level (solves)
+  std::vector<int> level_all_off;
+  int max_sn_n = 0, max_sn_m = 0;
+  // device
+  sb::DevBuf<sb::Sn> d_sn;
+  sb::DevBuf<sb::Pair> d_pairs;
+  sb::DevBuf<int> d_pair_beg, d_rel, d_lindx, d_snode, d_perm, d_Xjc, d_Xir, d_level_list, d_level_all;
+  sb::DevBuf<sb::UTile> d_tiles;
+  sb::DevBuf<long long> d_Ljc;
+  // numeric scratch
+  sb::DevBuf<double> d_diagX, d_lb, d_scal, d_vscratch, d_y;
+  // dense fast path (one supernode spanning the whole matrix): working copy, inverted diagonal
+  // blocks (32x32 each, column-major), grid-barrier counter, solve flags
+  bool dense_fast = false;
+  int npanels = 0;
+  sb::DevBuf<double> d_work, d_dinv, d_ys;
+  sb::DevBuf<unsigned> d_bar;
+  sb::DevBuf<int> d_ready;
+  int solve_epoch = 0;
+};
+
+namespace sb {
+int dense_factor_prepare(sb200_chol_plan *pl);
+int dense_factor(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb200_chol_pars pars, double *rect,
+                 double *d, int *flag, double *sval, void (*bounds)(sb200_chol_plan *, const double *, sb200_chol_pars));
+int dense_fwsolve(sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs,
+                  const double *dscale, const int *flag);
+int dense_bwsolve(sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs);
+int dense_compute_dinv(sb200_chol_plan *pl, const double *rect);
+}

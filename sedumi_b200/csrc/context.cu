@@ -154,6 +154,34 @@ int sb200_prof_end(char *buf, int64_t buflen) {
   return 0;
 }
 
+// ---- CUDA graphs: record the launches issued on the library stream between begin and end (only the
+// *_dev entry points are capture-safe: no allocation, no host copies, no synchronisation), then
+// replay them with one launch.  Removes the per-kernel launch latency of the latency-bound iteration.
+int sb200_graph_begin(void) {
+  SB_TRY(sb::ensure_init());
+  SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
+  SB_CUDA(cudaStreamBeginCapture(sb::ctx().stream, cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+int sb200_graph_end(void **graph_exec) {
+  cudaGraph_t g = nullptr;
+  SB_CUDA(cudaStreamEndCapture(sb::ctx().stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { sb::set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return 1; }
+  *graph_exec = (void *)ge;
+  return 0;
+}
+int sb200_graph_launch(void *graph_exec) {
+  SB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, sb::ctx().stream));
+  return 0;
+}
+int sb200_graph_destroy(void *graph_exec) {
+  SB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return 0;
+}
+
 int sb200_dev_alloc(void **p, int64_t bytes) {
   SB_TRY(sb::ensure_init());
   SB_CUDA(cudaMalloc(p, bytes > 0 ? (size_t)bytes : 1));

@@ -156,6 +156,81 @@ __global__ void sym_ops_kernel(const int *ns, const long long *offs, const int *
   }
 }
 
+// ---------------------------------------------------------------- fused psdscale for small blocks
+// One CTA per PSD block, everything in shared memory: T (masked triangle of U), X (optionally
+// X(perm,perm)), W = X*T, then Y = T'*W straight to global (optionally scattered to (perm,perm)).
+// Replaces 4-5 launches per call by one when max n_k <= PSD_SMALL_MAX (psdscale.m:76-110).
+static const int PSD_SMALL_MAX = 96;
+// 1024 threads = 32x32 thread grid; thread (tx,ty) owns rows {tx+32a} x cols {ty+32b}, a,b < NR.
+// Matrices are zero-padded to NP = 32*NR in shared memory, so the inner loops carry no bounds tests.
+template <int NR>
+__global__ void __launch_bounds__(1024)
+psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, const double *u, const int *perm,
+                      const double *x, int transp, double *y) {
+  extern __shared__ double sm[];
+  constexpr int NP = 32 * NR, LD = NP + 1;
+  const int n = ns[blockIdx.x];
+  double *T = sm, *X = sm + NP * LD, *W = X + NP * LD;
+  const double *U = u + offs[blockIdx.x], *Xg = x + offs[blockIdx.x];
+  double *Yg = y + offs[blockIdx.x];
+  const int *p = perm ? perm + poffs[blockIdx.x] : nullptr;
+  const bool prep = p && !transp, postp = p && transp;
+  for (int idx = threadIdx.x; idx < NP * NP; idx += blockDim.x) {
+    const int i = idx % NP, k = idx / NP;
+    double tv = 0.0, xv = 0.0;
+    if (i < n && k < n) {
+      const bool keep = transp ? (i <= k) : (i >= k);          // triu : tril  of the stored array
+      tv = keep ? U[i + (long long)k * n] : 0.0;
+      xv = prep ? Xg[p[i] + (long long)p[k] * n] : Xg[i + (long long)k * n];
+    }
+    T[i + k * LD] = tv;
+    X[i + k * LD] = xv;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  {  // W(i,c) = sum_k X(i,k) T(k,c)
+    double acc[NR][NR] = {};
+#pragma unroll 4
+    for (int k = 0; k < n; k++) {
+      double av[NR], bv[NR];
+#pragma unroll
+      for (int a = 0; a < NR; a++) { av[a] = X[tx + 32 * a + k * LD]; bv[a] = T[k + (ty + 32 * a) * LD]; }
+#pragma unroll
+      for (int a = 0; a < NR; a++)
+#pragma unroll
+        for (int b = 0; b < NR; b++) acc[a][b] += av[a] * bv[b];
+    }
+#pragma unroll
+    for (int a = 0; a < NR; a++)
+#pragma unroll
+      for (int b = 0; b < NR; b++) W[tx + 32 * a + (ty + 32 * b) * LD] = acc[a][b];
+  }
+  __syncthreads();
+  {  // Y(i,c) = sum_k T(k,i) W(k,c)
+    double acc[NR][NR] = {};
+#pragma unroll 4
+    for (int k = 0; k < n; k++) {
+      double av[NR], bv[NR];
+#pragma unroll
+      for (int a = 0; a < NR; a++) { av[a] = T[k + (tx + 32 * a) * LD]; bv[a] = W[k + (ty + 32 * a) * LD]; }
+#pragma unroll
+      for (int a = 0; a < NR; a++)
+#pragma unroll
+        for (int b = 0; b < NR; b++) acc[a][b] += av[a] * bv[b];
+    }
+#pragma unroll
+    for (int a = 0; a < NR; a++)
+#pragma unroll
+      for (int b = 0; b < NR; b++) {
+        const int i = tx + 32 * a, c = ty + 32 * b;
+        if (i < n && c < n) {
+          if (postp) Yg[p[i] + (long long)p[c] * n] = acc[a][b];
+          else Yg[i + (long long)c * n] = acc[a][b];
+        }
+      }
+  }
+}
+
 static std::map<uint64_t, sb200_psd_plan *> g_psd_plans;
 
 }  // namespace sb
@@ -257,6 +332,20 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
   SB_TRY(ensure_init());
   if (pl->nblk == 0) return 0;
   cudaStream_t st = ctx().stream;
+  if (pl->maxn <= PSD_SMALL_MAX) {
+    const int NR = (pl->maxn + 31) / 32, NP = 32 * NR;
+    const size_t shm = sizeof(double) * 3 * (size_t)NP * (NP + 1);
+    auto launch = [&](auto kern) -> int {
+      if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      kern<<<pl->nblk, 1024, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, u_dev, perm_dev, x_dev, transp, y_dev);
+      return 0;
+    };
+    if (NR == 1) SB_TRY(launch(psdscale_small_kernel<1>));
+    else if (NR == 2) SB_TRY(launch(psdscale_small_kernel<2>));
+    else SB_TRY(launch(psdscale_small_kernel<3>));
+    SB_LAUNCH_CHECK_N("psdscale_small_kernel");
+    return 0;
+  }
   tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
       pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, transp ? 1 : 0);
   SB_LAUNCH_CHECK_N("tri_transpose_kernel");

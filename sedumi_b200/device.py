@@ -76,7 +76,8 @@ EXPORTS = [
     "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
     "sb200_psd_plan_get", "sb200_psd_plan_lenud", "sb200_psd_plan_sumn", "sb200_invcholfac_dev", "sb200_psdscale_dev",
     "sb200_invcholfac", "sb200_psdscale", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
-    "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_prof_begin", "sb200_prof_end",
+    "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
+    "sb200_graph_destroy",
     "sb200_ada_plan_get", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
     "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3",
     "sb200_ddot_dense_dev", "sb200_qblkmul_dev", "sb200_quadadd_dev", "sb200_ddot_dense", "sb200_ddot_sparse",
@@ -202,6 +203,23 @@ class HotPath:
             self.solve()
         for i in range(npsdscale):
             self.psdscale(i & 1)
+
+    def capture(self, nsolve=4, npsdscale=12):
+        """Record one iteration into a CUDA graph; returns a callable that replays it."""
+        L = lib()
+        self.iteration(nsolve, npsdscale)          # warm: lazy allocations / attribute changes happen here
+        self.sync()
+        l0 = L.sb200_kernel_launches()
+        check(L.sb200_graph_begin(), "graph_begin")
+        try:
+            self.iteration(nsolve, npsdscale)
+        finally:
+            g = VP()
+            rc = L.sb200_graph_end(C.byref(g))
+        check(rc, "graph_end")
+        self.launches_per_iteration = int(L.sb200_kernel_launches() - l0)
+        self._graph = g
+        return lambda: check(L.sb200_graph_launch(g), "graph_launch")
 
     def sync(self):
         check(lib().sb200_sync(), "sync")

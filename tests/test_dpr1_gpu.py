@@ -1,0 +1,68 @@
+"""Parity of the dense-column plugins dpr1fact / fwdpr1 / bwdpr1 against the reference MEX on a
+problem whose LP block holds dense columns (SURVEY.md section 8d, config 4'')."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import ROOT, gpu, ref, relerr
+from sedumi_b200.host import cones, problems, setup
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import refpath  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_problem(seed=4, ndense=3, maxuden=5e2, scale_spread=0.0):
+    raw = problems.synth_blockdiag_sdp(nblk=4, n=10, m=48, nlink=6, density=0.08, dense_lp=ndense, seed=seed)
+    At, b, c, K = cones.pretransfo(*raw)[:4]
+    S = setup.build_setup(At, b, c, K, denf=0.3, perm=np.arange(At.shape[1]))     # low denf: force dense detection
+    assert len(S.dense.cols) == ndense and S.dense.l == ndense
+    d = problems.scaling(K, "S1", seed=seed)
+    if scale_spread:
+        d["l"] = d["l"] * 10.0 ** np.random.default_rng(seed).uniform(-scale_spread, scale_spread, d["l"].size)
+    R = refpath.RefHotPath(S)
+    udsqr, ADA, absd = R.assemble(d)
+    L = R.factor(ADA, absd)
+    DC = refpath.DenseColumnRef(S, L)
+    return S, d, L, DC
+
+
+@pytest.mark.parametrize("seed,spread,maxu", [(4, 0.0, 5e2), (5, 2.0, 5e2), (6, 3.0, 2.0), (7, 1.0, 1.05)])
+def test_dpr1fact_and_solves(seed, spread, maxu):
+    S, d, L, DC = _dense_problem(seed=seed, scale_spread=spread)
+    LAD, Ld, sym, smult = DC.inputs(d, L["d"].copy())
+    Lr, dr = ref.dpr1fact(LAD, Ld, sym, smult, maxu, nlhs=2)
+    Lg, dg = gpu.dpr1fact(LAD, Ld, sym, smult, maxu, nlhs=2)
+    assert np.array_equal(Lr["betajc"], Lg["betajc"]) and np.array_equal(Lr["dopiv"], Lg["dopiv"])
+    assert np.array_equal(Lr["pivperm"], Lg["pivperm"])
+    assert relerr(Lg["beta"], Lr["beta"]) <= 1e-10 and relerr(Lg["p"], Lr["p"]) <= 1e-10
+    assert relerr(dg, dr) <= 1e-10
+    for Ld_ in (Lr,):
+        Ld_.update(dz=sym["dz"], first=sym["first"], perm=sym["perm"])            # deninfac.m:73-75
+    b = np.random.default_rng(seed).standard_normal((S.m, 3))
+    assert relerr(gpu.fwdpr1(Lr, b), ref.fwdpr1(Lr, b)) <= 1e-10
+    assert relerr(gpu.bwdpr1(Lr, b), ref.bwdpr1(Lr, b)) <= 1e-10
+
+
+def test_dpr1_with_dependent_rows():
+    """Skipped Cholesky pivots (L.d = 0) meeting a dense column: the dependency branch of dodpr1fact."""
+    S, d, L, DC = _dense_problem(seed=8)
+    LAD, Ld, sym, smult = DC.inputs(d, L["d"].copy())
+    Ld = Ld.copy()
+    Ld[[3, 11, 17]] = 0.0
+    Lr, dr = ref.dpr1fact(LAD, Ld, sym, smult, 5e2, nlhs=2)
+    Lg, dg = gpu.dpr1fact(LAD, Ld, sym, smult, 5e2, nlhs=2)
+    assert np.array_equal(Lr["betajc"], Lg["betajc"]) and np.array_equal(Lr["dopiv"], Lg["dopiv"])
+    assert np.array_equal(Lr["pivperm"], Lg["pivperm"])
+    assert relerr(Lg["beta"], Lr["beta"]) <= 1e-10 and relerr(dg, dr) <= 1e-10
+
+
+def test_no_dense_columns_is_identity():
+    """Lden.betajc = 0 (deninfac.m:81): fwdpr1/bwdpr1 return b unchanged (fwdpr1.c:132-135)."""
+    b = np.arange(12.0).reshape(6, 2)
+    Lden = {"betajc": 0.0}
+    assert np.array_equal(gpu.fwdpr1(Lden, b), b) and np.array_equal(gpu.bwdpr1(Lden, b), b)
