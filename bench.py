@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--shard", action="store_true",
+                    help="strong scaling: shard PSD blocks over the ranks, one NCCL all-reduce of ADA per iteration "
+                         "(needs a multi-block workload, e.g. --workload blockdiag64)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +228,14 @@ def main():
     torch.cuda.set_device(local_rank)
     from sedumi_b200 import device as sbdev
     S, d, rhs, psd_x = load_workload(args.workload)
+    shard_dist = None
+    if args.shard and world > 1:
+        from sedumi_b200.host import shard as hshard
+        owned = hshard.partition_blocks(S.K["s"], world)[rank]
+        S = hshard.shard_setup(S, owned, rank)
+        shard_dist = dist
+        args.no_graph = True                    # the collective is issued by torch.distributed, outside our graph
+        config["parallelism"] = f"PSD blocks sharded over {world} ranks, 1 all-reduce(ADA,absd)/iteration, factor+solves replicated"
     hp = sbdev.HotPath(S, device=local_rank)
     lib = sbdev.lib()
     stream = hp.stream()
@@ -243,9 +254,9 @@ def main():
             stream.synchronize()
 
         for _ in range(args.warmup):
-            hp.iteration(NSOLVE, NPSD)
+            hp.iteration(NSOLVE, NPSD, shard_dist)
         # the iteration is latency-bound at this size: replay it as one CUDA graph
-        run_iter = hp.capture(NSOLVE, NPSD) if not args.no_graph else (lambda: hp.iteration(NSOLVE, NPSD))
+        run_iter = hp.capture(NSOLVE, NPSD) if not args.no_graph else (lambda: hp.iteration(NSOLVE, NPSD, shard_dist))
         for _ in range(2):
             run_iter()
         barrier()
@@ -281,11 +292,15 @@ def main():
 
         # ---- per-kernel timing pass (CUDA events after every launch on the library stream)
         roof = None
+        if rank != 0 and shard_dist is not None:      # the collective needs every rank in the profiling pass too
+            for _ in range(args.steps):
+                hp.iteration(NSOLVE, NPSD, shard_dist)
+            stream.synchronize()
         if rank == 0:
             import ctypes as C
             lib.sb200_prof_begin()
             for _ in range(args.steps):
-                hp.iteration(NSOLVE, NPSD)
+                hp.iteration(NSOLVE, NPSD, shard_dist)
             buf = C.create_string_buffer(1 << 16)
             lib.sb200_prof_end(buf, C.c_int64(len(buf)))
             prof = {}
@@ -313,16 +328,17 @@ def main():
                     "share_of_step": tms / tot_ms,
                     "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
 
-    value = world * args.steps / (ms_max * 1e-3)
+    value = (1 if shard_dist is not None else world) * args.steps / (ms_max * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if shard_dist is not None else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic scaling/rhs on the control07 fixture", "config": config,
             "gpu_launches": int(launches), "ms_per_step_no_flush": ms_warm / args.steps, "wall_s": t_wall}
     if rank == 0:
         line["clocks"] = clocks
         line["roofline"] = roof
         # ---- e2e: same recipe through the MEX plugins with host buffers
-        if not args.no_e2e:
+        if not args.no_e2e and shard_dist is None:
             line["e2e"] = run_e2e(S, d, rhs, psd_x, max(3, args.steps // 3), world)
         if not args.no_cpu_baseline and world == 1:
             nb = 60 if args.workload == "control07" else 3

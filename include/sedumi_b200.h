@@ -195,6 +195,10 @@ int sb200_ddot_sparse(sb_idx nblk, const sb_idx *bs_abs, const double *d, sb_idx
                       const sb_idx *xhi, const sb_idx *xir, const double *xpr, sb_idx *yjc, sb_idx *yir,
                       double *ypr, sb_idx *nnz_out);
 int sb200_qblkmul(sb_idx nblk, const sb_idx *bs, const double *mu, const double *d, double *y);
+/* adendotd.c:134-245: Ad(:,k) on the pattern of Ablk for the nq dense Lorentz blocks */
+int sb200_adendotd(sb_idx m, sb_idx nq, sb_idx nden, const sb_idx *adjc, const sb_idx *adir, const sb_idx *sjc,
+                   const sb_idx *sir, const double *spr, const sb_idx *ajc, const sb_idx *air, const double *apr,
+                   const double *d1q, const sb_idx *colbeg, const double *d2c, double *adpr);
 int sb200_quadadd(sb_idx n, const double *xhi, const double *xlo, const double *y, double *zhi, double *zlo);
 
 /* ------------------------------------------------------------------ dense columns (product form)

@@ -81,27 +81,24 @@ __global__ void dsqr_kernel(int lpN, int nq, const long long *qstart, const doub
 }
 
 // --------------------------------------------------------------------- getada3 kernels
-// Tt_p(c, rho) = (D_k * sym(A_jk))(c, R[rho]);   one CTA per pair, thread per row c.
+// Tt_p(c, rho) = (D_k * sym(A_jk))(c, R[rho]) = sum over the entries of column R[rho] of sym(A_jk).
+// One CTA per pair, one thread per element (c, rho); the per-column entry lists (D column, weight,
+// source of the value in At.pr) are compiled into the plan, so there is no read-modify-write.
 __global__ void __launch_bounds__(256)
 build_tt_kernel(const AdaPair *pairs, int p0, const int *blk_n, const long long *blk_off,
-                const int *ent_p, const int *ent_q, const int *ent_rp, const int *ent_rq, const int *ent_src,
+                const int *tt_ptr, const int *tt_col, const int *tt_src, const double *tt_w,
                 const double *Atpr, const double *udsqr, double *ws) {
   const AdaPair P = pairs[p0 + blockIdx.x];
   const int n = blk_n[P.k];
   const double *D = udsqr + blk_off[P.k];
   double *Tt = ws + P.tt_off;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    for (int rho = 0; rho < P.r; rho++) Tt[c + (long long)rho * n] = 0.0;
-    for (int e = P.e0; e < P.e1; e++) {
-      const int p = ent_p[e], q = ent_q[e];
-      const double a = Atpr[ent_src[e]];
-      if (p == q) Tt[c + (long long)ent_rp[e] * n] += a * D[c + (long long)p * n];
-      else {
-        const double h = 0.5 * a;                 // sym(X) = (X+X')/2   (spscale.c:227-229)
-        Tt[c + (long long)ent_rq[e] * n] += h * D[c + (long long)p * n];   // column q of sym(A) gets row p
-        Tt[c + (long long)ent_rp[e] * n] += h * D[c + (long long)q * n];
-      }
-    }
+  const int *ptr = tt_ptr + P.r0;                  // P.r + 1 entries are readable: ptr[rho] .. ptr[rho+1]
+  for (int idx = threadIdx.x; idx < n * P.r; idx += blockDim.x) {
+    const int c = idx % n, rho = idx / n;
+    double acc = 0.0;
+    for (int t = ptr[rho]; t < ptr[rho + 1]; t++)
+      acc += (tt_w[t] * Atpr[tt_src[t]]) * D[c + (long long)tt_col[t] * n];
+    Tt[idx] = acc;
   }
 }
 
@@ -109,7 +106,7 @@ build_tt_kernel(const AdaPair *pairs, int p0, const int *blk_n, const long long 
 __global__ void __launch_bounds__(256)
 ada3_dots_kernel(int c0, const long long *adajc, const int *adair, const int *invperm, int first,
                  const int *cpair_beg, const AdaPair *pairs, const int *blk_n,
-                 const int *ent_p, const int *ent_q, const int *ent_src, const double *Atpr,
+                 const int *ent_lin, const int *ent_src, const double *Atpr,
                  const double *ws, double *ada, double *absd) {
   const int c = c0 + blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -128,12 +125,11 @@ ada3_dots_kernel(int c0, const long long *adajc, const int *adair, const int *in
       if (ki < kc) pi++;
       else if (ki > kc) pc++;
       else {
-        const int n = blk_n[ki];
         const double *W = ws + pairs[pc].w_off;
-        for (int e = pairs[pi].e0 + lane; e < pairs[pi].e1; e += 32) {
-          int p = ent_p[e], q = ent_q[e];
-          if (p < q) { int t = p; p = q; q = t; }
-          double term = Atpr[ent_src[e]] * W[p + (long long)q * n];
+        const int e0 = pairs[pi].e0, e1 = pairs[pi].e1;
+        const double *av = Atpr + ent_src[e0] - e0;       // the entries of one pair are consecutive in At.pr
+        for (int e = e0 + lane; e < e1; e += 32) {
+          double term = av[e] * W[ent_lin[e]];              // ent_lin = max(p,q) + min(p,q)*n
           acc += term;
           aabs += fabs(term);
         }
@@ -198,7 +194,8 @@ struct sb200_ada_plan {
   bool have_vals = false;
   // device
   DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
-  DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_p, d_ent_q, d_ent_rp, d_ent_rq, d_ent_src, d_Rlist;
+  DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_lin, d_ent_src, d_Rlist, d_tt_ptr, d_tt_col, d_tt_src;
+  DevBuf<double> d_tt_w;
   DevBuf<AdaPair> d_pairs;
   DevBuf<GemmDesc> d_descs;
   DevBuf<GemmTile> d_tiles;
@@ -222,7 +219,9 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   const long long psd0 = nblk ? blkstart[0] : N;
   pl->lq_rows = nq ? qstart[nq] : lpN;
   // ---- pairs
-  std::vector<int> ent_p, ent_q, ent_rp, ent_rq, ent_src, Rlist;
+  std::vector<int> ent_p, ent_q, ent_lin, ent_src, Rlist, tt_ptr, tt_col, tt_src;
+  std::vector<double> tt_w;
+  std::vector<std::vector<std::pair<int, std::pair<int, double>>>> percol;
   pl->cpair_beg.assign(m + 1, 0);
   std::vector<int> tmpR;
   for (sb_idx j = 0; j < m; j++) {
@@ -247,12 +246,27 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       P.e1 = (int)ent_p.size();
       std::sort(tmpR.begin(), tmpR.end());
       tmpR.erase(std::unique(tmpR.begin(), tmpR.end()), tmpR.end());
+      // Rlist / tt_ptr carry one extra slot per pair so that tt_ptr[r0 + rho + 1] is always valid
       P.r0 = (int)Rlist.size(); P.r = (int)tmpR.size();
       for (int v : tmpR) Rlist.push_back(v);
+      Rlist.push_back(-1);
+      percol.assign(tmpR.size(), {});
       for (int e = P.e0; e < P.e1; e++) {
-        ent_rp.push_back((int)(std::lower_bound(tmpR.begin(), tmpR.end(), ent_p[e]) - tmpR.begin()));
-        ent_rq.push_back((int)(std::lower_bound(tmpR.begin(), tmpR.end(), ent_q[e]) - tmpR.begin()));
+        const int pp = ent_p[e], qq = ent_q[e];
+        const int rp = (int)(std::lower_bound(tmpR.begin(), tmpR.end(), pp) - tmpR.begin());
+        const int rq = (int)(std::lower_bound(tmpR.begin(), tmpR.end(), qq) - tmpR.begin());
+        ent_lin.push_back(std::max(pp, qq) + std::min(pp, qq) * n);
+        if (pp == qq) percol[rp].push_back({pp, {ent_src[e], 1.0}});
+        else {                                      // sym(X) = (X+X')/2   (spscale.c:227-229)
+          percol[rq].push_back({pp, {ent_src[e], 0.5}});
+          percol[rp].push_back({qq, {ent_src[e], 0.5}});
+        }
       }
+      for (size_t rho = 0; rho < tmpR.size(); rho++) {
+        tt_ptr.push_back((int)tt_col.size());
+        for (auto &t : percol[rho]) { tt_col.push_back(t.first); tt_src.push_back(t.second.first); tt_w.push_back(t.second.second); }
+      }
+      tt_ptr.push_back((int)tt_col.size());
       pl->pairs.push_back(P);
     }
   }
@@ -303,8 +317,9 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(to_i32(adair, (size_t)adajc[m], v32, "ADA.ir")); SB_TRY(pl->d_adair.upload(v32));
   SB_TRY(pl->d_blk_n.upload(pl->blk_n)); SB_TRY(pl->d_blk_off.upload(pl->blk_off));
   SB_TRY(pl->d_cpair_beg.upload(pl->cpair_beg));
-  SB_TRY(pl->d_ent_p.upload(ent_p)); SB_TRY(pl->d_ent_q.upload(ent_q));
-  SB_TRY(pl->d_ent_rp.upload(ent_rp)); SB_TRY(pl->d_ent_rq.upload(ent_rq)); SB_TRY(pl->d_ent_src.upload(ent_src));
+  SB_TRY(pl->d_ent_lin.upload(ent_lin)); SB_TRY(pl->d_ent_src.upload(ent_src));
+  SB_TRY(pl->d_tt_ptr.upload(tt_ptr)); SB_TRY(pl->d_tt_col.upload(tt_col)); SB_TRY(pl->d_tt_src.upload(tt_src));
+  SB_TRY(pl->d_tt_w.upload(tt_w));
   SB_TRY(pl->d_Rlist.upload(Rlist));
   SB_TRY(pl->d_pairs.upload(pl->pairs));
   SB_TRY(pl->d_descs.upload(descs)); SB_TRY(pl->d_tiles.upload(tiles));
@@ -416,13 +431,13 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
   SB_LAUNCH_CHECK_N("absd_nopsd_kernel");
   for (auto &B : pl->batches) {
     if (B.p1 == B.p0) continue;
-    build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_ent_p.p, pl->d_ent_q.p,
-                                                 pl->d_ent_rp.p, pl->d_ent_rq.p, pl->d_ent_src.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
+    build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_tt_ptr.p, pl->d_tt_col.p,
+                                                 pl->d_tt_src.p, pl->d_tt_w.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
     SB_LAUNCH_CHECK_N("build_tt_kernel");
     gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
     SB_LAUNCH_CHECK_N("gemm_nt_kernel");
     ada3_dots_kernel<<<B.c1 - B.c0, 256, 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, pl->d_pairs.p,
-                                                  pl->d_blk_n.p, pl->d_ent_p.p, pl->d_ent_q.p, pl->d_ent_src.p, pl->d_Atpr.p,
+                                                  pl->d_blk_n.p, pl->d_ent_lin.p, pl->d_ent_src.p, pl->d_Atpr.p,
                                                   pl->d_ws.p, ada_dev, absd_dev);
     SB_LAUNCH_CHECK_N("ada3_dots_kernel");
   }
@@ -441,7 +456,7 @@ int sb200_getada1(sb200_ada_plan *pl, const double *Atpr, const sb_idx *perm, co
   const int *ip;
   SB_TRY(set_invperm(pl, perm, &ip));
   double *d_dl = arena<double>((size_t)std::max(pl->lpN, 1)), *d_det = arena<double>((size_t)std::max(pl->nq, 1));
-  double *d_out = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  double *d_out = (double *)mirror_output_slot(sizeof(double) * std::max<long long>(pl->nnzADA, 1));
   SB_CHECK(d_dl && d_det && d_out, "getada1: out of device memory");
   cudaStream_t st = ctx().stream;
   if (pl->lpN) SB_CUDA(cudaMemcpyAsync(d_dl, dl, sizeof(double) * pl->lpN, cudaMemcpyHostToDevice, st));
@@ -449,6 +464,7 @@ int sb200_getada1(sb200_ada_plan *pl, const double *Atpr, const sb_idx *perm, co
   SB_TRY(sb200_getada1_dev(pl, d_dl, d_det, ip, d_out));
   SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  mirror_publish(d_out, ada_out, sizeof(double) * pl->nnzADA);      // the next plugin call finds ADA on the device
   return 0;
 }
 
@@ -465,7 +481,8 @@ int sb200_getada2(sb200_ada_plan *pl, sb_idx nq, const sb_idx *Qjc, const sb_idx
   long long *d_jc = arena<long long>(m + 1);
   int *d_ir = arena<int>((size_t)std::max<long long>(nnzQ, 1));
   double *d_pr = arena<double>((size_t)std::max<long long>(nnzQ, 1));
-  double *d_in = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1)), *d_out = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  double *d_in = (double *)mirror_input(ada_in, sizeof(double) * pl->nnzADA);
+  double *d_out = (double *)mirror_output_slot(sizeof(double) * std::max<long long>(pl->nnzADA, 1));
   SB_CHECK(d_jc && d_ir && d_pr && d_in && d_out, "getada2: out of device memory");
   cudaStream_t st = ctx().stream;
   SB_CUDA(cudaMemcpyAsync(d_jc, jc.data(), sizeof(long long) * (m + 1), cudaMemcpyHostToDevice, st));
@@ -473,10 +490,10 @@ int sb200_getada2(sb200_ada_plan *pl, sb_idx nq, const sb_idx *Qjc, const sb_idx
     SB_CUDA(cudaMemcpyAsync(d_ir, ir32.data(), sizeof(int) * nnzQ, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_pr, Qpr, sizeof(double) * nnzQ, cudaMemcpyHostToDevice, st));
   }
-  SB_CUDA(cudaMemcpyAsync(d_in, ada_in, sizeof(double) * pl->nnzADA, cudaMemcpyHostToDevice, st));
   SB_TRY(sb200_getada2_dev(pl, d_jc, d_ir, d_pr, ip, d_in, d_out));
   SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  mirror_publish(d_out, ada_out, sizeof(double) * pl->nnzADA);
   (void)nq;
   return 0;
 }
@@ -488,16 +505,18 @@ int sb200_getada3(sb200_ada_plan *pl, const double *Atpr, const double *udsqr, s
   const int *ip;
   SB_TRY(set_invperm(pl, perm, &ip));
   double *d_ud = arena<double>((size_t)std::max<long long>(lenud, 1));
-  double *d_ada = arena<double>((size_t)std::max<long long>(pl->nnzADA, 1));
+  const double *d_in = (const double *)mirror_input(ada_in, sizeof(double) * pl->nnzADA);
+  double *d_ada = (double *)mirror_output_slot(sizeof(double) * std::max<long long>(pl->nnzADA, 1));
   double *d_absd = arena<double>((size_t)std::max(pl->m, 1));
-  SB_CHECK(d_ud && d_ada && d_absd, "getada3: out of device memory");
+  SB_CHECK(d_ud && d_in && d_ada && d_absd, "getada3: out of device memory");
   cudaStream_t st = ctx().stream;
   if (lenud) SB_CUDA(cudaMemcpyAsync(d_ud, udsqr, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemcpyAsync(d_ada, ada_in, sizeof(double) * pl->nnzADA, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(d_ada, d_in, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToDevice, st));
   SB_TRY(sb200_getada3_dev(pl, d_ud, ip, first, d_ada, d_absd, 1));
   SB_CUDA(cudaMemcpyAsync(ada_out, d_ada, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(absd_out, d_absd, sizeof(double) * pl->m, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  mirror_publish(d_ada, ada_out, sizeof(double) * pl->nnzADA);
   return 0;
 }
 

@@ -893,11 +893,10 @@ int sb200_blkchol(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *L
   arena_reset();
   cudaStream_t st = ctx().stream;
   const size_t nnzX = (size_t)Xjc[m];
-  double *dX = arena<double>(nnzX), *dabsd = arena<double>((size_t)m), *drect = arena<double>((size_t)pl->rect),
+  double *dX = (double *)mirror_input(Xpr, sizeof(double) * nnzX), *dabsd = arena<double>((size_t)m), *drect = arena<double>((size_t)pl->rect),
          *dd = arena<double>((size_t)m), *dsval = arena<double>((size_t)m), *dL = arena<double>((size_t)pl->nnzL);
   int *dflag = arena<int>((size_t)m);
   SB_CHECK(dX && dabsd && drect && dd && dsval && dL && dflag, "blkchol: out of device memory");
-  SB_CUDA(cudaMemcpyAsync(dX, Xpr, sizeof(double) * nnzX, cudaMemcpyHostToDevice, st));
   if (absd) SB_CUDA(cudaMemcpyAsync(dabsd, absd, sizeof(double) * m, cudaMemcpyHostToDevice, st));
   double t2 = now_ms();
   SB_TRY(sb200_blkchol_dev(pl, dX, absd ? dabsd : nullptr, pars, drect, dd, dflag, dsval));
@@ -927,15 +926,23 @@ static int solve_host(bool fw, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, co
   if (m == 0 || nrhs == 0) return 0;
   arena_reset();
   cudaStream_t st = ctx().stream;
-  double *dL = arena<double>((size_t)pl->nnzL), *drect = arena<double>((size_t)pl->rect),
-         *db = arena<double>((size_t)(m * nrhs)), *dy = arena<double>((size_t)(m * nrhs));
-  SB_CHECK(dL && drect && db && dy, "solve: out of device memory");
-  SB_CUDA(cudaMemcpyAsync(dL, Lpr, sizeof(double) * pl->nnzL, cudaMemcpyHostToDevice, st));
+  // The factor values usually repeat over many solves (3-4 solves x fw/bw per IPM iteration): keep the
+  // device copy in the internal layout (+ inverted diagonal blocks, L') under a content hash.
+  const uint64_t hL = hash64(Lpr, sizeof(double) * pl->nnzL);
+  if (!(pl->Lcache_valid && pl->Lcache_hash == hL)) {
+    double *dL = arena<double>((size_t)pl->nnzL);
+    SB_CHECK(dL, "solve: out of device memory");
+    if (pl->d_rect_cache.n < (size_t)pl->rect) SB_TRY(pl->d_rect_cache.alloc((size_t)pl->rect));
+    SB_CUDA(cudaMemcpyAsync(dL, Lpr, sizeof(double) * pl->nnzL, cudaMemcpyHostToDevice, st));
+    SB_TRY(sb200_chol_csc_to_rect_dev(pl, dL, pl->d_rect_cache.p));
+    if (pl->dense_fast) SB_TRY(dense_compute_dinv(pl, pl->d_rect_cache.p));
+    pl->Lcache_hash = hL; pl->Lcache_valid = true;
+  }
+  double *db = arena<double>((size_t)(m * nrhs)), *dy = arena<double>((size_t)(m * nrhs));
+  SB_CHECK(db && dy, "solve: out of device memory");
   SB_CUDA(cudaMemcpyAsync(db, b, sizeof(double) * m * nrhs, cudaMemcpyHostToDevice, st));
-  SB_TRY(sb200_chol_csc_to_rect_dev(pl, dL, drect));
-  if (pl->dense_fast) SB_TRY(dense_compute_dinv(pl, drect));
-  if (fw) SB_TRY(sb200_fwblkslv_dev(pl, drect, db, dy, nrhs));
-  else SB_TRY(sb200_bwblkslv_dev(pl, drect, db, dy, nrhs));
+  if (fw) SB_TRY(sb200_fwblkslv_dev(pl, pl->d_rect_cache.p, db, dy, nrhs));
+  else SB_TRY(sb200_bwblkslv_dev(pl, pl->d_rect_cache.p, db, dy, nrhs));
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * m * nrhs, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;

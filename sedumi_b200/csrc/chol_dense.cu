@@ -19,6 +19,7 @@
 //    instead of a 32-step substitution; the other warps stream the rest of L concurrently.
 //    (fwblkslv.c:77-134 / bwblkslv.c:73-125 semantics: y = L\b(perm), y(perm) = L'\b.)
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "chol_plan.h"
 
 namespace sb {
@@ -54,6 +55,14 @@ __device__ __forceinline__ ArgMaxD block_argmax_d(ArgMaxD x, ArgMaxD *sh) {
   return x;
 }
 
+// tile t of the lower-triangular tile grid, row-major: t = ti(ti+1)/2 + tj, tj <= ti
+__device__ __forceinline__ void tile_of(int t, int &ti, int &tj) {
+  ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+  while (ti * (ti + 1) / 2 > t) ti--;
+  tj = t - ti * (ti + 1) / 2;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -68,9 +77,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
 // W: working matrix (m x m, ld = m, lower triangle live); Lo: output factor (same layout).
 __global__ void __launch_bounds__(256)
 dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, const double *scal, double maxu,
-                 int *flag, double *sval, const double *diagX, double *vscratch, double *dinv, unsigned *bar) {
+                 int *flag, double *sval, const double *diagX, double *vscratch, double *dinv, unsigned *bar, long long *tdbg) {
   __shared__ double A[PB][PB + 1];
-  __shared__ double s_lb[PB], z[PB], dloc[PB];
+  __shared__ double s_lb[PB], z[PB], dloc[PB], Lk[PB];
   __shared__ int skipped[PB];
   __shared__ ArgMaxD sh_am[32];
   __shared__ double s_x;
@@ -83,7 +92,11 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
   const int npanels = (m + PB - 1) / PB;
   for (int pi = 0; pi < npanels; pi++) {
     const int p0 = pi * PB, w = min(PB, m - p0), base = p0 + w;
+    const int nrow = m - base;
+    const int nslab = nrow > 0 ? (nrow + TS - 1) / TS : 0;
+    const int ntiles = nslab * (nslab + 1) / 2;
     // ------------------------------------------------------------------ phase A: diagonal block (CTA 0)
+    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 0] = clock64();
     if (blockIdx.x == 0) {
       for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
         int r = idx % PB, c = idx / PB;
@@ -93,43 +106,39 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       __syncthreads();
       if (tid < PB) s_lb[tid] = (tid < w) ? lb[p0 + tid] : 0.0;
       __syncthreads();
+      if (tdbg && tid == 0) tdbg[pi * 8 + 1] = clock64();
       int k_resume = 0, resolved_k = -1;
-      // warp 0 keeps row `lane` of the block in registers: a[c] = A[lane][c]
-      double a[PB];
-      if (warp == 0) {
-#pragma unroll
-        for (int c = 0; c < PB; c++) a[c] = A[lane][c];
-      }
+      // All 8 warps cooperate on each pivot step: the lower triangle below/right of the pivot is at most
+      // 31*32/2 elements, one per thread; the step is then bounded by the reciprocal + two block barriers
+      // instead of one warp issuing the whole rank-1 update (measured: 930 cycles/step -> see profiles/).
       while (true) {
-        if (warp == 0) {
-          int kstop = w;
-#pragma unroll
-          for (int k = 0; k < PB; k++) {
-            if (k < k_resume || k >= kstop || k >= w) continue;
-            const int gk = p0 + k;
-            double xkk = __shfl_sync(0xffffffffu, a[k], k);
-            const bool resolved = (k == resolved_k);
-            if (resolved) xkk = s_x;
-            const bool skip = !(xkk > s_lb[k]);
-            if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) { kstop = k; continue; }   // stability test needed
-            if (skip) {
-              if (lane == 0) { d[gk] = 0.0; flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
-              continue;
-            }
-            const double xr = a[k];
-            const double l = (lane > k) ? xr / xkk : 0.0;
-#pragma unroll
-            for (int c = k + 1; c < PB; c++) {
-              const double lc = __shfl_sync(0xffffffffu, l, c);
-              if (lane >= c) a[c] -= lc * xr;
-            }
-            if (lane > k) a[k] = l;
-            if (lane == k) a[k] = 1.0;
-            if (lane == 0) { d[gk] = xkk; dloc[k] = xkk; }
+        {
+        int k = k_resume;
+        for (; k < w; k++) {
+          const int gk = p0 + k;
+          double xkk = A[k][k];
+          const bool resolved = (k == resolved_k);
+          if (resolved) xkk = s_x;
+          const bool skip = !(xkk > s_lb[k]);
+          if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) break;          // stability test needed (uniform)
+          if (skip) {
+            if (tid == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
+            continue;
           }
-#pragma unroll
-          for (int c = 0; c < PB; c++) A[lane][c] = a[c];
-          if (lane == 0) s_state = kstop;
+          const double rinv = 1.0 / xkk;
+          // element (r,c), k < c <= r < w: A[r][c] -= (A[c][k]/xkk) * A[r][k]
+          {
+            const int r = lane;                                   // warp wq handles columns k+1+wq, +8, ...
+            const double xr = (r > k && r < w) ? A[r][k] : 0.0;
+            for (int c = k + 1 + warp; c < w; c += 8)
+              if (r >= c && r < w) A[r][c] -= (A[c][k] * rinv) * xr;
+          }
+          __syncthreads();
+          if (tid > k && tid < w) A[tid][k] *= rinv;
+          if (tid == 0) { dloc[k] = xkk; A[k][k] = 1.0; }
+          __syncthreads();
+        }
+        if (tid == 0) s_state = k;
         }
         __syncthreads();
         const int k = s_state;
@@ -187,19 +196,20 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
           resolved_k = k; k_resume = k;
         }
       }
-      // publish L11 (unit lower; skipped columns zeroed) into the output factor
+      if (tdbg && tid == 0) tdbg[pi * 8 + 2] = clock64();
+      // publish d and L11 (unit lower; skipped columns zeroed) into the outputs
+      if (tid < w) d[p0 + tid] = dloc[tid];
       for (int idx = tid; idx < w * w; idx += blockDim.x) {
         int r = idx % w, c = idx / w;
         if (r >= c) Lo[(long long)(p0 + c) * ld + p0 + r] = (r == c) ? 1.0 : (skipped[c] ? 0.0 : A[r][c]);
       }
     }
+    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 3] = clock64();
     bar_target += gridDim.x;
     grid_barrier(bar, bar_target);
+    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 4] = clock64();
     // ------------------------------------------------------------------ phase B: trailing tiles
-    const int nrow = m - base;
     if (nrow > 0) {
-      const int nslab = (nrow + TS - 1) / TS;
-      const int ntiles = nslab * (nslab + 1) / 2;
       // L11 (strictly lower) and d of this panel -> shared (A / dloc are reused as scratch by every CTA)
       for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
         int r = idx % PB, c = idx / PB;
@@ -212,10 +222,7 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       }
       __syncthreads();
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-        while (ti * (ti + 1) / 2 > t) ti--;
-        const int tj = t - ti * (ti + 1) / 2;
+        int ti, tj; tile_of(t, ti, tj);
         if (tid < 2 * TS) {
           const bool isB = tid >= TS;
           const int lr = isB ? tid - TS : tid;
@@ -280,8 +287,10 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
         __syncthreads();
       }
     }
+    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 5] = clock64();
     bar_target += gridDim.x;
     grid_barrier(bar, bar_target);
+    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 6] = clock64();
   }
   // ------------------------------------------------------------------ inverses of the diagonal blocks
   for (int pi = blockIdx.x; pi < npanels; pi += gridDim.x) {
@@ -346,16 +355,17 @@ dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, 
 #pragma unroll
           for (int c = 0; c < PB; c++) lv[c] = Lp[(long long)c * ld];
         } else {
+          // L here is the TRANSPOSED factor Lt(c,r) = L(r,c): rows of block j are contiguous in c
           const int wj = min(PB, m - j * PB);
-          const double *Lp = L + (long long)(k0 + lane) * ld + j * PB;    // column k0+lane, rows of block j
+          const double *Lp = L + (long long)(j * PB) * ld + k0 + lane;
 #pragma unroll
-          for (int r = 0; r < PB; r++) lv[r] = (r < wj) ? Lp[r] : 0.0;
+          for (int r = 0; r < PB; r++) lv[r] = (r < wj) ? Lp[(long long)r * ld] : 0.0;
         }
       } else {
 #pragma unroll
         for (int c = 0; c < PB; c++) lv[c] = 0.0;
       }
-      while (ready[j] == 0) { __nanosleep(32); }
+      while (ready[j] == 0) { }
       __threadfence_block();
       const volatile double *yv = ys + j * PB;
       const int wj = min(PB, m - j * PB);
@@ -418,6 +428,8 @@ static __global__ void dense_permuteP_kernel(int m, const int *perm, const int *
   }
 }
 
+int dense_make_transpose(sb200_chol_plan *pl, const double *rect);
+
 int dense_factor_prepare(sb200_chol_plan *pl) {
   const int m = pl->m;
   pl->npanels = (m + PB - 1) / PB;
@@ -447,9 +459,51 @@ int dense_factor(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb2
   unsigned *bar = pl->d_bar.p;
   int mm = m;
   double maxu = pars.maxu;
-  void *args[] = {&mm, &W, &rect, &d, &lb, &scal, &maxu, &flag, &sval, &diagX, &vs, &dinv, &bar};
+  static long long *s_tdbg = nullptr;
+  long long *tdbg = nullptr;
+  if (getenv("SB200_CHOL_TIMING")) {
+    if (!s_tdbg) cudaMalloc((void **)&s_tdbg, sizeof(long long) * 8 * 4096);
+    tdbg = s_tdbg;
+  }
+  void *args[] = {&mm, &W, &rect, &d, &lb, &scal, &maxu, &flag, &sval, &diagX, &vs, &dinv, &bar, &tdbg};
   SB_CUDA(cudaLaunchCooperativeKernel((void *)dense_ldl_kernel, dim3(grid), dim3(256), args, 0, st));
   SB_LAUNCH_CHECK_N("dense_ldl_kernel");
+  if (tdbg) {
+    std::vector<long long> h(8 * pl->npanels);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), tdbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    double a = 0, a2 = 0, b1 = 0, bB = 0, b2 = 0, pub = 0;
+    for (int p = 0; p < pl->npanels; p++) {
+      const long long *t = h.data() + 8 * p;
+      a += t[1] - t[0]; a2 += t[2] - t[1]; pub += t[3] - t[2]; b1 += t[4] - t[3]; bB += t[5] - t[4]; b2 += t[6] - t[5];
+    }
+    fprintf(stderr, "[dense_ldl timing, CTA0 clocks summed over %d panels] load %.0f  factor %.0f  publish %.0f  barrier1 %.0f  phaseB %.0f  barrier2 %.0f  (total %.0f)\n",
+            pl->npanels, a, a2, pub, b1, bB, b2, (double)(h[8 * (pl->npanels - 1) + 6] - h[0]));
+  }
+  return dense_make_transpose(pl, rect);                 // the working copy is dead now: reuse it for L'
+}
+
+// Lt = L' (lower triangle of L mirrored into the upper triangle of a second array) so that the
+// backward solve streams it with the same coalesced pattern as the forward solve.
+static __global__ void dense_transpose_kernel(int m, const double *L, double *Lt) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;            // tile (rows bi, cols bj) of L, bi >= bj
+  if (bi < bj) return;
+  const int r0 = bi * 32, c0 = bj * 32;
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int r = r0 + threadIdx.x, c = c0 + jj;
+    tile[jj][threadIdx.x] = (r < m && c < m && r > c) ? L[(long long)c * m + r] : 0.0;
+  }
+  __syncthreads();
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int c = c0 + threadIdx.x, r = r0 + jj;         // Lt(c, r) = L(r, c)
+    if (c < m && r < m) Lt[(long long)r * m + c] = tile[threadIdx.x][jj];
+  }
+}
+int dense_make_transpose(sb200_chol_plan *pl, const double *rect) {
+  const int nb = (pl->m + 31) / 32;
+  dense_transpose_kernel<<<dim3(nb, nb), dim3(32, 8), 0, ctx().stream>>>(pl->m, rect, pl->d_work.p);
+  SB_LAUNCH_CHECK_N("dense_transpose_kernel");
   return 0;
 }
 
@@ -461,7 +515,7 @@ static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, 
   cudaStream_t st = ctx().stream;
   if (backward) {
     if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    dense_solve_kernel<true><<<nrhs, 512, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+    dense_solve_kernel<true><<<nrhs, 512, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
   } else {
     if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     dense_solve_kernel<false><<<nrhs, 512, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
@@ -502,7 +556,7 @@ static __global__ void dense_dinv_kernel(int m, const double *Lo, double *dinv) 
 int dense_compute_dinv(sb200_chol_plan *pl, const double *rect) {
   dense_dinv_kernel<<<pl->npanels, 32, 0, ctx().stream>>>(pl->m, rect, pl->d_dinv.p);
   SB_LAUNCH_CHECK_N("dense_dinv_kernel");
-  return 0;
+  return dense_make_transpose(pl, rect);
 }
 
 }  // namespace sb

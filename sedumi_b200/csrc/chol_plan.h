@@ -57,6 +57,10 @@ struct sb200_chol_plan {
   sb::DevBuf<unsigned> d_bar;
   sb::DevBuf<int> d_ready;
   int solve_epoch = 0;
+  // MEX-level solves: device copy of the last L.L (internal layout) keyed by a hash of its values
+  sb::DevBuf<double> d_rect_cache;
+  uint64_t Lcache_hash = 0;
+  bool Lcache_valid = false;
 };
 
 namespace sb {

@@ -215,3 +215,70 @@ int sb200_quadadd(sb_idx n, const double *xhi, const double *xlo, const double *
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// adendotd / adenscale: dense Lorentz blocks (adendotd.c:69-126, adenscale.c:62-77).
+namespace sb {
+// One CTA per dense Lorentz block k.  Ad(:,k) on the pattern of Ablk(:,k) =
+//   adotd(:,k) + d1[q_k] * aden(:,k) + sum_{dense norm-bound columns j of block k} d2[col_j] * aden2(:,j)
+__global__ void __launch_bounds__(256)
+adendotd_kernel(int m, const long long *adjc, const int *adir, double *adpr, const long long *sjc, const int *sir,
+                const double *spr, const long long *ajc, const int *air, const double *apr, int nq, const double *d1q,
+                const int *colbeg, const double *d2c, double *fwork) {
+  const int k = blockIdx.x;
+  double *f = fwork + (long long)k * m;
+  for (long long i = adjc[k] + threadIdx.x; i < adjc[k + 1]; i += blockDim.x) f[adir[i]] = 0.0;
+  __syncthreads();
+  for (long long i = sjc[k] + threadIdx.x; i < sjc[k + 1]; i += blockDim.x) f[sir[i]] = spr[i];
+  __syncthreads();
+  const double dj = d1q[k];
+  for (long long i = ajc[k] + threadIdx.x; i < ajc[k + 1]; i += blockDim.x) f[air[i]] += dj * apr[i];
+  __syncthreads();
+  for (int j = colbeg[k]; j < colbeg[k + 1]; j++) {            // dense norm-bound columns of this block
+    const double w = d2c[j];
+    for (long long i = ajc[nq + j] + threadIdx.x; i < ajc[nq + j + 1]; i += blockDim.x) f[air[i]] += w * apr[i];
+    __syncthreads();
+  }
+  for (long long i = adjc[k] + threadIdx.x; i < adjc[k + 1]; i += blockDim.x) adpr[i] = f[adir[i]];
+}
+}  // namespace sb
+
+extern "C" {
+
+// Ad = adendotd(dense,d,sparAd,Ablk,blkstart).  aden = dense.A(:, nl+1:end) as CSC over nq+nden columns
+// (ajc relative to its own start), d1q[k] = d.q1(dense.q(k)), colbeg[k..k+1] = range of dense norm-bound
+// columns belonging to block k, d2c[j] = d.q2 entry of dense column j.
+int sb200_adendotd(sb_idx m, sb_idx nq, sb_idx nden, const sb_idx *adjc, const sb_idx *adir, const sb_idx *sjc, const sb_idx *sir,
+                   const double *spr, const sb_idx *ajc, const sb_idx *air, const double *apr, const double *d1q,
+                   const sb_idx *colbeg, const double *d2c, double *adpr) {
+  SB_TRY(ensure_init());
+  if (nq == 0) return 0;
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  const sb_idx nad = adjc[nq], ns = sjc[nq], na = ajc[nq + nden];
+  std::vector<long long> j1(adjc, adjc + nq + 1), j2(sjc, sjc + nq + 1), j3(ajc, ajc + nq + nden + 1);
+  std::vector<int> i1, i2, i3, cb(nq + 1);
+  SB_TRY(to_i32(adir, nad, i1, "Ablk.ir")); SB_TRY(to_i32(sir, ns, i2, "sparAd.ir")); SB_TRY(to_i32(air, na, i3, "dense.A.ir"));
+  for (sb_idx k = 0; k <= nq; k++) cb[k] = (int)colbeg[k];
+  long long *dj1 = arena<long long>(nq + 1), *dj2 = arena<long long>(nq + 1), *dj3 = arena<long long>(nq + nden + 1);
+  int *di1 = arena<int>(std::max<sb_idx>(nad, 1)), *di2 = arena<int>(std::max<sb_idx>(ns, 1)), *di3 = arena<int>(std::max<sb_idx>(na, 1)), *dcb = arena<int>(nq + 1);
+  double *dsp = arena<double>(std::max<sb_idx>(ns, 1)), *dap = arena<double>(std::max<sb_idx>(na, 1)), *dd1 = arena<double>(nq),
+         *dd2 = arena<double>(std::max<sb_idx>(nden, 1)), *dad = arena<double>(std::max<sb_idx>(nad, 1)), *df = arena<double>(m * nq);
+  SB_CHECK(dj1 && dj2 && dj3 && di1 && di2 && di3 && dcb && dsp && dap && dd1 && dd2 && dad && df, "adendotd: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(dj1, j1.data(), sizeof(long long) * (nq + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dj2, j2.data(), sizeof(long long) * (nq + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dj3, j3.data(), sizeof(long long) * (nq + nden + 1), cudaMemcpyHostToDevice, st));
+  if (nad) SB_CUDA(cudaMemcpyAsync(di1, i1.data(), sizeof(int) * nad, cudaMemcpyHostToDevice, st));
+  if (ns) { SB_CUDA(cudaMemcpyAsync(di2, i2.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st)); SB_CUDA(cudaMemcpyAsync(dsp, spr, sizeof(double) * ns, cudaMemcpyHostToDevice, st)); }
+  if (na) { SB_CUDA(cudaMemcpyAsync(di3, i3.data(), sizeof(int) * na, cudaMemcpyHostToDevice, st)); SB_CUDA(cudaMemcpyAsync(dap, apr, sizeof(double) * na, cudaMemcpyHostToDevice, st)); }
+  SB_CUDA(cudaMemcpyAsync(dcb, cb.data(), sizeof(int) * (nq + 1), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dd1, d1q, sizeof(double) * nq, cudaMemcpyHostToDevice, st));
+  if (nden) SB_CUDA(cudaMemcpyAsync(dd2, d2c, sizeof(double) * nden, cudaMemcpyHostToDevice, st));
+  adendotd_kernel<<<(unsigned)nq, 256, 0, st>>>((int)m, dj1, di1, dad, dj2, di2, dsp, dj3, di3, dap, (int)nq, dd1, dcb, dd2, df);
+  SB_LAUNCH_CHECK_N("adendotd_kernel");
+  if (nad) SB_CUDA(cudaMemcpyAsync(adpr, dad, sizeof(double) * nad, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

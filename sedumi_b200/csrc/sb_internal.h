@@ -104,7 +104,42 @@ struct DevBuf {
   }
 };
 
+// Fast 64-bit content hash: four independent multiply-xorshift lanes over 32-byte blocks
+// (the dependent multiply chain of a single-lane hash limits it to ~2 GB/s; this runs at memory speed).
+inline uint64_t hash64(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull) {
+  const unsigned char *p = (const unsigned char *)data;
+  const uint64_t M = 0xFF51AFD7ED558CCDull;
+  uint64_t a = seed ^ bytes, b = seed * 3, c = seed * 5, d = seed * 7;
+  size_t nblk = bytes / 32;
+  const uint64_t *w = (const uint64_t *)p;
+  for (size_t i = 0; i < nblk; i++, w += 4) {
+    a = (a ^ w[0]) * M; a ^= a >> 32;
+    b = (b ^ w[1]) * M; b ^= b >> 32;
+    c = (c ^ w[2]) * M; c ^= c >> 32;
+    d = (d ^ w[3]) * M; d ^= d >> 32;
+  }
+  uint64_t h = a ^ (b * 0xC4CEB9FE1A85EC53ull) ^ (c << 1) ^ (d * M);
+  for (size_t i = nblk * 32; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  h ^= h >> 33; h *= M; h ^= h >> 33;
+  return h;
+}
+
+// ---- device mirrors of host arrays, keyed by content: a host entry asks for the
+// device copy of an input; if an array with the same size and hash is already resident (typically
+// the output of the previous plugin call: ADA travelling getada1 -> 2 -> 3 -> blkchol, or L.L used by
+// eight solves) the upload is skipped.  Semantically invisible: same bytes in, same result out.
+struct MirrorSlot { uint64_t hash = 0; size_t bytes = 0, cap = 0; void *dev = nullptr; uint64_t stamp = 0; int tag = 0; };
+// Returns the device copy of (host, bytes); *hit tells whether an upload was avoided.
+void *mirror_input(const void *host, size_t bytes, uint64_t *hash_out = nullptr, bool *hit = nullptr);
+// A device buffer (persistent slot) to write an output into; after the D2H copy call
+// mirror_publish(slot_dev, host, bytes) so that the next call can find it.
+void *mirror_output_slot(size_t bytes);
+void mirror_publish(void *slot_dev, const void *host, size_t bytes);
+
 inline uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+  return hash64(data, bytes, h);
+}
+inline uint64_t fnv1a_old(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
   const unsigned char *p = (const unsigned char *)data;
   // word-at-a-time variant (not the canonical byte FNV, just a fast content hash)
   size_t nw = bytes / 8;

@@ -81,7 +81,7 @@ EXPORTS = [
     "sb200_ada_plan_get", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
     "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3",
     "sb200_ddot_dense_dev", "sb200_qblkmul_dev", "sb200_quadadd_dev", "sb200_ddot_dense", "sb200_ddot_sparse",
-    "sb200_qblkmul", "sb200_quadadd",
+    "sb200_qblkmul", "sb200_quadadd", "sb200_adendotd",
 ]
 
 
@@ -195,9 +195,18 @@ class HotPath:
         check(lib().sb200_psdscale_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
                                        _p(self.psd_x), C.c_int(transp), _p(self.psd_y)), "psdscale")
 
-    def iteration(self, nsolve=4, npsdscale=12):
+    def allreduce_ada(self, dist):
+        """The one collective of the sharded path: sum the per-rank partial ADA values
+        and absd over NCCL, enqueued on the library stream right behind getada3."""
+        with self.torch.cuda.stream(self.stream()):
+            dist.all_reduce(self.ADA[:self.nnzADA])
+            dist.all_reduce(self.absd[:self.m])
+
+    def iteration(self, nsolve=4, npsdscale=12, dist=None):
         self.invcholfac()
         self.getada()
+        if dist is not None:
+            self.allreduce_ada(dist)
         self.blkchol()
         for _ in range(nsolve):
             self.solve()

@@ -38,12 +38,21 @@ def test_dpr1fact_and_solves(seed, spread, maxu):
     Lr, dr = ref.dpr1fact(LAD, Ld, sym, smult, maxu, nlhs=2)
     Lg, dg = gpu.dpr1fact(LAD, Ld, sym, smult, maxu, nlhs=2)
     assert np.array_equal(Lr["betajc"], Lg["betajc"]) and np.array_equal(Lr["dopiv"], Lg["dopiv"])
-    assert np.array_equal(Lr["pivperm"], Lg["pivperm"])
-    assert relerr(Lg["beta"], Lr["beta"]) <= 1e-10 and relerr(Lg["p"], Lr["p"]) <= 1e-10
-    assert relerr(dg, dr) <= 1e-10
-    for Ld_ in (Lr,):
+    for Ld_ in (Lr, Lg):
         Ld_.update(dz=sym["dz"], first=sym["first"], perm=sym["perm"])            # deninfac.m:73-75
     b = np.random.default_rng(seed).standard_normal((S.m, 3))
+    if np.array_equal(Lr["pivperm"], Lg["pivperm"]):
+        assert relerr(Lg["beta"], Lr["beta"]) <= 1e-10 and relerr(Lg["p"], Lr["p"]) <= 1e-10
+        assert relerr(dg, dr) <= 1e-10
+    else:
+        # Postponed rows are ordered by qsort with a comparator that returns `char` (kdcmpdec,
+        # sdmauxCmp.c:60-63): the upper bits qsort reads are undefined, so the reference's order of
+        # the postponed rows is not reproducible.  Any order is a valid product-form factor: check
+        # the factor by what it must satisfy instead.
+        assert sorted(Lr["pivperm"].ravel()) == sorted(Lg["pivperm"].ravel())
+        M = np.diag(Ld.ravel()) + LAD.toarray() @ np.diag(smult.ravel()) @ LAD.toarray().T
+        z = gpu.bwdpr1(Lg, gpu.fwdpr1(Lg, b) / dg.reshape(-1, 1))
+        assert relerr(z, np.linalg.solve(M, b)) <= 1e-8
     assert relerr(gpu.fwdpr1(Lr, b), ref.fwdpr1(Lr, b)) <= 1e-10
     assert relerr(gpu.bwdpr1(Lr, b), ref.bwdpr1(Lr, b)) <= 1e-10
 
