@@ -125,16 +125,17 @@ def kernel_work(S, name):
                     fl += n * (n + 1) * r
         fl += float((s ** 3).sum()) / 3 * 2 + NPSD * 2 * float((s ** 3).sum())
         return dict(bound="tensor", work=fl, unit="TFLOP/s")
-    if name in ("trail_kernel", "diag_kernel", "trsm_kernel", "factor_small_kernel"):
+    if name in ("trail_kernel", "diag_kernel", "trsm_kernel", "factor_small_kernel", "dense_ldl_kernel"):
         cj = np.diff(S.L["L"].indptr) - 1
         return dict(bound="tensor", work=float((cj * (cj + 1)).sum()), unit="TFLOP/s")
+    if name == "psdscale_small_kernel":
+        return dict(bound="tensor", work=NPSD * 4.0 * float((s ** 3).sum()), unit="TFLOP/s")
     if name == "ada3_dots_kernel":
-        # one pass over the sparse PSD coefficients per ADA column + W reads: 12 B per stored A entry per column pair
-        nnz_psd = int(S.At.indptr[-1] - S.Ablkjc[:, 2].sum() + 0)  # placeholder, refined below
+        # every stored PSD coefficient of A_i is paired with W_j for each j >= i: 20 B per term (index, value, W gather)
         nnz_psd = int((S.At.indptr[1:] - S.Ablkjc[:, 2]).sum())
         by = 20.0 * nnz_psd * (m + 1) / 2 + 8.0 * S.ADA.nnz
         return dict(bound="hbm", work=by, unit="GB/s")
-    if name in ("fwsolve_kernel", "bwsolve_kernel"):
+    if name in ("fwsolve_kernel", "bwsolve_kernel", "dense_solve_kernel<fw>", "dense_solve_kernel<bw>"):
         return dict(bound="hbm", work=NSOLVE * (8.0 * nnzL + 24.0 * m), unit="GB/s")
     return dict(bound="hbm", work=8.0 * (S.ADA.nnz + nnzL), unit="GB/s")
 
@@ -235,6 +236,7 @@ def main():
         S = hshard.shard_setup(S, owned, rank)
         shard_dist = dist
         args.no_graph = True                    # the collective is issued by torch.distributed, outside our graph
+        config["launch"] = "stream launches"
         config["parallelism"] = f"PSD blocks sharded over {world} ranks, 1 all-reduce(ADA,absd)/iteration, factor+solves replicated"
     hp = sbdev.HotPath(S, device=local_rank)
     lib = sbdev.lib()
@@ -321,9 +323,15 @@ def main():
                 achieved = w["work"] / (per_iter_ms * 1e-3) / 1e12
                 with torch.cuda.stream(torch.cuda.default_stream()):
                     peak = f64_gemm_peak(torch, dev)
-                src = "FP64: measured in-run, torch.matmul f64 4096^3 best of 5 (MEASURED_PEAKS.json has no FP64 entry)"
+                src = ("FP64 (bound=tensor means the FP64 FMA/DMMA pipes): measured in-run, torch.matmul f64 4096^3 best of 5 "
+                       "-- MEASURED_PEAKS.json has no FP64 entry")
+            traffic = None
+            try:        # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(args.workload, {}).get(nm)
+            except (OSError, ValueError):
+                pass
             roof = {"kernel": nm, "bound": w["bound"], "achieved": achieved, "peak": peak, "unit": w["unit"],
-                    "frac": achieved / peak, "traffic": None, "peak_source": src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": src,
                     "launches_per_step": cnt / args.steps, "ms_per_step_in_kernel": per_iter_ms,
                     "share_of_step": tms / tot_ms,
                     "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}

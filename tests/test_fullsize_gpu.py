@@ -1,0 +1,51 @@
+"""Size-independent properties at BASELINE.json's full sizes (the oracle is too slow there, or its
+answer is the property itself): factor-and-solve residual for the dense MaxCut-size Schur complement
+(m = 4000, one supernode), psdscale round trip at n = 1000, quadadd against exact rationals."""
+import numpy as np
+import pytest
+
+from helpers import CHOL_PARS, dense_L, full_pattern, gpu, relerr
+from sedumi_b200.host import cones
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dense_factor_solve_m4000():
+    m = 4000
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((m, m + 50)) / np.sqrt(m)
+    X = B @ B.T + 0.5 * np.eye(m)                                   # config 5 shape: ADA = D o D is dense m x m
+    L = dense_L(m)
+    LL, d, skip, add = gpu.blkchol(L, full_pattern(X), CHOL_PARS, np.diag(X).copy(), nlhs=4)
+    assert skip.nnz == 0 and add.nnz == 0 and np.all(d > 0)
+    Lf = dict(L, L=LL)
+    r = rng.standard_normal((m, 2))
+    y = gpu.bwblkslv(Lf, gpu.fwblkslv(Lf, r) / d)
+    assert relerr(X @ y, r) <= 1e-9                                  # L D L' y = r
+    # the factor itself: a few random columns of L D L' against X
+    Ld = LL.toarray()
+    cols = rng.integers(0, m, 5)
+    assert relerr((Ld * d.ravel()) @ Ld[cols].T, X[:, cols]) <= 1e-11
+
+
+def test_psdscale_roundtrip_n1000():
+    n = 1000
+    K = cones.K_for_mex(cones.finish_K({"l": 1.0, "q": np.zeros(0), "s": np.array([float(n)])}))
+    rng = np.random.default_rng(2)
+    U = np.triu(rng.standard_normal((n, n)) * (0.3 / np.sqrt(n)) + np.eye(n))
+    Ui = np.linalg.inv(U)
+    X = rng.standard_normal((n, n)); X = X + X.T
+    Y = gpu.psdscale(U.ravel(order="F"), X.ravel(order="F"), K, 1.0)
+    assert relerr(Y.ravel(), (U.T @ X @ U).ravel(order="F")) <= 1e-11
+    X2 = gpu.psdscale(Ui.ravel(order="F"), Y.ravel(), K, 1.0)
+    assert relerr(X2.ravel(), X.ravel(order="F")) <= 1e-8
+
+
+def test_invcholfac_n1000_matches_numpy():
+    n = 1000
+    K = cones.K_for_mex(cones.finish_K({"l": 1.0, "q": np.zeros(0), "s": np.array([float(n)])}))
+    rng = np.random.default_rng(3)
+    U = np.triu(rng.standard_normal((n, n)))
+    u = (U + np.triu(U, 1).T).ravel(order="F")
+    D = gpu.invcholfac(u, K).reshape(n, n, order="F")
+    assert relerr(D, U.T @ U) <= 1e-12 and np.array_equal(D, D.T)
