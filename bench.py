@@ -38,6 +38,10 @@ def load_workload(name):
         raw = problems.load_fixture("arch0")
     elif name == "blockdiag64":
         raw = problems.synth_blockdiag_sdp()
+    elif name == "maxcut4000":
+        raw = problems.synth_maxcut()
+    elif name == "maxcut1000":
+        raw = problems.synth_maxcut(n=1000, p=0.02)
     elif name == "blockdiag_small":
         raw = problems.synth_blockdiag_sdp(nblk=8, n=60, m=400, nlink=16, density=0.03)
     else:

@@ -29,7 +29,9 @@ struct AdaPair {      // one (constraint, PSD block) with nonzeros
   int e0, e1;         // entries [e0,e1) in ent_*
   int r0, r;          // rows R: Rlist[r0 .. r0+r)
   long long tt_off;   // offset of Tt (n x r) in the batch workspace
-  long long w_off;    // offset of W (n x n) in the batch workspace
+  long long w_off;    // offset of W in the batch workspace: n x n (dense mode) or |U_k| values (sparse mode)
+  int sparse;         // 1: W is only evaluated on U_k, the union pattern of block k
+  int pad_;
 };
 
 // --------------------------------------------------------------------- sparse A'WA on a pattern
@@ -99,6 +101,31 @@ build_tt_kernel(const AdaPair *pairs, int p0, const int *blk_n, const long long 
     for (int t = ptr[rho]; t < ptr[rho + 1]; t++)
       acc += (tt_w[t] * Atpr[tt_src[t]]) * D[c + (long long)tt_col[t] * n];
     Tt[idx] = acc;
+  }
+}
+
+// Sparse mode (blocks whose constraints touch only a small part of the n x n block, e.g. MaxCut where
+// A_j = e_j e_j'): W_j is needed only on U_k = union of the patterns of all A_ik -- the same observation
+// the reference exploits with its incremental `dz` pattern (getada3.c:305-326).  One thread per (pair, u):
+//   W_j(p_u,q_u) = sum_rho D(p_u, R[rho]) * Tt(q_u, rho)
+__global__ void __launch_bounds__(256)
+sparse_w_kernel(const AdaPair *pairs, int p0, int npairs, const int *blk_n, const long long *blk_off, const int *ublk_off,
+                const int *u_p, const int *u_q, const int *Rlist, const double *udsqr, double *ws) {
+  for (int pi = blockIdx.y; pi < npairs; pi += gridDim.y) {
+    const AdaPair P = pairs[p0 + pi];
+    if (!P.sparse) continue;
+    const int n = blk_n[P.k];
+    const int u0 = ublk_off[P.k], nu = ublk_off[P.k + 1] - u0;
+    const double *D = udsqr + blk_off[P.k];
+    const double *Tt = ws + P.tt_off;
+    double *W = ws + P.w_off;
+    const int *R = Rlist + P.r0;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+      const int pp = u_p[u0 + u], qq = u_q[u0 + u];
+      double acc = 0.0;
+      for (int rho = 0; rho < P.r; rho++) acc += D[pp + (long long)R[rho] * n] * Tt[qq + (long long)rho * n];
+      W[u] = acc;
+    }
   }
 }
 
@@ -187,7 +214,7 @@ struct sb200_ada_plan {
   std::vector<int> blk_n; std::vector<long long> blk_off, blk_start;
   std::vector<AdaPair> pairs;
   std::vector<int> cpair_beg;
-  struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; };
+  struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; int nsparse; };
   std::vector<Batch> batches;
   long long ws_max = 0;
   uint64_t key = 0, val_hash = 0;
@@ -196,6 +223,9 @@ struct sb200_ada_plan {
   DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
   DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_lin, d_ent_src, d_Rlist, d_tt_ptr, d_tt_col, d_tt_src;
   DevBuf<double> d_tt_w;
+  DevBuf<int> d_ublk_off, d_u_p, d_u_q;
+  std::vector<int> blk_sparse;
+  int max_nu = 0;
   DevBuf<AdaPair> d_pairs;
   DevBuf<GemmDesc> d_descs;
   DevBuf<GemmTile> d_tiles;
@@ -271,6 +301,33 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     }
   }
   pl->cpair_beg[m] = (int)pl->pairs.size();
+  // ---- union pattern U_k per block; blocks that use less than a quarter of their lower triangle
+  // evaluate W only there ("sparse mode"), and their entries index into U_k instead of the n x n array
+  std::vector<std::vector<int>> ulin(nblk);
+  for (auto &P : pl->pairs)
+    for (int e = P.e0; e < P.e1; e++) ulin[P.k].push_back(ent_lin[e]);
+  std::vector<int> ublk_off(nblk + 1, 0), u_p, u_q;
+  pl->blk_sparse.assign(nblk, 0);
+  for (sb_idx k = 0; k < nblk; k++) {
+    auto &v = ulin[k];
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    const long long n = pl->blk_n[k];
+    pl->blk_sparse[k] = ((long long)v.size() * 8 <= n * (n + 1));
+    ublk_off[k] = (int)u_p.size();
+    if (pl->blk_sparse[k]) {
+      for (int lin : v) { u_p.push_back((int)(lin % n)); u_q.push_back((int)(lin / n)); }
+      pl->max_nu = std::max(pl->max_nu, (int)v.size());
+    }
+  }
+  ublk_off[nblk] = (int)u_p.size();
+  for (auto &P : pl->pairs) {
+    P.sparse = pl->blk_sparse[P.k];
+    if (P.sparse) {
+      const auto &v = ulin[P.k];
+      for (int e = P.e0; e < P.e1; e++) ent_lin[e] = (int)(std::lower_bound(v.begin(), v.end(), ent_lin[e]) - v.begin());
+    }
+  }
   // ---- batches of whole constraints, workspace bounded
   const long long BUDGET = (long long)96 << 20;     // doubles (768 MB)
   std::vector<GemmDesc> descs(pl->pairs.size());
@@ -283,14 +340,16 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       long long need = 0;
       for (int p = pl->cpair_beg[c]; p < pl->cpair_beg[c + 1]; p++) {
         long long n = pl->blk_n[pl->pairs[p].k];
-        need += n * n + n * pl->pairs[p].r;
+        const long long wsz = pl->pairs[p].sparse ? (ublk_off[pl->pairs[p].k + 1] - ublk_off[pl->pairs[p].k]) : n * n;
+        need += wsz + n * pl->pairs[p].r;
       }
       if (ws > 0 && ws + need > BUDGET) break;
       for (int p = pl->cpair_beg[c]; p < pl->cpair_beg[c + 1]; p++) {
         AdaPair &P = pl->pairs[p];
         long long n = pl->blk_n[P.k];
         P.tt_off = ws; ws += n * P.r;
-        P.w_off = ws; ws += n * n;
+        P.w_off = ws; ws += P.sparse ? (ublk_off[P.k + 1] - ublk_off[P.k]) : n * n;
+        if (P.sparse) { B.nsparse++; continue; }
         GemmDesc g{};
         g.offA = pl->blk_off[P.k]; g.gatherOff = P.r0; g.lda = (int)n; g.a_tri = TRI_NONE;
         g.offB = P.tt_off; g.ldb = (int)n; g.b_tri = TRI_NONE;
@@ -320,6 +379,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(pl->d_ent_lin.upload(ent_lin)); SB_TRY(pl->d_ent_src.upload(ent_src));
   SB_TRY(pl->d_tt_ptr.upload(tt_ptr)); SB_TRY(pl->d_tt_col.upload(tt_col)); SB_TRY(pl->d_tt_src.upload(tt_src));
   SB_TRY(pl->d_tt_w.upload(tt_w));
+  SB_TRY(pl->d_ublk_off.upload(ublk_off)); SB_TRY(pl->d_u_p.upload(u_p)); SB_TRY(pl->d_u_q.upload(u_q));
   SB_TRY(pl->d_Rlist.upload(Rlist));
   SB_TRY(pl->d_pairs.upload(pl->pairs));
   SB_TRY(pl->d_descs.upload(descs)); SB_TRY(pl->d_tiles.upload(tiles));
@@ -434,8 +494,16 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_tt_ptr.p, pl->d_tt_col.p,
                                                  pl->d_tt_src.p, pl->d_tt_w.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
     SB_LAUNCH_CHECK_N("build_tt_kernel");
-    gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
-    SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+    if (B.ntiles) {
+      gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
+      SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+    }
+    if (B.nsparse) {
+      dim3 g((unsigned)std::min((pl->max_nu + 255) / 256, 64), (unsigned)std::min(B.p1 - B.p0, 65535));
+      sparse_w_kernel<<<g, 256, 0, st>>>(pl->d_pairs.p, B.p0, B.p1 - B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_ublk_off.p, pl->d_u_p.p, pl->d_u_q.p,
+                                         pl->d_Rlist.p, udsqr_dev, pl->d_ws.p);
+      SB_LAUNCH_CHECK_N("sparse_w_kernel");
+    }
     ada3_dots_kernel<<<B.c1 - B.c0, 256, 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, pl->d_pairs.p,
                                                   pl->d_blk_n.p, pl->d_ent_lin.p, pl->d_ent_src.p, pl->d_Atpr.p,
                                                   pl->d_ws.p, ada_dev, absd_dev);

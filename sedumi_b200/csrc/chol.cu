@@ -666,7 +666,7 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
   SB_TRY(pl->d_scal.alloc(8));
   SB_TRY(pl->d_vscratch.alloc(std::max(pl->max_sn_m, 1)));
   pl->dense_fast = (nsuper == 1 && m >= 1 && pl->sn[0].m == m && pl->sn[0].n == m &&
-                    (size_t)m * 8 + 4096 <= 200 * 1024);
+                    (size_t)m * 8 + 8 * 2 * 1024 * 8 + 8192 <= 200 * 1024);   // shared memory of the dataflow solves
   if (pl->dense_fast) SB_TRY(dense_factor_prepare(pl));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));       // host vectors go out of scope
   return 0;

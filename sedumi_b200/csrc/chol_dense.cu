@@ -323,60 +323,81 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
 // ---------------------------------------------------------------------------------- solves
 // One CTA of 32 warps per right-hand side.  Warp b owns block rows b, b+32, ... (ascending), y and
 // the ready flags live in shared memory when the whole vector fits (m <= 8192), else in global.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// 8 warps.  Warp q owns block rows q, q+8, ... (ascending in solve order).  For its block row it walks the
+// already-solved blocks j; the 32x32 block L(b, j) is staged through a private 2-deep cp.async ring in
+// shared memory, so the global-load latency of block j+1/j+2 hides behind the wait for y_j and the FMAs.
+// BACKWARD reads the transposed factor, which makes both directions the same coalesced stream.
+static const int SOLVE_WARPS = 8;
 template <bool BACKWARD>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(SOLVE_WARPS * 32)
 dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
                    const double *dscale, const int *flag, const double *lb, int nb) {
   extern __shared__ double smem[];
-  double *ys = smem;                                    // m doubles
-  volatile int *ready = (volatile int *)(smem + ((m + 1) & ~1));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double *ys = smem;                                    // m doubles (rounded up to even)
+  double *ring = smem + ((m + 1) & ~1);                 // SOLVE_WARPS x 2 x 1024 doubles
+  volatile int *ready = (volatile int *)(ring + SOLVE_WARPS * 2 * PB * PB);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double *bb = b + (long long)blockIdx.x * m;
   double *yy = yout + (long long)blockIdx.x * m;
   const int ld = m;
+  double *myring = ring + warp * 2 * PB * PB;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) ready[i] = 0;
   __syncthreads();
-  for (int step = warp; step < nb; step += nw) {
+  for (int step = warp; step < nb; step += SOLVE_WARPS) {
     const int br = BACKWARD ? (nb - 1 - step) : step;
     const int k0 = br * PB, w = min(PB, m - k0);
-    // inverse of this block row's diagonal block: independent of everything, fetch first
+    const int nprev = step;                              // number of solved blocks this row depends on
+    // element (row k0+lane, column of block j) -> ring slot [c][lane]; rows beyond the matrix are not fetched
+    auto fetch = [&](int t) {                            // t-th dependency in solve order
+      if (t < nprev && lane < w) {
+        const int j = BACKWARD ? (nb - 1 - t) : t;
+        const double *Lp = L + (long long)(j * PB) * ld + k0 + lane;
+        double *dst = myring + (t & 1) * PB * PB + lane;
+        const int wj = min(PB, m - j * PB);
+        for (int c = 0; c < wj; c++) cp_async8(dst + c * PB, Lp + (long long)c * ld);
+      }
+      cp_async_commit();
+    };
+    fetch(0); fetch(1);
     const double *Di = dinv + (long long)br * PB * PB;
     double di[PB];
 #pragma unroll
     for (int c = 0; c < PB; c++) di[c] = BACKWARD ? Di[lane * PB + c] : Di[c * PB + lane];
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     if (lane < w) acc0 = BACKWARD ? bb[k0 + lane] : bb[perm[k0 + lane]];
-    const int jbeg = BACKWARD ? nb - 1 : 0, jend = br, jstep = BACKWARD ? -1 : 1;
-    for (int j = jbeg; j != jend; j += jstep) {
-      double lv[PB];
-      if (lane < w) {
-        if (!BACKWARD) {
-          const double *Lp = L + (long long)(j * PB) * ld + k0 + lane;
-#pragma unroll
-          for (int c = 0; c < PB; c++) lv[c] = Lp[(long long)c * ld];
-        } else {
-          // L here is the TRANSPOSED factor Lt(c,r) = L(r,c): rows of block j are contiguous in c
-          const int wj = min(PB, m - j * PB);
-          const double *Lp = L + (long long)(j * PB) * ld + k0 + lane;
-#pragma unroll
-          for (int r = 0; r < PB; r++) lv[r] = (r < wj) ? Lp[(long long)r * ld] : 0.0;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < PB; c++) lv[c] = 0.0;
-      }
-      while (ready[j] == 0) { }
+    for (int t = 0; t < nprev; t++) {
+      const int j = BACKWARD ? (nb - 1 - t) : t;
+      cp_async_wait<1>();                                // group t has landed (only t+1 may be in flight)
+      while (ready[j] == 0) { __nanosleep(20); }          // back off: spinning warps starve the shared-memory pipe
       __threadfence_block();
+      __syncwarp();
       const volatile double *yv = ys + j * PB;
+      const double *lv = myring + (t & 1) * PB * PB + lane;
       const int wj = min(PB, m - j * PB);
+      if (lane < w) {
+        if (wj == PB) {
 #pragma unroll
-      for (int c = 0; c < PB; c += 4) {
-        acc0 -= lv[c] * ((c < wj) ? yv[c] : 0.0);
-        acc1 -= lv[c + 1] * ((c + 1 < wj) ? yv[c + 1] : 0.0);
-        acc2 -= lv[c + 2] * ((c + 2 < wj) ? yv[c + 2] : 0.0);
-        acc3 -= lv[c + 3] * ((c + 3 < wj) ? yv[c + 3] : 0.0);
+          for (int c = 0; c < PB; c += 4) {
+            acc0 -= lv[c * PB] * yv[c];
+            acc1 -= lv[(c + 1) * PB] * yv[c + 1];
+            acc2 -= lv[(c + 2) * PB] * yv[c + 2];
+            acc3 -= lv[(c + 3) * PB] * yv[c + 3];
+          }
+        } else {
+          for (int c = 0; c < wj; c++) acc0 -= lv[c * PB] * yv[c];
+        }
       }
+      __syncwarp();                                      // everyone is done with slot t&1
+      fetch(t + 2);
     }
+    cp_async_wait<0>();
     const double acc = (acc0 + acc1) + (acc2 + acc3);
     // diagonal block: y = inv(L11) s  (forward)  or  y = inv(L11)' s  (backward)
     double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
@@ -510,15 +531,15 @@ int dense_make_transpose(sb200_chol_plan *pl, const double *rect) {
 static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs,
                         const double *dscale, const int *flag) {
   const int m = pl->m, nb = (m + PB - 1) / PB;
-  size_t shm = sizeof(double) * ((m + 1) & ~1) + sizeof(int) * nb;
+  size_t shm = sizeof(double) * (((m + 1) & ~1) + SOLVE_WARPS * 2 * PB * PB) + sizeof(int) * nb;
   SB_CHECK(shm <= 200 * 1024, "dense solve: m=%d too large for the shared-memory dataflow kernel", m);
   cudaStream_t st = ctx().stream;
   if (backward) {
     if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    dense_solve_kernel<true><<<nrhs, 512, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+    dense_solve_kernel<true><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
   } else {
     if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    dense_solve_kernel<false><<<nrhs, 512, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+    dense_solve_kernel<false><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
   }
   SB_LAUNCH_CHECK_N(backward ? "dense_solve_kernel<bw>" : "dense_solve_kernel<fw>");
   return 0;

@@ -161,16 +161,21 @@ __global__ void sym_ops_kernel(const int *ns, const long long *offs, const int *
 // X(perm,perm)), W = X*T, then Y = T'*W straight to global (optionally scattered to (perm,perm)).
 // Replaces 4-5 launches per call by one when max n_k <= PSD_SMALL_MAX (psdscale.m:76-110).
 static const int PSD_SMALL_MAX = 96;
-// 1024 threads = 32x32 thread grid; thread (tx,ty) owns rows {tx+32a} x cols {ty+32b}, a,b < NR.
-// Matrices are zero-padded to NP = 32*NR in shared memory, so the inner loops carry no bounds tests.
+static const int PSD_CS = 16;        // output columns per CTA
+// Y(:,c) = T' * (X * T(:,c)) is independent per output column c, so a block is split over
+// ceil(n/16) CTAs (blockIdx.y) that each keep T and X in shared memory and own 16 columns of W and Y:
+// no inter-CTA synchronisation, 4-5x more SMs busy than one CTA per block.
+// 512 threads = 32 (rows tx) x 16 (columns ty); thread owns rows {tx+32a, a<NR} of column ty.
 template <int NR>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, const double *u, const int *perm,
                       const double *x, int transp, double *y) {
   extern __shared__ double sm[];
   constexpr int NP = 32 * NR, LD = NP + 1;
   const int n = ns[blockIdx.x];
-  double *T = sm, *X = sm + NP * LD, *W = X + NP * LD;
+  const int c0 = blockIdx.y * PSD_CS;
+  if (c0 >= n) return;
+  double *T = sm, *X = sm + NP * LD, *W = X + NP * LD;      // W: NP x PSD_CS (ld = LD)
   const double *U = u + offs[blockIdx.x], *Xg = x + offs[blockIdx.x];
   double *Yg = y + offs[blockIdx.x];
   const int *p = perm ? perm + poffs[blockIdx.x] : nullptr;
@@ -187,47 +192,40 @@ psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, co
     X[i + k * LD] = xv;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty < 16
+  const int c = c0 + ty;
   {  // W(i,c) = sum_k X(i,k) T(k,c)
-    double acc[NR][NR] = {};
+    double acc[NR] = {};
+    if (c < n) {
 #pragma unroll 4
-    for (int k = 0; k < n; k++) {
-      double av[NR], bv[NR];
+      for (int k = 0; k < n; k++) {
+        const double bv = T[k + c * LD];
 #pragma unroll
-      for (int a = 0; a < NR; a++) { av[a] = X[tx + 32 * a + k * LD]; bv[a] = T[k + (ty + 32 * a) * LD]; }
-#pragma unroll
-      for (int a = 0; a < NR; a++)
-#pragma unroll
-        for (int b = 0; b < NR; b++) acc[a][b] += av[a] * bv[b];
+        for (int a = 0; a < NR; a++) acc[a] += X[tx + 32 * a + k * LD] * bv;
+      }
     }
 #pragma unroll
-    for (int a = 0; a < NR; a++)
-#pragma unroll
-      for (int b = 0; b < NR; b++) W[tx + 32 * a + (ty + 32 * b) * LD] = acc[a][b];
+    for (int a = 0; a < NR; a++) W[tx + 32 * a + ty * LD] = acc[a];
   }
   __syncthreads();
   {  // Y(i,c) = sum_k T(k,i) W(k,c)
-    double acc[NR][NR] = {};
+    double acc[NR] = {};
+    if (c < n) {
 #pragma unroll 4
-    for (int k = 0; k < n; k++) {
-      double av[NR], bv[NR];
+      for (int k = 0; k < n; k++) {
+        const double bv = W[k + ty * LD];
 #pragma unroll
-      for (int a = 0; a < NR; a++) { av[a] = T[k + (tx + 32 * a) * LD]; bv[a] = W[k + (ty + 32 * a) * LD]; }
+        for (int a = 0; a < NR; a++) acc[a] += T[k + (tx + 32 * a) * LD] * bv;
+      }
 #pragma unroll
-      for (int a = 0; a < NR; a++)
-#pragma unroll
-        for (int b = 0; b < NR; b++) acc[a][b] += av[a] * bv[b];
-    }
-#pragma unroll
-    for (int a = 0; a < NR; a++)
-#pragma unroll
-      for (int b = 0; b < NR; b++) {
-        const int i = tx + 32 * a, c = ty + 32 * b;
-        if (i < n && c < n) {
-          if (postp) Yg[p[i] + (long long)p[c] * n] = acc[a][b];
-          else Yg[i + (long long)c * n] = acc[a][b];
+      for (int a = 0; a < NR; a++) {
+        const int i = tx + 32 * a;
+        if (i < n) {
+          if (postp) Yg[p[i] + (long long)p[c] * n] = acc[a];
+          else Yg[i + (long long)c * n] = acc[a];
         }
       }
+    }
   }
 }
 
@@ -334,10 +332,10 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
   cudaStream_t st = ctx().stream;
   if (pl->maxn <= PSD_SMALL_MAX) {
     const int NR = (pl->maxn + 31) / 32, NP = 32 * NR;
-    const size_t shm = sizeof(double) * 3 * (size_t)NP * (NP + 1);
+    const size_t shm = sizeof(double) * (2 * (size_t)NP + PSD_CS) * (NP + 1);
     auto launch = [&](auto kern) -> int {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      kern<<<pl->nblk, 1024, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, u_dev, perm_dev, x_dev, transp, y_dev);
+      kern<<<dim3(pl->nblk, (pl->maxn + PSD_CS - 1) / PSD_CS), 512, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, u_dev, perm_dev, x_dev, transp, y_dev);
       return 0;
     };
     if (NR == 1) SB_TRY(launch(psdscale_small_kernel<1>));

@@ -45,6 +45,10 @@ def _problem(name):
         raw = problems.synth_small_mixed(seed=7, m=30, l=0, q=(), s=(9, 6), density=0.25)
     elif name == "small_free_rot":
         raw = problems.synth_small_mixed(seed=9, m=25, l=3, q=(3,), s=(5,), f=2, r=(4,))
+    elif name == "maxcut_small":                      # A_j = e_j e_j': W only needed on the diagonal (sparse mode)
+        raw = problems.synth_maxcut(n=48, p=0.2, seed=2)
+    elif name == "blockdiag_sparse":                  # very sparse coefficients in larger blocks (sparse mode)
+        raw = problems.synth_blockdiag_sdp(nblk=3, n=40, m=30, nlink=4, density=0.004, seed=6)
     elif name == "blockdiag_small":
         raw = problems.synth_blockdiag_sdp(nblk=4, n=20, m=60, nlink=6, density=0.05, seed=5)
     else:
@@ -53,7 +57,8 @@ def _problem(name):
     return setup.build_setup(At, b, c, K)
 
 
-@pytest.mark.parametrize("name", ["small_mixed", "small_sdp", "small_free_rot", "blockdiag_small", "arch0", "control07"])
+@pytest.mark.parametrize("name", ["small_mixed", "small_sdp", "small_free_rot", "blockdiag_small", "maxcut_small",
+                                  "blockdiag_sparse", "arch0", "control07"])
 @pytest.mark.parametrize("kind", ["S0", "S1"])
 def test_ada_chain(name, kind):
     S = _problem(name)
