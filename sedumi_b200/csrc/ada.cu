@@ -32,6 +32,7 @@ struct AdaPair {      // one (constraint, PSD block) with nonzeros
   long long w_off;    // offset of W in the batch workspace: n x n (dense mode) or |U_k| values (sparse mode)
   int sparse;         // 1: W is only evaluated on U_k, the union pattern of block k
   int pad_;
+  long long part_off; // constraints with several blocks: offset of this pair's partial sums (npartners(k)+1)
 };
 
 // --------------------------------------------------------------------- sparse A'WA on a pattern
@@ -129,48 +130,146 @@ sparse_w_kernel(const AdaPair *pairs, int p0, int npairs, const int *blk_n, cons
   }
 }
 
-// One CTA per ADA column c (a constraint of the batch); warp per stored entry (i,c).
+// <A_ik, W_ck> for every stored ADA entry.  One CTA per (constraint c, PSD block k) pair: W_ck is staged
+// in shared memory (packed lower triangle, or its values on U_k in sparse mode; read in place when it
+// does not fit) and every constraint i of block k with invperm(i) <= invperm(c) takes its inner
+// product from there, a group of G lanes per partner.  Constraints that live in ONE block write
+// ADA(i,c) directly (nobody else touches column c); constraints spanning several blocks write
+// per-pair partial sums that ada3_reduce_kernel adds in block order -- deterministic, no atomics.
+// (Replaces the reference's per-entry accumulation, getada3.c:198-268.)
+struct BlkPartner { int j, e0, e1, pad; };
+
+struct ColSlots {        // row -> position inside one ADA column: shared-memory map, or binary search
+  const int *rows; int collen; const int *slot;
+  __device__ int find(int i) const {
+    if (slot) return slot[i];
+    int l = 0, h = collen;
+    while (l < h) { int mid = (l + h) >> 1; if (rows[mid] < i) l = mid + 1; else h = mid; }
+    return (l < collen && rows[l] == i) ? l : -1;
+  }
+};
+
+__device__ __forceinline__ void build_slots(int *slot, const int *rows, int collen, int m) {
+  for (int t = threadIdx.x; t < m; t += blockDim.x) slot[t] = -1;
+  __syncthreads();
+  for (int t = threadIdx.x; t < collen; t += blockDim.x) slot[rows[t]] = t;
+  __syncthreads();
+}
+
+template <int G>
 __global__ void __launch_bounds__(256)
-ada3_dots_kernel(int c0, const long long *adajc, const int *adair, const int *invperm, int first,
-                 const int *cpair_beg, const AdaPair *pairs, const int *blk_n,
-                 const int *ent_lin, const int *ent_src, const double *Atpr,
-                 const double *ws, double *ada, double *absd) {
-  const int c = c0 + blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *invperm, int first,
+                 const int *cpair_beg, const AdaPair *pairs, const int *blk_n, const int *ublk_off,
+                 const int *blkp_beg, const BlkPartner *blkp,
+                 const int *ent_lin, const int *ent_pk, const int *ent_src, const double *Atpr,
+                 double *ws, double *ada, double *absd, int wcap, int use_map, int m) {
+  extern __shared__ double dots_sm[];
+  double *Wsm = dots_sm;
+  int *slot = (int *)(dots_sm + wcap);
+  const AdaPair P = pairs[p0 + blockIdx.x];
+  const int c = P.j;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const bool multi = cpair_beg[c + 1] - cpair_beg[c] > 1;
   const int ipc = invperm[c];
-  const int pcb = cpair_beg[c], pce = cpair_beg[c + 1];
-  for (long long inz = adajc[c] + warp; inz < adajc[c + 1]; inz += nw) {
-    const int i = adair[inz];
-    const int ipi = invperm[i];
-    if (ipi > ipc) continue;
-    const bool diag = (i == c);
-    if (!diag && pcb == pce) continue;
+  const long long colbeg = adajc[c];
+  ColSlots cs{adair + colbeg, (int)(adajc[c + 1] - colbeg), nullptr};
+  if (!multi) {
+    if (use_map) { build_slots(slot, cs.rows, cs.collen, m); cs.slot = slot; }
+    if (tid == 0) {
+      const int sd = ipc >= first ? cs.find(c) : -1;
+      absd[c] = sd >= 0 ? ada[colbeg + sd] : 0.0;
+    }
+  }
+  const int n = blk_n[P.k];
+  const double *Wg = ws + P.w_off;
+  const int wsize = P.sparse ? (ublk_off[P.k + 1] - ublk_off[P.k]) : n * (n + 1) / 2;
+  const bool stage = wsize <= wcap;
+  if (stage) {
+    if (P.sparse) for (int t = tid; t < wsize; t += blockDim.x) Wsm[t] = Wg[t];
+    else
+      for (int q = warp; q < n; q += nw) {
+        const double *src = Wg + (long long)q * n;
+        double *dst = Wsm + ((long long)q * (2 * n - q + 1)) / 2 - q;       // packed column q, indexed by row p >= q
+        for (int pp = q + lane; pp < n; pp += 32) dst[pp] = src[pp];
+      }
+  }
+  __syncthreads();
+  const int *eidx = stage ? ent_pk : ent_lin;
+  const double *Wp = stage ? Wsm : Wg;
+  constexpr int GPW = 32 / G;                      // partner groups per warp
+  const int grp = lane / G, gl = lane % G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));   // groups diverge: sync only the group
+  const int tb = blkp_beg[P.k], te = blkp_beg[P.k + 1];
+  double *part = ws + P.part_off;                 // multi: one partial per partner, then the |.| sum of the diagonal
+  for (int t = tb + warp * GPW + grp; t < te; t += nw * GPW) {
+    const BlkPartner Q = blkp[t];
+    if (invperm[Q.j] > ipc) continue;
+    const double *av = Atpr + ent_src[Q.e0] - Q.e0;     // the entries of one pair are consecutive in At.pr
     double acc = 0.0, aabs = 0.0;
-    int pi = cpair_beg[i], pie = cpair_beg[i + 1], pc = pcb;
-    while (pi < pie && pc < pce) {                 // merge the two block lists (sorted by block)
-      const int ki = pairs[pi].k, kc = pairs[pc].k;
-      if (ki < kc) pi++;
-      else if (ki > kc) pc++;
-      else {
-        const double *W = ws + pairs[pc].w_off;
-        const int e0 = pairs[pi].e0, e1 = pairs[pi].e1;
-        const double *av = Atpr + ent_src[e0] - e0;       // the entries of one pair are consecutive in At.pr
-        for (int e = e0 + lane; e < e1; e += 32) {
-          double term = av[e] * W[ent_lin[e]];              // ent_lin = max(p,q) + min(p,q)*n
-          acc += term;
-          aabs += fabs(term);
+    int e = Q.e0 + gl;
+    for (; e + 3 * G < Q.e1; e += 4 * G) {
+      const double a0 = av[e], a1 = av[e + G], a2 = av[e + 2 * G], a3 = av[e + 3 * G];
+      const int i0 = eidx[e], i1 = eidx[e + G], i2 = eidx[e + 2 * G], i3 = eidx[e + 3 * G];
+      const double t0 = a0 * Wp[i0], t1 = a1 * Wp[i1], t2 = a2 * Wp[i2], t3 = a3 * Wp[i3];
+      acc += t0; aabs += fabs(t0);
+      acc += t1; aabs += fabs(t1);
+      acc += t2; aabs += fabs(t2);
+      acc += t3; aabs += fabs(t3);
+    }
+    for (; e < Q.e1; e += G) {
+      const double term = av[e] * Wp[eidx[e]];
+      acc += term;
+      aabs += fabs(term);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      acc += __shfl_down_sync(gmask, acc, o, G);
+      aabs += __shfl_down_sync(gmask, aabs, o, G);
+    }
+    if (gl == 0) {
+      if (multi) {
+        part[t - tb] = acc;
+        if (Q.j == c) part[te - tb] = aabs;
+      } else {
+        const int sl = cs.find(Q.j);
+        if (sl >= 0) {
+          ada[colbeg + sl] += acc;
+          if (Q.j == c && ipc >= first) absd[c] += aabs;
         }
-        pi++; pc++;
       }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      acc += __shfl_down_sync(0xffffffffu, acc, o);
-      aabs += __shfl_down_sync(0xffffffffu, aabs, o);
-    }
-    if (lane == 0) {
-      double base = ada[inz];
-      if (diag && ipc >= first) absd[c] = base + aabs;
-      ada[inz] = base + acc;
+  }
+}
+
+// Constraints spanning several PSD blocks: add the per-pair partial sums into column c, block by block.
+__global__ void __launch_bounds__(256)
+ada3_reduce_kernel(int c0, const long long *adajc, const int *adair, const int *invperm, int first,
+                   const int *cpair_beg, const AdaPair *pairs, const int *blkp_beg, const BlkPartner *blkp,
+                   const double *ws, double *ada, double *absd, int use_map, int m) {
+  extern __shared__ int red_slot[];
+  const int c = c0 + blockIdx.x;
+  const int pcb = cpair_beg[c], pce = cpair_beg[c + 1];
+  if (pce - pcb <= 1) return;
+  const int ipc = invperm[c];
+  const long long colbeg = adajc[c];
+  ColSlots cs{adair + colbeg, (int)(adajc[c + 1] - colbeg), nullptr};
+  if (use_map) { build_slots(red_slot, cs.rows, cs.collen, m); cs.slot = red_slot; }
+  if (threadIdx.x == 0) {
+    const int sd = ipc >= first ? cs.find(c) : -1;
+    absd[c] = sd >= 0 ? ada[colbeg + sd] : 0.0;
+  }
+  for (int pc = pcb; pc < pce; pc++) {
+    __syncthreads();                               // two blocks can feed the same entry: keep them in order
+    const int k = pairs[pc].k;
+    const double *part = ws + pairs[pc].part_off;
+    const int tb = blkp_beg[k], te = blkp_beg[k + 1];
+    for (int t = tb + threadIdx.x; t < te; t += blockDim.x) {
+      const int i = blkp[t].j;
+      if (invperm[i] > ipc) continue;
+      const int sl = cs.find(i);
+      if (sl < 0) continue;
+      ada[colbeg + sl] += part[t - tb];
+      if (i == c && ipc >= first) absd[c] += part[te - tb];
     }
   }
 }
@@ -214,7 +313,7 @@ struct sb200_ada_plan {
   std::vector<int> blk_n; std::vector<long long> blk_off, blk_start;
   std::vector<AdaPair> pairs;
   std::vector<int> cpair_beg;
-  struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; int nsparse; };
+  struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; int nsparse; int nmulti; };
   std::vector<Batch> batches;
   long long ws_max = 0;
   uint64_t key = 0, val_hash = 0;
@@ -223,7 +322,10 @@ struct sb200_ada_plan {
   DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
   DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_lin, d_ent_src, d_Rlist, d_tt_ptr, d_tt_col, d_tt_src;
   DevBuf<double> d_tt_w;
-  DevBuf<int> d_ublk_off, d_u_p, d_u_q;
+  DevBuf<int> d_ublk_off, d_u_p, d_u_q, d_blkp_beg, d_ent_pk;
+  DevBuf<BlkPartner> d_blkp;
+  int wcap = 0, use_map = 0, dots_group = 32;
+  size_t dots_smem = 0;
   std::vector<int> blk_sparse;
   int max_nu = 0;
   DevBuf<AdaPair> d_pairs;
@@ -328,6 +430,39 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       for (int e = P.e0; e < P.e1; e++) ent_lin[e] = (int)(std::lower_bound(v.begin(), v.end(), ent_lin[e]) - v.begin());
     }
   }
+  // ---- shared-memory staging of W in the dots kernel: packed index per entry, partner lists per block
+  std::vector<int> ent_pk(ent_lin.size());
+  std::vector<int> blkp_beg(nblk + 1, 0);
+  for (auto &P : pl->pairs) blkp_beg[P.k + 1]++;
+  for (sb_idx k = 0; k < nblk; k++) blkp_beg[k + 1] += blkp_beg[k];
+  std::vector<BlkPartner> blkp(pl->pairs.size());
+  {
+    std::vector<int> fill(blkp_beg.begin(), blkp_beg.end() - 1);
+    for (auto &P : pl->pairs) {
+      blkp[fill[P.k]++] = BlkPartner{P.j, P.e0, P.e1, 0};
+      const long long n = pl->blk_n[P.k];
+      for (int e = P.e0; e < P.e1; e++) {
+        if (P.sparse) ent_pk[e] = ent_lin[e];
+        else { const long long pp = ent_lin[e] % n, qq = ent_lin[e] / n; ent_pk[e] = (int)((qq * (2 * n - qq + 1)) / 2 - qq + pp); }
+      }
+    }
+  }
+  pl->use_map = (m <= 10000);          // row -> slot map of one ADA column in shared memory (<= 40 KB)
+  {
+    const long long mapb = pl->use_map ? (((long long)m * 4 + 7) & ~7LL) : 0;
+    const long long cap = (220 * 1024 - mapb) / 8;
+    long long wc = 1;
+    for (sb_idx k = 0; k < nblk; k++) {
+      if (blkp_beg[k + 1] == blkp_beg[k]) continue;
+      const long long n = pl->blk_n[k];
+      const long long wsz = pl->blk_sparse[k] ? (ublk_off[k + 1] - ublk_off[k]) : n * (n + 1) / 2;
+      if (wsz <= cap) wc = std::max(wc, wsz);
+    }
+    pl->wcap = (int)wc;
+    pl->dots_smem = (size_t)(wc * 8 + mapb);
+    const double avg = pl->pairs.empty() ? 0.0 : (double)ent_lin.size() / (double)pl->pairs.size();
+    pl->dots_group = avg <= 6.0 ? 4 : (avg <= 12.0 ? 8 : (avg <= 24.0 ? 16 : 32));
+  }
   // ---- batches of whole constraints, workspace bounded
   const long long BUDGET = (long long)96 << 20;     // doubles (768 MB)
   std::vector<GemmDesc> descs(pl->pairs.size());
@@ -342,6 +477,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
         long long n = pl->blk_n[pl->pairs[p].k];
         const long long wsz = pl->pairs[p].sparse ? (ublk_off[pl->pairs[p].k + 1] - ublk_off[pl->pairs[p].k]) : n * n;
         need += wsz + n * pl->pairs[p].r;
+        if (pl->cpair_beg[c + 1] - pl->cpair_beg[c] > 1) need += blkp_beg[pl->pairs[p].k + 1] - blkp_beg[pl->pairs[p].k] + 1;
       }
       if (ws > 0 && ws + need > BUDGET) break;
       for (int p = pl->cpair_beg[c]; p < pl->cpair_beg[c + 1]; p++) {
@@ -349,6 +485,8 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
         long long n = pl->blk_n[P.k];
         P.tt_off = ws; ws += n * P.r;
         P.w_off = ws; ws += P.sparse ? (ublk_off[P.k + 1] - ublk_off[P.k]) : n * n;
+        P.part_off = ws;
+        if (pl->cpair_beg[c + 1] - pl->cpair_beg[c] > 1) { ws += blkp_beg[P.k + 1] - blkp_beg[P.k] + 1; B.nmulti++; }
         if (P.sparse) { B.nsparse++; continue; }
         GemmDesc g{};
         g.offA = pl->blk_off[P.k]; g.gatherOff = P.r0; g.lda = (int)n; g.a_tri = TRI_NONE;
@@ -380,6 +518,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(pl->d_tt_ptr.upload(tt_ptr)); SB_TRY(pl->d_tt_col.upload(tt_col)); SB_TRY(pl->d_tt_src.upload(tt_src));
   SB_TRY(pl->d_tt_w.upload(tt_w));
   SB_TRY(pl->d_ublk_off.upload(ublk_off)); SB_TRY(pl->d_u_p.upload(u_p)); SB_TRY(pl->d_u_q.upload(u_q));
+  SB_TRY(pl->d_blkp_beg.upload(blkp_beg)); SB_TRY(pl->d_blkp.upload(blkp)); SB_TRY(pl->d_ent_pk.upload(ent_pk));
   SB_TRY(pl->d_Rlist.upload(Rlist));
   SB_TRY(pl->d_pairs.upload(pl->pairs));
   SB_TRY(pl->d_descs.upload(descs)); SB_TRY(pl->d_tiles.upload(tiles));
@@ -504,10 +643,29 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
                                          pl->d_Rlist.p, udsqr_dev, pl->d_ws.p);
       SB_LAUNCH_CHECK_N("sparse_w_kernel");
     }
-    ada3_dots_kernel<<<B.c1 - B.c0, 256, 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, pl->d_pairs.p,
-                                                  pl->d_blk_n.p, pl->d_ent_lin.p, pl->d_ent_src.p, pl->d_Atpr.p,
-                                                  pl->d_ws.p, ada_dev, absd_dev);
+    {
+#define SB_DOTS(G)                                                                                                       \
+  do {                                                                                                                   \
+    static bool attr_done = false;                                                                                       \
+    if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(ada3_dots_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_done = true; } \
+    ada3_dots_kernel<G><<<B.p1 - B.p0, 256, pl->dots_smem, st>>>(B.p0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, \
+        pl->d_pairs.p, pl->d_blk_n.p, pl->d_ublk_off.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ent_lin.p, pl->d_ent_pk.p,  \
+        pl->d_ent_src.p, pl->d_Atpr.p, pl->d_ws.p, ada_dev, absd_dev, pl->wcap, pl->use_map, pl->m);                       \
+  } while (0)
+      switch (pl->dots_group) {
+        case 4: SB_DOTS(4); break;
+        case 8: SB_DOTS(8); break;
+        case 16: SB_DOTS(16); break;
+        default: SB_DOTS(32); break;
+      }
+#undef SB_DOTS
+    }
     SB_LAUNCH_CHECK_N("ada3_dots_kernel");
+    if (B.nmulti) {
+      ada3_reduce_kernel<<<B.c1 - B.c0, 256, pl->use_map ? (size_t)pl->m * 4 : 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
+          pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ws.p, ada_dev, absd_dev, pl->use_map, pl->m);
+      SB_LAUNCH_CHECK_N("ada3_reduce_kernel");
+    }
   }
   if (symmetrise) {
     makesym_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ada_dev);
