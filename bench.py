@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NSOLVE, NPSD = 4, 12
+FRAMES = (np.zeros(0), np.zeros(0))
 METRIC = "IPM iterations/sec (ADA'+Cholesky+solve) over the hot-path recipe"
 
 
@@ -53,6 +54,8 @@ def load_workload(name):
     rng = np.random.default_rng(problems.SEED0)
     rhs = rng.standard_normal((S.m, 1))
     psd_x = rng.standard_normal(int((np.asarray(K["s"]) ** 2).sum()))
+    global FRAMES
+    FRAMES = problems.synth_frames(K["s"])         # (lab, frms): product-form spectral factor of the PSD iterate
     return S, d, rhs, psd_x
 
 
@@ -175,8 +178,10 @@ def run_reference(S, d, rhs, psd_x, steps, warmup):
             R.solve(L, rhs)
         t1 = time.perf_counter()
         for i in range(NPSD):
-            R.psdscale(d, psd_x, i & 1)
+            ps = R.psdscale(d, psd_x, i & 1)
         t_np += time.perf_counter() - t1
+        if len(S.K["s"]):
+            R.scaling_tail(d, FRAMES[0], FRAMES[1], np.asarray(ps).ravel())
     wall = time.perf_counter() - t0
     t_mex = R.mex.mex_seconds() - t_mex0
     # time inside the reference's mexFunctions + the restated M pieces; harness marshalling excluded
@@ -204,7 +209,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.workload} (BASELINE.json configs[1]: K.s=[70,35], m=666, dense ADA, 1 supernode)"
               if args.workload == "control07" else args.workload,
-              "recipe": f"invcholfac,getada1,getada2,getada3,blkchol,{NSOLVE}x(fwblkslv,./d,bwblkslv),{NPSD}xpsdscale",
+              "recipe": f"invcholfac,getada1,getada2,getada3,blkchol,{NSOLVE}x(fwblkslv,./d,bwblkslv),{NPSD}xpsdscale,"
+                        "psdinvjmul,2xpsdframeit,urotorder,givensrot (SURVEY 8d)",
               "scaling_state": "S1 mid-run NT scaling (SURVEY 8d), seed 20260926", "parallelism": f"replicas x{args.gpus}",
               "l2": "L2 flushed (256 MiB write) between timed iterations",
               "launch": "one CUDA graph per iteration" if not args.no_graph else "stream launches"}
@@ -250,6 +256,7 @@ def main():
         hp.set_scaling(d)
         hp.set_rhs(rhs)
         hp.psd_x[:psd_x.size].copy_(torch.from_numpy(psd_x))
+        hp.set_frames(*FRAMES)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         stream.synchronize()
 
@@ -379,6 +386,8 @@ def run_e2e(S, d, rhs, psd_x, steps, world):
     nq = len(S.K["q"])
     DAt = {"q": sp.csc_matrix((nq, S.m))}
     xfull = np.r_[np.zeros(1), psd_x]
+    lenud = int((np.asarray(S.K["s"]) ** 2).sum())
+    sumn = int(np.asarray(S.K["s"]).sum())
 
     def step():
         ud = gpu.invcholfac(d["u"], Km, d["perm"])
@@ -391,7 +400,13 @@ def run_e2e(S, d, rhs, psd_x, steps, world):
             p = gpu.fwblkslv(Lf, rhs)
             y = gpu.bwblkslv(Lf, p / Ld)
         for i in range(NPSD):
-            gpu.psdscale({"u": d["u"], "perm": d["perm"]}, xfull, Km, float(i & 1))
+            ps = gpu.psdscale({"u": d["u"], "perm": d["perm"]}, xfull, Km, float(i & 1))
+        if lenud:
+            gpu.psdinvjmul(FRAMES[0], FRAMES[1], ps, Km)
+            f = gpu.psdframeit(FRAMES[0], FRAMES[1], Km)
+            f = gpu.psdframeit(FRAMES[0], FRAMES[1], Km)
+            u2, p2, gjc, g = gpu.urotorder(d["u"], Km, 1.1, nlhs=4)
+            gpu.givensrot(gjc, g, f, Km)
         return y
 
     step()
@@ -401,10 +416,10 @@ def run_e2e(S, d, rhs, psd_x, steps, world):
         step()
     t = gpu.mex_seconds() - t0
     wall = time.perf_counter() - w0
-    lenud = int((np.asarray(S.K["s"]) ** 2).sum())
     nA, nL, m = S.ADA.nnz, S.L["L"].nnz, S.m
-    h2d = 8 * (lenud + (S.K["l"]) + 3 * nA + S.At.nnz * 0 + nA + m + NSOLVE * 2 * (nL + m) + NPSD * 2 * lenud + lenud)
-    d2h = 8 * (lenud + 3 * nA + m + nL + 3 * m + NSOLVE * 2 * m + NPSD * lenud)
+    h2d = 8 * (lenud + (S.K["l"]) + 3 * nA + S.At.nnz * 0 + nA + m + NSOLVE * 2 * (nL + m) + NPSD * 2 * lenud + lenud
+               + (2 * lenud + sumn) + 2 * (lenud + sumn) + lenud + 2 * lenud)      # psdinvjmul, 2 psdframeit, urotorder, givensrot
+    d2h = 8 * (lenud + 3 * nA + m + nL + 3 * m + NSOLVE * 2 * m + NPSD * lenud + lenud + 2 * lenud + (lenud + 2 * sumn) + lenud)
     return {"value": world * steps / t, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "timed": "time inside the plugins' mexFunction (host numpy buffers in/out, all H2D/D2H inside), "
                      f"Python marshalling of mxArrays excluded; wall incl. marshalling {wall / steps * 1e3:.2f} ms/step",

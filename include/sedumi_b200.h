@@ -143,6 +143,13 @@ int sb200_psdinvjmul(sb_idx nblk, const sb_idx *n, const double *xlab, const dou
 /* urotorder.c:312-490 / givensrot.c:93-168.  perm_out 0-based inside each block; gjc_out n_k entries
  * per block (0-based rotation offsets, last = count); g in the worst-case layout n_k(n_k-1) doubles
  * per block for urotorder, packed back to back for givensrot (as the MEX interface carries it). */
+/* Device-pointer variants for hosts that keep the scaling state on the GPU.  perm/gjc are int32;
+ * g uses the worst-case layout: rotations of block k start at sum_{j<k} n_j(n_j-1) doubles.
+ * work_dev: lenud + sum(n) doubles of scratch. */
+int sb200_urotorder_dev(sb_idx nblk, const sb_idx *n, const double *u_dev, double maxu, double *u_out_dev,
+                        int *perm_dev, int *gjc_dev, double *g_dev, double *work_dev);
+int sb200_givensrot_dev(sb_idx nblk, const sb_idx *n, const int *gjc_dev, const double *g_dev,
+                        const double *x_dev, double *y_dev);
 int sb200_urotorder(sb_idx nblk, const sb_idx *n, const double *u, double maxu, double *u_out,
                     sb_idx *perm_out, sb_idx *gjc_out, double *g_out);
 int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen,

@@ -81,7 +81,18 @@ class RefHotPath:
     def psdscale(self, d, x, transp):
         return restate.psdscale({"u": d["u"], "perm": d["perm"]}, x, self.S.K, transp)
 
-    def iteration(self, d, rhs, psd_x, nsolve=4, npsdscale=12):
+    def scaling_tail(self, d, lab, frms, y_psd):
+        """psdinvjmul -> 2 x psdframeit -> urotorder -> givensrot on the reference's own MEX
+        (updtransfo.m:99-108; SURVEY 8d recipe)."""
+        Km, mex = self.Km, self.mex
+        z = mex.psdinvjmul(lab, frms, y_psd, Km)
+        f = mex.psdframeit(lab, frms, Km)
+        f = mex.psdframeit(lab, frms, Km)
+        u, perm, gjc, g = mex.urotorder(d["u"], Km, 1.1, nlhs=4)
+        q = mex.givensrot(gjc, g, f, Km)
+        return dict(z=z, frame=f, u=u, perm=perm, gjc=gjc, g=g, q=q)
+
+    def iteration(self, d, rhs, psd_x, nsolve=4, npsdscale=12, frames=None):
         udsqr, ADA, absd = self.assemble(d)
         L = self.factor(ADA, absd)
         y = None
@@ -90,7 +101,10 @@ class RefHotPath:
         ps = None
         for i in range(npsdscale):
             ps = self.psdscale(d, psd_x, i & 1)
-        return dict(udsqr=udsqr, ADA=ADA, absd=absd, L=L, y=y, psd=ps)
+        out = dict(udsqr=udsqr, ADA=ADA, absd=absd, L=L, y=y, psd=ps)
+        if frames is not None and len(self.S.K["s"]):
+            out["tail"] = self.scaling_tail(d, frames[0], frames[1], np.asarray(ps).ravel())
+        return out
 
 
 class DenseColumnRef:

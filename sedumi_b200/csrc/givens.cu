@@ -14,6 +14,7 @@
 // bit-identical to the reference built without FMA (gcc -O2 on x86-64).  Parallelism: one CTA per
 // PSD block; inside a step, columns are independent (one thread per column).
 #include <algorithm>
+#include <map>
 #include "sb_internal.h"
 
 namespace sb {
@@ -197,7 +198,61 @@ static int make_blocks(sb_idx nblk, const sb_idx *n, std::vector<UrotBlk> &blks,
   return 0;
 }
 
+// Block descriptors on the device, worst-case rotation layout; cached per block-size list so that the
+// *_dev entries can be recorded into a CUDA graph (no allocation or copy at call time after the first).
+static std::map<uint64_t, UrotBlk *> g_blk_cache;
+static int device_blocks(sb_idx nblk, const sb_idx *n, UrotBlk **out, long long &lenud, long long &sumn, long long &gtot, int &maxn) {
+  std::vector<UrotBlk> blks;
+  SB_TRY(make_blocks(nblk, n, blks, lenud, sumn, gtot));
+  maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
+  uint64_t h = fnv1a(&nblk, sizeof nblk); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
+  auto it = g_blk_cache.find(h);
+  if (it != g_blk_cache.end()) { *out = it->second; return 0; }
+  UrotBlk *d = nullptr;
+  SB_CUDA(cudaMalloc(&d, sizeof(UrotBlk) * std::max<size_t>(blks.size(), 1)));
+  SB_CUDA(cudaMemcpy(d, blks.data(), sizeof(UrotBlk) * blks.size(), cudaMemcpyHostToDevice));
+  g_blk_cache[h] = d;
+  *out = d;
+  return 0;
+}
+
 extern "C" {
+
+// Device-resident urotorder.  u_dev is read, work_dev (lenud + sum n doubles) is scratch; outputs:
+// u_out_dev (lenud), perm_dev / gjc_dev (sum n ints: 0-based inside each block / cumulative rotation
+// counts), g_dev in the worst-case layout (block k at sum_{j<k} n_j(n_j-1) doubles).
+int sb200_urotorder_dev(sb_idx nblk, const sb_idx *n, const double *u_dev, double maxu, double *u_out_dev,
+                        int *perm_dev, int *gjc_dev, double *g_dev, double *work_dev) {
+  SB_TRY(ensure_init());
+  UrotBlk *db; long long lenud, sumn, gtot; int maxn;
+  SB_TRY(device_blocks(nblk, n, &db, lenud, sumn, gtot, maxn));
+  if (lenud == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  double *W = work_dev, *d = work_dev + lenud;
+  SB_CUDA(cudaMemcpyAsync(W, u_dev, sizeof(double) * lenud, cudaMemcpyDeviceToDevice, st));
+  if (gtot) SB_CUDA(cudaMemsetAsync(g_dev, 0, sizeof(double) * gtot, st));
+  SB_CUDA(cudaMemsetAsync(gjc_dev, 0, sizeof(int) * sumn, st));
+  urotorder_kernel<<<(unsigned)nblk, 256, 0, st>>>(db, W, perm_dev, gjc_dev, g_dev, d, maxu * maxu);
+  SB_LAUNCH_CHECK_N("urotorder_kernel");
+  uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, W, perm_dev, u_out_dev);
+  SB_LAUNCH_CHECK_N("uperm_sym_kernel");
+  return 0;
+}
+
+// Device-resident givensrot on the outputs of sb200_urotorder_dev (worst-case rotation layout).
+// y_dev may alias x_dev.
+int sb200_givensrot_dev(sb_idx nblk, const sb_idx *n, const int *gjc_dev, const double *g_dev, const double *x_dev,
+                        double *y_dev) {
+  SB_TRY(ensure_init());
+  UrotBlk *db; long long lenud, sumn, gtot; int maxn;
+  SB_TRY(device_blocks(nblk, n, &db, lenud, sumn, gtot, maxn));
+  if (lenud == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  if (y_dev != x_dev) SB_CUDA(cudaMemcpyAsync(y_dev, x_dev, sizeof(double) * lenud, cudaMemcpyDeviceToDevice, st));
+  matgivens_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nblk), 128, 0, st>>>(db, gjc_dev, g_dev, y_dev);
+  SB_LAUNCH_CHECK_N("matgivens_kernel");
+  return 0;
+}
 
 // [u,perm,gjc,g] = urotorder(u,K,maxu): host entry.  perm_out: 0-based inside each block (the stub
 // composes it with permIN); gjc_out: per block n_k entries (gjc[n_k-1] = number of rotations);

@@ -76,7 +76,7 @@ EXPORTS = [
     "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
     "sb200_psd_plan_get", "sb200_psd_plan_lenud", "sb200_psd_plan_sumn", "sb200_invcholfac_dev", "sb200_psdscale_dev",
     "sb200_invcholfac", "sb200_psdscale", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
-    "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
+    "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_urotorder_dev", "sb200_givensrot_dev", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
     "sb200_graph_destroy",
     "sb200_ada_plan_get", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
     "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3",
@@ -142,6 +142,17 @@ class HotPath:
         self.flag = torch.zeros(max(m, 1), dtype=torch.int32, device=self.dev)
         self.psd_x, self.psd_y = z(self.lenud), z(self.lenud)
         self.rhs = self.y = self.w = None
+        # scaling update (updtransfo.m:99-108): frames of the PSD iterate, re-ordered factor, rotation list
+        sumn = int(s.sum())
+        self.sumn = sumn
+        self.s64 = _i64(s)
+        self.frms, self.lab = z(self.lenud), z(sumn)
+        self.psd_z, self.psd_f = z(self.lenud), z(self.lenud)
+        self.u_new, self.urot_work = z(self.lenud), z(self.lenud + sumn)
+        self.g = z(int((s * (s - 1)).sum()))
+        self.perm_new = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
+        self.gjc = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
+        self.maxu_urot = 1.1                        # updtransfo.m:100
 
     # ------------------------------------------------------------------ data movement
     def set_scaling(self, d: dict, non_blocking=False) -> int:
@@ -195,6 +206,42 @@ class HotPath:
         check(lib().sb200_psdscale_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
                                        _p(self.psd_x), C.c_int(transp), _p(self.psd_y)), "psdscale")
 
+    def set_frames(self, lab: np.ndarray, frms: np.ndarray) -> int:
+        """Spectral factor of the PSD iterate (vfrm.lab PSD part, vfrm.s), host -> device."""
+        t = self.torch
+        lab = np.ascontiguousarray(np.asarray(lab, dtype=np.float64).ravel()[-self.sumn:]) if self.sumn else np.zeros(0)
+        frms = np.ascontiguousarray(np.asarray(frms, dtype=np.float64).ravel())
+        if lab.size:
+            self.lab[:lab.size].copy_(t.from_numpy(lab))
+            self.frms[:frms.size].copy_(t.from_numpy(frms))
+        return lab.nbytes + frms.nbytes
+
+    def psdinvjmul(self):
+        """z = psdinvjmul(lab, frms, psd_y): solves X Z + Z X = 2 Y per block (psdinvjmul.c:101-157)."""
+        check(lib().sb200_psdinvjmul_dev(self.psd, _p(self.lab), _p(self.frms), _p(self.psd_y), _p(self.psd_z)), "psdinvjmul")
+
+    def psdframeit(self):
+        check(lib().sb200_psdframeit_dev(self.psd, _p(self.lab), _p(self.frms), _p(self.psd_f)), "psdframeit")
+
+    def urotorder(self):
+        check(lib().sb200_urotorder_dev(I64(len(self.s)), _p(self.s64), _p(self.d_u), C.c_double(self.maxu_urot),
+                                        _p(self.u_new), _p(self.perm_new), _p(self.gjc), _p(self.g), _p(self.urot_work)),
+              "urotorder")
+
+    def givensrot(self):
+        check(lib().sb200_givensrot_dev(I64(len(self.s)), _p(self.s64), _p(self.gjc), _p(self.g), _p(self.psd_f),
+                                        _p(self.psd_z)), "givensrot")
+
+    def update_scaling_tail(self):
+        """psdinvjmul -> 2 x psdframeit -> urotorder -> givensrot (SURVEY 8d recipe; updtransfo.m:99-108)."""
+        if not self.lenud:
+            return
+        self.psdinvjmul()
+        self.psdframeit()
+        self.psdframeit()
+        self.urotorder()
+        self.givensrot()
+
     def allreduce_ada(self, dist):
         """The one collective of the sharded path: sum the per-rank partial ADA values
         and absd over NCCL, enqueued on the library stream right behind getada3."""
@@ -212,6 +259,7 @@ class HotPath:
             self.solve()
         for i in range(npsdscale):
             self.psdscale(i & 1)
+        self.update_scaling_tail()
 
     def capture(self, nsolve=4, npsdscale=12):
         """Record one iteration into a CUDA graph; returns a callable that replays it."""

@@ -185,3 +185,24 @@ def scaling(K: dict, kind: str = "S1", seed: int = SEED0, base: dict | None = No
     d["u"] = np.concatenate(us) if us else np.zeros(0)
     d["perm"] = np.concatenate(perms).reshape(-1, 1) if perms else np.zeros((0, 0))
     return d
+
+
+def synth_frames(s, seed: int = SEED0 + 7):
+    """Spectral factor of a PSD iterate in SeDuMi's product form (what qrK leaves in vfrm.s,
+    qrK.c:86-122): per block an n x n column-major array whose column k < n-1 holds the Householder
+    vector q_k in rows k..n-1 and whose last column holds beta_0..beta_{n-2}, Q_k = I - q_k q_k'/beta_k
+    (orthogonal iff beta_k = |q_k|^2/2); eigenvalue labels `lab` > 0.  Returns (lab, frms)."""
+    rng = np.random.default_rng(seed)
+    labs, frames = [], []
+    for n in np.asarray(s, dtype=np.int64).ravel():
+        n = int(n)
+        F = np.zeros((n, n))
+        for k in range(n - 1):
+            q = rng.standard_normal(n - k)
+            F[k:, k] = q
+            F[k, n - 1] = 0.5 * float(q @ q)
+        labs.append(np.exp(0.5 * rng.standard_normal(n)))
+        frames.append(F.ravel(order="F"))
+    if not labs:
+        return np.zeros(0), np.zeros(0)
+    return np.concatenate(labs), np.concatenate(frames)

@@ -24,19 +24,37 @@ def _run(raw, perm=None, seed=3):
     rng = np.random.default_rng(seed)
     rhs = rng.standard_normal((S.m, 2))
     psd_x = rng.standard_normal(int((np.asarray(K["s"]) ** 2).sum()))
+    lab, frms = problems.synth_frames(K["s"], seed=seed)
     hp = device.HotPath(S)
     st = hp.stream()
     with torch.cuda.stream(st):
         hp.set_scaling(d)
         hp.set_rhs(rhs)
         hp.psd_x[:psd_x.size].copy_(torch.from_numpy(psd_x))
+        hp.set_frames(lab, frms)
         st.synchronize()
         hp.iteration(1, 2)
         hp.sync()
+        n2 = psd_x.size
+        tail = dict(z=hp.psd_z.cpu().numpy()[:n2].copy(), frame=hp.psd_f.cpu().numpy()[:n2],
+                    u=hp.u_new.cpu().numpy()[:n2], perm=hp.perm_new.cpu().numpy()[:hp.sumn], gjc=hp.gjc.cpu().numpy()[:hp.sumn])
         out = dict(ADA=hp.ADA.cpu().numpy()[:S.ADA.nnz], absd=hp.absd.cpu().numpy()[:S.m],
                    d=hp.dvec.cpu().numpy()[:S.m], y=hp.y.cpu().numpy().T, psd=hp.psd_y.cpu().numpy()[:psd_x.size],
                    udsqr=hp.udsqr.cpu().numpy()[:psd_x.size])
-    ref = refpath.RefHotPath(S).iteration(d, rhs, psd_x, 1, 2)
+    ref = refpath.RefHotPath(S).iteration(d, rhs, psd_x, 1, 2, frames=(lab, frms))
+    if psd_x.size:
+        # scaling-update tail: psdinvjmul, psdframeit, urotorder (discrete outputs exact), givensrot.
+        # hp.psd_z was overwritten by givensrot (last call of the recipe), so z is checked separately below.
+        rt = ref["tail"]
+        assert relerr(tail["frame"], rt["frame"].ravel()) <= 1e-10
+        assert np.array_equal(tail["u"], rt["u"].ravel())
+        assert np.array_equal(tail["perm"] + 1, rt["perm"].ravel().astype(np.int64))      # 1-based inside each block
+        assert np.array_equal(tail["gjc"], rt["gjc"].ravel().astype(np.int64))
+        assert relerr(tail["z"], rt["q"].ravel()) <= 1e-10
+        with torch.cuda.stream(st):
+            hp.psdinvjmul()
+            hp.sync()
+            assert relerr(hp.psd_z.cpu().numpy()[:psd_x.size], rt["z"].ravel()) <= 1e-9
     assert relerr(out["udsqr"], ref["udsqr"].ravel()) <= 1e-10
     assert relerr(out["ADA"], ref["ADA"].data) <= 1e-10
     assert relerr(out["absd"], ref["absd"].ravel()) <= 1e-10
@@ -52,6 +70,35 @@ def test_control07():
 
 def test_arch0():
     _run(problems.load_fixture("arch0"))
+
+
+def test_late_scaling_with_rotations():
+    """S2 ("late") scaling: ill-conditioned factors, urotorder really pivots."""
+    import refpath
+    raw = problems.synth_small_mixed(seed=11, m=30, l=0, q=(), s=(12, 8), density=0.25)
+    At, b, c, K = cones.pretransfo(*raw)[:4]
+    d = problems.scaling(K, "S2", seed=5)
+    Km = cones.K_for_mex(K)
+    u, perm, gjc, g = refpath.ref_dir().urotorder(d["u"], Km, 1.1, nlhs=4)
+    import torch
+    from sedumi_b200 import device
+    S = setup.build_setup(At, b, c, K)
+    hp = device.HotPath(S)
+    with torch.cuda.stream(hp.stream()):
+        hp.set_scaling(d)
+        lab, frms = problems.synth_frames(K["s"], seed=2)
+        hp.set_frames(lab, frms)
+        hp.psdframeit()
+        hp.urotorder()
+        hp.givensrot()
+        hp.sync()
+        assert np.array_equal(hp.u_new.cpu().numpy()[:u.size], u.ravel())
+        assert np.array_equal(hp.gjc.cpu().numpy()[:hp.sumn], gjc.ravel().astype(np.int64))
+        assert np.array_equal(hp.perm_new.cpu().numpy()[:hp.sumn] + 1, perm.ravel().astype(np.int64))
+        f = refpath.ref_dir().psdframeit(lab, frms, Km)
+        q = refpath.ref_dir().givensrot(gjc, g, f, Km)
+        assert relerr(hp.psd_z.cpu().numpy()[:u.size], q.ravel()) <= 1e-10
+    assert gjc.ravel()[-1] > 0 or gjc.ravel()[11] > 0, "test input does not rotate; pick another seed"
 
 
 def test_small_sdp():
