@@ -90,15 +90,14 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned bar_target = 0;
   const int npanels = (m + PB - 1) / PB;
-  for (int pi = 0; pi < npanels; pi++) {
+  volatile unsigned *la_fail = bar + 4;            // la_fail[pi] = 1: the look-ahead factorisation of panel pi gave up
+  // ------------------------------------------------------------------ phase A: diagonal block of panel pi (one CTA)
+  // allow_test = false (look-ahead, the rows below the block are still being updated by the other
+  // CTAs): returns false as soon as a pivot needs the reference's stability test, nothing published.
+  auto phaseA = [&](const int pi, const bool allow_test, const bool preloaded) -> bool {
     const int p0 = pi * PB, w = min(PB, m - p0), base = p0 + w;
-    const int nrow = m - base;
-    const int nslab = nrow > 0 ? (nrow + TS - 1) / TS : 0;
-    const int ntiles = nslab * (nslab + 1) / 2;
-    // ------------------------------------------------------------------ phase A: diagonal block (CTA 0)
-    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 0] = clock64();
-    if (blockIdx.x == 0) {
-      for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
+    {
+      if (!preloaded) for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
         int r = idx % PB, c = idx / PB;
         A[r][c] = (r < w && c < w && r >= c) ? W[(long long)(p0 + c) * ld + p0 + r] : 0.0;
       }
@@ -106,7 +105,6 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       __syncthreads();
       if (tid < PB) s_lb[tid] = (tid < w) ? lb[p0 + tid] : 0.0;
       __syncthreads();
-      if (tdbg && tid == 0) tdbg[pi * 8 + 1] = clock64();
       int k_resume = 0, resolved_k = -1;
       // All 8 warps cooperate on each pivot step: the lower triangle below/right of the pivot is at most
       // 31*32/2 elements, one per thread; the step is then bounded by the reciprocal + two block barriers
@@ -134,6 +132,8 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
               if (r >= c && r < w) A[r][c] -= (A[c][k] * rinv) * xr;
           }
           __syncthreads();
+          // (scaling the column one step later, in the shadow of the next update, saves a barrier but
+          // measured 17 % slower: the extra loop-carried state lengthens the dependent chain)
           if (tid > k && tid < w) A[tid][k] *= rinv;
           if (tid == 0) { dloc[k] = xkk; A[k][k] = 1.0; }
           __syncthreads();
@@ -143,6 +143,7 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
         __syncthreads();
         const int k = s_state;
         if (k >= w) break;
+        if (!allow_test) return false;               // uniform: s_state is shared
         // ---- stability test for column k (rare): the reference compares x_kk with |x[idamax+1]|/maxu
         // (blkchol2.c:66-70,122); needs the fully updated sub-column, i.e. the tail rows as well.
         {
@@ -204,24 +205,39 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
         if (r >= c) Lo[(long long)(p0 + c) * ld + p0 + r] = (r == c) ? 1.0 : (skipped[c] ? 0.0 : A[r][c]);
       }
     }
-    if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 3] = clock64();
-    bar_target += gridDim.x;
-    grid_barrier(bar, bar_target);
+    return true;
+  };
+  if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[0] = clock64();
+  if (blockIdx.x == 0) phaseA(0, true, false);
+  if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[3] = clock64();
+  bar_target += gridDim.x;
+  grid_barrier(bar, bar_target);
+  for (int pi = 0; pi < npanels; pi++) {
+    const int p0 = pi * PB, w = min(PB, m - p0), base = p0 + w;
+    const int nrow = m - base;
+    const int nslab = nrow > 0 ? (nrow + TS - 1) / TS : 0;
+    const int ntiles = nslab * (nslab + 1) / 2;
     if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 4] = clock64();
-    // ------------------------------------------------------------------ phase B: trailing tiles
+    // ------------------------------------------------------------------ phase B: trailing tiles, and on CTA 0
+    // (which owns the tile holding the next diagonal block) the look-ahead factorisation of panel pi+1
     if (nrow > 0) {
-      // L11 (strictly lower) and d of this panel -> shared (A / dloc are reused as scratch by every CTA)
-      for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
-        int r = idx % PB, c = idx / PB;
-        A[r][c] = (r < w && c < w && r > c) ? Lo[(long long)(p0 + c) * ld + p0 + r] : 0.0;
-      }
-      if (tid < PB) {
-        const double dj = (tid < w) ? d[p0 + tid] : 0.0;
-        dloc[tid] = dj;
-        s_lb[tid] = (dj > 0.0) ? 1.0 / dj : 0.0;        // reciprocal pivots (0 marks a skipped pivot)
+      // L11 (strictly lower) and d of this panel -> shared (A / dloc are reused as scratch by every CTA).
+      // The panel CTA factored this block itself a moment ago: A and dloc still hold it.
+      const bool solo = gridDim.x == 1;
+      if (solo || blockIdx.x != 0) {
+        for (int idx = tid; idx < PB * PB; idx += blockDim.x) {
+          int r = idx % PB, c = idx / PB;
+          A[r][c] = (r < w && c < w && r > c) ? Lo[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+        }
+        if (tid < PB) dloc[tid] = (tid < w) ? d[p0 + tid] : 0.0;
       }
       __syncthreads();
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      if (tid < PB) s_lb[tid] = (dloc[tid] > 0.0) ? 1.0 / dloc[tid] : 0.0;        // reciprocal pivots (0 marks a skipped pivot)
+      __syncthreads();
+      // with more than one CTA, CTA 0 is the dedicated panel CTA (look-ahead below) and takes no tile
+      const int t_first = solo ? 0 : (blockIdx.x == 0 ? ntiles : (int)blockIdx.x - 1);
+      const int t_step = solo ? 1 : (int)gridDim.x - 1;
+      for (int t = t_first; t < ntiles; t += t_step) {
         int ti, tj; tile_of(t, ti, tj);
         if (tid < 2 * TS) {
           const bool isB = tid >= TS;
@@ -272,6 +288,7 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
               for (int q = 0; q < 4; q++) acc[i][q] += av[i] * bv[q];
           }
           const int r0 = base + ti * TS, c0 = base + tj * TS;
+          const bool lead_skip = !solo && t == 0;
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const int c = c0 + ty + 16 * q;
@@ -279,18 +296,86 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
 #pragma unroll
               for (int i = 0; i < 4; i++) {
                 const int r = r0 + tx + 16 * i;
-                if (r < m && r >= c) W[(long long)c * ld + r] -= acc[i][q];
+                // the leading PB x PB block of tile 0 belongs to the panel CTA (look-ahead below)
+                if (r < m && r >= c && !(lead_skip && r < base + PB && c < base + PB)) W[(long long)c * ld + r] -= acc[i][q];
               }
             }
           }
         }
         __syncthreads();
       }
+      if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 1] = clock64();
+      if (blockIdx.x == 0 && pi + 1 < npanels) {
+        // look-ahead: factor the next diagonal block while the other CTAs update the trailing matrix.
+        bool pre = false;
+        if (!solo) {
+          // The block is formed here from the not yet updated W (some other CTA updates W itself as part
+          // of tile 0), with the same operation order as the tile code: rows base..base+wn-1 of L21, then
+          // W(blk) - L21 D L21'.
+          const int wn = min(PB, m - base);
+          // all global loads first: 4 panel entries (row r, columns sub+8i) and 4 entries of the block per thread
+          const int rr = tid >> 3, sub = tid & 7;
+          double a[4], vpre[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int c = sub + 8 * i;
+            a[i] = (rr < wn && c < w) ? W[(long long)(p0 + c) * ld + base + rr] : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int idx = tid + 256 * i, r = idx % PB, c = idx / PB;
+            vpre[i] = (r < wn && c < wn && r >= c) ? W[(long long)(base + c) * ld + base + r] : 0.0;
+          }
+          // forward substitution along the row, 8 lanes per row; same operations per element as the tile code
+#pragma unroll
+          for (int j = 0; j < PB; j++) {
+            const double rj = s_lb[j];
+            const double xj = __shfl_sync(0xffffffffu, a[j >> 3], (lane & ~7) | (j & 7));
+            if (rj > 0.0) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int c = sub + 8 * i;
+                if (c > j) a[i] -= xj * A[c][j];
+              }
+              if (sub == (j & 7)) a[j >> 3] = xj * rj;
+            } else if (sub == (j & 7)) a[j >> 3] = 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int c = sub + 8 * i;
+            As[c][rr] = a[i];
+            Bs[c][rr] = a[i] * dloc[c];
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int idx = tid + 256 * i, r = idx % PB, c = idx / PB;
+            double v = 0.0;
+            if (r < wn && c < wn && r >= c) {
+              double acc = 0.0;
+#pragma unroll 8
+              for (int j = 0; j < PB; j++) acc += As[j][r] * Bs[j][c];
+              v = vpre[i] - acc;
+              W[(long long)(base + c) * ld + base + r] = v;      // sole writer of this block (the tile code skips it)
+            }
+            A[r][c] = v;
+          }
+          __syncthreads();
+          pre = true;
+        }
+        const bool ok = phaseA(pi + 1, false, pre);
+        if (!ok && tid == 0) la_fail[pi + 1] = 1u;
+      }
     }
     if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 5] = clock64();
     bar_target += gridDim.x;
     grid_barrier(bar, bar_target);
     if (tdbg && blockIdx.x == 0 && tid == 0) tdbg[pi * 8 + 6] = clock64();
+    if (pi + 1 < npanels && la_fail[pi + 1]) {     // rare: a pivot of the next panel needs the stability test,
+      if (blockIdx.x == 0) phaseA(pi + 1, true, false);   // which reads the fully updated rows below the block
+      bar_target += gridDim.x;
+      grid_barrier(bar, bar_target);
+    }
   }
   // ------------------------------------------------------------------ inverses of the diagonal blocks
   for (int pi = blockIdx.x; pi < npanels; pi += gridDim.x) {
@@ -456,7 +541,7 @@ int dense_factor_prepare(sb200_chol_plan *pl) {
   pl->npanels = (m + PB - 1) / PB;
   SB_TRY(pl->d_work.alloc((size_t)m * m));
   SB_TRY(pl->d_dinv.alloc((size_t)pl->npanels * PB * PB));
-  SB_TRY(pl->d_bar.alloc(4));
+  SB_TRY(pl->d_bar.alloc(4 + (size_t)pl->npanels + 1));
   return 0;
 }
 
@@ -468,13 +553,13 @@ int dense_factor(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb2
   dense_permuteP_kernel<<<m, 256, 0, st>>>(m, pl->d_perm.p, pl->d_Xjc.p, pl->d_Xir.p, Xpr, pl->d_work.p, pl->d_diagX.p);
   SB_LAUNCH_CHECK_N("dense_permuteP_kernel");
   bounds(pl, absd, pars);
-  SB_CUDA(cudaMemsetAsync(pl->d_bar.p, 0, sizeof(unsigned) * 4, st));
+  SB_CUDA(cudaMemsetAsync(pl->d_bar.p, 0, sizeof(unsigned) * (4 + pl->npanels + 1), st));
   // cooperative launch: every CTA must be resident
   int per_sm = 0;
   SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_ldl_kernel, 256, 0));
   SB_CHECK(per_sm >= 1, "dense_ldl_kernel cannot be resident");
   const int nslab = (std::max(m - PB, 0) + TS - 1) / TS;
-  int want = std::max(1, nslab * (nslab + 1) / 2);
+  int want = nslab > 0 ? nslab * (nslab + 1) / 2 + 1 : 1;      // the tiles of the first panel + the panel CTA
   int grid = std::min(want, per_sm * ctx().sm_count);
   double *W = pl->d_work.p, *dinv = pl->d_dinv.p, *lb = pl->d_lb.p, *scal = pl->d_scal.p, *diagX = pl->d_diagX.p, *vs = pl->d_vscratch.p;
   unsigned *bar = pl->d_bar.p;
@@ -493,13 +578,15 @@ int dense_factor(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb2
     std::vector<long long> h(8 * pl->npanels);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), tdbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-    double a = 0, a2 = 0, b1 = 0, bB = 0, b2 = 0, pub = 0;
-    for (int p = 0; p < pl->npanels; p++) {
+    // probes of CTA 0 (the panel CTA): [4] start of phase B(p), [1] look-ahead starts, [2] (slot of panel p+1)
+    // its factorisation is done, [5] published, [6] grid barrier passed
+    double prep = 0, fac = 0, pub = 0, bar = 0;
+    for (int p = 0; p + 1 < pl->npanels; p++) {
       const long long *t = h.data() + 8 * p;
-      a += t[1] - t[0]; a2 += t[2] - t[1]; pub += t[3] - t[2]; b1 += t[4] - t[3]; bB += t[5] - t[4]; b2 += t[6] - t[5];
+      prep += t[1] - t[4]; fac += t[8 + 2] - t[1]; pub += t[5] - t[8 + 2]; bar += t[6] - t[5];
     }
-    fprintf(stderr, "[dense_ldl timing, CTA0 clocks summed over %d panels] load %.0f  factor %.0f  publish %.0f  barrier1 %.0f  phaseB %.0f  barrier2 %.0f  (total %.0f)\n",
-            pl->npanels, a, a2, pub, b1, bB, b2, (double)(h[8 * (pl->npanels - 1) + 6] - h[0]));
+    fprintf(stderr, "[dense_ldl timing, panel CTA clocks summed over %d panels] first panel %.0f  load L11 %.0f  form+factor next block %.0f  publish %.0f  barrier %.0f  (total %.0f)\n",
+            pl->npanels, (double)(h[3] - h[0]), prep, fac, pub, bar, (double)(h[8 * (pl->npanels - 1) + 6] - h[0]));
   }
   return dense_make_transpose(pl, rect);                 // the working copy is dead now: reuse it for L'
 }

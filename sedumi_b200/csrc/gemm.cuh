@@ -40,7 +40,52 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem, int src_bytes) {   // src_bytes 0: zero-fill
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// One operand slab (64 rows x GK k-values) global -> shared, element (i, kk) -> S[kk][i].
+// Fast path: 16-byte copies, no predicates (interior tile, k-slab fully inside the nonzero range,
+// even leading dimension and 16-byte aligned base).  General path: 8-byte copies, zero-filled where
+// the element is out of range or structurally zero.
+__device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const double *g, int ld, int rows, int r0, int K, int k0,
+                                                int tri, const int *gather, bool vec_ok) {
+  const int tid = threadIdx.x;
+  bool fast = vec_ok && (r0 + GT <= rows) && (k0 + GK <= K);
+  if (tri == TRI_K_LE_ROW) fast = fast && (k0 + GK - 1 <= r0);
+  if (tri == TRI_K_GE_ROW) fast = fast && (k0 >= r0 + GT - 1);
+  if (fast) {
+    const int i = (tid & 31) * 2;
+#pragma unroll
+    for (int r = 0; r < GK / 8; r++) {
+      const int kk = (tid >> 5) + 8 * r, k = k0 + kk;
+      const long long col = gather ? gather[k] : k;
+      cp_async_16(&S[kk][i], g + r0 + i + col * ld);
+    }
+  } else {
+    const int i = tid & 63, gi = r0 + i;
+#pragma unroll
+    for (int r = 0; r < GK / 4; r++) {
+      const int kk = (tid >> 6) + 4 * r, k = k0 + kk;
+      bool nz = (k < K) && (gi < rows);
+      if (tri == TRI_K_LE_ROW) nz = nz && (k <= gi);
+      if (tri == TRI_K_GE_ROW) nz = nz && (k >= gi);
+      const double *src = g;
+      if (nz) src = g + gi + (long long)(gather ? gather[k] : k) * ld;
+      cp_async_8(&S[kk][i], src, nz ? 8 : 0);
+    }
+  }
+}
+
 // 256 threads = 8 warps; warp w owns rows [32*(w&1), +32) x cols [16*(w>>1), +16) of the tile.
+// Two-stage cp.async pipeline: slab s+1 is in flight while the DMMAs of slab s run.
 static __global__ void __launch_bounds__(256)
 gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA, const double *baseB,
                double *baseC, const int *gatherBase) {
@@ -50,7 +95,7 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   double *gC = baseC + g.offC;
   const int *gather = (g.gatherOff >= 0) ? gatherBase + g.gatherOff : nullptr;
   const int i0 = tl.ti * GT, c0 = tl.tj * GT;
-  __shared__ double As[GK][GT + 4], Bs[GK][GT + 4];
+  __shared__ __align__(16) double As[2][GK][GT + 4], Bs[2][GK][GT + 4];
   // k-range that can be nonzero for this tile
   int klo = 0, khi = g.K;
   if (g.a_tri == TRI_K_LE_ROW) khi = min(khi, i0 + GT);
@@ -58,6 +103,8 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   if (g.b_tri == TRI_K_LE_ROW) khi = min(khi, c0 + GT);
   if (g.b_tri == TRI_K_GE_ROW) klo = max(klo, c0);
   klo = (klo / GK) * GK;
+  const bool vecA = ((((unsigned long long)gA) & 15) == 0) && ((g.lda & 1) == 0);
+  const bool vecB = ((((unsigned long long)gB) & 15) == 0) && ((g.ldb & 1) == 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16;
   const int qr = lane >> 2, qc = lane & 3;        // fragment coordinates
@@ -66,39 +113,34 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 2; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-  for (int k0 = klo; k0 < khi; k0 += GK) {
-    // stage the slab: element (i, kk) -> As[kk][i]
-    for (int idx = threadIdx.x; idx < GT * GK; idx += 256) {
-      int i = idx % GT, kk = idx / GT;
-      int k = k0 + kk, gi = i0 + i, gc = c0 + i;
-      double av = 0.0, bv = 0.0;
-      if (k < g.K) {
-        if (gi < g.M) {
-          bool nz = (g.a_tri == TRI_NONE) || (g.a_tri == TRI_K_LE_ROW ? k <= gi : k >= gi);
-          if (nz) av = gA[gi + (long long)(gather ? gather[k] : k) * g.lda];
-        }
-        if (gc < g.N) {
-          bool nz = (g.b_tri == TRI_NONE) || (g.b_tri == TRI_K_LE_ROW ? k <= gc : k >= gc);
-          if (nz) bv = gB[gc + (long long)k * g.ldb];
-        }
-      }
-      As[kk][i] = av;
-      Bs[kk][i] = bv;
+  const int nslab = khi > klo ? (khi - klo + GK - 1) / GK : 0;
+  if (nslab > 0) {
+    gemm_stage_slab(As[0], gA, g.lda, g.M, i0, g.K, klo, g.a_tri, gather, vecA);
+    gemm_stage_slab(Bs[0], gB, g.ldb, g.N, c0, g.K, klo, g.b_tri, nullptr, vecB);
+    cp_async_commit();
+  }
+  for (int s = 0; s < nslab; s++) {
+    const int buf = s & 1;
+    cp_async_wait_all();
+    __syncthreads();                               // slab s has landed; everyone is done with slab s-1
+    if (s + 1 < nslab) {
+      const int k0 = klo + (s + 1) * GK;
+      gemm_stage_slab(As[buf ^ 1], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
+      gemm_stage_slab(Bs[buf ^ 1], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
+      cp_async_commit();
     }
-    __syncthreads();
 #pragma unroll
     for (int k4 = 0; k4 < GK; k4 += 4) {
       double af[4], bf[2];
 #pragma unroll
-      for (int a = 0; a < 4; a++) af[a] = As[k4 + qc][wr + 8 * a + qr];     // A frag: row = lane/4, k = lane%4
+      for (int a = 0; a < 4; a++) af[a] = As[buf][k4 + qc][wr + 8 * a + qr];     // A frag: row = lane/4, k = lane%4
 #pragma unroll
-      for (int b = 0; b < 2; b++) bf[b] = Bs[k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
+      for (int b = 0; b < 2; b++) bf[b] = Bs[buf][k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 2; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    __syncthreads();
   }
   // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
 #pragma unroll
