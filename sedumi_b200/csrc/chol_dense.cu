@@ -415,27 +415,41 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// 8 warps.  Warp q owns block rows q, q+8, ... (ascending in solve order).  For its block row it walks the
-// already-solved blocks j; the 32x32 block L(b, j) is staged through a private 2-deep cp.async ring in
-// shared memory, so the global-load latency of block j+1/j+2 hides behind the wait for y_j and the FMAs.
+// Dataflow triangular solve.  A thread-block CLUSTER of CL CTAs x 8 warps works on one right-hand side;
+// warp g of the cluster (g = warp*CL + cta rank) owns block rows g, g+8*CL, ... (ascending in solve order).
+// For its block row it walks the already-solved blocks j; the 32x32 block L(b, j) is staged through a
+// private 2-deep cp.async ring in shared memory, so the global-load latency of block j+1/j+2 hides behind
+// the wait for y_j and the FMAs.  A solved y_b is broadcast into the shared memory of every CTA of the
+// cluster (distributed shared memory) followed by its ready flag, so the consumers poll local shared
+// memory: the dependent chain costs one DSMEM store per block row instead of a trip through L2, and
+// the factor streams through CL SMs instead of one (one CTA pulls ~40 GB/s here; the solve of m=666
+// was bound by exactly that).  CL = 1 is the plain single-CTA kernel.
 // BACKWARD reads the transposed factor, which makes both directions the same coalesced stream.
 static const int SOLVE_WARPS = 8;
-template <bool BACKWARD>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32)
-dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
-                   const double *dscale, const int *flag, const double *lb, int nb) {
+static const int SOLVE_CLUSTER = 8;
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;\n" ::: "memory"); }
+
+template <bool BACKWARD, int CL>
+__device__ __forceinline__ void
+dense_solve_body(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
+                 const double *dscale, const int *flag, const double *lb, int nb) {
   extern __shared__ double smem[];
   double *ys = smem;                                    // m doubles (rounded up to even)
   double *ring = smem + ((m + 1) & ~1);                 // SOLVE_WARPS x 2 x 1024 doubles
   volatile int *ready = (volatile int *)(ring + SOLVE_WARPS * 2 * PB * PB);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double *bb = b + (long long)blockIdx.x * m;
-  double *yy = yout + (long long)blockIdx.x * m;
+  namespace cg = cooperative_groups;
+  unsigned crank = 0;
+  if (CL > 1) crank = cg::this_cluster().block_rank();
+  const int rhs = blockIdx.x / CL;
+  const double *bb = b + (long long)rhs * m;
+  double *yy = yout + (long long)rhs * m;
   const int ld = m;
   double *myring = ring + warp * 2 * PB * PB;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) ready[i] = 0;
   __syncthreads();
-  for (int step = warp; step < nb; step += SOLVE_WARPS) {
+  if (CL > 1) cg::this_cluster().sync();                // nobody writes a remote flag before it is cleared
+  for (int step = warp * CL + (int)crank; step < nb; step += SOLVE_WARPS * CL) {
     const int br = BACKWARD ? (nb - 1 - step) : step;
     const int k0 = br * PB, w = min(PB, m - k0);
     const int nprev = step;                              // number of solved blocks this row depends on
@@ -456,12 +470,22 @@ dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, 
 #pragma unroll
     for (int c = 0; c < PB; c++) di[c] = BACKWARD ? Di[lane * PB + c] : Di[c * PB + lane];
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    if (lane < w) acc0 = BACKWARD ? bb[k0 + lane] : bb[perm[k0 + lane]];
+    // everything the epilogue needs from global memory is fetched now, off the dependent chain
+    int pk = 0;
+    double dk = 1.0;
+    if (lane < w) {
+      pk = perm[k0 + lane];
+      acc0 = BACKWARD ? bb[k0 + lane] : bb[pk];
+      if (!BACKWARD && dscale) {                          // ./d with deninfac's repair of skipped pivots
+        dk = dscale[k0 + lane];
+        if (flag && flag[k0 + lane] == 1 && dk <= lb[k0 + lane]) dk = 1.0;
+      }
+    }
     for (int t = 0; t < nprev; t++) {
       const int j = BACKWARD ? (nb - 1 - t) : t;
       cp_async_wait<1>();                                // group t has landed (only t+1 may be in flight)
       while (ready[j] == 0) { __nanosleep(20); }          // back off: spinning warps starve the shared-memory pipe
-      __threadfence_block();
+      if (CL > 1) fence_cluster(); else __threadfence_block();
       __syncwarp();
       const volatile double *yv = ys + j * PB;
       const double *lv = myring + (t & 1) * PB * PB + lane;
@@ -495,19 +519,39 @@ dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, 
     }
     const double yv = (y0 + y1) + (y2 + y3);
     if (lane < w) {
-      ys[k0 + lane] = yv;
-      if (!BACKWARD) {
-        if (dscale) {                                     // ./d with deninfac's repair of skipped pivots
-          double dk = dscale[k0 + lane];
-          if (flag && flag[k0 + lane] == 1 && dk <= lb[k0 + lane]) dk = 1.0;
-          yy[k0 + lane] = yv / dk;
-        } else yy[k0 + lane] = yv;
-      } else yy[perm[k0 + lane]] = yv;
+      if (CL > 1) {
+#pragma unroll
+        for (int r = 0; r < CL; r++) cg::this_cluster().map_shared_rank(ys, r)[k0 + lane] = yv;
+      } else ys[k0 + lane] = yv;
     }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) ready[br] = 1;
+    if (CL > 1) {
+      fence_cluster();
+      __syncwarp();
+      if (lane < CL) ((volatile int *)cg::this_cluster().map_shared_rank((int *)ready, lane))[br] = 1;
+    } else {
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ready[br] = 1;
+    }
+    if (lane < w) {                                       // the result leaves after the consumers have been released
+      if (!BACKWARD) yy[k0 + lane] = dscale ? yv / dk : yv;
+      else yy[pk] = yv;
+    }
   }
+  if (CL > 1) cg::this_cluster().sync();                // no CTA may exit while peers still write into its shared memory
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32)
+dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
+                   const double *dscale, const int *flag, const double *lb, int nb) {
+  dense_solve_body<BACKWARD, 1>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb);
+}
+template <bool BACKWARD>
+__global__ void __cluster_dims__(SOLVE_CLUSTER, 1, 1) __launch_bounds__(SOLVE_WARPS * 32)
+dense_solve_cluster_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
+                           const double *dscale, const int *flag, const double *lb, int nb) {
+  dense_solve_body<BACKWARD, SOLVE_CLUSTER>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb);
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -621,12 +665,25 @@ static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, 
   size_t shm = sizeof(double) * (((m + 1) & ~1) + SOLVE_WARPS * 2 * PB * PB) + sizeof(int) * nb;
   SB_CHECK(shm <= 200 * 1024, "dense solve: m=%d too large for the shared-memory dataflow kernel", m);
   cudaStream_t st = ctx().stream;
+  static const bool use_cluster = !(getenv("SB200_SOLVE_CLUSTER") && atoi(getenv("SB200_SOLVE_CLUSTER")) == 0);
+  // a cluster only pays when there are block rows for more than one CTA's warps to overlap
+  const bool cl = use_cluster && nb > 2;
   if (backward) {
-    if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    dense_solve_kernel<true><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+    if (cl) {
+      if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      dense_solve_cluster_kernel<true><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+    } else {
+      if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      dense_solve_kernel<true><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+    }
   } else {
-    if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    dense_solve_kernel<false><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+    if (cl) {
+      if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      dense_solve_cluster_kernel<false><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+    } else {
+      if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      dense_solve_kernel<false><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+    }
   }
   SB_LAUNCH_CHECK_N(backward ? "dense_solve_kernel<bw>" : "dense_solve_kernel<fw>");
   return 0;
