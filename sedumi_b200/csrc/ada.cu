@@ -634,7 +634,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
                                                  pl->d_tt_src.p, pl->d_tt_w.p, pl->d_Atpr.p, udsqr_dev, pl->d_ws.p);
     SB_LAUNCH_CHECK_N("build_tt_kernel");
     if (B.ntiles) {
-      gemm_nt_kernel<<<B.ntiles, 256, 0, st>>>(pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
+      gemm_nt_launch(B.ntiles, ctx().sm_count, st, pl->d_descs.p, pl->d_tiles.p + B.tile0, udsqr_dev, pl->d_ws.p, pl->d_ws.p, pl->d_Rlist.p);
       SB_LAUNCH_CHECK_N("gemm_nt_kernel");
     }
     if (B.nsparse) {

@@ -10,8 +10,8 @@
 // the total work, not with the number of problems.
 //
 // FP64 on sm_100a has no tcgen05 kind; the tensor path for doubles is the legacy
-// mma.sync m8n8k4 DMMA, used by the 64x64 tile kernel below (each warp owns a 32x16
-// sub-tile = 4x2 DMMA fragments).  Operands are staged through shared memory.
+// mma.sync m8n8k4 DMMA, used by the 64x64 tile kernel below (each warp owns a 32x32
+// sub-tile = 4x4 DMMA fragments).  Operands are staged through shared memory.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -34,6 +34,7 @@ struct GemmTile { int prob, ti, tj; };
 
 static const int GT = 64;     // tile edge
 static const int GK = 16;     // k-slab
+// threads per tile: 128 * KG (KG k-groups of 4 warps; each warp owns a 32x32 sub-tile = 4x4 DMMA fragments)
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -55,6 +56,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Fast path: 16-byte copies, no predicates (interior tile, k-slab fully inside the nonzero range,
 // even leading dimension and 16-byte aligned base).  General path: 8-byte copies, zero-filled where
 // the element is out of range or structurally zero.
+template <int KG>
 __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const double *g, int ld, int rows, int r0, int K, int k0,
                                                 int tri, const int *gather, bool vec_ok) {
   const int tid = threadIdx.x;
@@ -64,16 +66,16 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
   if (fast) {
     const int i = (tid & 31) * 2;
 #pragma unroll
-    for (int r = 0; r < GK / 8; r++) {
-      const int kk = (tid >> 5) + 8 * r, k = k0 + kk;
+    for (int r = 0; r < GK / (4 * KG); r++) {
+      const int kk = (tid >> 5) + 4 * KG * r, k = k0 + kk;
       const long long col = gather ? gather[k] : k;
       cp_async_16(&S[kk][i], g + r0 + i + col * ld);
     }
   } else {
     const int i = tid & 63, gi = r0 + i;
 #pragma unroll
-    for (int r = 0; r < GK / 4; r++) {
-      const int kk = (tid >> 6) + 4 * r, k = k0 + kk;
+    for (int r = 0; r < GK / (2 * KG); r++) {
+      const int kk = (tid >> 6) + 2 * KG * r, k = k0 + kk;
       bool nz = (k < K) && (gi < rows);
       if (tri == TRI_K_LE_ROW) nz = nz && (k <= gi);
       if (tri == TRI_K_GE_ROW) nz = nz && (k >= gi);
@@ -84,9 +86,15 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
   }
 }
 
-// 256 threads = 8 warps; warp w owns rows [32*(w&1), +32) x cols [16*(w>>1), +16) of the tile.
+// KG = 2: 256 threads = 2 k-groups x 4 warps; warp w owns rows [32*(w&1), +32) x cols [32*((w>>1)&1), +32) of the
+// tile (16 DMMAs per 8 shared-memory fragment loads) and, inside every k-slab, the k4-steps of its
+// k-group (w>>2); the two partial tiles are added through shared memory at the end.  Splitting k inside
+// the CTA keeps 8 warps busy per tile: the per-block products here often have fewer tiles than the GPU
+// has SMs (ncu, n=1000: 256 tiles, 9 % warp occupancy with 4 warps per tile).
+// KG = 1 (128 threads, no split) is used when a launch has tiles to spare: more CTAs per SM.
 // Two-stage cp.async pipeline: slab s+1 is in flight while the DMMAs of slab s run.
-static __global__ void __launch_bounds__(256)
+template <int KG>
+static __global__ void __launch_bounds__(128 * KG)
 gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA, const double *baseB,
                double *baseC, const int *gatherBase) {
   const GemmTile tl = tiles[blockIdx.x];
@@ -106,17 +114,17 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   const bool vecA = ((((unsigned long long)gA) & 15) == 0) && ((g.lda & 1) == 0);
   const bool vecB = ((((unsigned long long)gB) & 15) == 0) && ((g.ldb & 1) == 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16;
+  const int wr = (warp & 1) * 32, wc = ((warp >> 1) & 1) * 32, kgrp = warp >> 2;
   const int qr = lane >> 2, qc = lane & 3;        // fragment coordinates
-  double acc[4][2][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
-    for (int b = 0; b < 2; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
   const int nslab = khi > klo ? (khi - klo + GK - 1) / GK : 0;
   if (nslab > 0) {
-    gemm_stage_slab(As[0], gA, g.lda, g.M, i0, g.K, klo, g.a_tri, gather, vecA);
-    gemm_stage_slab(Bs[0], gB, g.ldb, g.N, c0, g.K, klo, g.b_tri, nullptr, vecB);
+    gemm_stage_slab<KG>(As[0], gA, g.lda, g.M, i0, g.K, klo, g.a_tri, gather, vecA);
+    gemm_stage_slab<KG>(Bs[0], gB, g.ldb, g.N, c0, g.K, klo, g.b_tri, nullptr, vecB);
     cp_async_commit();
   }
   for (int s = 0; s < nslab; s++) {
@@ -125,28 +133,64 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
     __syncthreads();                               // slab s has landed; everyone is done with slab s-1
     if (s + 1 < nslab) {
       const int k0 = klo + (s + 1) * GK;
-      gemm_stage_slab(As[buf ^ 1], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
-      gemm_stage_slab(Bs[buf ^ 1], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
+      gemm_stage_slab<KG>(As[buf ^ 1], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
+      gemm_stage_slab<KG>(Bs[buf ^ 1], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
       cp_async_commit();
     }
 #pragma unroll
-    for (int k4 = 0; k4 < GK; k4 += 4) {
-      double af[4], bf[2];
+    for (int kq = 0; kq < GK; kq += 4 * KG) {
+      const int k4 = kq + 4 * kgrp;
+      double af[4], bf[4];
 #pragma unroll
       for (int a = 0; a < 4; a++) af[a] = As[buf][k4 + qc][wr + 8 * a + qr];     // A frag: row = lane/4, k = lane%4
 #pragma unroll
-      for (int b = 0; b < 2; b++) bf[b] = Bs[buf][k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
+      for (int b = 0; b < 4; b++) bf[b] = Bs[buf][k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
   }
+  // add the two k-groups: group 1 parks its partial tile in the (now idle) staging buffers
+  if (KG == 2) {
+    __syncthreads();
+    double *red = &As[0][0][0];                      // 2*GK*(GT+4) doubles >= 4 warps x 32 lanes x 16 values
+    const int slot = (warp & 3) * 32 + lane;          // value v of thread t lives at [v*128 + t]: conflict-free
+    if (kgrp == 1) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) { red[(a * 4 + b) * 128 + slot] = acc[a][b][0]; }
+    }
+    __syncthreads();
+    if (kgrp == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] += red[(a * 4 + b) * 128 + slot];
+    }
+    __syncthreads();
+    double *red2 = &Bs[0][0][0];
+    if (kgrp == 1) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) { red2[(a * 4 + b) * 128 + slot] = acc[a][b][1]; }
+    }
+    __syncthreads();
+    if (kgrp == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][1] += red2[(a * 4 + b) * 128 + slot];
+    }
+  }
+  if (kgrp != 0) return;
   // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
-    for (int b = 0; b < 2; b++)
+    for (int b = 0; b < 4; b++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         int gi = i0 + wr + 8 * a + qr, gc = c0 + wc + 8 * b + 2 * qc + e;
@@ -156,6 +200,14 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
           *p = g.accumulate ? (*p + v) : v;
         }
       }
+}
+
+// Launch: one CTA per tile; the k-split variant when the launch cannot fill the GPU otherwise.
+static inline void gemm_nt_launch(int ntiles, int sm_count, cudaStream_t st, const GemmDesc *descs, const GemmTile *tiles,
+                                  const double *baseA, const double *baseB, double *baseC, const int *gatherBase) {
+  if (ntiles <= 0) return;
+  if (ntiles >= 6 * sm_count) gemm_nt_kernel<1><<<ntiles, 128, 0, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  else gemm_nt_kernel<2><<<ntiles, 256, 0, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
 }
 
 // Host helper: append the tiles of one problem to a tile list.

@@ -315,7 +315,7 @@ int sb200_invcholfac_dev(sb200_psd_plan *pl, const double *u_dev, const int *per
   tri_transpose_kernel<<<dim3(std::min(1024, ((pl->maxn + 31) / 32) * ((pl->maxn + 31) / 32)), pl->nblk), dim3(32, 8), 0, st>>>(
       pl->d_n.p, pl->d_off.p, u_dev, pl->d_Tt.p, 1);
   SB_LAUNCH_CHECK_N("tri_transpose_kernel");
-  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_ichol.p, pl->d_tiles_lower.p, pl->d_Tt.p, pl->d_Tt.p,
+  gemm_nt_launch(pl->ntiles_lower, ctx().sm_count, st, pl->d_desc_ichol.p, pl->d_tiles_lower.p, pl->d_Tt.p, pl->d_Tt.p,
                                                    pl->d_Wt.p, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   perm_block_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, perm_dev, pl->d_Wt.p, y_dev, 0, 1);
@@ -353,11 +353,11 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
     SB_LAUNCH_CHECK_N("perm_block_kernel");
     xs = pl->d_Xp.p;
   }
-  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s1_up : pl->d_desc_s1_lo).p, pl->d_tiles_full.p,
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, (transp ? pl->d_desc_s1_up : pl->d_desc_s1_lo).p, pl->d_tiles_full.p,
                                                   pl->d_Tt.p, xs, pl->d_Wt.p, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   bool postp = perm_dev && transp;
-  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>((transp ? pl->d_desc_s2_up : pl->d_desc_s2_lo).p, pl->d_tiles_full.p,
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, (transp ? pl->d_desc_s2_up : pl->d_desc_s2_lo).p, pl->d_tiles_full.p,
                                                   pl->d_Tt.p, pl->d_Wt.p, postp ? pl->d_Y.p : y_dev, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   if (postp) {                         // XX(PP,PP) = XX   (psdscale.m:104-109)
@@ -438,7 +438,7 @@ int sb200_psdframeit_dev(sb200_psd_plan *pl, const double *lab_dev, const double
   // B(c,k) = lab_k * Qb(k,c): transpose of Q with the k-index scaled -> d_Xp
   transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, lab_dev, pl->d_Xp.p);
   SB_LAUNCH_CHECK_N("transpose_scale_kernel");
-  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Wt.p, pl->d_Xp.p, x_dev, nullptr);
+  gemm_nt_launch(pl->ntiles_lower, ctx().sm_count, st, pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Wt.p, pl->d_Xp.p, x_dev, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, x_dev, x_dev, nullptr, 0);
   SB_LAUNCH_CHECK_N("sym_ops_kernel");
@@ -454,18 +454,18 @@ int sb200_psdinvjmul_dev(sb200_psd_plan *pl, const double *xlab_dev, const doubl
   sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, y_dev, pl->d_Y.p, nullptr, 1);   // Ys from tril(Y)
   SB_LAUNCH_CHECK_N("sym_ops_kernel");
   // P = Q Ys           (A = Q, B = Ys symmetric)            -> d_Xp
-  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>(pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   // M = P Q' (lower)   (A = P, B = Q)                       -> d_Y
-  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Tt.p, pl->d_Y.p, nullptr);
+  gemm_nt_launch(pl->ntiles_lower, ctx().sm_count, st, pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Tt.p, pl->d_Y.p, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Y.p, pl->d_Y.p, xlab_dev, 2);
   SB_LAUNCH_CHECK_N("sym_ops_kernel");
   // R = Q' M           (A = Q', B = M symmetric)            -> d_Xp
-  gemm_nt_kernel<<<pl->ntiles_full, 256, 0, st>>>(pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Wt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Wt.p, pl->d_Y.p, pl->d_Xp.p, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   // Z = R Q (lower)    (A = R, B = Q')                      -> z
-  gemm_nt_kernel<<<pl->ntiles_lower, 256, 0, st>>>(pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Wt.p, z_dev, nullptr);
+  gemm_nt_launch(pl->ntiles_lower, ctx().sm_count, st, pl->d_desc_lower.p, pl->d_tiles_lower.p, pl->d_Xp.p, pl->d_Wt.p, z_dev, nullptr);
   SB_LAUNCH_CHECK_N("gemm_nt_kernel");
   sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, z_dev, z_dev, nullptr, 0);
   SB_LAUNCH_CHECK_N("sym_ops_kernel");
