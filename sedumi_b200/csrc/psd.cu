@@ -33,6 +33,19 @@ struct sb200_psd_plan {
   int nqgroups = 0;
   sb::DevBuf<sb::GemmTile> d_tiles_full, d_tiles_lower;
   int ntiles_full = 0, ntiles_lower = 0;
+  // blocked (compact WY) Householder accumulation for large blocks: step s handles panel P_k-1-s of
+  // every block that still has one; three GEMM launches per step
+  bool wy = false;            // GEMM-based WY (blocks too large for wy_rows_kernel's shared memory)
+  bool wy_rows = false;       // wy_rows_kernel
+  size_t wy_rows_smem = 0;
+  int wy_steps = 0, wy_npanels = 0;
+  struct WyStep { int d1, d2, d3; int t1, n1, t2, n2, t3, n3; };   // descriptor / tile ranges per step
+  std::vector<WyStep> wy_sched;
+  sb::DevBuf<sb::GemmDesc> d_wy_desc;
+  sb::DevBuf<sb::GemmTile> d_wy_tiles;
+  sb::DevBuf<int> d_wy_pblk, d_wy_pidx;          // per panel: block, panel index
+  sb::DevBuf<long long> d_wy_toff;               // per block: offset of its first T (32x32 each)
+  sb::DevBuf<double> d_wy_T, d_wy_Y, d_wy_Y2;
   // workspaces (lenud doubles each)
   sb::DevBuf<double> d_Tt, d_Wt, d_Xp, d_Y;
   sb::DevBuf<int> d_perm;
@@ -111,6 +124,164 @@ householder_q_kernel(const int *grp_blk, const int *grp_j0, const int *ns, const
     for (int i = c + lane; i < n; i += 32) q[i] += a * v[i];
     __syncwarp();
   }
+}
+
+// ---- compact-WY pieces (blocks too large for the one-warp-per-column kernel above).
+// T_p^{-1} = striu(V_p' V_p) + diag(beta_p) for panel p (32 reflectors) of a block; exact for any beta:
+// (I - V T V')(I - v v'/b) = I - [V v] [[T, -T V'v/b],[0, 1/b]] [V v]'.   One CTA per (block, panel).
+static const int WYB = 32;
+__global__ void __launch_bounds__(256)
+wy_t_kernel(const int *pblk, const int *pidx, const int *ns, const long long *offs, const long long *toff,
+            const double *frms, double *Tall) {
+  const int k = pblk[blockIdx.x], p = pidx[blockIdx.x];
+  const int n = ns[k];
+  const double *F = frms + offs[k];
+  const double *beta = F + (long long)n * n - n;
+  const int c0 = p * WYB, bp = min(WYB, n - 1 - c0);
+  __shared__ double U[WYB][WYB + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int idx = threadIdx.x; idx < WYB * WYB; idx += blockDim.x) U[idx / WYB][idx % WYB] = 0.0;
+  __syncthreads();
+  for (int pr = warp; pr < bp * bp; pr += 8) {
+    const int a = pr / bp, b = pr % bp;
+    if (a >= b) continue;
+    const double *va = F + (long long)(c0 + a) * n, *vb = F + (long long)(c0 + b) * n;
+    double t = 0.0;
+    for (int r = c0 + b + lane; r < n; r += 32) t += va[r] * vb[r];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) U[a][b] = t;
+  }
+  if (threadIdx.x < bp) U[threadIdx.x][threadIdx.x] = beta[c0 + threadIdx.x];
+  __syncthreads();
+  // T = inv(U), U upper triangular: lane j solves U t = e_j from the bottom up
+  double *T = Tall + (toff[k] + p) * WYB * WYB;
+  if (warp == 0) {
+    const int j = lane;
+    double t[WYB];
+#pragma unroll
+    for (int i = 0; i < WYB; i++) t[i] = 0.0;
+    if (j < bp) {
+#pragma unroll
+      for (int i = WYB - 1; i >= 0; i--) {
+        if (i < bp && i <= j) {
+          double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int q = 0; q < WYB; q++) if (q > i && q <= j) acc -= U[i][q] * t[q];
+          t[i] = acc / U[i][i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < WYB; i++) T[i + j * WYB] = t[i];     // column-major 32x32, zero padded
+  }
+}
+
+// Q from the panels' T factors, eight columns of Q per CTA.  Row i of R = Q' evolves independently of the
+// others:  r <- r - ((r V_p) T_p') V_p'  for p = last..0, so a CTA keeps its 8 rows of R in shared memory
+// and streams each panel V_p (rows c0..n-1, 32 reflectors) twice through a double-buffered cp.async
+// ring: once for Y = R V_p, once for R -= (Y T_p') V_p'.  Compared with one warp per column applying the
+// reflectors one by one, the 8 columns share every load of V (8x less L2 traffic, which bounded that
+// kernel: 2.7 ms per call at n=1000) and the dot/axpy pairs become two small matrix products.
+static const int WY_RW = 8, WY_CH = 128;
+__global__ void __launch_bounds__(256)
+wy_rows_kernel(const int *grp_blk, const int *grp_j0, const int *ns, const long long *offs, const long long *toff,
+               const double *frms, const double *Tall, double *Q) {
+  extern __shared__ double wy_sm[];
+  const int k = grp_blk[blockIdx.x], i0 = grp_j0[blockIdx.x];
+  const int n = ns[k];
+  const int nld = (n + 1) & ~1;
+  double *Rs = wy_sm;                                              // [WY_RW][nld]
+  double (*Vs)[WY_CH][WYB + 1] = (double (*)[WY_CH][WYB + 1])(Rs + WY_RW * nld);   // [2][CH][33]
+  double *Ys = (double *)(Vs + 2);                                 // [WY_RW][WYB]
+  double *Y2s = Ys + WY_RW * WYB;
+  double (*Ts)[WYB + 1] = (double (*)[WYB + 1])(Y2s + WY_RW * WYB);
+  const double *F = frms + offs[k];
+  const int tid = threadIdx.x, ti = tid >> 5, tc = tid & 31;
+  for (int idx = tid; idx < WY_RW * nld; idx += blockDim.x) {
+    const int i = idx / nld, r = idx % nld;
+    Rs[idx] = (r == i0 + i && r < n) ? 1.0 : 0.0;
+  }
+  const int P = (n - 1 + WYB - 1) / WYB;
+  const int pstart = min(P - 1, (min(i0 + WY_RW, n) - 1) / WYB);   // later panels leave these unit rows alone
+  for (int p = pstart; p >= 0; p--) {
+    const int c0 = p * WYB, bp = min(WYB, n - 1 - c0);
+    const int nch = (n - c0 + WY_CH - 1) / WY_CH;
+    auto stage = [&](int buf, int r0) {
+      const int rr = tid & (WY_CH - 1), r = r0 + rr;
+#pragma unroll
+      for (int q = 0; q < WYB / 2; q++) {
+        const int c = (tid >> 7) + 2 * q;
+        const bool valid = (c < bp) && (r < n) && (r >= c0 + c);
+        cp_async_8(&Vs[buf][rr][c], valid ? F + r + (long long)(c0 + c) * n : F, valid ? 8 : 0);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();                                 // previous panel (or the initialisation) is complete
+    const double *T = Tall + (toff[k] + p) * WYB * WYB;
+    for (int idx = tid; idx < WYB * WYB; idx += blockDim.x) Ts[idx % WYB][idx / WYB] = T[idx];    // Ts[c][kk] = T(c,kk)
+    // ---- Y = R V_p
+    double acc = 0.0;
+    stage(0, c0);
+    for (int ch = 0; ch < nch; ch++) {
+      cp_async_wait_all();
+      __syncthreads();
+      if (ch + 1 < nch) stage((ch + 1) & 1, c0 + (ch + 1) * WY_CH);
+      const int r0 = c0 + ch * WY_CH, lim = min(WY_CH, n - r0);
+      const double *rrow = Rs + ti * nld + r0;
+      const double (*V)[WYB + 1] = Vs[ch & 1];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int rr = 0;
+      for (; rr + 3 < lim; rr += 4) {
+        a0 += rrow[rr] * V[rr][tc]; a1 += rrow[rr + 1] * V[rr + 1][tc];
+        a2 += rrow[rr + 2] * V[rr + 2][tc]; a3 += rrow[rr + 3] * V[rr + 3][tc];
+      }
+      for (; rr < lim; rr++) a0 += rrow[rr] * V[rr][tc];
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    Ys[ti * WYB + tc] = acc;
+    __syncthreads();
+    // ---- Y2 = Y T_p'
+    {
+      double y2 = 0.0;
+#pragma unroll 8
+      for (int kk = 0; kk < WYB; kk++) y2 += Ys[ti * WYB + kk] * Ts[tc][kk];
+      Y2s[ti * WYB + tc] = y2;
+    }
+    __syncthreads();
+    // ---- R -= Y2 V_p'
+    stage(0, c0);
+    for (int ch = 0; ch < nch; ch++) {
+      cp_async_wait_all();
+      __syncthreads();
+      if (ch + 1 < nch) stage((ch + 1) & 1, c0 + (ch + 1) * WY_CH);
+      const int r0 = c0 + ch * WY_CH;
+      const double (*V)[WYB + 1] = Vs[ch & 1];
+      const double *y2 = Y2s + ti * WYB;
+#pragma unroll
+      for (int q = 0; q < WY_CH / 32; q++) {
+        const int rr = tc + 32 * q;
+        if (r0 + rr < n) {
+          double sacc = 0.0;
+#pragma unroll 8
+          for (int c = 0; c < WYB; c++) sacc += y2[c] * V[rr][c];
+          Rs[ti * nld + r0 + rr] -= sacc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (i0 + ti < n) {
+    double *q = Q + offs[k] + (long long)(i0 + ti) * n;
+    for (int r = tc; r < n; r += 32) q[r] = Rs[ti * nld + r];
+  }
+}
+
+__global__ void set_identity_kernel(const int *ns, const long long *offs, double *R) {
+  const int n = ns[blockIdx.y];
+  double *A = R + offs[blockIdx.y];
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x)
+    A[idx] = (idx % n == idx / n) ? 1.0 : 0.0;
 }
 
 // out = transpose(in) per block, optionally scaling row k of the result's k-index:  out(c,k) = in(k,c) * (lab ? lab[k] : 1)
@@ -269,6 +440,72 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
     gemm_add_tiles(tlower, k, nk, nk, true);
   }
   pl->ntiles_full = (int)tfull.size(); pl->ntiles_lower = (int)tlower.size();
+  // ---- compact-WY schedule
+  {
+    const int nld = (pl->maxn + 1) & ~1;
+    pl->wy_rows_smem = sizeof(double) * ((size_t)WY_RW * nld + 2 * WY_CH * (WYB + 1) + 2 * WY_RW * WYB + WYB * (WYB + 1));
+    // small blocks: the one-warp-per-column kernel is a single short launch (47 us at n=70 against 65 us
+    // for T factors + row kernel)
+    pl->wy_rows = pl->maxn > 96 && pl->wy_rows_smem <= 220 * 1024;
+    pl->wy = pl->maxn > 96 && !pl->wy_rows;
+  }
+  if (pl->wy || pl->wy_rows) {
+    std::vector<GemmDesc> wd;
+    std::vector<GemmTile> wt;
+    std::vector<int> pblk, pidx;
+    std::vector<long long> toff(pl->nblk, 0), yoff(pl->nblk, 0);
+    long long tcount = 0, ycount = 0;
+    int maxP = 0;
+    for (int k = 0; k < pl->nblk; k++) {
+      const int nk = pl->n[k], P = (nk - 1 + WYB - 1) / WYB;
+      toff[k] = tcount; yoff[k] = ycount;
+      for (int p2 = 0; p2 < P; p2++) { pblk.push_back(k); pidx.push_back(p2); }
+      tcount += P; ycount += (long long)nk * WYB;
+      maxP = std::max(maxP, P);
+    }
+    pl->wy_npanels = (int)pblk.size(); pl->wy_steps = maxP;
+    for (int st = 0; st < maxP; st++) {
+      sb200_psd_plan::WyStep W{};
+      std::vector<GemmDesc> g1, g2, g3;
+      std::vector<GemmTile> t1, t2, t3;
+      for (int k = 0; k < pl->nblk; k++) {
+        const int nk = pl->n[k], P = (nk - 1 + WYB - 1) / WYB;
+        const int p2 = P - 1 - st;
+        if (p2 < 0) continue;
+        const int c0 = p2 * WYB, bp = std::min(WYB, nk - 1 - c0), np = nk - c0;
+        const long long sub = pl->off[k] + c0 + (long long)c0 * nk;      // (c0, c0) corner inside the block
+        GemmDesc a{}; a.gatherOff = -1; a.alpha = 1.0;
+        // Y(i,c) = sum_r R(i,r) V(r,c):  A = R sub-block, B = F' rows c (k >= row mask)
+        a.offA = sub; a.lda = nk; a.a_tri = TRI_NONE;
+        a.offB = sub; a.ldb = nk; a.b_tri = TRI_K_GE_ROW;
+        a.offC = yoff[k]; a.ldc = nk; a.M = np; a.N = bp; a.K = np; a.lower = 0; a.accumulate = 0;
+        gemm_add_tiles(t1, (int)g1.size(), np, bp, false); g1.push_back(a);
+        // Y2 = Y T'
+        GemmDesc b{}; b.gatherOff = -1; b.alpha = 1.0;
+        b.offA = yoff[k]; b.lda = nk; b.a_tri = TRI_NONE;
+        b.offB = (toff[k] + p2) * WYB * WYB; b.ldb = WYB; b.b_tri = TRI_NONE;
+        b.offC = yoff[k]; b.ldc = nk; b.M = np; b.N = bp; b.K = bp; b.lower = 0; b.accumulate = 0;
+        gemm_add_tiles(t2, (int)g2.size(), np, bp, false); g2.push_back(b);
+        // R(i,r) -= sum_c Y2(i,c) V(r,c):  B = F rows r (k <= row mask)
+        GemmDesc c{}; c.gatherOff = -1; c.alpha = -1.0;
+        c.offA = yoff[k]; c.lda = nk; c.a_tri = TRI_NONE;
+        c.offB = sub; c.ldb = nk; c.b_tri = TRI_K_LE_ROW;
+        c.offC = sub; c.ldc = nk; c.M = np; c.N = np; c.K = bp; c.lower = 0; c.accumulate = 1;
+        gemm_add_tiles(t3, (int)g3.size(), np, np, false); g3.push_back(c);
+      }
+      auto push = [&](std::vector<GemmDesc> &g, std::vector<GemmTile> &t, int &d0, int &tt0, int &nt) {
+        d0 = (int)wd.size(); tt0 = (int)wt.size(); nt = (int)t.size();
+        for (auto &x : t) x.prob += d0;
+        wd.insert(wd.end(), g.begin(), g.end()); wt.insert(wt.end(), t.begin(), t.end());
+      };
+      push(g1, t1, W.d1, W.t1, W.n1); push(g2, t2, W.d2, W.t2, W.n2); push(g3, t3, W.d3, W.t3, W.n3);
+      pl->wy_sched.push_back(W);
+    }
+    SB_TRY(pl->d_wy_desc.upload(wd)); SB_TRY(pl->d_wy_tiles.upload(wt));
+    SB_TRY(pl->d_wy_pblk.upload(pblk)); SB_TRY(pl->d_wy_pidx.upload(pidx)); SB_TRY(pl->d_wy_toff.upload(toff));
+    SB_TRY(pl->d_wy_T.alloc((size_t)tcount * WYB * WYB));
+    SB_TRY(pl->d_wy_Y.alloc((size_t)ycount)); SB_TRY(pl->d_wy_Y2.alloc((size_t)ycount));
+  }
   SB_TRY(pl->d_n.upload(pl->n)); SB_TRY(pl->d_off.upload(pl->off)); SB_TRY(pl->d_poff.upload(pl->poff));
   SB_TRY(pl->d_desc_ichol.upload(ichol));
   SB_TRY(pl->d_desc_s1_lo.upload(s1lo)); SB_TRY(pl->d_desc_s1_up.upload(s1up));
@@ -420,9 +657,42 @@ int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *
 // ---- Householder-frame operations.  frms_dev: lenud doubles (real blocks); lab/xlab: sum(n_k) doubles.
 static int build_q(sb200_psd_plan *pl, const double *frms_dev) {   // Q -> d_Tt, Q' -> d_Wt
   cudaStream_t st = ctx().stream;
+  int tp = (pl->maxn + 31) / 32;
+  if (pl->wy_rows) {
+    wy_t_kernel<<<pl->wy_npanels, 256, 0, st>>>(pl->d_wy_pblk.p, pl->d_wy_pidx.p, pl->d_n.p, pl->d_off.p, pl->d_wy_toff.p, frms_dev, pl->d_wy_T.p);
+    SB_LAUNCH_CHECK_N("wy_t_kernel");
+    static bool attr_done = false;
+    if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(wy_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_done = true; }
+    wy_rows_kernel<<<pl->nqgroups, 256, pl->wy_rows_smem, st>>>(pl->d_qcol_blk.p, pl->d_qcol_j0.p, pl->d_n.p, pl->d_off.p, pl->d_wy_toff.p,
+                                                                frms_dev, pl->d_wy_T.p, pl->d_Tt.p);
+    SB_LAUNCH_CHECK_N("wy_rows_kernel");
+    transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, nullptr, pl->d_Wt.p);
+    SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+    return 0;
+  }
+  if (pl->wy) {
+    // R = Q' accumulated right to left, panel by panel:  R <- R (I - V_p T_p V_p')' = R - (R V_p) T_p' V_p'
+    wy_t_kernel<<<pl->wy_npanels, 256, 0, st>>>(pl->d_wy_pblk.p, pl->d_wy_pidx.p, pl->d_n.p, pl->d_off.p, pl->d_wy_toff.p, frms_dev, pl->d_wy_T.p);
+    SB_LAUNCH_CHECK_N("wy_t_kernel");
+    transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, frms_dev, nullptr, pl->d_Xp.p);   // F'
+    SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+    set_identity_kernel<<<dim3((unsigned)std::min<long long>(((long long)pl->maxn * pl->maxn + 255) / 256, 1024), pl->nblk), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_Wt.p);
+    SB_LAUNCH_CHECK_N("set_identity_kernel");
+    for (auto &W : pl->wy_sched) {
+      // descriptors carry absolute indices into d_wy_desc; tiles reference them
+      gemm_nt_launch(W.n1, ctx().sm_count, st, pl->d_wy_desc.p, pl->d_wy_tiles.p + W.t1, pl->d_Wt.p, pl->d_Xp.p, pl->d_wy_Y.p, nullptr);
+      SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+      gemm_nt_launch(W.n2, ctx().sm_count, st, pl->d_wy_desc.p, pl->d_wy_tiles.p + W.t2, pl->d_wy_Y.p, pl->d_wy_T.p, pl->d_wy_Y2.p, nullptr);
+      SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+      gemm_nt_launch(W.n3, ctx().sm_count, st, pl->d_wy_desc.p, pl->d_wy_tiles.p + W.t3, pl->d_wy_Y2.p, frms_dev, pl->d_Wt.p, nullptr);
+      SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+    }
+    transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Wt.p, nullptr, pl->d_Tt.p);
+    SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+    return 0;
+  }
   householder_q_kernel<<<pl->nqgroups, 256, 0, st>>>(pl->d_qcol_blk.p, pl->d_qcol_j0.p, pl->d_n.p, pl->d_off.p, frms_dev, pl->d_Tt.p);
   SB_LAUNCH_CHECK_N("householder_q_kernel");
-  int tp = (pl->maxn + 31) / 32;
   transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, nullptr, pl->d_Wt.p);
   SB_LAUNCH_CHECK_N("transpose_scale_kernel");
   return 0;

@@ -20,7 +20,7 @@ def _frames(K, seed):
     return ref.qrK(x, cones.K_for_mex(K))            # vfrm.s layout: reflectors + beta column
 
 
-@pytest.mark.parametrize("s", [(1,), (2,), (7,), (33, 5), (70, 35), (130,)])
+@pytest.mark.parametrize("s", [(1,), (2,), (7,), (33, 5), (70, 35), (130,), (200, 40), (257,), (129, 2, 161)])
 def test_psdframeit(s):
     K = _K(s)
     Km = cones.K_for_mex(K)
@@ -35,7 +35,7 @@ def test_psdframeit(s):
     assert relerr(gpu.psdframeit(labfull, frms, Km), xr) <= 1e-10
 
 
-@pytest.mark.parametrize("s", [(1,), (6,), (40, 9), (70, 35), (100,)])
+@pytest.mark.parametrize("s", [(1,), (6,), (40, 9), (70, 35), (100,), (150, 20)])
 def test_psdinvjmul(s):
     K = _K(s)
     Km = cones.K_for_mex(K)
