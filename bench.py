@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 NSOLVE, NPSD = 4, 12
 FRAMES = (np.zeros(0), np.zeros(0))
+LOR = None
 METRIC = "IPM iterations/sec (ADA'+Cholesky+solve) over the hot-path recipe"
 
 
@@ -37,6 +38,8 @@ def load_workload(name):
         raw = problems.load_fixture("control07")
     elif name == "arch0":
         raw = problems.load_fixture("arch0")
+    elif name == "nb":
+        raw = problems.load_fixture("nb")           # BASELINE configs[2]: 793 Lorentz cones, no PSD block
     elif name == "blockdiag64":
         raw = problems.synth_blockdiag_sdp()
     elif name == "maxcut4000":
@@ -54,8 +57,11 @@ def load_workload(name):
     rng = np.random.default_rng(problems.SEED0)
     rhs = rng.standard_normal((S.m, 1))
     psd_x = rng.standard_normal(int((np.asarray(K["s"]) ** 2).sum()))
-    global FRAMES
+    global FRAMES, LOR
     FRAMES = problems.synth_frames(K["s"])         # (lab, frms): product-form spectral factor of the PSD iterate
+    nq, qd = len(K["q"]), int((np.asarray(K["q"]) - 1).sum()) if len(K["q"]) else 0
+    LOR = (rng.standard_normal(nq), rng.standard_normal(qd), rng.standard_normal(S.m), 1e-17 * rng.standard_normal(S.m),
+           rng.standard_normal(S.m))                # mu, x(norm-bound part), residual hi/lo/increment for the Lorentz streams
     return S, d, rhs, psd_x
 
 
@@ -172,16 +178,22 @@ def run_reference(S, d, rhs, psd_x, steps, warmup):
     t0 = time.perf_counter()
     t_np = 0.0
     for _ in range(steps):
+        t1 = time.perf_counter()
+        m0 = R.mex.mex_seconds()
         udsqr, ADA, absd = R.assemble(d)
+        if not len(S.K["s"]):                        # getada.m restated in numpy: count it (minus the MEX time inside it)
+            t_np += (time.perf_counter() - t1) - (R.mex.mex_seconds() - m0)
         L = R.factor(ADA, absd)
         for _ in range(NSOLVE):
             R.solve(L, rhs)
-        t1 = time.perf_counter()
-        for i in range(NPSD):
-            ps = R.psdscale(d, psd_x, i & 1)
-        t_np += time.perf_counter() - t1
         if len(S.K["s"]):
+            t1 = time.perf_counter()
+            for i in range(NPSD):
+                ps = R.psdscale(d, psd_x, i & 1)
+            t_np += time.perf_counter() - t1
             R.scaling_tail(d, FRAMES[0], FRAMES[1], np.asarray(ps).ravel())
+        else:
+            R.lorentz_streams(d, LOR[0], LOR[1], LOR[2], LOR[3], LOR[4])
     wall = time.perf_counter() - t0
     t_mex = R.mex.mex_seconds() - t_mex0
     # time inside the reference's mexFunctions + the restated M pieces; harness marshalling excluded
@@ -257,6 +269,9 @@ def main():
         hp.set_rhs(rhs)
         hp.psd_x[:psd_x.size].copy_(torch.from_numpy(psd_x))
         hp.set_frames(*FRAMES)
+        if hp.nq:
+            for dst, src in ((hp.q_mu, LOR[0]), (hp.q_x, LOR[1]), (hp.r_hi, LOR[2]), (hp.r_lo, LOR[3]), (hp.r_y, LOR[4])):
+                dst[:src.size].copy_(torch.from_numpy(src))
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         stream.synchronize()
 
@@ -389,7 +404,12 @@ def run_e2e(S, d, rhs, psd_x, steps, world):
     lenud = int((np.asarray(S.K["s"]) ** 2).sum())
     sumn = int(np.asarray(S.K["s"]).sum())
 
+    qbs = S.K["qblkstart"].reshape(1, -1)
+
     def step():
+        if nq:                                       # getDAtm.m:40-43 through the ddot plugin
+            tr = hsetup.extractA(S.At, S.Ablkjc, 1, 2, int(S.K["mainblks"][0]), int(S.K["mainblks"][1]))
+            DAt["q"] = sp.csc_matrix(sp.diags(d["q1"]) @ tr + gpu.ddot(d["q2"], S.At, qbs, S.Ablkjc))
         ud = gpu.invcholfac(d["u"], Km, d["perm"])
         A1 = gpu.getada1(ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], dstruct, S.K["qblkstart"].reshape(1, -1))
         A2 = gpu.getada2(A1, DAt, S.Aord, Km)
@@ -399,8 +419,14 @@ def run_e2e(S, d, rhs, psd_x, steps, world):
         for _ in range(NSOLVE):
             p = gpu.fwblkslv(Lf, rhs)
             y = gpu.bwblkslv(Lf, p / Ld)
-        for i in range(NPSD):
+        for i in range(NPSD if lenud else 0):
             ps = gpu.psdscale({"u": d["u"], "perm": d["perm"]}, xfull, Km, float(i & 1))
+        if not lenud and nq:
+            for _ in range(6):
+                gpu.qblkmul(LOR[0], LOR[1], qbs)
+            for _ in range(3):
+                gpu.ddot(d["q2"], LOR[1], qbs)
+            gpu.quadadd(LOR[2], LOR[3], LOR[4], nlhs=2)
         if lenud:
             gpu.psdinvjmul(FRAMES[0], FRAMES[1], ps, Km)
             f = gpu.psdframeit(FRAMES[0], FRAMES[1], Km)

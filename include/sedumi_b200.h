@@ -175,6 +175,11 @@ int sb200_ada_set_At_values(sb200_ada_plan *plan, const double *Atpr);
 /* device-resident variants: invperm_dev = inverse of the ordering (int32) or NULL = natural */
 int sb200_getada1_dev(sb200_ada_plan *plan, const double *dl_dev, const double *ddet_dev,
                       const int *invperm_dev, double *ada_out_dev);
+/* getDAtm.m:40-43 on the device: DAt.q = diag(d.q1) A(trace rows,:) + ddot(d.q2, A) into the plan's own
+ * CSC (nq x m, pattern fixed by At); sb200_ada_plan_datq returns its device arrays for getada2_dev. */
+int sb200_getdatm_dev(sb200_ada_plan *plan, const double *q1_dev, const double *q2_dev);
+int sb200_ada_plan_datq(sb200_ada_plan *plan, const long long **jc_dev, const int **ir_dev,
+                        const double **pr_dev, sb_idx *nnz);
 int sb200_getada2_dev(sb200_ada_plan *plan, const long long *Qjc_dev, const int *Qir_dev,
                       const double *Qpr_dev, const int *invperm_dev, const double *ada_in_dev,
                       double *ada_out_dev);

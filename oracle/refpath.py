@@ -52,6 +52,10 @@ class RefHotPath:
     def assemble(self, d):
         """sedumi.m:450-452: returns (udsqr, ADA, absd)."""
         S, mex = self.S, self.mex
+        if len(S.K["s"]) == 0:                      # sedumi.m:446-448: the M path, restated in numpy
+            import restate
+            ADA, absd = restate.getada_m(S.At, S.K, d, self.DAtq(d), pattern=S.ADA)
+            return np.zeros(0), ADA, absd.reshape(-1, 1)
         udsqr = mex.invcholfac(d["u"], self.Km, d["perm"])
         A1 = mex.getada1(self.ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], {"l": d["l"], "det": d["det"]},
                          S.K["qblkstart"].reshape(1, -1))
@@ -92,6 +96,17 @@ class RefHotPath:
         q = mex.givensrot(gjc, g, f, Km)
         return dict(z=z, frame=f, u=u, perm=perm, gjc=gjc, g=g, q=q)
 
+    def lorentz_streams(self, d, mu, xq, rhi, rlo, ry):
+        """6 x qblkmul, 3 x ddot (dense), 1 x quadadd on the reference's MEX (SURVEY 8d recipe, sum(K.s)==0)."""
+        bs = self.S.K["qblkstart"].reshape(1, -1)
+        y = dd = None
+        for _ in range(6):
+            y = self.mex.qblkmul(mu, xq, bs)
+        for _ in range(3):
+            dd = self.mex.ddot(d["q2"], xq, bs)
+        zhi, zlo = self.mex.quadadd(rhi, rlo, ry, nlhs=2)
+        return dict(y=y, dd=dd, zhi=zhi, zlo=zlo)
+
     def iteration(self, d, rhs, psd_x, nsolve=4, npsdscale=12, frames=None):
         udsqr, ADA, absd = self.assemble(d)
         L = self.factor(ADA, absd)
@@ -99,7 +114,7 @@ class RefHotPath:
         for _ in range(nsolve):
             y = self.solve(L, rhs)
         ps = None
-        for i in range(npsdscale):
+        for i in range(npsdscale if len(self.S.K["s"]) else 0):
             ps = self.psdscale(d, psd_x, i & 1)
         out = dict(udsqr=udsqr, ADA=ADA, absd=absd, L=L, y=y, psd=ps)
         if frames is not None and len(self.S.K["s"]):

@@ -120,3 +120,26 @@ def ada_dense_formula(At, K, d, udsqr):
         r += n * n
         off += n * n
     return ADA
+
+
+def getada_m(At, K, d, DAtq, pattern=None):
+    """getada.m:14-40 (the M path sedumi.m:446-448 takes when sum(K.s)==0):
+        ADA = DAt.q'*DAt.q + Alq'*diag([d.l; -d.det; d.det(k) on the norm-bound rows of cone k])*Alq,
+        absd = diag(ADA).
+    Returns (ADA as CSC on `pattern` if given, absd)."""
+    import scipy.sparse as sp
+    nl = int(K["l"])
+    q = np.asarray(K["q"], dtype=np.int64)
+    nq = len(q)
+    lq = nl + int(q.sum())
+    sv = np.r_[np.asarray(d["l"], dtype=np.float64).ravel(), -np.asarray(d["det"], dtype=np.float64).ravel(),
+               np.repeat(np.asarray(d["det"], dtype=np.float64).ravel(), q - 1) if nq else np.zeros(0)]
+    Alq = sp.csc_matrix(At)[:lq, :]
+    ADA = (DAtq.T @ DAtq + Alq.T @ sp.diags(sv) @ Alq).toarray()
+    absd = np.diag(ADA).copy()
+    if pattern is None:
+        return sp.csc_matrix(ADA), absd
+    P = sp.csc_matrix(pattern)
+    rows = P.indices
+    cols = np.repeat(np.arange(P.shape[1]), np.diff(P.indptr))
+    return sp.csc_matrix((ADA[rows, cols], P.indices.copy(), P.indptr.copy()), shape=P.shape), absd

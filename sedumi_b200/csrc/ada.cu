@@ -83,6 +83,60 @@ __global__ void dsqr_kernel(int lpN, int nq, const long long *qstart, const doub
   }
 }
 
+// ---- dense route for B'WB when B is (nearly) full (nb.mat: 66 % of At is nonzero; getada.m itself switches
+// to full storage above 20 %, getada.m:27-34): Bd(i, r) = B(r0 + r, i) as an m x R matrix, the product
+// in K-chunks on the DMMA engine, and a gather onto the ADA pattern that adds the chunks in order.
+__global__ void dense_from_csc_kernel(int m, const long long *lo, const long long *hi, const int *Bir, const double *Bpr,
+                                      long long r0, long long R, double *Bd) {
+  const int c = blockIdx.x;
+  for (long long p = lo[c] + threadIdx.x; p < hi[c]; p += blockDim.x) {
+    const long long r = Bir[p] - r0;
+    if (r >= 0 && r < R) Bd[c + r * m] = Bpr[p];
+  }
+}
+__global__ void scale_cols_kernel(long long tot, int m, const double *w, const double *Bd, double *Bw) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x)
+    Bw[idx] = Bd[idx] * w[idx / m];
+}
+__global__ void __launch_bounds__(256)
+gather_dense_kernel(int m, const long long *adajc, const int *adair, const int *invperm, const double *Cp, int nchunk,
+                    const double *in, double *out, int accumulate) {
+  const int c = blockIdx.x;
+  const int ipc = invperm[c];
+  for (long long inz = adajc[c] + threadIdx.x; inz < adajc[c + 1]; inz += blockDim.x) {
+    const int i = adair[inz];
+    double v = accumulate ? in[inz] : 0.0;
+    if (invperm[i] <= ipc) {
+      double acc = 0.0;
+      for (int p = 0; p < nchunk; p++) acc += Cp[(long long)p * m * m + i + (long long)c * m];
+      v += acc;
+    }
+    out[inz] = v;
+  }
+}
+
+// getDAtm.m:40-43:  DAt.q(k,j) = d.q1(k) * A(trace row of cone k, j) + sum_{i in norm rows of cone k} d.q2(i) * A(i,j).
+// The pattern (one entry per (column, Lorentz cone touched)) is compiled into the plan; WIDE = one warp
+// per entry (long cones), otherwise one thread per entry.
+template <bool WIDE>
+__global__ void datq_kernel(long long nent, const int *cone, const int *tsrc, const long long *lo, const long long *hi,
+                            const int *Air, const double *Atpr, const double *q1, const double *q2, long long q2row0, double *out) {
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long e = WIDE ? (gid >> 5) : gid;
+  if (e >= nent) return;
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  if (WIDE) {
+    for (long long p = lo[e] + lane; p < hi[e]; p += 32) acc += q2[Air[p] - q2row0] * Atpr[p];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
+  } else {
+    for (long long p = lo[e]; p < hi[e]; p++) acc += q2[Air[p] - q2row0] * Atpr[p];
+  }
+  const int t = tsrc[e];
+  out[e] = (t >= 0 ? q1[cone[e]] * Atpr[t] : 0.0) + acc;
+}
+
 // --------------------------------------------------------------------- getada3 kernels
 // Tt_p(c, rho) = (D_k * sym(A_jk))(c, R[rho]) = sum over the entries of column R[rho] of sym(A_jk).
 // One CTA per pair, one thread per element (c, rho); the per-column entry lists (D column, weight,
@@ -329,6 +383,17 @@ struct sb200_ada_plan {
   std::vector<int> blk_sparse;
   int max_nu = 0;
   DevBuf<AdaPair> d_pairs;
+  // dense route (B'WB with nearly full B)
+  struct DenseSet { long long R = 0; int nchunk = 0, ntiles = 0; DevBuf<GemmDesc> descs; DevBuf<GemmTile> tiles; };
+  std::map<long long, DenseSet *> dense_sets;
+  DevBuf<double> d_Bd_lq, d_Bd, d_Bw, d_Cp;
+  long long cap_Bd = 0, cap_Cp = 0;
+  bool lq_dense = false, lq_dense_valid = false;
+  // DAt.q (nq x m CSC, pattern fixed by At): getDAtm on the device
+  long long dq_nnz = 0; bool dq_wide = false;
+  DevBuf<long long> d_dq_jc, d_dq_lo, d_dq_hi;
+  DevBuf<int> d_dq_ir, d_dq_tsrc;
+  DevBuf<double> d_dq_pr;
   DevBuf<GemmDesc> d_descs;
   DevBuf<GemmTile> d_tiles;
   DevBuf<double> d_Atpr, d_dsqr, d_ws;
@@ -501,6 +566,51 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     pl->ws_max = std::max(pl->ws_max, ws);
     pl->batches.push_back(B);
   }
+  {
+    long long nnz_lq = 0;
+    for (sb_idx j = 0; j < m; j++) nnz_lq += (nblk ? Ajc1[j] : Ajc[j + 1]) - Ajc[j];
+    pl->lq_dense = pl->lq_rows >= 64 && nnz_lq >= 32 * (long long)m && nnz_lq * 5 > pl->lq_rows * (long long)m &&
+                   pl->lq_rows * (long long)m <= ((long long)64 << 20);
+  }
+  // ---- pattern of DAt.q: per column the Lorentz cones it touches (trace row and/or norm-bound rows)
+  if (nq > 0) {
+    std::vector<long long> qjc(m + 1, 0), qlo, qhi;
+    std::vector<int> qir, qts;
+    const long long tr0 = lpN, nb0 = qstart[0], nb1 = qstart[nq];
+    long long seglen = 0;
+    for (sb_idx j = 0; j < m; j++) {
+      qjc[j] = (long long)qir.size();
+      sb_idx p = Ajc[j];
+      const sb_idx pend = nblk ? Ajc1[j] : Ajc[j + 1];
+      while (p < pend && Air[p] < tr0) p++;
+      sb_idx pt = p;                                   // trace entries [pt, pn)
+      while (p < pend && Air[p] < tr0 + nq) p++;
+      sb_idx pn = p;                                   // norm-bound entries [pn, pe)
+      while (p < pend && Air[p] < nb1) p++;
+      const sb_idx pe = p;
+      SB_CHECK(pn == pe || Air[pn] >= nb0, "getDAtm: row %lld between the Lorentz trace and norm-bound parts", (long long)Air[pn]);
+      sb_idx a = pt, b2 = pn;
+      while (a < pn || b2 < pe) {
+        const int ka = a < pn ? (int)(Air[a] - tr0) : 0x7fffffff;
+        int kb = 0x7fffffff;
+        if (b2 < pe) kb = (int)(std::upper_bound(qstart, qstart + nq + 1, Air[b2]) - qstart) - 1;
+        const int kk = std::min(ka, kb);
+        qir.push_back(kk);
+        qts.push_back(ka == kk ? (int)a : -1);
+        if (ka == kk) a++;
+        long long l0 = b2;
+        if (kb == kk) while (b2 < pe && Air[b2] < qstart[kk + 1]) b2++;
+        qlo.push_back(l0); qhi.push_back(b2);
+        seglen += b2 - l0;
+      }
+    }
+    qjc[m] = (long long)qir.size();
+    pl->dq_nnz = (long long)qir.size();
+    pl->dq_wide = pl->dq_nnz > 0 && seglen / pl->dq_nnz >= 16;
+    SB_TRY(pl->d_dq_jc.upload(qjc)); SB_TRY(pl->d_dq_ir.upload(qir)); SB_TRY(pl->d_dq_tsrc.upload(qts));
+    SB_TRY(pl->d_dq_lo.upload(qlo)); SB_TRY(pl->d_dq_hi.upload(qhi));
+    SB_TRY(pl->d_dq_pr.alloc((size_t)std::max<long long>(pl->dq_nnz, 1)));
+  }
   // ---- upload
   std::vector<long long> v64;
   auto up64 = [&](DevBuf<long long> &d, const sb_idx *p, size_t n) { v64.assign(p, p + n); return d.upload(v64); };
@@ -568,7 +678,7 @@ int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
   if (pl->have_vals && h == pl->val_hash) return 0;
   SB_CUDA(cudaMemcpyAsync(pl->d_Atpr.p, Atpr, sizeof(double) * pl->nnzA, cudaMemcpyHostToDevice, ctx().stream));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));
-  pl->val_hash = h; pl->have_vals = true;
+  pl->val_hash = h; pl->have_vals = true; pl->lq_dense_valid = false;
   return 0;
 }
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *pl) { return pl->nnzADA; }
@@ -586,6 +696,62 @@ static int set_invperm(sb200_ada_plan *pl, const sb_idx *perm, const int **out) 
   return 0;
 }
 
+// out = (accumulate ? in : 0) + Bd W Bd' on the ADA pattern (entries with invperm[i] <= invperm[c]), Bd m x R dense.
+static int ata_dense(sb200_ada_plan *pl, const double *Bd, long long R, const double *w_dev, const int *invperm,
+                     const double *in, double *out, int accumulate) {
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  auto it = pl->dense_sets.find(R);
+  sb200_ada_plan::DenseSet *ds;
+  if (it == pl->dense_sets.end()) {
+    ds = new sb200_ada_plan::DenseSet();
+    ds->R = R;
+    const long long KC = 256;
+    const long long cap = std::max<long long>(1, ((long long)32 << 20) / ((long long)m * m));
+    ds->nchunk = (int)std::max<long long>(1, std::min((R + KC - 1) / KC, cap));
+    const long long kc = (((R + ds->nchunk - 1) / ds->nchunk) + GK - 1) / GK * GK;
+    ds->nchunk = (int)((R + kc - 1) / kc);
+    std::vector<GemmDesc> descs; std::vector<GemmTile> tiles;
+    for (int p = 0; p < ds->nchunk; p++) {
+      GemmDesc g{};
+      g.gatherOff = -1; g.alpha = 1.0; g.lda = g.ldb = g.ldc = m; g.a_tri = g.b_tri = TRI_NONE;
+      g.offA = g.offB = (long long)p * kc * m; g.offC = (long long)p * m * m;
+      g.M = g.N = m; g.K = (int)std::min<long long>(kc, R - (long long)p * kc); g.lower = 0; g.accumulate = 0;
+      descs.push_back(g);
+      gemm_add_tiles(tiles, p, m, m, false);
+    }
+    ds->ntiles = (int)tiles.size();
+    SB_TRY(ds->descs.upload(descs)); SB_TRY(ds->tiles.upload(tiles));
+    SB_CUDA(cudaStreamSynchronize(st));
+    pl->dense_sets[R] = ds;
+  } else ds = it->second;
+  const long long tot = (long long)m * R;
+  if (tot > pl->cap_Bd) { SB_TRY(pl->d_Bw.alloc((size_t)tot)); pl->cap_Bd = tot; }
+  const long long ctot = (long long)ds->nchunk * m * m;
+  if (ctot > pl->cap_Cp) { SB_TRY(pl->d_Cp.alloc((size_t)ctot)); pl->cap_Cp = ctot; }
+  const double *Bw = Bd;
+  if (w_dev) {
+    scale_cols_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>(tot, m, w_dev, Bd, pl->d_Bw.p);
+    SB_LAUNCH_CHECK_N("scale_cols_kernel");
+    Bw = pl->d_Bw.p;
+  }
+  gemm_nt_launch(ds->ntiles, ctx().sm_count, st, ds->descs.p, ds->tiles.p, Bd, Bw, pl->d_Cp.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  gather_dense_kernel<<<m, 256, 0, st>>>(m, pl->d_adajc.p, pl->d_adair.p, invperm, pl->d_Cp.p, ds->nchunk, in, out, accumulate);
+  SB_LAUNCH_CHECK_N("gather_dense_kernel");
+  return 0;
+}
+static int densify(sb200_ada_plan *pl, const long long *lo, const long long *hi, const int *ir, const double *pr, long long r0,
+                   long long R, DevBuf<double> &dst) {
+  cudaStream_t st = ctx().stream;
+  const long long tot = (long long)pl->m * R;
+  if ((long long)dst.n < tot) SB_TRY(dst.alloc((size_t)tot));
+  SB_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(double) * tot, st));
+  dense_from_csc_kernel<<<pl->m, 256, 0, st>>>(pl->m, lo, hi, ir, pr, r0, R, dst.p);
+  SB_LAUNCH_CHECK_N("dense_from_csc_kernel");
+  return 0;
+}
+
 // getada1 on device values.  invperm_dev NULL = natural order (entries with i <= j).
 int sb200_getada1_dev(sb200_ada_plan *pl, const double *dl_dev, const double *ddet_dev, const int *invperm_dev,
                       double *ada_out_dev) {
@@ -597,6 +763,13 @@ int sb200_getada1_dev(sb200_ada_plan *pl, const double *dl_dev, const double *dd
         pl->lpN, pl->nq, pl->d_qstart.p, dl_dev, ddet_dev, pl->d_dsqr.p);
     SB_LAUNCH_CHECK_N("dsqr_kernel");
   }
+  if (pl->lq_dense) {
+    if (!pl->lq_dense_valid) {
+      SB_TRY(densify(pl, pl->d_Ajc.p, pl->d_Ajc1.p, pl->d_Air.p, pl->d_Atpr.p, 0, pl->lq_rows, pl->d_Bd_lq));
+      pl->lq_dense_valid = true;
+    }
+    return ata_dense(pl, pl->d_Bd_lq.p, pl->lq_rows, pl->d_dsqr.p, invperm_dev ? invperm_dev : pl->d_ident.p, nullptr, ada_out_dev, 0);
+  }
   ata_pattern_kernel<<<pl->m, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, pl->d_Ajc.p, pl->d_Ajc1.p, pl->d_Air.p,
                                             pl->d_Atpr.p, pl->d_dsqr.p, invperm_dev ? invperm_dev : pl->d_ident.p,
                                             nullptr, ada_out_dev, 0, 1);
@@ -604,11 +777,43 @@ int sb200_getada1_dev(sb200_ada_plan *pl, const double *dl_dev, const double *dd
   return 0;
 }
 
+// getDAtm on the device: DAt.q values into the plan's own CSC (pattern fixed by At); q2 is d.q2, the
+// concatenated norm-bound parts.  sb200_ada_plan_datq hands the device arrays out (for getada2_dev).
+int sb200_getdatm_dev(sb200_ada_plan *pl, const double *q1_dev, const double *q2_dev) {
+  SB_TRY(ensure_init());
+  if (pl->nq == 0 || pl->dq_nnz == 0) return 0;
+  const long long n = pl->dq_nnz;
+  const long long q2row0 = pl->lpN + pl->nq;
+  if (pl->dq_wide)
+    datq_kernel<true><<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx().stream>>>(n, pl->d_dq_ir.p, pl->d_dq_tsrc.p, pl->d_dq_lo.p, pl->d_dq_hi.p,
+        pl->d_Air.p, pl->d_Atpr.p, q1_dev, q2_dev, q2row0, pl->d_dq_pr.p);
+  else
+    datq_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(n, pl->d_dq_ir.p, pl->d_dq_tsrc.p, pl->d_dq_lo.p, pl->d_dq_hi.p,
+        pl->d_Air.p, pl->d_Atpr.p, q1_dev, q2_dev, q2row0, pl->d_dq_pr.p);
+  SB_LAUNCH_CHECK_N("datq_kernel");
+  return 0;
+}
+int sb200_ada_plan_datq(sb200_ada_plan *pl, const long long **jc_dev, const int **ir_dev, const double **pr_dev, sb_idx *nnz) {
+  *jc_dev = pl->d_dq_jc.p; *ir_dev = pl->d_dq_ir.p; *pr_dev = pl->d_dq_pr.p; *nnz = pl->dq_nnz;
+  return 0;
+}
+
 // getada2 on device values: ada_out = ada_in + Q'Q (upper in perm order), Q = DAt.q as device CSC.
+static int getada2_impl(sb200_ada_plan *pl, const long long *Qjc_dev, const int *Qir_dev, const double *Qpr_dev, long long nnzQ,
+                        const int *invperm_dev, const double *ada_in_dev, double *ada_out_dev);
 int sb200_getada2_dev(sb200_ada_plan *pl, const long long *Qjc_dev, const int *Qir_dev, const double *Qpr_dev,
                       const int *invperm_dev, const double *ada_in_dev, double *ada_out_dev) {
+  // nnz(Q) is known when Q is the plan's own DAt.q (sb200_getdatm_dev); otherwise take the sparse route
+  return getada2_impl(pl, Qjc_dev, Qir_dev, Qpr_dev, Qpr_dev == pl->d_dq_pr.p ? pl->dq_nnz : -1, invperm_dev, ada_in_dev, ada_out_dev);
+}
+static int getada2_impl(sb200_ada_plan *pl, const long long *Qjc_dev, const int *Qir_dev, const double *Qpr_dev, long long nnzQ,
+                        const int *invperm_dev, const double *ada_in_dev, double *ada_out_dev) {
   SB_TRY(ensure_init());
   if (pl->m == 0) return 0;
+  if (pl->nq >= 64 && nnzQ >= 32 * (long long)pl->m && nnzQ * 5 > (long long)pl->nq * pl->m && (long long)pl->nq * pl->m <= ((long long)64 << 20)) {
+    SB_TRY(densify(pl, Qjc_dev, Qjc_dev + 1, Qir_dev, Qpr_dev, 0, pl->nq, pl->d_Bd));
+    return ata_dense(pl, pl->d_Bd.p, pl->nq, nullptr, invperm_dev ? invperm_dev : pl->d_ident.p, ada_in_dev, ada_out_dev, 1);
+  }
   ata_pattern_kernel<<<pl->m, 256, 0, ctx().stream>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, Qjc_dev, Qjc_dev + 1, Qir_dev,
                                                        Qpr_dev, nullptr, invperm_dev ? invperm_dev : pl->d_ident.p,
                                                        ada_in_dev, ada_out_dev, 1, 1);
@@ -716,7 +921,7 @@ int sb200_getada2(sb200_ada_plan *pl, sb_idx nq, const sb_idx *Qjc, const sb_idx
     SB_CUDA(cudaMemcpyAsync(d_ir, ir32.data(), sizeof(int) * nnzQ, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_pr, Qpr, sizeof(double) * nnzQ, cudaMemcpyHostToDevice, st));
   }
-  SB_TRY(sb200_getada2_dev(pl, d_jc, d_ir, d_pr, ip, d_in, d_out));
+  SB_TRY(getada2_impl(pl, d_jc, d_ir, d_pr, nnzQ, ip, d_in, d_out));
   SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   mirror_publish(d_out, ada_out, sizeof(double) * pl->nnzADA);

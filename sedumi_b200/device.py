@@ -79,7 +79,7 @@ EXPORTS = [
     "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_urotorder_dev", "sb200_givensrot_dev", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
     "sb200_graph_destroy",
     "sb200_ada_plan_get", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
-    "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3",
+    "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3", "sb200_getdatm_dev", "sb200_ada_plan_datq",
     "sb200_ddot_dense_dev", "sb200_qblkmul_dev", "sb200_quadadd_dev", "sb200_ddot_dense", "sb200_ddot_sparse",
     "sb200_qblkmul", "sb200_quadadd", "sb200_adendotd",
 ]
@@ -134,6 +134,18 @@ class HotPath:
         f64 = dict(dtype=torch.float64, device=self.dev)
         z = lambda n: torch.zeros(max(int(n), 1), **f64)
         self.d_l, self.d_det = z(self.lpN), z(self.nq)
+        # Lorentz part of the scaling and of the iterate (getDAtm, qblkmul/ddot/quadadd streams)
+        q = np.asarray(K["q"], dtype=np.int64)
+        self.qdim = int((q - 1).sum()) if self.nq else 0
+        self.d_q1, self.d_q2 = z(self.nq), z(self.qdim)
+        if self.nq:
+            bsq = np.r_[0, np.cumsum(q - 1)].astype(np.int64)
+            self.qbs = torch.from_numpy(bsq).to(self.dev)
+            self.q_mu, self.q_x, self.q_y, self.q_dd = z(self.nq), z(self.qdim), z(self.qdim), z(self.nq)
+            self.r_hi, self.r_lo, self.r_y = z(m), z(m), z(m)
+            jc, ir, pr, nnz = C.c_void_p(), C.c_void_p(), C.c_void_p(), I64(0)
+            check(L.sb200_ada_plan_datq(self.ada, C.byref(jc), C.byref(ir), C.byref(pr), C.byref(nnz)), "datq")
+            self.datq = (jc, ir, pr, int(nnz.value))
         self.d_u, self.udsqr = z(self.lenud), z(self.lenud)
         self.d_perm = torch.zeros(max(int(s.sum()), 1), dtype=torch.int32, device=self.dev)
         self.has_perm = False
@@ -159,7 +171,9 @@ class HotPath:
         """Host -> device copy of the NT scaling; returns bytes moved."""
         t = self.torch
         nbytes = 0
-        for name, dst in (("l", self.d_l), ("det", self.d_det), ("u", self.d_u)):
+        for name, dst in (("l", self.d_l), ("det", self.d_det), ("u", self.d_u), ("q1", self.d_q1), ("q2", self.d_q2)):
+            if name not in d:
+                continue
             a = np.ascontiguousarray(np.asarray(d[name], dtype=np.float64).ravel())
             if a.size:
                 dst[:a.size].copy_(t.from_numpy(a), non_blocking=non_blocking)
@@ -188,9 +202,12 @@ class HotPath:
 
     def getada(self):
         L = lib()
+        if self.nq:        # getDAtm.m:40-43 on the device; its pattern lives in the plan
+            check(L.sb200_getdatm_dev(self.ada, _p(self.d_q1), _p(self.d_q2)), "getdatm")
         check(L.sb200_getada1_dev(self.ada, _p(self.d_l), _p(self.d_det), None, _p(self.ADA)), "getada1")
         if self.nq:
-            raise SB200Error("device-resident getada2 needs DAt.q on the device (Lorentz path: next round)")
+            jc, ir, pr, _ = self.datq
+            check(L.sb200_getada2_dev(self.ada, jc, ir, pr, None, _p(self.ADA), _p(self.ADA)), "getada2")
         check(L.sb200_getada3_dev(self.ada, _p(self.udsqr), None, I64(0), _p(self.ADA), _p(self.absd), C.c_int(1)), "getada3")
 
     def blkchol(self):
@@ -232,6 +249,18 @@ class HotPath:
         check(lib().sb200_givensrot_dev(I64(len(self.s)), _p(self.s64), _p(self.gjc), _p(self.g), _p(self.psd_f),
                                         _p(self.psd_z)), "givensrot")
 
+    def lorentz_streams(self):
+        """The Lorentz-cone vector work of one iteration (SURVEY 8d recipe for sum(K.s)==0):
+        6 x qblkmul, 3 x ddot (dense), 1 x quadadd on device-resident vectors."""
+        if not self.nq:
+            return
+        L = lib()
+        for _ in range(6):
+            check(L.sb200_qblkmul_dev(I64(self.nq), _p(self.qbs), I64(self.qdim), _p(self.q_mu), _p(self.q_x), _p(self.q_y)), "qblkmul")
+        for _ in range(3):
+            check(L.sb200_ddot_dense_dev(I64(self.nq), _p(self.qbs), _p(self.d_q2), _p(self.q_x), I64(self.qdim), I64(1), _p(self.q_dd)), "ddot")
+        check(L.sb200_quadadd_dev(I64(self.m), _p(self.r_hi), _p(self.r_lo), _p(self.r_y), _p(self.r_hi), _p(self.r_lo)), "quadadd")
+
     def update_scaling_tail(self):
         """psdinvjmul -> 2 x psdframeit -> urotorder -> givensrot (SURVEY 8d recipe; updtransfo.m:99-108)."""
         if not self.lenud:
@@ -257,9 +286,12 @@ class HotPath:
         self.blkchol()
         for _ in range(nsolve):
             self.solve()
-        for i in range(npsdscale):
-            self.psdscale(i & 1)
-        self.update_scaling_tail()
+        if self.lenud:
+            for i in range(npsdscale):
+                self.psdscale(i & 1)
+            self.update_scaling_tail()
+        else:
+            self.lorentz_streams()
 
     def capture(self, nsolve=4, npsdscale=12):
         """Record one iteration into a CUDA graph; returns a callable that replays it."""

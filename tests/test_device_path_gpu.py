@@ -72,6 +72,53 @@ def test_arch0():
     _run(problems.load_fixture("arch0"))
 
 
+def test_nb_lorentz_only_device_path():
+    """BASELINE config 2 (nb.mat: 793 Lorentz cones, no PSD block): getDAtm + getada1 + getada2 on the
+    device against getada.m restated (the M path sedumi.m:446-448 takes), then factor/solve and the
+    qblkmul/ddot/quadadd streams against the reference MEX."""
+    import torch
+    import refpath
+    from sedumi_b200 import device
+    At, b, c, K = cones.pretransfo(*problems.load_fixture("nb"))[:4]
+    S = setup.build_setup(At, b, c, K)
+    d = problems.scaling(K, "S1", seed=3)
+    rng = np.random.default_rng(4)
+    rhs = rng.standard_normal((S.m, 1))
+    nq, qd = len(K["q"]), int((np.asarray(K["q"]) - 1).sum())
+    mu, xq = rng.standard_normal(nq), rng.standard_normal(qd)
+    rhi, rlo, ry = rng.standard_normal(S.m), 1e-17 * rng.standard_normal(S.m), rng.standard_normal(S.m)
+    hp = device.HotPath(S)
+    st = hp.stream()
+    R = refpath.RefHotPath(S)
+    with torch.cuda.stream(st):
+        hp.set_scaling(d)
+        hp.set_rhs(rhs)
+        for dst, src in ((hp.q_mu, mu), (hp.q_x, xq), (hp.r_hi, rhi), (hp.r_lo, rlo), (hp.r_y, ry)):
+            dst[:src.size].copy_(torch.from_numpy(src))
+        st.synchronize()
+        hp.iteration(1, 0)
+        hp.sync()
+        # DAt.q values (pattern order = CSC of the reference's DAt.q)
+        import ctypes as C
+        Q = R.DAtq(d)
+        Q.sort_indices()
+        nnz = hp.datq[3]
+        assert nnz == Q.nnz
+        got = np.empty(nnz)
+        device.check(device.lib().sb200_d2h(got.ctypes.data_as(C.c_void_p), hp.datq[2], C.c_int64(8 * nnz)), "d2h")
+        assert relerr(got, Q.data) <= 1e-12
+        ref = R.iteration(d, rhs, np.zeros(0), 1, 0)
+        assert relerr(hp.ADA.cpu().numpy()[:S.ADA.nnz], ref["ADA"].data) <= 1e-10
+        assert relerr(hp.absd.cpu().numpy()[:S.m], ref["absd"].ravel()) <= 1e-10
+        assert relerr(hp.dvec.cpu().numpy()[:S.m], ref["L"]["d"]) <= 1e-10
+        assert relerr(hp.y.cpu().numpy().T, ref["y"]) <= 1e-8
+        ls = R.lorentz_streams(d, mu, xq, rhi, rlo, ry)
+        assert relerr(hp.q_y.cpu().numpy()[:qd], ls["y"].ravel()) <= 1e-14
+        assert relerr(hp.q_dd.cpu().numpy()[:nq], ls["dd"].ravel()) <= 1e-12
+        assert np.array_equal(hp.r_hi.cpu().numpy()[:S.m], ls["zhi"].ravel())
+        assert np.array_equal(hp.r_lo.cpu().numpy()[:S.m], ls["zlo"].ravel())
+
+
 def test_late_scaling_with_rotations():
     """S2 ("late") scaling: ill-conditioned factors, urotorder really pivots."""
     import refpath
