@@ -136,7 +136,12 @@ def kernel_work(S, name):
                 if sel.size:
                     r = np.unique(np.r_[sel % n, sel // n]).size
                     fl += n * (n + 1) * r
-        fl += float((s ** 3).sum()) / 3 * 2 + NPSD * 2 * float((s ** 3).sum())
+        n3 = float((s ** 3).sum())
+        # invcholfac (n^3/3 MACs), psdscale (two triangular products, n^3 flops each), psdinvjmul (two full 2n^3
+        # + two lower n^3 products), 2 x psdframeit (lower, n^3), compact-WY accumulation of Q for large blocks
+        fl += n3 / 3 * 2 + NPSD * 2 * n3 + 6 * n3 + 2 * n3
+        if s.size and s.max() > 2300:
+            fl += 3 * 4.0 / 3.0 * n3
         return dict(bound="tensor", work=fl, unit="TFLOP/s")
     if name in ("trail_kernel", "diag_kernel", "trsm_kernel", "factor_small_kernel", "dense_ldl_kernel"):
         cj = np.diff(S.L["L"].indptr) - 1

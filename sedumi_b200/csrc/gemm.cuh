@@ -34,6 +34,8 @@ struct GemmTile { int prob, ti, tj; };
 
 static const int GT = 64;     // tile edge
 static const int GK = 16;     // k-slab
+static const int GST = 3;     // cp.async pipeline depth (52 KB per CTA: four 128-thread CTAs per SM, the register limit)
+static const int GEMM_SMEM = GST * 2 * GK * (GT + 4) * 8;     // dynamic shared memory per tile CTA
 // threads per tile: 128 * KG (KG k-groups of 4 warps; each warp owns a 32x32 sub-tile = 4x4 DMMA fragments)
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
@@ -51,6 +53,7 @@ __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // One operand slab (64 rows x GK k-values) global -> shared, element (i, kk) -> S[kk][i].
 // Fast path: 16-byte copies, no predicates (interior tile, k-slab fully inside the nonzero range,
@@ -92,7 +95,9 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
 // the CTA keeps 8 warps busy per tile: the per-block products here often have fewer tiles than the GPU
 // has SMs (ncu, n=1000: 256 tiles, 9 % warp occupancy with 4 warps per tile).
 // KG = 1 (128 threads, no split) is used when a launch has tiles to spare: more CTAs per SM.
-// Two-stage cp.async pipeline: slab s+1 is in flight while the DMMAs of slab s run.
+// GST-stage cp.async pipeline: slabs s+1..s+GST-1 are in flight while the DMMAs of slab s run (with two
+// stages the copy of the next slab was issued one slab-time (~250 cycles at full DMMA rate) before it was
+// needed, less than the L2 latency).
 template <int KG>
 static __global__ void __launch_bounds__(128 * KG)
 gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA, const double *baseB,
@@ -103,7 +108,9 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   double *gC = baseC + g.offC;
   const int *gather = (g.gatherOff >= 0) ? gatherBase + g.gatherOff : nullptr;
   const int i0 = tl.ti * GT, c0 = tl.tj * GT;
-  __shared__ __align__(16) double As[2][GK][GT + 4], Bs[2][GK][GT + 4];
+  extern __shared__ __align__(16) double gemm_sm[];
+  double (*As)[GK][GT + 4] = (double (*)[GK][GT + 4])gemm_sm;                       // [GST][GK][GT+4]
+  double (*Bs)[GK][GT + 4] = (double (*)[GK][GT + 4])(gemm_sm + GST * GK * (GT + 4));
   // k-range that can be nonzero for this tile
   int klo = 0, khi = g.K;
   if (g.a_tri == TRI_K_LE_ROW) khi = min(khi, i0 + GT);
@@ -122,19 +129,26 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
 #pragma unroll
     for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
   const int nslab = khi > klo ? (khi - klo + GK - 1) / GK : 0;
-  if (nslab > 0) {
-    gemm_stage_slab<KG>(As[0], gA, g.lda, g.M, i0, g.K, klo, g.a_tri, gather, vecA);
-    gemm_stage_slab<KG>(Bs[0], gB, g.ldb, g.N, c0, g.K, klo, g.b_tri, nullptr, vecB);
+  // prologue: GST-1 slabs in flight (a group is committed per slot even when empty, so the wait counts stay uniform)
+#pragma unroll
+  for (int s = 0; s < GST - 1; s++) {
+    if (s < nslab) {
+      gemm_stage_slab<KG>(As[s], gA, g.lda, g.M, i0, g.K, klo + s * GK, g.a_tri, gather, vecA);
+      gemm_stage_slab<KG>(Bs[s], gB, g.ldb, g.N, c0, g.K, klo + s * GK, g.b_tri, nullptr, vecB);
+    }
     cp_async_commit();
   }
   for (int s = 0; s < nslab; s++) {
-    const int buf = s & 1;
-    cp_async_wait_all();
-    __syncthreads();                               // slab s has landed; everyone is done with slab s-1
-    if (s + 1 < nslab) {
-      const int k0 = klo + (s + 1) * GK;
-      gemm_stage_slab<KG>(As[buf ^ 1], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
-      gemm_stage_slab<KG>(Bs[buf ^ 1], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
+    const int buf = s % GST;
+    cp_async_wait_group<GST - 2>();                // slab s has landed
+    __syncthreads();                               // ... for everyone; and everyone is done with slab s-1
+    {
+      const int sn = s + GST - 1;                  // refill the buffer slab s-1 just released
+      if (sn < nslab) {
+        const int k0 = klo + sn * GK;
+        gemm_stage_slab<KG>(As[sn % GST], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
+        gemm_stage_slab<KG>(Bs[sn % GST], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
+      }
       cp_async_commit();
     }
 #pragma unroll
@@ -152,6 +166,7 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
     }
   }
   // add the two k-groups: group 1 parks its partial tile in the (now idle) staging buffers
+  cp_async_wait_all();
   if (KG == 2) {
     __syncthreads();
     double *red = &As[0][0][0];                      // 2*GK*(GT+4) doubles >= 4 warps x 32 lanes x 16 values
@@ -206,8 +221,14 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
 static inline void gemm_nt_launch(int ntiles, int sm_count, cudaStream_t st, const GemmDesc *descs, const GemmTile *tiles,
                                   const double *baseA, const double *baseB, double *baseC, const int *gatherBase) {
   if (ntiles <= 0) return;
-  if (ntiles >= 6 * sm_count) gemm_nt_kernel<1><<<ntiles, 128, 0, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
-  else gemm_nt_kernel<2><<<ntiles, 256, 0, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    attr_done = true;
+  }
+  if (ntiles >= 6 * sm_count) gemm_nt_kernel<1><<<ntiles, 128, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  else gemm_nt_kernel<2><<<ntiles, 256, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
 }
 
 // Host helper: append the tiles of one problem to a tile list.
