@@ -156,6 +156,12 @@ int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const doubl
                     const double *x, double *y);
 /* host entries: u, x, y are the lenud-long PSD parts; perm 0-based inside each block or NULL */
 int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm, double *y);
+/* Mixed real / Hermitian blocks (K.s with K.rsdpN = nreal leading real blocks).  Layout of the reference:
+ * a real block is n^2 doubles, a Hermitian block [vec Re; vec Im] = 2 n^2 doubles (invcholfac.c:122-160,
+ * psdscale.m:68-118).  The complex algebra runs on the real embedding [[Re,-Im],[Im,Re]] of order 2n. */
+int sb200_invcholfac_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm, double *y);
+int sb200_psdscale_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm,
+                     const double *x, int transp, double *y);
 int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm,
                    const double *x, int transp, double *y);
 

@@ -24,10 +24,13 @@ import scipy.sparse as sp
 
 
 def psdscale(ud, x, K, transp=False):
-    """y = psdscale(ud,x,K,transp)  (psdscale.m:45-119), real blocks."""
+    """y = psdscale(ud,x,K,transp)  (psdscale.m:45-119): per block Y = T'*X*T with T = tril/triu(U); the
+    blocks after K.rsdpN are Hermitian, stored [vec Re; vec Im], and get the imaginary diagonal of Y zeroed
+    (psdscale.m:111-116)."""
     Ks = np.asarray(K["s"], dtype=np.int64).ravel()
     if Ks.size == 0:
         return np.zeros(0)
+    nr = int(K.get("rsdpN", Ks.size)) if isinstance(K, dict) else Ks.size
     perm = None
     if isinstance(ud, dict):
         p = np.asarray(ud.get("perm", np.zeros(0))).ravel()
@@ -36,31 +39,43 @@ def psdscale(ud, x, K, transp=False):
     else:
         u = np.asarray(ud, dtype=float).ravel()
     x = np.asarray(x, dtype=float).ravel()
-    N = int((Ks ** 2).sum())
+    N = int((Ks ** 2).sum() + (Ks[nr:] ** 2).sum())
     xi = x.size - N
     y = np.zeros(N)
     ui = yi = pi = 0
-    for n in Ks:
+    for i, n in enumerate(Ks):
         n = int(n)
         q = n * n
+        cplx = i >= nr
         TT = u[ui:ui + q].reshape(n, n, order="F")
         ui += q
+        if cplx:
+            TT = TT + 1j * u[ui:ui + q].reshape(n, n, order="F")
+            ui += q
         TT = np.triu(TT) if transp else np.tril(TT)
         XX = x[xi:xi + q].reshape(n, n, order="F")
         xi += q
+        if cplx:
+            XX = XX + 1j * x[xi:xi + q].reshape(n, n, order="F")
+            xi += q
         if perm is not None and not transp:
             PP = perm[pi:pi + n]
             pi += n
             XX = XX[np.ix_(PP, PP)]
-        XX = TT.T @ XX @ TT
+        XX = TT.conj().T @ XX @ TT
         if perm is not None and transp:
             PP = perm[pi:pi + n]
             pi += n
             Z = np.empty_like(XX)
             Z[np.ix_(PP, PP)] = XX
             XX = Z
-        y[yi:yi + q] = XX.ravel(order="F")
+        y[yi:yi + q] = XX.real.ravel(order="F")
         yi += q
+        if cplx:
+            Z = XX.imag.copy()
+            Z[np.diag_indices(n)] = 0.0
+            y[yi:yi + q] = Z.ravel(order="F")
+            yi += q
     return y
 
 

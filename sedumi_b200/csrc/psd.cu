@@ -400,6 +400,54 @@ psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, co
   }
 }
 
+// ---------------------------------------------------------------- Hermitian PSD blocks
+// A Hermitian block of order n arrives as [vec Re; vec Im] (2 n^2 doubles).  The complex algebra runs on
+// the real embedding E(Z) = [[Re Z, -Im Z],[Im Z, Re Z]] (a *-homomorphism: E(Z^H) = E(Z)', E(XY) = E(X)E(Y)),
+// i.e. as a real block of order 2n through the same DMMA products; real blocks are carried along as they are.
+struct HermBlk { int n, cplx, poff, pad; long long raw_off, emb_off; };
+
+// emb = E(op(raw)):  op = gather by perm (src(P[p],P[q])), triangular mask on the source (1: keep row<=col,
+// 2: keep row>=col), conjugate transpose (tc).
+__global__ void herm_embed_kernel(const HermBlk *blks, const double *raw, double *emb, const int *perm, int tc, int mask) {
+  const HermBlk B = blks[blockIdx.y];
+  const int n = B.n, ne = B.cplx ? 2 * n : n;
+  const double *re = raw + B.raw_off, *im = re + (long long)n * n;
+  double *E = emb + B.emb_off;
+  const int *P = perm ? perm + B.poff : nullptr;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % n), q = (int)(idx / n);
+    int sp = tc ? q : p, sq = tc ? p : q;
+    if (P) { sp = P[sp]; sq = P[sq]; }
+    const bool keep = mask == 0 || (mask == 1 ? sp <= sq : sp >= sq);
+    const long long si = sp + (long long)sq * n;
+    double zr = keep ? re[si] : 0.0, zi = (keep && B.cplx) ? im[si] : 0.0;
+    if (tc) zi = -zi;
+    E[p + (long long)q * ne] = zr;
+    if (B.cplx) {
+      E[(p + n) + (long long)(q + n) * ne] = zr;
+      E[(p + n) + (long long)q * ne] = zi;
+      E[p + (long long)(q + n) * ne] = -zi;
+    }
+  }
+}
+// raw(P[p],P[q]) (or raw(p,q)) = the complex entry (p,q) of emb; the imaginary diagonal can be forced to 0.
+__global__ void herm_extract_kernel(const HermBlk *blks, const double *emb, double *raw, const int *perm, int zero_imag_diag) {
+  const HermBlk B = blks[blockIdx.y];
+  const int n = B.n, ne = B.cplx ? 2 * n : n;
+  double *re = raw + B.raw_off, *im = re + (long long)n * n;
+  const double *E = emb + B.emb_off;
+  const int *P = perm ? perm + B.poff : nullptr;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % n), q = (int)(idx / n);
+    const int dp = P ? P[p] : p, dq = P ? P[q] : q;
+    const long long di = dp + (long long)dq * n;
+    re[di] = E[p + (long long)q * ne];
+    if (B.cplx) im[di] = (zero_imag_diag && dp == dq) ? 0.0 : E[(p + n) + (long long)q * ne];
+  }
+}
+
 static std::map<uint64_t, sb200_psd_plan *> g_psd_plans;
 
 }  // namespace sb
@@ -772,6 +820,119 @@ int sb200_psdinvjmul(sb_idx nblk, const sb_idx *n, const double *xlab, const dou
   SB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
   SB_TRY(sb200_psdinvjmul_dev(pl, dl, df, dy, dz));
   SB_CUDA(cudaMemcpyAsync(z, dz, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
+// ---------------------------------------------------------------- Hermitian variants of the host entries
+// n[0..nreal) are real symmetric blocks, n[nreal..nblk) Hermitian ones (K.s / K.rsdpN).  Data layout as in
+// the reference: real block n^2 doubles, Hermitian block [vec Re; vec Im].  perm: 0-based inside each block.
+struct HermCtx {
+  sb200_psd_plan *pl = nullptr;        // plan of the embedded orders
+  HermBlk *d_blks = nullptr;
+  long long raw_len = 0;
+  int sumn = 0, maxn = 0, nblk = 0;
+  int *d_perm = nullptr;
+};
+static std::map<uint64_t, HermCtx *> g_herm;
+static int herm_get(sb_idx nblk, sb_idx nreal, const sb_idx *n, HermCtx **out) {
+  SB_TRY(ensure_init());
+  SB_CHECK(nreal >= 0 && nreal <= nblk, "number of real PSD blocks out of range");
+  uint64_t h = fnv1a(&nblk, sizeof nblk); h = fnv1a(&nreal, sizeof nreal, h); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
+  auto it = g_herm.find(h);
+  if (it != g_herm.end()) { *out = it->second; return 0; }
+  HermCtx *c = new HermCtx();
+  std::vector<sb_idx> ne(nblk);
+  std::vector<HermBlk> blks(nblk);
+  long long raw = 0, emb = 0; int po = 0;
+  for (sb_idx k = 0; k < nblk; k++) {
+    SB_CHECK(n[k] >= 1 && n[k] < 23170, "PSD block order %lld out of range", (long long)n[k]);
+    const int cplx = k >= nreal;
+    ne[k] = cplx ? 2 * n[k] : n[k];
+    blks[k] = HermBlk{(int)n[k], cplx, po, 0, raw, emb};
+    raw += (cplx ? 2 : 1) * n[k] * n[k]; emb += ne[k] * ne[k]; po += (int)n[k];
+    c->maxn = std::max(c->maxn, (int)n[k]);
+  }
+  c->raw_len = raw; c->sumn = po; c->nblk = (int)nblk;
+  SB_TRY(sb200_psd_plan_get(&c->pl, nblk, ne.data()));
+  SB_CUDA(cudaMalloc(&c->d_blks, sizeof(HermBlk) * std::max<size_t>(blks.size(), 1)));
+  SB_CUDA(cudaMemcpy(c->d_blks, blks.data(), sizeof(HermBlk) * blks.size(), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMalloc(&c->d_perm, sizeof(int) * std::max(po, 1)));
+  g_herm[h] = c;
+  *out = c;
+  return 0;
+}
+static int herm_perm(HermCtx *c, const sb_idx *n, const sb_idx *perm, const int **out) {
+  *out = nullptr;
+  if (!perm) return 0;
+  std::vector<int> p32((size_t)c->sumn);
+  int po = 0;
+  for (int k = 0; k < c->nblk; k++)
+    for (int i = 0; i < n[k]; i++, po++) {
+      SB_CHECK(perm[po] >= 0 && perm[po] < n[k], "perm entry out of range in PSD block %d", k);
+      p32[po] = (int)perm[po];
+    }
+  SB_CUDA(cudaMemcpyAsync(c->d_perm, p32.data(), sizeof(int) * p32.size(), cudaMemcpyHostToDevice, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = c->d_perm;
+  return 0;
+}
+static inline dim3 herm_grid(const HermCtx *c) {
+  return dim3((unsigned)std::min<long long>(((long long)c->maxn * c->maxn + 255) / 256, 1024), (unsigned)c->nblk);
+}
+
+// Y(perm,perm) = U^H U, U = triu(u)   (invcholfac.c:122-160 incl. the prpi branch)
+int sb200_invcholfac_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm, double *y) {
+  HermCtx *c;
+  SB_TRY(herm_get(nblk, nreal, n, &c));
+  if (c->raw_len == 0) return 0;
+  sb200_psd_plan *pl = c->pl;
+  arena_reset();
+  double *du = arena<double>((size_t)c->raw_len), *dy = arena<double>((size_t)c->raw_len);
+  SB_CHECK(du && dy, "invcholfac: out of device memory");
+  const int *dperm;
+  SB_TRY(herm_perm(c, n, perm, &dperm));
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * c->raw_len, cudaMemcpyHostToDevice, st));
+  herm_embed_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, du, pl->d_Tt.p, nullptr, 1, 1);      // E(U^H)
+  SB_LAUNCH_CHECK_N("herm_embed_kernel");
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Tt.p, pl->d_Y.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  herm_extract_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, pl->d_Y.p, dy, dperm, 1);
+  SB_LAUNCH_CHECK_N("herm_extract_kernel");
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * c->raw_len, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Y = T^H X T, T = tril(U) / triu(U) (transp), X permuted before (!transp) or Y after (transp)   (psdscale.m:45-119)
+int sb200_psdscale_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm, const double *x,
+                     int transp, double *y) {
+  HermCtx *c;
+  SB_TRY(herm_get(nblk, nreal, n, &c));
+  if (c->raw_len == 0) return 0;
+  sb200_psd_plan *pl = c->pl;
+  arena_reset();
+  double *du = arena<double>((size_t)c->raw_len), *dx = arena<double>((size_t)c->raw_len), *dy = arena<double>((size_t)c->raw_len);
+  SB_CHECK(du && dx && dy, "psdscale: out of device memory");
+  const int *dperm;
+  SB_TRY(herm_perm(c, n, perm, &dperm));
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * c->raw_len, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * c->raw_len, cudaMemcpyHostToDevice, st));
+  herm_embed_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, du, pl->d_Tt.p, nullptr, 1, transp ? 1 : 2);       // E(T^H)
+  SB_LAUNCH_CHECK_N("herm_embed_kernel");
+  herm_embed_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, dx, pl->d_Xp.p, transp ? nullptr : dperm, 0, 0); // E(X(P,P))
+  SB_LAUNCH_CHECK_N("herm_embed_kernel");
+  // Wt = E(T^H) E(X)' ; Y = E(T^H) Wt' = T^H X T
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Xp.p, pl->d_Wt.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  gemm_nt_launch(pl->ntiles_full, ctx().sm_count, st, pl->d_desc_full.p, pl->d_tiles_full.p, pl->d_Tt.p, pl->d_Wt.p, pl->d_Y.p, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  herm_extract_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, pl->d_Y.p, dy, transp ? dperm : nullptr, 1);
+  SB_LAUNCH_CHECK_N("herm_extract_kernel");
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * c->raw_len, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

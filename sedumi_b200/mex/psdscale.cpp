@@ -9,25 +9,26 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   ConeK K;
   read_cone(prhs[2], K);
   if (K.sdpN == 0) { plhs[0] = mxCreateDoubleMatrix(0, 0, mxREAL); return; }      // y = [] (psdscale.m:47-50)
-  if (K.rsdpN != K.sdpN) mexErrMsgTxt("psdscale: Hermitian PSD blocks are not supported by the B200 plugin yet.");
+  const bool herm = K.rsdpN != K.sdpN;             // Hermitian blocks: [vec Re; vec Im] each (psdscale.m:55-58,68-72)
   bool transp = nrhs >= 4 && numel(prhs[3]) > 0 && mxGetScalar(prhs[3]) != 0.0;
   const mxArray *UD = prhs[0], *ufield = UD, *pfield = NULL;
   if (mxIsStruct(UD)) {
     ufield = need_field(UD, "u", "Missing field ud.u.");
     pfield = mxGetField(UD, 0, "perm");
   }
-  sb_idx N = K.rDim;
+  sb_idx N = K.rDim + K.hDim;
   MEX_REQUIRE(numel(ufield) >= (mwSize)N, "ud.u size mismatch");
   MEX_REQUIRE(numel(prhs[1]) >= (mwSize)N, "x size mismatch");
   MEX_REQUIRE(!mxIsSparse(prhs[1]), "x must be full");
   std::vector<sb_idx> perm;
   bool isperm = pfield && numel(pfield) > 0;
   if (isperm) {
-    MEX_REQUIRE(numel(pfield) >= (mwSize)K.rLen, "ud.perm size mismatch");
+    MEX_REQUIRE(numel(pfield) >= (mwSize)(K.rLen + K.hLen), "ud.perm size mismatch");
     idx_from_double(pfield, perm, 1, "ud.perm");
   }
   const double *x = mxGetPr(prhs[1]) + (numel(prhs[1]) - (mwSize)N);     // PSD part is the tail (psdscale.m:58)
   plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
-  int rc = sb200_psdscale(K.sdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]));
+  int rc = herm ? sb200_psdscale_h(K.sdpN, K.rsdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]))
+                : sb200_psdscale(K.sdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]));
   if (rc) { mxDestroyArray(plhs[0]); plhs[0] = NULL; sb_check(rc, "psdscale"); }
 }

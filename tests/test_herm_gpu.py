@@ -1,0 +1,85 @@
+"""Hermitian PSD blocks (K.s entries after K.rsdpN, stored [vec Re; vec Im]): plugins against the reference's
+complex branches (invcholfac.c:131-141, psdframeit.c:86-97, ...) and the numpy restatement of psdscale.m."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, gpu, ref, relerr
+from sedumi_b200.host import cones
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _K(sreal, sherm):
+    K = {"l": 2.0, "q": np.array([3.0]), "s": np.array(list(sreal) + list(sherm), dtype=float), "rsdpN": len(sreal)}
+    return cones.finish_K(K)
+
+
+def _factor(K, rng, junk_lower=True):
+    """d.u: per block an upper-triangular factor with positive real diagonal; the strictly lower part holds
+    junk that triu() must ignore.  Hermitian blocks: [vec Re; vec Im]."""
+    out = []
+    nr = K["rsdpN"]
+    for i, n in enumerate(K["s"].astype(int)):
+        U = np.triu(rng.standard_normal((n, n))) + (0 if i < nr else 1j * np.triu(rng.standard_normal((n, n)), 1))
+        U[np.diag_indices(n)] = np.abs(U[np.diag_indices(n)].real) + 0.5
+        J = np.tril(rng.standard_normal((n, n)), -1) * (1.0 if junk_lower else 0.0)
+        out.append((U.real + J).ravel(order="F"))
+        if i >= nr:
+            out.append((U.imag + J).ravel(order="F"))
+    return np.concatenate(out)
+
+
+def _herm_vec(K, rng):
+    out = []
+    nr = K["rsdpN"]
+    for i, n in enumerate(K["s"].astype(int)):
+        X = rng.standard_normal((n, n)) + (0 if i < nr else 1j * rng.standard_normal((n, n)))
+        X = X + X.conj().T
+        out.append(X.real.ravel(order="F"))
+        if i >= nr:
+            out.append(X.imag.ravel(order="F"))
+    return np.concatenate(out)
+
+
+def _perm(K, rng):
+    return np.concatenate([rng.permutation(int(n)) + 1.0 for n in K["s"]]).reshape(-1, 1)
+
+
+CASES = [((), (3,)), ((4,), (5,)), ((), (1, 2)), ((7, 2), (9, 33)), ((), (70,))]
+
+
+@pytest.mark.parametrize("sreal,sherm", CASES)
+@pytest.mark.parametrize("withperm", [False, True])
+def test_invcholfac_hermitian(sreal, sherm, withperm):
+    K = _K(sreal, sherm)
+    Km = cones.K_for_mex(K)
+    rng = np.random.default_rng(len(sherm) + 10 * sum(sherm))
+    u = _factor(K, rng)
+    args = (u, Km) + ((_perm(K, rng),) if withperm else ())
+    yr = ref.invcholfac(*args)
+    yg = gpu.invcholfac(*args)
+    assert yg.shape == yr.shape
+    assert relerr(yg, yr) <= 1e-10
+
+
+@pytest.mark.parametrize("sreal,sherm", CASES)
+@pytest.mark.parametrize("transp", [0.0, 1.0])
+@pytest.mark.parametrize("withperm", [False, True])
+def test_psdscale_hermitian(sreal, sherm, transp, withperm):
+    import restate
+    K = _K(sreal, sherm)
+    Km = cones.K_for_mex(K)
+    rng = np.random.default_rng(3 + len(sreal) + 10 * sum(sherm))
+    u = _factor(K, rng, junk_lower=False)
+    u = u + 0.0          # psdscale uses tril(U) for transp=0: give the lower triangle real content as well
+    x = _herm_vec(K, rng)
+    ud = {"u": _factor(K, rng), "perm": _perm(K, rng) if withperm else np.zeros((0, 0))}
+    xfull = np.r_[rng.standard_normal(4), x]           # psdscale reads the PSD part from the tail
+    yr = restate.psdscale(ud, xfull, K, bool(transp))
+    yg = gpu.psdscale(ud, xfull, Km, transp)
+    assert relerr(yg.ravel(), yr) <= 1e-10
