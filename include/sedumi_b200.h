@@ -162,6 +162,11 @@ int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx
 int sb200_invcholfac_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm, double *y);
 int sb200_psdscale_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, const sb_idx *perm,
                      const double *x, int transp, double *y);
+/* frms of a Hermitian block: [Re c | Im c | beta] = 2 n^2 + n doubles, the last column of c is the complex
+ * sign vector (psdframeit.c:80-97, reflect.c:218-262); lab/xlab: sum(n) doubles. */
+int sb200_psdframeit_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *lab, const double *frms, double *x);
+int sb200_psdinvjmul_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *xlab, const double *frms,
+                       const double *y, double *z);
 int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *perm,
                    const double *x, int transp, double *y);
 

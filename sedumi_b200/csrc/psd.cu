@@ -419,10 +419,13 @@ __global__ void herm_embed_kernel(const HermBlk *blks, const double *raw, double
     const int p = (int)(idx % n), q = (int)(idx / n);
     int sp = tc ? q : p, sq = tc ? p : q;
     if (P) { sp = P[sp]; sq = P[sq]; }
-    const bool keep = mask == 0 || (mask == 1 ? sp <= sq : sp >= sq);
+    bool keep = mask == 0 || mask == 3 || (mask == 1 ? sp <= sq : sp >= sq);
+    bool flip = false;                                     // mask 3: Hermitian completion from the lower triangle
+    if (mask == 3 && sp < sq) { const int t = sp; sp = sq; sq = t; flip = true; }
     const long long si = sp + (long long)sq * n;
     double zr = keep ? re[si] : 0.0, zi = (keep && B.cplx) ? im[si] : 0.0;
-    if (tc) zi = -zi;
+    if (tc != flip) zi = -zi;
+    if (mask == 3 && sp == sq) zi = 0.0;
     E[p + (long long)q * ne] = zr;
     if (B.cplx) {
       E[(p + n) + (long long)(q + n) * ne] = zr;
@@ -445,6 +448,57 @@ __global__ void herm_extract_kernel(const HermBlk *blks, const double *emb, doub
     const long long di = dp + (long long)dq * n;
     re[di] = E[p + (long long)q * ne];
     if (B.cplx) im[di] = (zero_imag_diag && dp == dq) ? 0.0 : E[(p + n) + (long long)q * ne];
+  }
+}
+
+// Columns of Qb = H_0 ... H_{n-2} diag(qsgn) for a Hermitian block, H_c = I - c_c c_c^H / beta_c (reflect.c:218-262:
+// frames [Re c | Im c | beta], the last column of c is the complex sign vector).  One warp per column, written
+// straight into the real embedding: column j of E(Qb) = [Re q; Im q], column j+n = [-Im q; Re q].
+__global__ void __launch_bounds__(256)
+householder_q_cplx_kernel(const HermBlk *blks, const int *grp_blk, const int *grp_j0, const long long *fr_off,
+                          const double *frms, double *Qe) {
+  const int k = grp_blk[blockIdx.x];
+  const HermBlk B = blks[k];
+  const int n = B.n, ne = 2 * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = grp_j0[blockIdx.x] + warp;
+  if (j >= n) return;
+  const double *cr = frms + fr_off[k], *ci = cr + (long long)n * n, *beta = ci + (long long)n * n;
+  double *qr = Qe + B.emb_off + (long long)j * ne, *qi = qr + n;
+  const double sr = cr[(long long)(n - 1) * n + j], si = ci[(long long)(n - 1) * n + j];
+  for (int i = lane; i < n; i += 32) { qr[i] = (i == j) ? sr : 0.0; qi[i] = (i == j) ? si : 0.0; }
+  __syncwarp();
+  for (int c = min(j, n - 2); c >= 0; c--) {
+    const double *vr = cr + (long long)c * n, *vi = ci + (long long)c * n;
+    double tr = 0.0, ti = 0.0;                           // t = v^H q
+    for (int i = c + lane; i < n; i += 32) {
+      tr += vr[i] * qr[i] + vi[i] * qi[i];
+      ti += vr[i] * qi[i] - vi[i] * qr[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) { tr += __shfl_xor_sync(0xffffffffu, tr, o); ti += __shfl_xor_sync(0xffffffffu, ti, o); }
+    const double ar = -tr / beta[c], ai = -ti / beta[c];
+    for (int i = c + lane; i < n; i += 32) {
+      const double xr = vr[i], xi = vi[i];
+      qr[i] += ar * xr - ai * xi;
+      qi[i] += ar * xi + ai * xr;
+    }
+    __syncwarp();
+  }
+  double *q2 = Qe + B.emb_off + (long long)(j + n) * ne;
+  for (int i = lane; i < n; i += 32) { q2[i] = -qi[i]; q2[n + i] = qr[i]; }
+}
+
+// Real frames of the mixed layout -> the embedded layout; Hermitian slots get "no reflection" frames (zero
+// vectors, beta = 1) so that the real builder leaves an identity there (it is overwritten afterwards).
+__global__ void herm_frames_kernel(const HermBlk *blks, const long long *fr_off, const double *frms, double *Femb) {
+  const HermBlk B = blks[blockIdx.y];
+  const int n = B.n, ne = B.cplx ? 2 * n : n;
+  const double *F = frms + fr_off[blockIdx.y];
+  double *E = Femb + B.emb_off;
+  const long long tot = (long long)ne * ne;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    if (!B.cplx) E[idx] = F[idx];
+    else E[idx] = (idx / ne == ne - 1) ? 1.0 : 0.0;
   }
 }
 
@@ -747,11 +801,16 @@ static int build_q(sb200_psd_plan *pl, const double *frms_dev) {   // Q -> d_Tt,
 }
 
 // x = psdframeit(lab, frms, K):  X_k = Qb' diag(lab_k) Qb   (psdframeit.c:65-99)
+static int psdframeit_core(sb200_psd_plan *pl, const double *lab_dev, double *x_dev);
 int sb200_psdframeit_dev(sb200_psd_plan *pl, const double *lab_dev, const double *frms_dev, double *x_dev) {
   SB_TRY(ensure_init());
   if (pl->nblk == 0) return 0;
-  cudaStream_t st = ctx().stream;
   SB_TRY(build_q(pl, frms_dev));
+  return psdframeit_core(pl, lab_dev, x_dev);
+}
+// X = Q' diag(lab) Q with Q in d_Tt and Q' in d_Wt
+static int psdframeit_core(sb200_psd_plan *pl, const double *lab_dev, double *x_dev) {
+  cudaStream_t st = ctx().stream;
   int tp = (pl->maxn + 31) / 32;
   // B(c,k) = lab_k * Qb(k,c): transpose of Q with the k-index scaled -> d_Xp
   transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, lab_dev, pl->d_Xp.p);
@@ -764,11 +823,15 @@ int sb200_psdframeit_dev(sb200_psd_plan *pl, const double *lab_dev, const double
 }
 
 // z = psdinvjmul(xlab, xfrm, y, K):  solve X Z + Z X = 2 Y in the eigenbasis of X   (psdinvjmul.c:101-157)
+static int psdinvjmul_core(sb200_psd_plan *pl, const double *xlab_dev, const double *y_dev, double *z_dev);
 int sb200_psdinvjmul_dev(sb200_psd_plan *pl, const double *xlab_dev, const double *frms_dev, const double *y_dev, double *z_dev) {
   SB_TRY(ensure_init());
   if (pl->nblk == 0) return 0;
-  cudaStream_t st = ctx().stream;
   SB_TRY(build_q(pl, frms_dev));                                      // Q = d_Tt, Q' = d_Wt
+  return psdinvjmul_core(pl, xlab_dev, y_dev, z_dev);
+}
+static int psdinvjmul_core(sb200_psd_plan *pl, const double *xlab_dev, const double *y_dev, double *z_dev) {
+  cudaStream_t st = ctx().stream;
   sym_ops_kernel<<<blk_grid(pl, 256), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, y_dev, pl->d_Y.p, nullptr, 1);   // Ys from tril(Y)
   SB_LAUNCH_CHECK_N("sym_ops_kernel");
   // P = Q Ys           (A = Q, B = Ys symmetric)            -> d_Xp
@@ -933,6 +996,118 @@ int sb200_psdscale_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u
   herm_extract_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, pl->d_Y.p, dy, transp ? dperm : nullptr, 1);
   SB_LAUNCH_CHECK_N("herm_extract_kernel");
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * c->raw_len, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
+// Frames of the mixed layout: real block n^2 doubles (last column = beta), Hermitian block 2 n^2 + n
+// ([Re c | Im c | beta], psdframeit.c:80-97).  lab: sum(n) eigenvalues.
+struct HermFrames { long long *d_fr_off = nullptr; int *d_grp_blk = nullptr, *d_grp_j0 = nullptr; int ngrp = 0; long long fr_len = 0; };
+static std::map<HermCtx *, HermFrames *> g_herm_frames;
+static int herm_frames_get(HermCtx *c, const sb_idx *n, sb_idx nreal, HermFrames **out) {
+  auto it = g_herm_frames.find(c);
+  if (it != g_herm_frames.end()) { *out = it->second; return 0; }
+  HermFrames *f = new HermFrames();
+  std::vector<long long> off(c->nblk);
+  std::vector<int> gb, gj;
+  long long o = 0;
+  for (int k = 0; k < c->nblk; k++) {
+    off[k] = o;
+    const bool cplx = k >= nreal;
+    o += cplx ? 2 * n[k] * n[k] + n[k] : n[k] * n[k];
+    if (cplx) for (int j0 = 0; j0 < n[k]; j0 += 8) { gb.push_back(k); gj.push_back(j0); }
+  }
+  f->fr_len = o; f->ngrp = (int)gb.size();
+  SB_CUDA(cudaMalloc(&f->d_fr_off, sizeof(long long) * std::max(c->nblk, 1)));
+  SB_CUDA(cudaMemcpy(f->d_fr_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMalloc(&f->d_grp_blk, sizeof(int) * std::max<size_t>(gb.size(), 1)));
+  SB_CUDA(cudaMalloc(&f->d_grp_j0, sizeof(int) * std::max<size_t>(gb.size(), 1)));
+  if (!gb.empty()) {
+    SB_CUDA(cudaMemcpy(f->d_grp_blk, gb.data(), sizeof(int) * gb.size(), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(f->d_grp_j0, gj.data(), sizeof(int) * gj.size(), cudaMemcpyHostToDevice));
+  }
+  g_herm_frames[c] = f;
+  *out = f;
+  return 0;
+}
+// Q (embedded) -> pl->d_Tt, Q' -> pl->d_Wt for a mixed real/Hermitian frame vector on the device.
+static int herm_build_q(HermCtx *c, HermFrames *f, const double *frms_dev) {
+  sb200_psd_plan *pl = c->pl;
+  cudaStream_t st = ctx().stream;
+  const int maxne = pl->maxn;
+  dim3 g((unsigned)std::min<long long>(((long long)maxne * maxne + 255) / 256, 1024), (unsigned)c->nblk);
+  herm_frames_kernel<<<g, 256, 0, st>>>(c->d_blks, f->d_fr_off, frms_dev, pl->d_Y.p);
+  SB_LAUNCH_CHECK_N("herm_frames_kernel");
+  SB_TRY(build_q(pl, pl->d_Y.p));
+  if (f->ngrp) {
+    householder_q_cplx_kernel<<<f->ngrp, 256, 0, st>>>(c->d_blks, f->d_grp_blk, f->d_grp_j0, f->d_fr_off, frms_dev, pl->d_Tt.p);
+    SB_LAUNCH_CHECK_N("householder_q_cplx_kernel");
+    int tp = (pl->maxn + 31) / 32;
+    transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, nullptr, pl->d_Wt.p);
+    SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+  }
+  return 0;
+}
+static void herm_lab(const HermCtx *c, const sb_idx *n, sb_idx nreal, const double *lab, std::vector<double> &labe) {
+  labe.clear();
+  long long po = 0;
+  for (int k = 0; k < c->nblk; k++) {
+    labe.insert(labe.end(), lab + po, lab + po + n[k]);
+    if (k >= nreal) labe.insert(labe.end(), lab + po, lab + po + n[k]);     // E(diag(lab)) = diag(lab, lab)
+    po += n[k];
+  }
+}
+
+// x = psdframeit(lab, frms, K) with Hermitian blocks: X = Qb^H diag(lab) Qb   (psdframeit.c:65-99)
+int sb200_psdframeit_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *lab, const double *frms, double *x) {
+  HermCtx *c; HermFrames *f;
+  SB_TRY(herm_get(nblk, nreal, n, &c));
+  if (c->raw_len == 0) return 0;
+  SB_TRY(herm_frames_get(c, n, nreal, &f));
+  sb200_psd_plan *pl = c->pl;
+  std::vector<double> labe;
+  herm_lab(c, n, nreal, lab, labe);
+  arena_reset();
+  double *dl = arena<double>(labe.size()), *df = arena<double>((size_t)f->fr_len), *dxe = arena<double>((size_t)pl->lenud),
+         *dx = arena<double>((size_t)c->raw_len);
+  SB_CHECK(dl && df && dxe && dx, "psdframeit: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dl, labe.data(), sizeof(double) * labe.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * f->fr_len, cudaMemcpyHostToDevice, st));
+  SB_TRY(herm_build_q(c, f, df));
+  SB_TRY(psdframeit_core(pl, dl, dxe));
+  herm_extract_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, dxe, dx, nullptr, 1);
+  SB_LAUNCH_CHECK_N("herm_extract_kernel");
+  SB_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * c->raw_len, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// z = psdinvjmul(xlab, xfrm, y, K) with Hermitian blocks   (psdinvjmul.c:101-157)
+int sb200_psdinvjmul_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *xlab, const double *frms, const double *y, double *z) {
+  HermCtx *c; HermFrames *f;
+  SB_TRY(herm_get(nblk, nreal, n, &c));
+  if (c->raw_len == 0) return 0;
+  SB_TRY(herm_frames_get(c, n, nreal, &f));
+  sb200_psd_plan *pl = c->pl;
+  std::vector<double> labe;
+  herm_lab(c, n, nreal, xlab, labe);
+  arena_reset();
+  double *dl = arena<double>(labe.size()), *df = arena<double>((size_t)f->fr_len), *dye = arena<double>((size_t)pl->lenud),
+         *dze = arena<double>((size_t)pl->lenud), *draw = arena<double>((size_t)c->raw_len);
+  SB_CHECK(dl && df && dye && dze && draw, "psdinvjmul: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dl, labe.data(), sizeof(double) * labe.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * f->fr_len, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(draw, y, sizeof(double) * c->raw_len, cudaMemcpyHostToDevice, st));
+  herm_embed_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, draw, dye, nullptr, 0, 3);       // E(Y), Y completed from its lower triangle
+  SB_LAUNCH_CHECK_N("herm_embed_kernel");
+  SB_TRY(herm_build_q(c, f, df));
+  SB_TRY(psdinvjmul_core(pl, dl, dye, dze));
+  herm_extract_kernel<<<herm_grid(c), 256, 0, st>>>(c->d_blks, dze, draw, nullptr, 1);
+  SB_LAUNCH_CHECK_N("herm_extract_kernel");
+  SB_CUDA(cudaMemcpyAsync(z, draw, sizeof(double) * c->raw_len, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -83,3 +83,43 @@ def test_psdscale_hermitian(sreal, sherm, transp, withperm):
     yr = restate.psdscale(ud, xfull, K, bool(transp))
     yg = gpu.psdscale(ud, xfull, Km, transp)
     assert relerr(yg.ravel(), yr) <= 1e-10
+
+
+def _frames(K, rng):
+    """vfrm.s from the reference's own qrK on a random (complex for the Hermitian blocks) matrix per block."""
+    x = []
+    nr = K["rsdpN"]
+    for i, n in enumerate(K["s"].astype(int)):
+        x.append(rng.standard_normal(n * n))
+        if i >= nr:
+            x.append(rng.standard_normal(n * n))
+    return ref.qrK(np.concatenate(x), cones.K_for_mex(K))
+
+
+FCASES = [((), (2,)), ((), (3,)), ((4,), (5,)), ((), (1, 6)), ((7, 2), (9, 33)), ((), (70,)), ((100,), (60,))]
+
+
+@pytest.mark.parametrize("sreal,sherm", FCASES)
+def test_psdframeit_hermitian(sreal, sherm):
+    K = _K(sreal, sherm)
+    Km = cones.K_for_mex(K)
+    rng = np.random.default_rng(7 + len(sreal) + 10 * sum(sherm))
+    frms = _frames(K, rng)
+    lab = rng.uniform(0.1, 3.0, int(K["s"].sum()))
+    xr = ref.psdframeit(lab, frms, Km)
+    xg = gpu.psdframeit(lab, frms, Km)
+    assert xg.shape == xr.shape
+    assert relerr(xg, xr) <= 1e-10
+
+
+@pytest.mark.parametrize("sreal,sherm", FCASES)
+def test_psdinvjmul_hermitian(sreal, sherm):
+    K = _K(sreal, sherm)
+    Km = cones.K_for_mex(K)
+    rng = np.random.default_rng(11 + len(sreal) + 10 * sum(sherm))
+    frms = _frames(K, rng)
+    xlab = rng.uniform(0.5, 2.0, int(K["s"].sum()))
+    y = _herm_vec(K, rng)
+    zr = ref.psdinvjmul(xlab, frms, y, Km)
+    zg = gpu.psdinvjmul(xlab, frms, y, Km)
+    assert relerr(zg, zr) <= 1e-10
