@@ -181,6 +181,11 @@ typedef struct sb200_ada_plan sb200_ada_plan;
 int sb200_ada_plan_get(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
                        const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk,
                        const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair);
+/* With Hermitian PSD blocks (K.rsdpN = nreal < nblk): blocks [nreal, nblk) occupy 2 n^2 rows of At, [Re (lower
+ * triangle); Im (strictly lower)] (pretransfo.m:456-480); udsqr holds [vec Re D; vec Im D] for them (spscale.c:332-435). */
+int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
+                         const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal,
+                         const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair);
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *plan);
 int sb200_ada_set_At_values(sb200_ada_plan *plan, const double *Atpr);
 /* device-resident variants: invperm_dev = inverse of the ordering (int32) or NULL = natural */

@@ -115,6 +115,26 @@ gather_dense_kernel(int m, const long long *adajc, const int *adair, const int *
   }
 }
 
+// udsqr as it arrives ([vec Re D; vec Im D] for Hermitian blocks) -> the embedded blocks [[Re,-Im],[Im,Re]]
+__global__ void ada_embed_d_kernel(const int *nraw, const int *cplx, const long long *rawoff, const long long *emboff,
+                                   const double *raw, double *emb) {
+  const int k = blockIdx.y, n = nraw[k], c = cplx[k], ne = c ? 2 * n : n;
+  const double *re = raw + rawoff[k], *im = re + (long long)n * n;
+  double *E = emb + emboff[k];
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % n), q = (int)(idx / n);
+    const double zr = re[idx];
+    E[p + (long long)q * ne] = zr;
+    if (c) {
+      const double zi = im[idx];
+      E[(p + n) + (long long)(q + n) * ne] = zr;
+      E[(p + n) + (long long)q * ne] = zi;
+      E[p + (long long)(q + n) * ne] = -zi;
+    }
+  }
+}
+
 // getDAtm.m:40-43:  DAt.q(k,j) = d.q1(k) * A(trace row of cone k, j) + sum_{i in norm rows of cone k} d.q2(i) * A(i,j).
 // The pattern (one entry per (column, Lorentz cone touched)) is compiled into the plan; WIDE = one warp
 // per entry (long cones), otherwise one thread per entry.
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(256)
 ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *invperm, int first,
                  const int *cpair_beg, const AdaPair *pairs, const int *blk_n, const int *ublk_off,
                  const int *blkp_beg, const BlkPartner *blkp,
-                 const int *ent_lin, const int *ent_pk, const int *ent_src, const double *Atpr,
+                 const int *ent_lin, const int *ent_pk, const int *ent_src, const double *Atpr, const double *ent_scale,
                  double *ws, double *ada, double *absd, int wcap, int use_map, int m) {
   extern __shared__ double dots_sm[];
   double *Wsm = dots_sm;
@@ -258,9 +278,16 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
   for (int t = tb + warp * GPW + grp; t < te; t += nw * GPW) {
     const BlkPartner Q = blkp[t];
     if (invperm[Q.j] > ipc) continue;
-    const double *av = Atpr + ent_src[Q.e0] - Q.e0;     // the entries of one pair are consecutive in At.pr
+    const double *av = Atpr + ent_src[Q.e0] - Q.e0;     // the entries of one pair are consecutive in At.pr ...
     double acc = 0.0, aabs = 0.0;
     int e = Q.e0 + gl;
+    if (ent_scale) {                                    // ... except with Hermitian blocks (embedded entries, signs)
+      for (; e < Q.e1; e += G) {
+        const double term = (Atpr[ent_src[e]] * ent_scale[e]) * Wp[eidx[e]];
+        acc += term;
+        aabs += fabs(term);
+      }
+    }
     for (; e + 3 * G < Q.e1; e += 4 * G) {
       const double a0 = av[e], a1 = av[e + G], a2 = av[e + 2 * G], a3 = av[e + 3 * G];
       const int i0 = eidx[e], i1 = eidx[e + G], i2 = eidx[e + 2 * G], i3 = eidx[e + 3 * G];
@@ -364,7 +391,10 @@ struct sb200_ada_plan {
   long long N = 0, nnzA = 0, nnzADA = 0;
   int lpN = 0, nq = 0, nblk = 0;
   long long lq_rows = 0;          // rows before the PSD part covered by dsqr
-  std::vector<int> blk_n; std::vector<long long> blk_off, blk_start;
+  std::vector<int> blk_n, blk_nraw, blk_cplx; std::vector<long long> blk_off, blk_start, blk_rawoff;
+  bool herm = false; long long lenud_emb = 0, lenud_raw = 0;
+  DevBuf<double> d_De, d_ent_scale;
+  DevBuf<int> d_blk_nraw, d_blk_cplx; DevBuf<long long> d_blk_rawoff;
   std::vector<AdaPair> pairs;
   std::vector<int> cpair_beg;
   struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; int nsparse; int nmulti; };
@@ -403,20 +433,29 @@ struct sb200_ada_plan {
 static std::map<uint64_t, sb200_ada_plan *> g_ada_plans;
 
 static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air, const sb_idx *Ajc1,
-                     sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, const sb_idx *blkstart, const sb_idx *blkn,
+                     sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal, const sb_idx *blkstart, const sb_idx *blkn,
                      const sb_idx *adajc, const sb_idx *adair) {
   pl->m = (int)m; pl->N = N; pl->nnzA = Ajc[m]; pl->nnzADA = adajc[m];
   pl->lpN = (int)lpN; pl->nq = (int)nq; pl->nblk = (int)nblk;
   SB_CHECK(pl->nnzA < 2147483647LL, "At has too many nonzeros for 32-bit entry indices");
-  long long off = 0;
+  // Hermitian blocks (k >= nreal) are handled through the real embedding E(Z) = [[Re Z, -Im Z],[Im Z, Re Z]] of
+  // order 2n: blk_n / blk_off describe the EMBEDDED blocks, blk_nraw / blk_rawoff the layout of udsqr as it arrives.
+  long long off = 0, rawoff = 0;
+  pl->herm = nreal < nblk;
   for (sb_idx k = 0; k < nblk; k++) {
-    pl->blk_n.push_back((int)blkn[k]); pl->blk_off.push_back(off); pl->blk_start.push_back(blkstart[k]);
-    off += blkn[k] * blkn[k];
+    const int cplx = k >= nreal;
+    const long long ne = cplx ? 2 * blkn[k] : blkn[k];
+    SB_CHECK(ne < 46340, "PSD block order %lld out of range", (long long)blkn[k]);
+    pl->blk_n.push_back((int)ne); pl->blk_off.push_back(off); pl->blk_start.push_back(blkstart[k]);
+    pl->blk_nraw.push_back((int)blkn[k]); pl->blk_cplx.push_back(cplx); pl->blk_rawoff.push_back(rawoff);
+    off += ne * ne; rawoff += (cplx ? 2 : 1) * blkn[k] * blkn[k];
   }
+  pl->lenud_emb = off; pl->lenud_raw = rawoff;
   const long long psd0 = nblk ? blkstart[0] : N;
   pl->lq_rows = nq ? qstart[nq] : lpN;
   // ---- pairs
   std::vector<int> ent_p, ent_q, ent_lin, ent_src, Rlist, tt_ptr, tt_col, tt_src;
+  std::vector<double> ent_sgn;
   std::vector<double> tt_w;
   std::vector<std::vector<std::pair<int, std::pair<int, double>>>> percol;
   pl->cpair_beg.assign(m + 1, 0);
@@ -429,15 +468,28 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       sb_idx row = Air[inz];
       SB_CHECK(row >= psd0 && row < N, "getada3: row %lld of At is not in the PSD part", (long long)row);
       int k = (int)(std::upper_bound(pl->blk_start.begin(), pl->blk_start.end(), (long long)row) - pl->blk_start.begin()) - 1;
-      const long long bs = pl->blk_start[k]; const int n = pl->blk_n[k];
-      SB_CHECK(row < bs + (long long)n * n, "getada3: row %lld beyond PSD block %d (Hermitian blocks unsupported)", (long long)row, k);
+      const long long bs = pl->blk_start[k]; const int n = pl->blk_n[k];     // n: embedded order
+      const int nr = pl->blk_nraw[k], cplx = pl->blk_cplx[k];
+      const long long span = (long long)(cplx ? 2 : 1) * nr * nr;
+      SB_CHECK(row < bs + span, "getada3: row %lld beyond PSD block %d", (long long)row, k);
       AdaPair P{}; P.j = (int)j; P.k = k; P.e0 = (int)ent_p.size();
       tmpR.clear();
-      while (inz < Ajc[j + 1] && Air[inz] < bs + (long long)n * n) {
-        long long idx = Air[inz] - bs;
-        int p = (int)(idx % n), q = (int)(idx / n);
-        ent_p.push_back(p); ent_q.push_back(q); ent_src.push_back((int)inz);
+      auto add_entry = [&](int p, int q, double sg) {
+        ent_p.push_back(p); ent_q.push_back(q); ent_src.push_back((int)inz); ent_sgn.push_back(sg);
         tmpR.push_back(p); tmpR.push_back(q);
+      };
+      while (inz < Ajc[j + 1] && Air[inz] < bs + span) {
+        long long idx = Air[inz] - bs;
+        const bool imag = idx >= (long long)nr * nr;
+        if (imag) idx -= (long long)nr * nr;
+        int p = (int)(idx % nr), q = (int)(idx / nr);
+        if (!cplx) add_entry(p, q, 1.0);
+        else if (!imag) {                              // Re part a at (p,q): E has a at (p,q) and (p+n,q+n)
+          add_entry(p, q, 1.0); add_entry(p + nr, q + nr, 1.0);
+        } else {                                       // Im part b at (p>q): E has +b at (p+n,q), -b at (q+n,p)  (+ mirrors)
+          SB_CHECK(p != q, "getada3: imaginary diagonal entry in Hermitian block %d", k);
+          add_entry(std::max(p, q) + nr, std::min(p, q), 1.0); add_entry(std::min(p, q) + nr, std::max(p, q), -1.0);
+        }
         inz++;
       }
       P.e1 = (int)ent_p.size();
@@ -453,10 +505,10 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
         const int rp = (int)(std::lower_bound(tmpR.begin(), tmpR.end(), pp) - tmpR.begin());
         const int rq = (int)(std::lower_bound(tmpR.begin(), tmpR.end(), qq) - tmpR.begin());
         ent_lin.push_back(std::max(pp, qq) + std::min(pp, qq) * n);
-        if (pp == qq) percol[rp].push_back({pp, {ent_src[e], 1.0}});
+        if (pp == qq) percol[rp].push_back({pp, {ent_src[e], ent_sgn[e]}});
         else {                                      // sym(X) = (X+X')/2   (spscale.c:227-229)
-          percol[rq].push_back({pp, {ent_src[e], 0.5}});
-          percol[rp].push_back({qq, {ent_src[e], 0.5}});
+          percol[rq].push_back({pp, {ent_src[e], 0.5 * ent_sgn[e]}});
+          percol[rp].push_back({qq, {ent_src[e], 0.5 * ent_sgn[e]}});
         }
       }
       for (size_t rho = 0; rho < tmpR.size(); rho++) {
@@ -625,6 +677,15 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(pl->d_blk_n.upload(pl->blk_n)); SB_TRY(pl->d_blk_off.upload(pl->blk_off));
   SB_TRY(pl->d_cpair_beg.upload(pl->cpair_beg));
   SB_TRY(pl->d_ent_lin.upload(ent_lin)); SB_TRY(pl->d_ent_src.upload(ent_src));
+  if (pl->herm) {
+    // <E(A_i), E(W)> = 2 Re tr(A_i^H W): every embedded entry carries sign * 1/2 (real blocks of a mixed plan: 1)
+    std::vector<double> sc(ent_sgn.size());
+    for (auto &P : pl->pairs)
+      for (int e = P.e0; e < P.e1; e++) sc[e] = ent_sgn[e] * (pl->blk_cplx[P.k] ? 0.5 : 1.0);
+    SB_TRY(pl->d_ent_scale.upload(sc));
+    SB_TRY(pl->d_blk_nraw.upload(pl->blk_nraw)); SB_TRY(pl->d_blk_cplx.upload(pl->blk_cplx)); SB_TRY(pl->d_blk_rawoff.upload(pl->blk_rawoff));
+    SB_TRY(pl->d_De.alloc((size_t)std::max<long long>(pl->lenud_emb, 1)));
+  }
   SB_TRY(pl->d_tt_ptr.upload(tt_ptr)); SB_TRY(pl->d_tt_col.upload(tt_col)); SB_TRY(pl->d_tt_src.upload(tt_src));
   SB_TRY(pl->d_tt_w.upload(tt_w));
   SB_TRY(pl->d_ublk_off.upload(ublk_off)); SB_TRY(pl->d_u_p.upload(u_p)); SB_TRY(pl->d_u_q.upload(u_q));
@@ -652,18 +713,26 @@ extern "C" {
 int sb200_ada_plan_get(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
                        const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk,
                        const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair) {
+  return sb200_ada_plan_get_h(plan, N, m, Ajc, Air, Ajc1, lpN, nq, qstart, nblk, nblk, blkstart, blkn, adajc, adair);
+}
+// Same with Hermitian PSD blocks: blocks [nreal, nblk) are Hermitian, rows [vec Re (lower triangle); vec Im (strictly
+// lower)] = 2 n^2 rows each (pretransfo.m:456-480), udsqr [vec Re D; vec Im D] (spscale.c:332-435 spcpxdxd).
+int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air,
+                         const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal,
+                         const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair) {
   SB_TRY(ensure_init());
+  SB_CHECK(nreal >= 0 && nreal <= nblk, "number of real PSD blocks out of range");
   uint64_t h = fnv1a(&N, sizeof N); h = fnv1a(&m, sizeof m, h);
   h = fnv1a(Ajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(Air, sizeof(sb_idx) * Ajc[m], h);
   h = fnv1a(Ajc1, sizeof(sb_idx) * m, h); h = fnv1a(&lpN, sizeof lpN, h); h = fnv1a(&nq, sizeof nq, h);
   if (nq) h = fnv1a(qstart, sizeof(sb_idx) * (nq + 1), h);
-  h = fnv1a(&nblk, sizeof nblk, h);
+  h = fnv1a(&nblk, sizeof nblk, h); h = fnv1a(&nreal, sizeof nreal, h);
   if (nblk) { h = fnv1a(blkstart, sizeof(sb_idx) * nblk, h); h = fnv1a(blkn, sizeof(sb_idx) * nblk, h); }
   h = fnv1a(adajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(adair, sizeof(sb_idx) * adajc[m], h);
   auto it = g_ada_plans.find(h);
   if (it != g_ada_plans.end()) { *plan = it->second; return 0; }
   sb200_ada_plan *pl = new sb200_ada_plan();
-  int rc = ada_build(pl, N, m, Ajc, Air, Ajc1, lpN, nq, qstart, nblk, blkstart, blkn, adajc, adair);
+  int rc = ada_build(pl, N, m, Ajc, Air, Ajc1, lpN, nq, qstart, nblk, nreal, blkstart, blkn, adajc, adair);
   if (rc) { delete pl; return rc; }
   pl->key = h;
   if (g_ada_plans.size() >= 8) { for (auto &kv : g_ada_plans) delete kv.second; g_ada_plans.clear(); }
@@ -833,6 +902,13 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
   absd_nopsd_kernel<<<(pl->m + 255) / 256, 256, 0, st>>>(pl->m, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
                                                          pl->d_cpair_beg.p, ada_dev, absd_dev, pl->nblk == 0);
   SB_LAUNCH_CHECK_N("absd_nopsd_kernel");
+  if (pl->herm) {
+    int maxn = 0; for (int v : pl->blk_nraw) maxn = std::max(maxn, v);
+    ada_embed_d_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)pl->nblk), 256, 0, st>>>(
+        pl->d_blk_nraw.p, pl->d_blk_cplx.p, pl->d_blk_rawoff.p, pl->d_blk_off.p, udsqr_dev, pl->d_De.p);
+    SB_LAUNCH_CHECK_N("ada_embed_d_kernel");
+    udsqr_dev = pl->d_De.p;
+  }
   for (auto &B : pl->batches) {
     if (B.p1 == B.p0) continue;
     build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_tt_ptr.p, pl->d_tt_col.p,
@@ -855,7 +931,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(ada3_dots_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_done = true; } \
     ada3_dots_kernel<G><<<B.p1 - B.p0, 256, pl->dots_smem, st>>>(B.p0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, \
         pl->d_pairs.p, pl->d_blk_n.p, pl->d_ublk_off.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ent_lin.p, pl->d_ent_pk.p,  \
-        pl->d_ent_src.p, pl->d_Atpr.p, pl->d_ws.p, ada_dev, absd_dev, pl->wcap, pl->use_map, pl->m);                       \
+        pl->d_ent_src.p, pl->d_Atpr.p, pl->herm ? pl->d_ent_scale.p : nullptr, pl->d_ws.p, ada_dev, absd_dev, pl->wcap, pl->use_map, pl->m); \
   } while (0)
       switch (pl->dots_group) {
         case 4: SB_DOTS(4); break;

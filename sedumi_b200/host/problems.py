@@ -206,3 +206,64 @@ def synth_frames(s, seed: int = SEED0 + 7):
     if not labs:
         return np.zeros(0), np.zeros(0)
     return np.concatenate(labs), np.concatenate(frames)
+
+
+def synth_hermitian_mixed(l=3, sreal=(4,), sherm=(3,), m=6, density=0.45, seed=SEED0 + 8):
+    """A small problem directly in SeDuMi's INTERNAL form with Hermitian PSD blocks (K.s = [real..., Hermitian...],
+    K.rsdpN = #real): At rows [x0, LP | vec(real blocks), lower triangle | per Hermitian block: Re part (lower
+    triangle incl. diagonal), Im part (strictly lower)], as pretransfo.m:436-480 leaves them.
+    Returns (At, b, c, K) with K already finished (cones.finish_K)."""
+    from . import cones
+    rng = np.random.default_rng(seed)
+    K = cones.finish_K({"l": float(l), "q": np.zeros(0), "s": np.array(list(sreal) + list(sherm), dtype=float),
+                        "rsdpN": len(sreal)})
+    N = int(K["N"])
+    rows, cols, vals = [], [], []
+    for j in range(m):
+        for r in range(1, l):
+            if rng.random() < 0.7:
+                rows.append(r); cols.append(j); vals.append(rng.standard_normal())
+        off = l
+        for n in sreal:
+            for q in range(n):
+                for p in range(q, n):
+                    if rng.random() < density:
+                        rows.append(off + p + q * n); cols.append(j); vals.append(rng.standard_normal())
+            off += n * n
+        for n in sherm:
+            for q in range(n):
+                for p in range(q, n):
+                    if rng.random() < density:
+                        rows.append(off + p + q * n); cols.append(j); vals.append(rng.standard_normal())
+            for q in range(n):
+                for p in range(q + 1, n):
+                    if rng.random() < density:
+                        rows.append(off + n * n + p + q * n); cols.append(j); vals.append(rng.standard_normal())
+            off += 2 * n * n
+    At = sp.csc_matrix((vals, (rows, cols)), shape=(N, m))
+    At.sort_indices()
+    return At, rng.standard_normal(m), rng.standard_normal(N), K
+
+
+def scaling_hermitian(K: dict, seed: int = SEED0):
+    """NT scaling for a cone with Hermitian blocks: like scaling(.., "S1") with complex upper-triangular factors
+    (real positive diagonal) stored [vec Re U; vec Im U] for the blocks after K.rsdpN."""
+    rng = np.random.default_rng(seed)
+    s = np.asarray(K["s"], dtype=np.int64)
+    nr = int(K.get("rsdpN", len(s)))
+    d = {"l": np.exp(rng.standard_normal(int(K["l"]))), "det": np.zeros(0), "q1": np.zeros(0), "q2": np.zeros(0)}
+    us, perms = [], []
+    for i, n in enumerate(s):
+        n = int(n)
+        G = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if i >= nr else 0)
+        R = np.linalg.qr(np.eye(n) + 0.3 * G, mode="r")
+        ph = np.diag(R) / np.abs(np.diag(R))
+        U = np.triu(R) * np.conj(ph)[:, None]                 # positive real diagonal
+        full = U + np.triu(U, 1).conj().T
+        us.append(full.real.ravel(order="F"))
+        if i >= nr:
+            us.append(np.triu(U, 1).imag.ravel(order="F") - np.triu(U, 1).imag.T.ravel(order="F"))
+        perms.append(rng.permutation(n) + 1.0)
+    d["u"] = np.concatenate(us) if us else np.zeros(0)
+    d["perm"] = np.concatenate(perms).reshape(-1, 1) if perms else np.zeros((0, 0))
+    return d

@@ -8,8 +8,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   const mxArray *ADA = prhs[0], *AT = prhs[1], *AJC1 = prhs[2], *AORD = prhs[3], *UDSQR = prhs[4];
   ConeK K;
   read_cone(prhs[5], K);
-  if (K.rsdpN != K.sdpN) mexErrMsgTxt("getada3: Hermitian PSD blocks are not supported by the B200 plugin yet.");
-  sb_idx lenud = K.rDim;
+  sb_idx lenud = K.rDim + K.hDim;                 // Hermitian blocks: [vec Re; vec Im] (getada3.c:404-412, spscale.c:472-480)
   sb_idx lenfull = K.lpN + K.qDim + lenud;
   const mxArray *bsf = need_field(prhs[5], "blkstart", "Missing K.blkstart.");
   MEX_REQUIRE(numel(bsf) == (mwSize)(2 + K.lorN + K.sdpN), "Size mismatch K.blkstart.");
@@ -41,8 +40,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   // Lorentz layout is irrelevant here: describe only the PSD part to the plan
   std::vector<sb_idx> Ajc_lq(m);            // columns restricted to the PSD part: start = Ajc1
   sb200_ada_plan *pl = NULL;
-  sb_check(sb200_ada_plan_get(&pl, (sb_idx)lenfull, (sb_idx)m, as_idx(mxGetJc(AT)), as_idx(mxGetIr(AT)), Ajc1.data(),
-                              0, 0, NULL, K.sdpN, blkstart.data(), K.s.data(), as_idx(adajc), as_idx(adair)), "getada3");
+  sb_check(sb200_ada_plan_get_h(&pl, (sb_idx)lenfull, (sb_idx)m, as_idx(mxGetJc(AT)), as_idx(mxGetIr(AT)), Ajc1.data(),
+                                0, 0, NULL, K.sdpN, K.rsdpN, blkstart.data(), K.s.data(), as_idx(adajc), as_idx(adair)), "getada3");
   mxArray *out0 = mxCreateSparse(m, m, adajc[m], mxREAL);
   memcpy(mxGetJc(out0), adajc, (m + 1) * sizeof(mwIndex));
   memcpy(mxGetIr(out0), adair, adajc[m] * sizeof(mwIndex));

@@ -123,3 +123,26 @@ def test_psdinvjmul_hermitian(sreal, sherm):
     zr = ref.psdinvjmul(xlab, frms, y, Km)
     zg = gpu.psdinvjmul(xlab, frms, y, Km)
     assert relerr(zg, zr) <= 1e-10
+
+
+@pytest.mark.parametrize("l,sreal,sherm,m,dens", [(3, (4,), (3,), 6, 0.45), (2, (), (5,), 9, 0.5), (4, (6, 3), (4, 7), 25, 0.3),
+                                                  (2, (), (20,), 40, 0.1), (2, (12,), (16, 2), 60, 0.15)])
+def test_getada3_hermitian(l, sreal, sherm, m, dens):
+    """[ADA,absd] = getada3(...) with Hermitian blocks against the reference's spcpxdxd path (spscale.c:332-435)."""
+    import refpath
+    from sedumi_b200.host import problems, setup
+    At, b, c, K = problems.synth_hermitian_mixed(l=l, sreal=sreal, sherm=sherm, m=m, density=dens, seed=17 + m)
+    S = setup.build_setup(At, b, c, K)
+    d = problems.scaling_hermitian(K, 3 + m)
+    R = refpath.RefHotPath(S)
+    Km = R.Km
+    udsqr = ref.invcholfac(d["u"], Km, d["perm"])
+    assert relerr(gpu.invcholfac(d["u"], Km, d["perm"]), udsqr) <= 1e-10
+    A1 = ref.getada1(R.ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], {"l": d["l"], "det": d["det"]}, S.K["qblkstart"].reshape(1, -1))
+    A2 = ref.getada2(A1, {"q": R.DAtq(d)}, S.Aord, Km)
+    Ar, absr = ref.getada3(A2, S.At, S.Ablkjc[:, 2], S.Aord, udsqr, Km, nlhs=2)
+    Ag, absg = gpu.getada3(A2, S.At, S.Ablkjc[:, 2], S.Aord, udsqr, Km, nlhs=2)
+    assert np.array_equal(Ag.indices, Ar.indices) and np.array_equal(Ag.indptr, Ar.indptr)
+    assert relerr(Ag.data, Ar.data) <= 1e-10
+    assert relerr(absg, absr) <= 1e-10
+    assert np.array_equal(Ag.toarray(), Ag.toarray().T)
