@@ -150,6 +150,13 @@ int sb200_urotorder_dev(sb_idx nblk, const sb_idx *n, const double *u_dev, doubl
                         int *perm_dev, int *gjc_dev, double *g_dev, double *work_dev);
 int sb200_givensrot_dev(sb_idx nblk, const sb_idx *n, const int *gjc_dev, const double *g_dev,
                         const double *x_dev, double *y_dev);
+/* Mixed real / Hermitian blocks (urotorder.c:420-455, givensrot.c:154-163): u = [vec Re; vec Im] for the blocks
+ * [nreal, nblk), rotations (Re x, Im x, y).  urotorder_h: g_out in the worst-case layout, block k at
+ * sum_{j<k} (real: n_j(n_j-1), Hermitian: 3 n_j(n_j-1)/2) doubles; givensrot_h: g packed as the reference packs it. */
+int sb200_urotorder_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, double maxu, double *u_out,
+                      sb_idx *perm_out, sb_idx *gjc_out, double *g_out);
+int sb200_givensrot_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen,
+                      const double *x, double *y);
 int sb200_urotorder(sb_idx nblk, const sb_idx *n, const double *u, double maxu, double *u_out,
                     sb_idx *perm_out, sb_idx *gjc_out, double *g_out);
 int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen,

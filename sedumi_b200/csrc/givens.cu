@@ -184,6 +184,172 @@ __global__ void matgivens_kernel(const UrotBlk *blks, const int *gjc_all, const 
   }
 }
 
+// ---------------------------------------------------------------- Hermitian blocks (urotorder.c:197-304, auxgivens.c:62-205)
+// Same algorithm on [Re U | Im U] with rotations [conj(x), y; y, -x] stored as (Re x, Im x, y); the arithmetic is
+// restated operation by operation (explicit round-to-nearest, the reference's association) for bit-identical output.
+__device__ void d_prpigivensrot(double *z, double *zi, const double *g, int n) {
+  double z2 = z[n], z2im = zi[n];
+  for (int i = n; i > 0; i--) {
+    const double gx = g[3 * (i - 1)], gxim = g[3 * (i - 1) + 1], gy = g[3 * (i - 1) + 2];
+    const double z1 = z[i - 1], z1im = zi[i - 1];
+    z[i] = add_(sub_(mul_(gy, z1), mul_(gx, z2)), mul_(gxim, z2im));
+    zi[i] = sub_(sub_(mul_(gy, z1im), mul_(gx, z2im)), mul_(gxim, z2));
+    const double n2 = add_(add_(mul_(gx, z1), mul_(gxim, z1im)), mul_(gy, z2));
+    const double n2im = add_(sub_(mul_(gx, z1im), mul_(gxim, z1)), mul_(gy, z2im));
+    z2 = n2; z2im = n2im;
+  }
+  z[0] = z2; zi[0] = z2im;
+}
+__device__ void d_prpigivensrotuj(double *z, double *zi, const double *g, int n) {
+  if (n < 1) return;
+  double z2 = z[n - 1];
+  z[n] = mul_(z2, g[3 * (n - 1) + 2]);
+  double z2im = mul_(-z2, g[3 * (n - 1) + 1]);
+  z2 = mul_(z2, g[3 * (n - 1)]);
+  for (int i = n - 1; i > 0; i--) {
+    const double gx = g[3 * (i - 1)], gxim = g[3 * (i - 1) + 1], gy = g[3 * (i - 1) + 2];
+    const double z1 = z[i - 1], z1im = zi[i - 1];
+    z[i] = add_(sub_(mul_(gy, z1), mul_(gx, z2)), mul_(gxim, z2im));
+    zi[i] = sub_(sub_(mul_(gy, z1im), mul_(gx, z2im)), mul_(gxim, z2));
+    const double n2 = add_(add_(mul_(gx, z1), mul_(gxim, z1im)), mul_(gy, z2));
+    const double n2im = add_(sub_(mul_(gx, z1im), mul_(gxim, z1)), mul_(gy, z2im));
+    z2 = n2; z2im = n2im;
+  }
+  z[0] = z2; zi[0] = z2im;
+}
+
+__global__ void __launch_bounds__(256)
+urotorder_cplx_kernel(const UrotBlk *blks, double *W, int *perm_all, int *gjc_all, double *g_all, double *d_all,
+                      double maxusqr) {
+  const UrotBlk B = blks[blockIdx.x];
+  const int n = B.n;
+  double *u = W + B.uoff, *upi = u + (long long)n * n;
+  int *perm = perm_all + B.poff, *gjc = gjc_all + B.poff;
+  double *d = d_all + B.poff;
+  double *g = g_all + B.goff;
+  __shared__ double s_h, s_red[32];
+  __shared__ int s_flag, s_pivk, s_inz, s_redi[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int j = tid; j < n; j += blockDim.x) perm[j] = j;
+  if (tid == 0) { d[0] = 0.0; s_h = 1.0; s_pivk = 0; s_inz = 0; }
+  __syncthreads();
+  for (int k = 0; k < n - 1; k++) {
+    double *rowuk = u + k, *rowukpi = upi + k;
+    __syncthreads();
+    if (tid == 0) { gjc[k] = s_inz; s_flag = (d[perm[k]] <= s_h); }
+    __syncthreads();
+    if (s_flag) {                                    // d(i) = |u(k:j,i)|^2 from scratch (the diagonal u(j,i) is real)
+      for (int j = k + tid; j < n; j += blockDim.x) {
+        const int i = perm[j];
+        const double *x = rowuk + (long long)i * n, *xi = rowukpi + (long long)i * n;
+        double sr = 0.0, si = 0.0;
+        for (int t = 0; t < j + 1 - k; t++) sr = add_(sr, mul_(x[t], x[t]));
+        for (int t = 0; t < j - k; t++) si = add_(si, mul_(xi[t], xi[t]));
+        d[i] = add_(sr, si);
+      }
+      __syncthreads();
+      if (tid == 0) s_h = mul_(d[perm[k]], DRELTOL);
+    }
+    double mx = 0.0;
+    for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+      const double a = rowuk[(long long)perm[j] * n], b = rowukpi[(long long)perm[j] * n];
+      mx = fmax(mx, add_(mul_(a, a), mul_(b, b)));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nw; w++) mx = fmax(mx, s_red[w]);
+      s_flag = (mx > mul_(maxusqr, d[perm[k]]));
+    }
+    __syncthreads();
+    if (!s_flag) continue;                           // uniform
+    double bd = 0.0; int bj = 0x7fffffff;
+    for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+      double v = d[perm[j]];
+      if (v > bd || (v == bd && v > 0.0 && j < bj)) { bd = v; bj = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_down_sync(0xffffffffu, bd, o); int oj = __shfl_down_sync(0xffffffffu, bj, o);
+      if (ov > bd || (ov == bd && ov > 0.0 && oj < bj)) { bd = ov; bj = oj; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[warp] = bd; s_redi[warp] = bj; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < nw; w++)
+        if (s_red[w] > bd || (s_red[w] == bd && bd > 0.0 && s_redi[w] < bj)) { bd = s_red[w]; bj = s_redi[w]; }
+      if (bd > 0.0) s_pivk = bj;
+      const int pivk = s_pivk, m = pivk - k;
+      const int j = perm[pivk];
+      double *uj = rowuk + (long long)j * n, *ujpi = rowukpi + (long long)j * n;
+      double *gk = g + 3 * (long long)s_inz;
+      double nexty = uj[m];
+      double y = mul_(nexty, nexty);
+      for (int i = m; i > 0; i--) {
+        const double gx = uj[i - 1], gxim = ujpi[i - 1], gy = nexty;
+        y = add_(y, add_(mul_(gx, gx), mul_(gxim, gxim)));
+        nexty = sqrt(y);
+        gk[3 * (i - 1)] = gx / nexty;
+        gk[3 * (i - 1) + 1] = gxim / nexty;
+        gk[3 * (i - 1) + 2] = gy / nexty;
+      }
+      uj[0] = nexty;
+      for (int t = pivk; t > k; t--) perm[t] = perm[t - 1];
+      perm[k] = j;
+    }
+    __syncthreads();
+    {
+      const int m = s_pivk - k;
+      const double *gk = g + 3 * (long long)s_inz;
+      for (int i = 1 + tid; k + i < n; i += blockDim.x) {
+        double *z = rowuk + (long long)perm[k + i] * n, *zi = rowukpi + (long long)perm[k + i] * n;
+        if (i <= m) d_prpigivensrotuj(z, zi, gk, i);
+        else d_prpigivensrot(z, zi, gk, m);
+      }
+      __syncthreads();
+      for (int j = k + 1 + tid; j < n; j += blockDim.x) {
+        const int i = perm[j];
+        const double x = rowuk[(long long)i * n], xi = rowukpi[(long long)i * n];
+        d[i] = sub_(d[i], add_(mul_(x, x), mul_(xi, xi)));
+      }
+      if (tid == 0) s_inz += m;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) gjc[n - 1] = s_inz;
+}
+
+// uperm + triu2herm: Re symmetric, Im skew-symmetric with zero diagonal (sdmauxTriu.c:108-145)
+__global__ void uperm_herm_kernel(const UrotBlk *blks, const double *W, const int *perm_all, double *uout) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  const int *perm = perm_all + B.poff;
+  const long long tot = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx % n), j = (int)(idx / n);
+    int lo = min(i, j), hi = max(i, j);
+    const long long src = B.uoff + lo + (long long)perm[hi] * n;
+    uout[B.uoff + idx] = W[src];
+    const double im = W[src + tot];
+    uout[B.uoff + tot + idx] = (i == j) ? 0.0 : (i < j ? im : -im);
+  }
+}
+
+__global__ void matgivens_cplx_kernel(const UrotBlk *blks, const int *gjc_all, const double *g_all, double *y) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  const int *gjc = gjc_all + B.poff;
+  const double *g = g_all + B.goff;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double *col = y + B.uoff + (long long)j * n, *coli = col + (long long)n * n;
+    for (int k = 0; k < n - 1; k++) {
+      const int m = gjc[k + 1] - gjc[k];
+      if (m > 0) d_prpigivensrot(col + k, coli + k, g + 3 * (long long)gjc[k], m);
+    }
+  }
+}
+
 }  // namespace sb
 using namespace sb;
 
@@ -322,6 +488,110 @@ int sb200_givensrot(sb_idx nblk, const sb_idx *n, const sb_idx *gjc, const doubl
   int maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
   matgivens_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nblk), 128, 0, st>>>(db, dgjc, dg, dy);
   SB_LAUNCH_CHECK_N("matgivens_kernel");
+  SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
+// ---- mixed real / Hermitian blocks (blocks [nreal, nblk) Hermitian: u = [vec Re; vec Im], rotations 3 doubles)
+static int make_blocks_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, std::vector<UrotBlk> &blks, long long &lenud, long long &sumn, long long &gtot) {
+  lenud = 0; sumn = 0; gtot = 0;
+  SB_CHECK(nreal >= 0 && nreal <= nblk, "number of real PSD blocks out of range");
+  for (sb_idx k = 0; k < nblk; k++) {
+    SB_CHECK(n[k] >= 1 && n[k] < 32768, "PSD block order out of range");
+    const bool cplx = k >= nreal;
+    UrotBlk b; b.n = (int)n[k]; b.uoff = lenud; b.poff = (int)sumn; b.goff = gtot;
+    blks.push_back(b);
+    lenud += (cplx ? 2 : 1) * n[k] * n[k]; sumn += n[k];
+    gtot += cplx ? 3 * n[k] * (n[k] - 1) / 2 : n[k] * (n[k] - 1);
+  }
+  return 0;
+}
+
+// g_out: worst-case layout, block k at sum_{j<k} (real: n_j(n_j-1), Hermitian: 3 n_j(n_j-1)/2) doubles.
+int sb200_urotorder_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *u, double maxu, double *u_out,
+                      sb_idx *perm_out, sb_idx *gjc_out, double *g_out) {
+  SB_TRY(ensure_init());
+  std::vector<UrotBlk> blks;
+  long long lenud, sumn, gtot;
+  SB_TRY(make_blocks_h(nblk, nreal, n, blks, lenud, sumn, gtot));
+  if (lenud == 0) return 0;
+  arena_reset();
+  UrotBlk *db = arena<UrotBlk>(blks.size());
+  double *W = arena<double>(lenud), *uo = arena<double>(lenud), *g = arena<double>(std::max<long long>(gtot, 1)), *d = arena<double>(sumn);
+  int *perm = arena<int>(sumn), *gjc = arena<int>(sumn);
+  SB_CHECK(db && W && uo && g && d && perm && gjc, "urotorder: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(UrotBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(W, u, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * std::max<long long>(gtot, 1), st));
+  SB_CUDA(cudaMemsetAsync(gjc, 0, sizeof(int) * sumn, st));
+  int maxr = 0, maxc = 0;
+  for (sb_idx k = 0; k < nblk; k++) (k < nreal ? maxr : maxc) = std::max(k < nreal ? maxr : maxc, (int)n[k]);
+  if (nreal > 0) {
+    urotorder_kernel<<<(unsigned)nreal, 256, 0, st>>>(db, W, perm, gjc, g, d, maxu * maxu);
+    SB_LAUNCH_CHECK_N("urotorder_kernel");
+    uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxr * maxr + 255) / 256, 1024), (unsigned)nreal), 256, 0, st>>>(db, W, perm, uo);
+    SB_LAUNCH_CHECK_N("uperm_sym_kernel");
+  }
+  if (nblk > nreal) {
+    urotorder_cplx_kernel<<<(unsigned)(nblk - nreal), 256, 0, st>>>(db + nreal, W, perm, gjc, g, d, maxu * maxu);
+    SB_LAUNCH_CHECK_N("urotorder_cplx_kernel");
+    uperm_herm_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxc * maxc + 255) / 256, 1024), (unsigned)(nblk - nreal)), 256, 0, st>>>(db + nreal, W, perm, uo);
+    SB_LAUNCH_CHECK_N("uperm_herm_kernel");
+  }
+  std::vector<int> hp(sumn), hg(sumn);
+  SB_CUDA(cudaMemcpyAsync(u_out, uo, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(hp.data(), perm, sizeof(int) * sumn, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(hg.data(), gjc, sizeof(int) * sumn, cudaMemcpyDeviceToHost, st));
+  if (gtot) SB_CUDA(cudaMemcpyAsync(g_out, g, sizeof(double) * gtot, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  for (long long i = 0; i < sumn; i++) { perm_out[i] = hp[i]; gjc_out[i] = hg[i]; }
+  return 0;
+}
+
+// g packed: the rotations of block k follow those of block k-1 (2 doubles each for real, 3 for Hermitian blocks).
+int sb200_givensrot_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const sb_idx *gjc, const double *g, sb_idx glen,
+                      const double *x, double *y) {
+  SB_TRY(ensure_init());
+  std::vector<UrotBlk> blks;
+  long long lenud, sumn, gtot;
+  SB_TRY(make_blocks_h(nblk, nreal, n, blks, lenud, sumn, gtot));
+  if (lenud == 0) return 0;
+  long long inz = 0;
+  std::vector<int> g32(sumn);
+  int maxr = 0, maxc = 0;
+  for (sb_idx k = 0; k < nblk; k++) {
+    UrotBlk &b = blks[k];
+    b.goff = inz;
+    for (int i = 0; i < b.n; i++) {
+      sb_idx v = gjc[b.poff + i];
+      SB_CHECK(v >= 0 && v <= (sb_idx)b.n * (b.n - 1) / 2 && (i == 0 || v >= gjc[b.poff + i - 1]), "givensrot: gjc is not a valid rotation count list");
+      g32[b.poff + i] = (int)v;
+    }
+    inz += (k < nreal ? 2 : 3) * gjc[b.poff + b.n - 1];
+    SB_CHECK(inz <= glen, "g size mismatch");
+    (k < nreal ? maxr : maxc) = std::max(k < nreal ? maxr : maxc, b.n);
+  }
+  arena_reset();
+  UrotBlk *db = arena<UrotBlk>(blks.size());
+  double *dy = arena<double>(lenud), *dg = arena<double>(std::max<long long>(inz, 1));
+  int *dgjc = arena<int>(sumn);
+  SB_CHECK(db && dy && dg && dgjc, "givensrot: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(UrotBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dy, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dgjc, g32.data(), sizeof(int) * sumn, cudaMemcpyHostToDevice, st));
+  if (inz) SB_CUDA(cudaMemcpyAsync(dg, g, sizeof(double) * inz, cudaMemcpyHostToDevice, st));
+  if (nreal > 0) {
+    matgivens_kernel<<<dim3((unsigned)((maxr + 127) / 128), (unsigned)nreal), 128, 0, st>>>(db, dgjc, dg, dy);
+    SB_LAUNCH_CHECK_N("matgivens_kernel");
+  }
+  if (nblk > nreal) {
+    matgivens_cplx_kernel<<<dim3((unsigned)((maxc + 127) / 128), (unsigned)(nblk - nreal)), 128, 0, st>>>(db + nreal, dgjc, dg, dy);
+    SB_LAUNCH_CHECK_N("matgivens_cplx_kernel");
+  }
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -75,7 +75,7 @@ EXPORTS = [
     "sb200_blkchol_dev", "sb200_chol_rect_to_csc_dev", "sb200_chol_csc_to_rect_dev", "sb200_blkchol",
     "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
     "sb200_psd_plan_get", "sb200_psd_plan_lenud", "sb200_psd_plan_sumn", "sb200_invcholfac_dev", "sb200_psdscale_dev",
-    "sb200_invcholfac", "sb200_psdscale", "sb200_invcholfac_h", "sb200_psdscale_h", "sb200_psdframeit_h", "sb200_psdinvjmul_h", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
+    "sb200_invcholfac", "sb200_psdscale", "sb200_invcholfac_h", "sb200_psdscale_h", "sb200_psdframeit_h", "sb200_psdinvjmul_h", "sb200_urotorder_h", "sb200_givensrot_h", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
     "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_urotorder_dev", "sb200_givensrot_dev", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
     "sb200_graph_destroy",
     "sb200_ada_plan_get", "sb200_ada_plan_get_h", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",

@@ -7,8 +7,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   MEX_REQUIRE(nlhs <= 4, "urotorder generates less output arguments.");
   ConeK K;
   read_cone(prhs[1], K);
-  if (K.rsdpN != K.sdpN) mexErrMsgTxt("urotorder: Hermitian PSD blocks are not supported by the B200 plugin yet.");
-  sb_idx lenud = K.rDim, sdplen = K.rLen;
+  const bool herm = K.rsdpN != K.sdpN;             // Hermitian blocks (urotorder.c:420-455)
+  sb_idx lenud = K.rDim + K.hDim, sdplen = K.rLen + K.hLen;
   double maxu = mxGetScalar(prhs[2]);
   MEX_REQUIRE((sb_idx)numel(prhs[0]) == lenud, "u size mismatch");
   const double *permOld = NULL;
@@ -17,14 +17,15 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     permOld = mxGetPr(prhs[3]);
   }
   sb_idx gworst = 0;
-  for (sb_idx k = 0; k < K.sdpN; k++) gworst += K.s[k] * (K.s[k] - 1);
+  for (sb_idx k = 0; k < K.sdpN; k++) gworst += k < K.rsdpN ? K.s[k] * (K.s[k] - 1) : 3 * K.s[k] * (K.s[k] - 1) / 2;
   mxArray *out[4];
   out[0] = mxCreateDoubleMatrix((mwSize)lenud, 1, mxREAL);
   out[1] = mxCreateDoubleMatrix((mwSize)sdplen, 1, mxREAL);
   out[2] = mxCreateDoubleMatrix((mwSize)sdplen, 1, mxREAL);
   std::vector<sb_idx> perm((size_t)(sdplen ? sdplen : 1)), gjc((size_t)(sdplen ? sdplen : 1));
   double *gw = (double *)mxCalloc((size_t)(gworst ? gworst : 1), sizeof(double));
-  int rc = sb200_urotorder(K.sdpN, K.s.data(), mxGetPr(prhs[0]), maxu, mxGetPr(out[0]), perm.data(), gjc.data(), gw);
+  int rc = herm ? sb200_urotorder_h(K.sdpN, K.rsdpN, K.s.data(), mxGetPr(prhs[0]), maxu, mxGetPr(out[0]), perm.data(), gjc.data(), gw)
+                : sb200_urotorder(K.sdpN, K.s.data(), mxGetPr(prhs[0]), maxu, mxGetPr(out[0]), perm.data(), gjc.data(), gw);
   if (rc) { mxFree(gw); for (int i = 0; i < 3; i++) mxDestroyArray(out[i]); sb_check(rc, "urotorder"); }
   double *permPr = mxGetPr(out[1]), *gjcPr = mxGetPr(out[2]);
   sb_idx inz = 0, poff = 0, goff = 0;
@@ -34,9 +35,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
       permPr[poff + i] = permOld ? permOld[poff + perm[poff + i]] : 1.0 + (double)perm[poff + i];
       gjcPr[poff + i] = (double)gjc[poff + i];
     }
-    sb_idx cnt = 2 * gjc[poff + nk - 1];
+    const bool cplx = k >= K.rsdpN;                     // rotations: 2 doubles, or 3 for a Hermitian block
+    sb_idx cnt = (cplx ? 3 : 2) * gjc[poff + nk - 1];
     memmove(gw + inz, gw + goff, (size_t)cnt * sizeof(double));
-    inz += cnt; poff += nk; goff += nk * (nk - 1);
+    inz += cnt; poff += nk; goff += cplx ? 3 * nk * (nk - 1) / 2 : nk * (nk - 1);
   }
   // g: length-inz column vector whose buffer comes from the MEX allocator (urotorder.c:459-475)
   out[3] = mxCreateDoubleMatrix(1, 1, mxREAL);

@@ -146,3 +146,41 @@ def test_getada3_hermitian(l, sreal, sherm, m, dens):
     assert relerr(Ag.data, Ar.data) <= 1e-10
     assert relerr(absg, absr) <= 1e-10
     assert np.array_equal(Ag.toarray(), Ag.toarray().T)
+
+
+def _bad_factor_h(K, rng):
+    """Upper-triangular (complex for the Hermitian blocks, real positive diagonal) factors whose leading columns
+    are tiny: forces pivoting in (prpi)rotorder.  Stored Hermitian-mirrored like d.u."""
+    out = []
+    nr = K["rsdpN"]
+    for i, n in enumerate(K["s"].astype(int)):
+        scale = 10.0 ** rng.uniform(-3, 0, n)
+        scale[: max(n // 3, 1)] *= 1e-3
+        U = np.triu(rng.standard_normal((n, n))) + (0 if i < nr else 1j * np.triu(rng.standard_normal((n, n)), 1))
+        U[np.diag_indices(n)] = np.abs(U[np.diag_indices(n)].real) + 0.5
+        U = U * scale[None, :]
+        full = U + np.triu(U, 1).conj().T
+        out.append(full.real.ravel(order="F"))
+        if i >= nr:
+            out.append(full.imag.ravel(order="F"))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("sreal,sherm,maxu", [((), (2,), 1.1), ((), (6,), 1.1), ((5,), (7, 3), 1.1), ((20,), (33,), 1.1), ((), (50,), 3.0)])
+def test_urotorder_givensrot_hermitian_bit_exact(sreal, sherm, maxu):
+    K = _K(sreal, sherm)
+    Km = cones.K_for_mex(K)
+    rng = np.random.default_rng(sum(sherm) + 3)
+    u = _bad_factor_h(K, rng)
+    permin = _perm(K, rng)
+    for extra in ((), (permin,)):
+        ur, pr, gjr, gr = ref.urotorder(u, Km, maxu, *extra, nlhs=4)
+        ug, pg, gjg, gg = gpu.urotorder(u, Km, maxu, *extra, nlhs=4)
+        assert np.array_equal(pg, pr) and np.array_equal(gjg, gjr)
+        assert gg.shape == gr.shape and np.array_equal(gg, gr)
+        assert np.array_equal(ug, ur)
+    assert gr.size > 0, "test input does not rotate"
+    x = _herm_vec(K, rng)
+    yr = ref.givensrot(gjr, gr, x, Km)
+    yg = gpu.givensrot(gjr, gr, x, Km)
+    assert np.array_equal(yg, yr)
