@@ -211,7 +211,7 @@ sparse_w_kernel(const AdaPair *pairs, int p0, int npairs, const int *blk_n, cons
 // ADA(i,c) directly (nobody else touches column c); constraints spanning several blocks write
 // per-pair partial sums that ada3_reduce_kernel adds in block order -- deterministic, no atomics.
 // (Replaces the reference's per-entry accumulation, getada3.c:198-268.)
-struct BlkPartner { int j, e0, e1, pad; };
+struct BlkPartner { int j, e0, e1, src0; };          // src0 = ent_src[e0]: first At.pr index of the pair
 
 struct ColSlots {        // row -> position inside one ADA column: shared-memory map, or binary search
   const int *rows; int collen; const int *slot;
@@ -275,10 +275,20 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));   // groups diverge: sync only the group
   const int tb = blkp_beg[P.k], te = blkp_beg[P.k + 1];
   double *part = ws + P.part_off;                 // multi: one partial per partner, then the |.| sum of the diagonal
-  for (int t = tb + warp * GPW + grp; t < te; t += nw * GPW) {
-    const BlkPartner Q = blkp[t];
-    if (invperm[Q.j] > ipc) continue;
-    const double *av = Atpr + ent_src[Q.e0] - Q.e0;     // the entries of one pair are consecutive in At.pr ...
+  // the descriptor and the order of the NEXT partner are fetched while the current one is worked on: the chain
+  // descriptor -> invperm -> entries -> W is four dependent loads, which bounded this loop
+  int t = tb + warp * GPW + grp;
+  BlkPartner Qn = t < te ? blkp[t] : BlkPartner{0, 0, 0, 0};
+  int ipn = t < te ? invperm[Qn.j] : 0;
+  for (; t < te; t += nw * GPW) {
+    const BlkPartner Q = Qn;
+    const int ipi = ipn;
+    {
+      const int tn = t + nw * GPW;
+      if (tn < te) { Qn = blkp[tn]; ipn = invperm[Qn.j]; }
+    }
+    if (ipi > ipc) continue;
+    const double *av = Atpr + Q.src0 - Q.e0;            // the entries of one pair are consecutive in At.pr ...
     double acc = 0.0, aabs = 0.0;
     int e = Q.e0 + gl;
     if (ent_scale) {                                    // ... except with Hermitian blocks (embedded entries, signs)
@@ -556,7 +566,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   {
     std::vector<int> fill(blkp_beg.begin(), blkp_beg.end() - 1);
     for (auto &P : pl->pairs) {
-      blkp[fill[P.k]++] = BlkPartner{P.j, P.e0, P.e1, 0};
+      blkp[fill[P.k]++] = BlkPartner{P.j, P.e0, P.e1, ent_src[P.e0]};
       const long long n = pl->blk_n[P.k];
       for (int e = P.e0; e < P.e1; e++) {
         if (P.sparse) ent_pk[e] = ent_lin[e];

@@ -113,6 +113,28 @@ householder_q_kernel(const int *grp_blk, const int *grp_j0, const int *ns, const
   const double *F = frms + offs[k];
   const double *beta = F + (long long)n * n - n;
   double *q = Q + offs[k] + (long long)j * n;
+  if (n <= 96) {
+    // the column lives in registers (rows lane, lane+32, lane+64); the next reflector is fetched while the
+    // dot product of the current one is reduced
+    double q0 = (lane == j) ? 1.0 : 0.0, q1 = (lane + 32 == j) ? 1.0 : 0.0, q2 = (lane + 64 == j) ? 1.0 : 0.0;
+    int c = min(j, n - 2);
+    auto ld = [&](int cc, int r) { return (cc >= 0 && r >= cc && r < n) ? F[(long long)cc * n + r] : 0.0; };
+    double v0 = ld(c, lane), v1 = ld(c, lane + 32), v2 = ld(c, lane + 64);
+    double bc = c >= 0 ? beta[c] : 1.0;
+    for (; c >= 0; c--) {
+      const double w0 = ld(c - 1, lane), w1 = ld(c - 1, lane + 32), w2 = ld(c - 1, lane + 64);
+      const double bn = c >= 1 ? beta[c - 1] : 1.0;
+      double t = v0 * q0 + v1 * q1 + v2 * q2;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      const double a = t / (-bc);                       // elqxq is called with -beta (reflect.c:214)
+      q0 += a * v0; q1 += a * v1; q2 += a * v2;
+      v0 = w0; v1 = w1; v2 = w2; bc = bn;
+    }
+    if (lane < n) q[lane] = q0;
+    if (lane + 32 < n) q[lane + 32] = q1;
+    if (lane + 64 < n) q[lane + 64] = q2;
+    return;
+  }
   for (int i = lane; i < n; i += 32) q[i] = (i == j) ? 1.0 : 0.0;
   __syncwarp();
   for (int c = min(j, n - 2); c >= 0; c--) {
@@ -139,19 +161,33 @@ wy_t_kernel(const int *pblk, const int *pidx, const int *ns, const long long *of
   const double *beta = F + (long long)n * n - n;
   const int c0 = p * WYB, bp = min(WYB, n - 1 - c0);
   __shared__ double U[WYB][WYB + 1];
+  __shared__ double Vc[32][WYB + 1];                 // a chunk of 32 rows of the panel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int idx = threadIdx.x; idx < WYB * WYB; idx += blockDim.x) U[idx / WYB][idx % WYB] = 0.0;
-  __syncthreads();
-  for (int pr = warp; pr < bp * bp; pr += 8) {
-    const int a = pr / bp, b = pr % bp;
-    if (a >= b) continue;
-    const double *va = F + (long long)(c0 + a) * n, *vb = F + (long long)(c0 + b) * n;
-    double t = 0.0;
-    for (int r = c0 + b + lane; r < n; r += 32) t += va[r] * vb[r];
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) U[a][b] = t;
+  // G = V'V as a small SYRK: rows streamed in chunks of 32 through shared memory, thread (ta,tb) owns the 2x2
+  // block G(2ta..2ta+1, 2tb..2tb+1); entries of V above a reflector's own diagonal are structural zeros
+  const int ta = threadIdx.x >> 4, tb = threadIdx.x & 15;
+  double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+  for (int r0 = c0; r0 < n; r0 += 32) {
+    for (int idx = threadIdx.x; idx < 32 * WYB; idx += blockDim.x) {
+      const int rr = idx & 31, cc = idx >> 5, r = r0 + rr;
+      Vc[rr][cc] = (cc < bp && r < n && r >= c0 + cc) ? F[(long long)(c0 + cc) * n + r] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 32; rr++) {
+      const double a0 = Vc[rr][2 * ta], a1 = Vc[rr][2 * ta + 1], b0 = Vc[rr][2 * tb], b1 = Vc[rr][2 * tb + 1];
+      g00 += a0 * b0; g01 += a0 * b1; g10 += a1 * b0; g11 += a1 * b1;
+    }
+    __syncthreads();
   }
-  if (threadIdx.x < bp) U[threadIdx.x][threadIdx.x] = beta[c0 + threadIdx.x];
+  // T^{-1} = striu(G) + diag(beta)
+  {
+    const int i0 = 2 * ta, j0 = 2 * tb;
+    U[i0][j0] = (i0 < j0) ? g00 : 0.0; U[i0][j0 + 1] = (i0 < j0 + 1) ? g01 : 0.0;
+    U[i0 + 1][j0] = (i0 + 1 < j0) ? g10 : 0.0; U[i0 + 1][j0 + 1] = (i0 + 1 < j0 + 1) ? g11 : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < WYB) U[threadIdx.x][threadIdx.x] = threadIdx.x < bp ? beta[c0 + threadIdx.x] : 1.0;
   __syncthreads();
   // T = inv(U), U upper triangular: lane j solves U t = e_j from the bottom up
   double *T = Tall + (toff[k] + p) * WYB * WYB;
@@ -351,25 +387,35 @@ psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, co
   double *Yg = y + offs[blockIdx.x];
   const int *p = perm ? perm + poffs[blockIdx.x] : nullptr;
   const bool prep = p && !transp, postp = p && transp;
-  for (int idx = threadIdx.x; idx < NP * NP; idx += blockDim.x) {
-    const int i = idx % NP, k = idx / NP;
-    double tv = 0.0, xv = 0.0;
-    if (i < n && k < n) {
-      const bool keep = transp ? (i <= k) : (i >= k);          // triu : tril  of the stored array
-      tv = keep ? U[i + (long long)k * n] : 0.0;
-      xv = prep ? Xg[p[i] + (long long)p[k] * n] : Xg[i + (long long)k * n];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty < 16
+  {  // stage T and X: warp ty takes columns ty, ty+16, ...; lane tx rows tx+32a (no division in the index math)
+    int pi[NR];
+#pragma unroll
+    for (int a = 0; a < NR; a++) pi[a] = (prep && tx + 32 * a < n) ? p[tx + 32 * a] : tx + 32 * a;
+    for (int k = ty; k < NP; k += 16) {
+      const long long pk = (prep && k < n) ? p[k] : k;
+#pragma unroll
+      for (int a = 0; a < NR; a++) {
+        const int i = tx + 32 * a;
+        double tv = 0.0, xv = 0.0;
+        if (i < n && k < n) {
+          const bool keep = transp ? (i <= k) : (i >= k);        // triu : tril  of the stored array
+          tv = keep ? U[i + (long long)k * n] : 0.0;
+          xv = Xg[pi[a] + pk * n];
+        }
+        T[i + k * LD] = tv;
+        X[i + k * LD] = xv;
+      }
     }
-    T[i + k * LD] = tv;
-    X[i + k * LD] = xv;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty < 16
   const int c = c0 + ty;
-  {  // W(i,c) = sum_k X(i,k) T(k,c)
+  {  // W(i,c) = sum_k X(i,k) T(k,c); T(k,c) is zero for k > c (triu) / k < c (tril)
     double acc[NR] = {};
     if (c < n) {
+      const int klo = transp ? 0 : c, khi = transp ? c + 1 : n;
 #pragma unroll 4
-      for (int k = 0; k < n; k++) {
+      for (int k = klo; k < khi; k++) {
         const double bv = T[k + c * LD];
 #pragma unroll
         for (int a = 0; a < NR; a++) acc[a] += X[tx + 32 * a + k * LD] * bv;

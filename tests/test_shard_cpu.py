@@ -30,7 +30,7 @@ def test_partition_is_balanced_and_complete():
     assert max(loads) / min(loads) < 1.2
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, compact):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import refpath
@@ -39,8 +39,12 @@ def _worker(rank, world, port, out):
     S = setup.build_setup(At, b, c, K, perm=np.arange(At.shape[1]))
     d = problems.scaling(K, "S1", seed=5)
     owned = shard.partition_blocks(K["s"], world)[rank]
-    T = shard.shard_setup(S, owned, rank)
-    udsqr, ADA, absd = refpath.RefHotPath(T).assemble(d)
+    if compact:
+        T, dr = shard.shard_compact(S, d, owned, rank)      # owner-computes cone: only this rank's PSD blocks
+        assert list(T.K["s"]) == [K["s"][k] for k in owned]
+    else:
+        T, dr = shard.shard_setup(S, owned, rank), d
+    udsqr, ADA, absd = refpath.RefHotPath(T).assemble(dr)
     vals = torch.from_numpy(ADA.data.copy())
     ab = torch.from_numpy(absd.ravel().copy())
     dist.all_reduce(vals)                       # the one collective of the path
@@ -54,9 +58,10 @@ def _worker(rank, world, port, out):
 
 
 @needs_ref
-def test_sharded_assembly_equals_full_world2():
+@pytest.mark.parametrize("compact", [False, True])
+def test_sharded_assembly_equals_full_world2(compact):
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + 7 * int(compact)) % 2000
+    mp.spawn(_worker, args=(2, port, out, compact), nprocs=2, join=True)
     assert out["ada"] <= 1e-12 and out["absd"] <= 1e-12
