@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <map>
 #include "gemm.cuh"
+#include <chrono>
 #include "sb_internal.h"
 
 namespace sb {
@@ -968,7 +969,11 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
 // ---- host-pointer entries (what the MEX stubs call).  perm: 0-based ordering (Aord.*perm).
 int sb200_getada1(sb200_ada_plan *pl, const double *Atpr, const sb_idx *perm, const double *dl, const double *ddet,
                   double *ada_out) {
+  static const bool trace = getenv("SB200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = trace ? now() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
   SB_TRY(sb200_ada_set_At_values(pl, Atpr));
+  if (trace) t1 = now();
   arena_reset();
   const int *ip;
   SB_TRY(set_invperm(pl, perm, &ip));
@@ -978,10 +983,14 @@ int sb200_getada1(sb200_ada_plan *pl, const double *Atpr, const sb_idx *perm, co
   cudaStream_t st = ctx().stream;
   if (pl->lpN) SB_CUDA(cudaMemcpyAsync(d_dl, dl, sizeof(double) * pl->lpN, cudaMemcpyHostToDevice, st));
   if (pl->nq) SB_CUDA(cudaMemcpyAsync(d_det, ddet, sizeof(double) * pl->nq, cudaMemcpyHostToDevice, st));
+  if (trace) t2 = now();
   SB_TRY(sb200_getada1_dev(pl, d_dl, d_det, ip, d_out));
+  if (trace) { cudaStreamSynchronize(st); t3 = now(); }
   SB_CUDA(cudaMemcpyAsync(ada_out, d_out, sizeof(double) * pl->nnzADA, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
+  if (trace) t4 = now();
   mirror_publish(d_out, ada_out, sizeof(double) * pl->nnzADA);      // the next plugin call finds ADA on the device
+  if (trace) fprintf(stderr, "[getada1] At values %.3f  setup %.3f  kernels %.3f  D2H %.3f  publish %.3f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
   return 0;
 }
 

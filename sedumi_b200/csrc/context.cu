@@ -1,5 +1,9 @@
 // context.cu -- library context: device selection, stream, error text, raw memory helpers.
 #include <stdarg.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "sb_internal.h"
 
 namespace sb {
@@ -10,6 +14,81 @@ static uint64_t g_call_stamp = 0;          // mirror slots stamped after this va
 static thread_local char g_err[1024] = "";
 
 Context &ctx() { return g_ctx; }
+
+// ---------------------------------------------------------------- chunked, multi-threaded content hash
+// hash64(data) = hash64_st(data)                                    for up to HASH_PAR_MIN bytes
+//              = hash64_st(array of hash64_st(chunk_i), seed)       above, chunks of HASH_CHUNK bytes,
+// so the value depends on the bytes only.  Workers are created on first use and sleep on a condition variable
+// between jobs (after a short spin, so that back-to-back plugin calls do not pay the wake-up).
+static const size_t HASH_PAR_MIN = 512 * 1024, HASH_CHUNK = 256 * 1024;
+namespace {
+struct HashPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv;
+  const unsigned char *data = nullptr;
+  size_t bytes = 0, nchunks = 0;
+  uint64_t seed = 0;
+  std::vector<uint64_t> out;
+  std::atomic<size_t> next{0}, done{0};
+  std::atomic<uint64_t> gen{0};
+  bool stop = false;
+  void work() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nchunks) break;
+      const size_t off = i * HASH_CHUNK, len = std::min(HASH_CHUNK, bytes - off);
+      out[i] = hash64_st(data + off, len, seed);
+      done.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      // spin briefly for the next job, then sleep
+      bool got = false;
+      for (int s = 0; s < 20000 && !got; s++) got = gen.load(std::memory_order_acquire) != seen;
+      if (!got) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || gen.load() != seen; });
+        if (stop) return;
+      }
+      seen = gen.load(std::memory_order_acquire);
+      work();
+    }
+  }
+  void start() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(3, hc > 1 ? hc - 1 : 0);
+    if (const char *e = getenv("SB200_HASH_THREADS")) nt = std::max(0, std::min(15, atoi(e) - 1));
+    for (int i = 0; i < nt; i++) th.emplace_back([this] { loop(); });
+  }
+  ~HashPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; gen.fetch_add(1); }
+    cv.notify_all();
+    for (auto &t : th) t.join();
+  }
+};
+HashPool *g_pool = nullptr;
+std::mutex g_pool_mu;
+}  // namespace
+
+uint64_t hash64(const void *data, size_t bytes, uint64_t seed) {
+  if (bytes <= HASH_PAR_MIN) return hash64_st(data, bytes, seed);
+  std::lock_guard<std::mutex> job(g_pool_mu);          // one job at a time
+  if (!g_pool) { g_pool = new HashPool(); g_pool->start(); }
+  HashPool &P = *g_pool;
+  P.data = (const unsigned char *)data; P.bytes = bytes; P.seed = seed;
+  P.nchunks = (bytes + HASH_CHUNK - 1) / HASH_CHUNK;
+  P.out.assign(P.nchunks, 0);
+  P.done.store(0); P.next.store(0);
+  { std::lock_guard<std::mutex> lk(P.mu); P.gen.fetch_add(1, std::memory_order_release); }
+  P.cv.notify_all();
+  P.work();                                             // the calling thread takes its share
+  while (P.done.load(std::memory_order_acquire) < P.nchunks) { }
+  // late workers may still be inside work() probing `next`: they only read nchunks/next, which stay valid
+  return hash64_st(P.out.data(), sizeof(uint64_t) * P.nchunks, seed ^ (uint64_t)bytes);
+}
 
 void set_error(const char *fmt, ...) {
   va_list ap;

@@ -104,9 +104,14 @@ struct DevBuf {
   }
 };
 
+// Content hash of a host buffer.  Buffers above 512 KB are hashed in 256 KB chunks by a small pool of host threads
+// (the plugin boundary hashes ~65 MB per IPM iteration to recognise plans and device mirrors; one core does
+// 15 GB/s); the result is a function of the bytes only, independent of the number of threads.
+uint64_t hash64(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull);
+
 // Fast 64-bit content hash: four independent multiply-xorshift lanes over 32-byte blocks
 // (the dependent multiply chain of a single-lane hash limits it to ~2 GB/s; this runs at memory speed).
-inline uint64_t hash64(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull) {
+inline uint64_t hash64_st(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull) {
   const unsigned char *p = (const unsigned char *)data;
   const uint64_t M = 0xFF51AFD7ED558CCDull;
   uint64_t a = seed ^ bytes, b = seed * 3, c = seed * 5, d = seed * 7;

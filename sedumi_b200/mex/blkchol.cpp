@@ -39,9 +39,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   const mwIndex *Ljc = mxGetJc(LL), *Lir = mxGetIr(LL);
   mwSize nnzL = Ljc[m];
   mxArray *myplhs[4];
-  myplhs[0] = mxCreateSparse(m, m, nnzL, mxREAL);
-  memcpy(mxGetJc(myplhs[0]), Ljc, (m + 1) * sizeof(mwIndex));
-  memcpy(mxGetIr(myplhs[0]), Lir, nnzL * sizeof(mwIndex));
+  myplhs[0] = sparse_with_pattern(m, m, Ljc, Lir);
   myplhs[1] = mxCreateDoubleMatrix(m, 1, mxREAL);
   std::vector<sb_idx> skip(m ? m : 1), add(m ? m : 1);
   std::vector<double> skipv(m ? m : 1), addv(m ? m : 1);

@@ -1,5 +1,7 @@
 // ADA = getada1(ADA,At,Ajc2,perm,d,blkstart)   LP + Lorentz-det part of A*D(d^2)*A'
 // (getada1.c:54-63 signature, :161-261 mexFunction)
+#include <time.h>
+#include <stdlib.h>
 #include "mex_common.h"
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -26,12 +28,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   MEX_REQUIRE(mxGetM(ADA) == m && mxGetN(ADA) == m, "Size mismatch ADA.");
   MEX_REQUIRE(mxIsSparse(ADA), "ADA should be sparse.");
   const mwIndex *adajc = mxGetJc(ADA), *adair = mxGetIr(ADA);
+  const bool trace = getenv("SB200_TRACE") != NULL;
+  struct timespec ts0, ts1, ts2;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   sb200_ada_plan *pl = NULL;
   sb_check(sb200_ada_plan_get(&pl, (sb_idx)mxGetM(AT), (sb_idx)m, as_idx(mxGetJc(AT)), as_idx(mxGetIr(AT)), Ajc2.data(),
                               lpN, nq, qstart.data(), 0, NULL, NULL, as_idx(adajc), as_idx(adair)), "getada1");
-  plhs[0] = mxCreateSparse(m, m, adajc[m], mxREAL);
-  memcpy(mxGetJc(plhs[0]), adajc, (m + 1) * sizeof(mwIndex));
-  memcpy(mxGetIr(plhs[0]), adair, adajc[m] * sizeof(mwIndex));
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  plhs[0] = sparse_with_pattern(m, m, adajc, adair);
+  clock_gettime(CLOCK_MONOTONIC, &ts2);
+  if (trace) fprintf(stderr, "[getada1 stub] plan lookup %.3f ms, output array %.3f ms\n", (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6,
+                     (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6);
   int rc = sb200_getada1(pl, mxGetPr(AT), perm.data(), mxGetPr(dl), mxGetPr(ddet), mxGetPr(plhs[0]));
   if (rc) { mxDestroyArray(plhs[0]); plhs[0] = NULL; sb_check(rc, "getada1"); }
 }

@@ -10,8 +10,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   mwSize m = mxGetM(ADA);
   MEX_REQUIRE(mxGetN(ADA) == m, "Size mismatch ADA.");
   MEX_REQUIRE(mxIsSparse(ADA), "ADA should be sparse.");
-  plhs[0] = mxDuplicateArray(ADA);
-  if (K.lorN <= 0) return;                                  // ready if no Lorentz blocks (getada2.c:151-152)
+  plhs[0] = sparse_with_pattern(m, m, mxGetJc(ADA), mxGetIr(ADA));
+  if (K.lorN <= 0) {                                        // ready if no Lorentz blocks (getada2.c:151-152)
+    memcpy(mxGetPr(plhs[0]), mxGetPr(ADA), mxGetJc(ADA)[m] * sizeof(double));
+    return;
+  }
   MEX_REQUIRE(mxIsStruct(DAT), "DAt should be a structure.");
   const mxArray *Q = need_field(DAT, "q", "Missing field DAt.q.");
   MEX_REQUIRE(mxGetM(Q) == (mwSize)K.lorN && mxGetN(Q) == m, "Size mismatch DAt.q");

@@ -42,9 +42,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   sb200_ada_plan *pl = NULL;
   sb_check(sb200_ada_plan_get_h(&pl, (sb_idx)lenfull, (sb_idx)m, as_idx(mxGetJc(AT)), as_idx(mxGetIr(AT)), Ajc1.data(),
                                 0, 0, NULL, K.sdpN, K.rsdpN, blkstart.data(), K.s.data(), as_idx(adajc), as_idx(adair)), "getada3");
-  mxArray *out0 = mxCreateSparse(m, m, adajc[m], mxREAL);
-  memcpy(mxGetJc(out0), adajc, (m + 1) * sizeof(mwIndex));
-  memcpy(mxGetIr(out0), adair, adajc[m] * sizeof(mwIndex));
+  mxArray *out0 = sparse_with_pattern(m, m, adajc, adair);
   mxArray *out1 = mxCreateDoubleMatrix(m, 1, mxREAL);
   int rc = sb200_getada3(pl, mxGetPr(AT), mxGetPr(UDSQR), lenud, perm.data(), first, mxGetPr(ADA), mxGetPr(out0), mxGetPr(out1));
   if (rc) { mxDestroyArray(out0); mxDestroyArray(out1); sb_check(rc, "getada3"); }

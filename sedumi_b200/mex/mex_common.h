@@ -80,3 +80,23 @@ static inline void read_cone(const mxArray *mxK, ConeK &K) {
     else { K.hDim += 2 * K.s[i] * K.s[i]; K.hLen += K.s[i]; }
   }
 }
+
+// A sparse m x n output with the pattern (jc, ir) and UNINITIALISED values: the index and value arrays come from
+// mxMalloc and are attached with mxSetIr/mxSetPr/mxSetNzmax (documented MEX API), so that a multi-megabyte output
+// (ADA, L.L) is not zero-filled by mxCreateSparse before it is overwritten (measured: 0.9 ms of a 1.5 ms getada1 call).
+static inline mxArray *sparse_with_pattern(mwSize m, mwSize n, const mwIndex *jc, const mwIndex *ir) {
+  const mwSize nnz = jc[n], cap = nnz ? nnz : 1;
+  mxArray *a = mxCreateSparse(m, n, 1, mxREAL);
+  mxFree(mxGetPr(a));
+  mxFree(mxGetIr(a));
+  mwIndex *nir = (mwIndex *)mxMalloc(cap * sizeof(mwIndex));
+  double *npr = (double *)mxMalloc(cap * sizeof(double));
+  if (!nir || !npr) mexErrMsgTxt("Memory allocation error.");
+  mxSetIr(a, nir);
+  mxSetPr(a, npr);
+  mxSetNzmax(a, cap);
+  memcpy(mxGetJc(a), jc, (n + 1) * sizeof(mwIndex));
+  memcpy(nir, ir, nnz * sizeof(mwIndex));
+  if (!nnz) { nir[0] = 0; npr[0] = 0.0; }
+  return a;
+}

@@ -33,7 +33,13 @@ def step():
         p = gpu.fwblkslv(Lf, rhs)
         gpu.bwblkslv(Lf, p / Ld)
     for i in range(12):
-        gpu.psdscale({"u": d["u"], "perm": d["perm"]}, xfull, Km, float(i & 1))
+        ps = gpu.psdscale({"u": d["u"], "perm": d["perm"]}, xfull, Km, float(i & 1))
+    F = bench.FRAMES
+    gpu.psdinvjmul(F[0], F[1], ps, Km)
+    f = gpu.psdframeit(F[0], F[1], Km)
+    f = gpu.psdframeit(F[0], F[1], Km)
+    u2, p2, gjc, g = gpu.urotorder(d["u"], Km, 1.1, nlhs=4)
+    gpu.givensrot(gjc, g, f, Km)
 
 
 step(); step()
