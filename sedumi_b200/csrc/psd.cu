@@ -446,6 +446,92 @@ psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, co
   }
 }
 
+// Same slab decomposition with the two products on the FP64 tensor pipe (DMMA.8x8x4): X and T stay in their
+// natural layouts, padded so that every fragment load is two shared-memory wavefronts (the minimum for doubles):
+//   A fragments (row fastest) come from X, ld = NP+8 (2 ld = 16 mod 32 words);
+//   fragments that walk k inside a column (B of stage 1: T(k,c); A of stage 2: T(k,i)) come from T, ld = NP+4;
+//   W = X T is written transposed (Wt[c][k], ld 24) so that stage 2 reads it as a B operand.
+// Warp w owns the 8-row strip w of the result (both 8-column fragments of the 16-column slab); the k-ranges skip the
+// structural zeros of the triangular factor.
+template <int NR>
+__global__ void __launch_bounds__(512)
+psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poffs, const double *u, const int *perm,
+                           const double *x, int transp, double *y) {
+  extern __shared__ double sm[];
+  constexpr int NP = 32 * NR, LDX = NP + 8, LDT = NP + 4, LDW = 24;
+  const int n = ns[blockIdx.x];
+  const int c0 = blockIdx.y * PSD_CS;
+  if (c0 >= n) return;
+  double *X = sm, *T = X + NP * LDX, *Wt = T + NP * LDT;          // Wt: [k][c'] as c' + k*LDW
+  const double *U = u + offs[blockIdx.x], *Xg = x + offs[blockIdx.x];
+  double *Yg = y + offs[blockIdx.x];
+  const int *p = perm ? perm + poffs[blockIdx.x] : nullptr;
+  const bool prep = p && !transp, postp = p && transp;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  {
+    int pi[NR];
+#pragma unroll
+    for (int a = 0; a < NR; a++) pi[a] = (prep && tx + 32 * a < n) ? p[tx + 32 * a] : tx + 32 * a;
+    for (int k = ty; k < NP; k += 16) {
+      const long long pk = (prep && k < n) ? p[k] : k;
+#pragma unroll
+      for (int a = 0; a < NR; a++) {
+        const int i = tx + 32 * a;
+        double tv = 0.0, xv = 0.0;
+        if (i < n && k < n) {
+          const bool keep = transp ? (i <= k) : (i >= k);
+          tv = keep ? U[i + (long long)k * n] : 0.0;
+          xv = Xg[pi[a] + pk * n];
+        }
+        T[i + k * LDT] = tv;
+        X[i + k * LDX] = xv;
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = ty, qr = tx >> 2, qc = tx & 3;
+  const int r8 = warp * 8;                           // this warp's 8-row strip
+  const bool active = r8 < n;
+  // ---- stage 1: W(i, c0+c') = sum_k X(i,k) T(k, c0+c'),  T(k,c) = 0 for k > c (triu) / k < c (tril)
+  if (active) {
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    const int klo = transp ? 0 : (c0 & ~3), khi = transp ? min(n, c0 + PSD_CS) : n;
+    for (int k4 = klo; k4 < khi; k4 += 4) {
+      const double af = X[(r8 + qr) + (k4 + qc) * LDX];
+      const double b0 = T[(k4 + qc) + (c0 + qr) * LDT], b1 = T[(k4 + qc) + (c0 + 8 + qr) * LDT];
+      dmma_m8n8k4(c00, c01, af, b0);
+      dmma_m8n8k4(c10, c11, af, b1);
+    }
+    // C fragment: row qr, columns 2qc, 2qc+1 of each 8-column fragment
+    Wt[(2 * qc) + (r8 + qr) * LDW] = c00; Wt[(2 * qc + 1) + (r8 + qr) * LDW] = c01;
+    Wt[(8 + 2 * qc) + (r8 + qr) * LDW] = c10; Wt[(8 + 2 * qc + 1) + (r8 + qr) * LDW] = c11;
+  }
+  __syncthreads();
+  // ---- stage 2: Y(i, c0+c') = sum_k T(k,i) W(k,c'),  T(k,i) = 0 for k > i (triu) / k < i (tril)
+  if (active) {
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    const int klo = transp ? 0 : (r8 & ~3), khi = transp ? min(n, r8 + 8) : n;
+    for (int k4 = klo; k4 < khi; k4 += 4) {
+      const double af = T[(k4 + qc) + (r8 + qr) * LDT];                 // A(i,k) = T(k,i)
+      const double b0 = Wt[qr + (k4 + qc) * LDW], b1 = Wt[(8 + qr) + (k4 + qc) * LDW];
+      dmma_m8n8k4(c00, c01, af, b0);
+      dmma_m8n8k4(c10, c11, af, b1);
+    }
+    const int i = r8 + qr;
+    if (i < n) {
+      const double v[4] = {c00, c01, c10, c11};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = c0 + (e >> 1) * 8 + 2 * qc + (e & 1);
+        if (c < n) {
+          if (postp) Yg[p[i] + (long long)p[c] * n] = v[e];
+          else Yg[i + (long long)c * n] = v[e];
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- Hermitian PSD blocks
 // A Hermitian block of order n arrives as [vec Re; vec Im] (2 n^2 doubles).  The complex algebra runs on
 // the real embedding E(Z) = [[Re Z, -Im Z],[Im Z, Re Z]] (a *-homomorphism: E(Z^H) = E(Z)', E(XY) = E(X)E(Y)),
@@ -717,15 +803,23 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
   cudaStream_t st = ctx().stream;
   if (pl->maxn <= PSD_SMALL_MAX) {
     const int NR = (pl->maxn + 31) / 32, NP = 32 * NR;
-    const size_t shm = sizeof(double) * (2 * (size_t)NP + PSD_CS) * (NP + 1);
+    static const bool use_fma = getenv("SB200_PSDSCALE_FMA") != nullptr;       // the first (FP64 FMA) version, for comparison
+    const size_t shm = use_fma ? sizeof(double) * (2 * (size_t)NP + PSD_CS) * (NP + 1)
+                               : sizeof(double) * ((size_t)NP * (NP + 8) + (size_t)NP * (NP + 4) + (size_t)NP * 24);
     auto launch = [&](auto kern) -> int {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
       kern<<<dim3(pl->nblk, (pl->maxn + PSD_CS - 1) / PSD_CS), 512, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, u_dev, perm_dev, x_dev, transp, y_dev);
       return 0;
     };
-    if (NR == 1) SB_TRY(launch(psdscale_small_kernel<1>));
-    else if (NR == 2) SB_TRY(launch(psdscale_small_kernel<2>));
-    else SB_TRY(launch(psdscale_small_kernel<3>));
+    if (use_fma) {
+      if (NR == 1) SB_TRY(launch(psdscale_small_kernel<1>));
+      else if (NR == 2) SB_TRY(launch(psdscale_small_kernel<2>));
+      else SB_TRY(launch(psdscale_small_kernel<3>));
+    } else {
+      if (NR == 1) SB_TRY(launch(psdscale_small_dmma_kernel<1>));
+      else if (NR == 2) SB_TRY(launch(psdscale_small_dmma_kernel<2>));
+      else SB_TRY(launch(psdscale_small_dmma_kernel<3>));
+    }
     SB_LAUNCH_CHECK_N("psdscale_small_kernel");
     return 0;
   }
