@@ -432,7 +432,7 @@ __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cl
 template <bool BACKWARD, int CL>
 __device__ __forceinline__ void
 dense_solve_body(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
-                 const double *dscale, const int *flag, const double *lb, int nb) {
+                 const double *dscale, const int *flag, const double *lb, int nb, unsigned long long *tdbg) {
   extern __shared__ double smem[];
   double *ys = smem;                                    // m doubles (rounded up to even)
   double *ring = smem + ((m + 1) & ~1);                 // SOLVE_WARPS x 2 x 1024 doubles
@@ -446,9 +446,12 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
   double *yy = yout + (long long)rhs * m;
   const int ld = m;
   double *myring = ring + warp * 2 * PB * PB;
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  if (tdbg && threadIdx.x == 0 && blockIdx.x == 0) tdbg[nb] = gtime();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) ready[i] = 0;
   __syncthreads();
   if (CL > 1) cg::this_cluster().sync();                // nobody writes a remote flag before it is cleared
+  if (tdbg && threadIdx.x == 0 && blockIdx.x == 0) tdbg[nb + 1] = gtime();
   for (int step = warp * CL + (int)crank; step < nb; step += SOLVE_WARPS * CL) {
     const int br = BACKWARD ? (nb - 1 - step) : step;
     const int k0 = br * PB, w = min(PB, m - k0);
@@ -533,25 +536,27 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
       __syncwarp();
       if (lane == 0) ready[br] = 1;
     }
+    if (tdbg && lane == 0 && blockIdx.x < CL) tdbg[br] = gtime();
     if (lane < w) {                                       // the result leaves after the consumers have been released
       if (!BACKWARD) yy[k0 + lane] = dscale ? yv / dk : yv;
       else yy[pk] = yv;
     }
   }
   if (CL > 1) cg::this_cluster().sync();                // no CTA may exit while peers still write into its shared memory
+  if (tdbg && threadIdx.x == 0 && blockIdx.x == 0) tdbg[nb + 2] = gtime();
 }
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32)
 dense_solve_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
-                   const double *dscale, const int *flag, const double *lb, int nb) {
-  dense_solve_body<BACKWARD, 1>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb);
+                   const double *dscale, const int *flag, const double *lb, int nb, unsigned long long *tdbg) {
+  dense_solve_body<BACKWARD, 1>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb, tdbg);
 }
 template <bool BACKWARD>
 __global__ void __cluster_dims__(SOLVE_CLUSTER, 1, 1) __launch_bounds__(SOLVE_WARPS * 32)
 dense_solve_cluster_kernel(int m, const double *L, const double *dinv, const int *perm, const double *b, double *yout,
-                           const double *dscale, const int *flag, const double *lb, int nb) {
-  dense_solve_body<BACKWARD, SOLVE_CLUSTER>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb);
+                           const double *dscale, const int *flag, const double *lb, int nb, unsigned long long *tdbg) {
+  dense_solve_body<BACKWARD, SOLVE_CLUSTER>(m, L, dinv, perm, b, yout, dscale, flag, lb, nb, tdbg);
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -666,26 +671,41 @@ static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, 
   SB_CHECK(shm <= 200 * 1024, "dense solve: m=%d too large for the shared-memory dataflow kernel", m);
   cudaStream_t st = ctx().stream;
   static const bool use_cluster = !(getenv("SB200_SOLVE_CLUSTER") && atoi(getenv("SB200_SOLVE_CLUSTER")) == 0);
+  static unsigned long long *s_tdbg = nullptr;
+  unsigned long long *tdbg = nullptr;
+  if (getenv("SB200_SOLVE_TIMING")) {
+    if (!s_tdbg) cudaMalloc((void **)&s_tdbg, sizeof(unsigned long long) * 8192);
+    tdbg = s_tdbg;
+    cudaMemsetAsync(tdbg, 0, sizeof(unsigned long long) * 8192, st);
+  }
   // a cluster only pays when there are block rows for more than one CTA's warps to overlap
   const bool cl = use_cluster && nb > 2;
   if (backward) {
     if (cl) {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      dense_solve_cluster_kernel<true><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+      dense_solve_cluster_kernel<true><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb, tdbg);
     } else {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      dense_solve_kernel<true><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb);
+      dense_solve_kernel<true><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, pl->d_work.p, pl->d_dinv.p, pl->d_perm.p, b, y, nullptr, nullptr, nullptr, nb, tdbg);
     }
   } else {
     if (cl) {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      dense_solve_cluster_kernel<false><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+      dense_solve_cluster_kernel<false><<<nrhs * SOLVE_CLUSTER, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb, tdbg);
     } else {
       if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(dense_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      dense_solve_kernel<false><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb);
+      dense_solve_kernel<false><<<nrhs, SOLVE_WARPS * 32, shm, st>>>(m, rect, pl->d_dinv.p, pl->d_perm.p, b, y, dscale, flag, pl->d_lb.p, nb, tdbg);
     }
   }
   SB_LAUNCH_CHECK_N(backward ? "dense_solve_kernel<bw>" : "dense_solve_kernel<fw>");
+  if (tdbg) {
+    std::vector<unsigned long long> h(nb + 3);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), tdbg, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[dense_solve %s timing, ns from kernel start] init+cluster sync %llu  rows:", backward ? "bw" : "fw", h[nb + 1] - h[nb]);
+    for (int i = 0; i < nb; i++) { const int br = backward ? nb - 1 - i : i; fprintf(stderr, " %lld", (long long)(h[br] - h[nb])); }
+    fprintf(stderr, "  end %llu\n", h[nb + 2] - h[nb]);
+  }
   return 0;
 }
 int dense_fwsolve(sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs, const double *dscale, const int *flag) {

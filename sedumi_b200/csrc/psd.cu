@@ -453,20 +453,33 @@ psdscale_small_kernel(const int *ns, const long long *offs, const int *poffs, co
 //   W = X T is written transposed (Wt[c][k], ld 24) so that stage 2 reads it as a B operand.
 // Warp w owns the 8-row strip w of the result (both 8-column fragments of the 16-column slab); the k-ranges skip the
 // structural zeros of the triangular factor.
+// The kernel computes a general small congruence Y = T' X T per block, which is also what psdframeit
+// (Qb' diag(lab) Qb) and psdinvjmul (Qb Ys Qb', jdiv, Qb' M Qb) are:
+//   T  = tsrc or tsrc' (ttrans), optionally masked to its upper (tmask 1) / lower (tmask 2) triangle;
+//   X  = xsrc, or xsrc(perm,perm) (prep), or the symmetric matrix held in tril(xsrc) (xsym), or diag(xdiag);
+//   Y  : optional jdiv  y_ij *= 2/(l_i+l_j), y_jj /= l_j  (psdinvjmul.c:69-84), then either stored as computed
+//        (optionally to (perm,perm), postp) or, symout, the lower triangle is stored and mirrored (exact symmetry).
+struct CongArgs {
+  const double *tsrc, *xsrc, *xdiag, *jdiv;
+  const int *perm;
+  int tmask, ttrans, xsym, prep, postp, symout;
+};
 template <int NR>
 __global__ void __launch_bounds__(512)
-psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poffs, const double *u, const int *perm,
-                           const double *x, int transp, double *y) {
+psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poffs, CongArgs A, double *y) {
   extern __shared__ double sm[];
   constexpr int NP = 32 * NR, LDX = NP + 8, LDT = NP + 4, LDW = 24;
   const int n = ns[blockIdx.x];
   const int c0 = blockIdx.y * PSD_CS;
   if (c0 >= n) return;
   double *X = sm, *T = X + NP * LDX, *Wt = T + NP * LDT;          // Wt: [k][c'] as c' + k*LDW
-  const double *U = u + offs[blockIdx.x], *Xg = x + offs[blockIdx.x];
+  const double *U = A.tsrc + offs[blockIdx.x];
+  const double *Xg = A.xsrc ? A.xsrc + offs[blockIdx.x] : nullptr;
+  const double *xd = A.xdiag ? A.xdiag + poffs[blockIdx.x] : nullptr;
+  const double *jl = A.jdiv ? A.jdiv + poffs[blockIdx.x] : nullptr;
   double *Yg = y + offs[blockIdx.x];
-  const int *p = perm ? perm + poffs[blockIdx.x] : nullptr;
-  const bool prep = p && !transp, postp = p && transp;
+  const int *p = A.perm ? A.perm + poffs[blockIdx.x] : nullptr;
+  const bool prep = p && A.prep, postp = p && A.postp;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   {
     int pi[NR];
@@ -479,9 +492,11 @@ psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poff
         const int i = tx + 32 * a;
         double tv = 0.0, xv = 0.0;
         if (i < n && k < n) {
-          const bool keep = transp ? (i <= k) : (i >= k);
-          tv = keep ? U[i + (long long)k * n] : 0.0;
-          xv = Xg[pi[a] + pk * n];
+          const bool keep = A.tmask == 0 || (A.tmask == 1 ? (i <= k) : (i >= k));
+          tv = keep ? (A.ttrans ? U[k + (long long)i * n] : U[i + (long long)k * n]) : 0.0;
+          if (xd) xv = (i == k) ? xd[i] : 0.0;
+          else if (A.xsym) xv = Xg[max(i, k) + (long long)min(i, k) * n];
+          else xv = Xg[pi[a] + pk * n];
         }
         T[i + k * LDT] = tv;
         X[i + k * LDX] = xv;
@@ -495,7 +510,7 @@ psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poff
   // ---- stage 1: W(i, c0+c') = sum_k X(i,k) T(k, c0+c'),  T(k,c) = 0 for k > c (triu) / k < c (tril)
   if (active) {
     double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-    const int klo = transp ? 0 : (c0 & ~3), khi = transp ? min(n, c0 + PSD_CS) : n;
+    const int klo = A.tmask == 2 ? (c0 & ~3) : 0, khi = A.tmask == 1 ? min(n, c0 + PSD_CS) : n;
     for (int k4 = klo; k4 < khi; k4 += 4) {
       const double af = X[(r8 + qr) + (k4 + qc) * LDX];
       const double b0 = T[(k4 + qc) + (c0 + qr) * LDT], b1 = T[(k4 + qc) + (c0 + 8 + qr) * LDT];
@@ -508,9 +523,9 @@ psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poff
   }
   __syncthreads();
   // ---- stage 2: Y(i, c0+c') = sum_k T(k,i) W(k,c'),  T(k,i) = 0 for k > i (triu) / k < i (tril)
-  if (active) {
+  if (active && !(A.symout && r8 + 8 <= c0)) {        // symout: strips entirely above the slab's diagonal are mirrored
     double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-    const int klo = transp ? 0 : (r8 & ~3), khi = transp ? min(n, r8 + 8) : n;
+    const int klo = A.tmask == 2 ? (r8 & ~3) : 0, khi = A.tmask == 1 ? min(n, r8 + 8) : n;
     for (int k4 = klo; k4 < khi; k4 += 4) {
       const double af = T[(k4 + qc) + (r8 + qr) * LDT];                 // A(i,k) = T(k,i)
       const double b0 = Wt[qr + (k4 + qc) * LDW], b1 = Wt[(8 + qr) + (k4 + qc) * LDW];
@@ -524,8 +539,12 @@ psdscale_small_dmma_kernel(const int *ns, const long long *offs, const int *poff
       for (int e = 0; e < 4; e++) {
         const int c = c0 + (e >> 1) * 8 + 2 * qc + (e & 1);
         if (c < n) {
-          if (postp) Yg[p[i] + (long long)p[c] * n] = v[e];
-          else Yg[i + (long long)c * n] = v[e];
+          double val = v[e];
+          if (jl) val = (i == c) ? val / jl[c] : val * (2.0 / (jl[i] + jl[c]));
+          if (A.symout) {
+            if (i >= c) { Yg[i + (long long)c * n] = val; if (i != c) Yg[c + (long long)i * n] = val; }
+          } else if (postp) Yg[p[i] + (long long)p[c] * n] = val;
+          else Yg[i + (long long)c * n] = val;
         }
       }
     }
@@ -778,6 +797,22 @@ static dim3 blk_grid(const sb200_psd_plan *pl, int per) {
   return dim3(std::max(gx, 1), pl->nblk);
 }
 
+// Y = T' X T for every block of a plan whose blocks are at most PSD_SMALL_MAX wide (one fused DMMA kernel).
+static int small_congruence(sb200_psd_plan *pl, const CongArgs &A, double *y_dev) {
+  const int NR = (pl->maxn + 31) / 32, NP = 32 * NR;
+  const size_t shm = sizeof(double) * ((size_t)NP * (NP + 8) + (size_t)NP * (NP + 4) + (size_t)NP * 24);
+  const dim3 grid(pl->nblk, (pl->maxn + PSD_CS - 1) / PSD_CS);
+  cudaStream_t st = ctx().stream;
+  auto launch = [&](auto kern) -> int {
+    if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    kern<<<grid, 512, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, A, y_dev);
+    return 0;
+  };
+  if (NR == 1) return launch(psdscale_small_dmma_kernel<1>);
+  if (NR == 2) return launch(psdscale_small_dmma_kernel<2>);
+  return launch(psdscale_small_dmma_kernel<3>);
+}
+
 // y = invcholfac(u, K, perm): perm_dev is int32 0-based (length sum n_k) or NULL.
 int sb200_invcholfac_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_dev, double *y_dev) {
   SB_TRY(ensure_init());
@@ -811,14 +846,14 @@ int sb200_psdscale_dev(sb200_psd_plan *pl, const double *u_dev, const int *perm_
       kern<<<dim3(pl->nblk, (pl->maxn + PSD_CS - 1) / PSD_CS), 512, shm, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, u_dev, perm_dev, x_dev, transp, y_dev);
       return 0;
     };
+    (void)NP;
     if (use_fma) {
       if (NR == 1) SB_TRY(launch(psdscale_small_kernel<1>));
       else if (NR == 2) SB_TRY(launch(psdscale_small_kernel<2>));
       else SB_TRY(launch(psdscale_small_kernel<3>));
     } else {
-      if (NR == 1) SB_TRY(launch(psdscale_small_dmma_kernel<1>));
-      else if (NR == 2) SB_TRY(launch(psdscale_small_dmma_kernel<2>));
-      else SB_TRY(launch(psdscale_small_dmma_kernel<3>));
+      CongArgs A{u_dev, x_dev, nullptr, nullptr, perm_dev, transp ? 1 : 2, 0, 0, transp ? 0 : 1, transp ? 1 : 0, 0};
+      SB_TRY(small_congruence(pl, A, y_dev));
     }
     SB_LAUNCH_CHECK_N("psdscale_small_kernel");
     return 0;
@@ -897,7 +932,7 @@ int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *
 }
 
 // ---- Householder-frame operations.  frms_dev: lenud doubles (real blocks); lab/xlab: sum(n_k) doubles.
-static int build_q(sb200_psd_plan *pl, const double *frms_dev) {   // Q -> d_Tt, Q' -> d_Wt
+static int build_q(sb200_psd_plan *pl, const double *frms_dev, bool need_transpose = true) {   // Q -> d_Tt, Q' -> d_Wt
   cudaStream_t st = ctx().stream;
   int tp = (pl->maxn + 31) / 32;
   if (pl->wy_rows) {
@@ -935,6 +970,7 @@ static int build_q(sb200_psd_plan *pl, const double *frms_dev) {   // Q -> d_Tt,
   }
   householder_q_kernel<<<pl->nqgroups, 256, 0, st>>>(pl->d_qcol_blk.p, pl->d_qcol_j0.p, pl->d_n.p, pl->d_off.p, frms_dev, pl->d_Tt.p);
   SB_LAUNCH_CHECK_N("householder_q_kernel");
+  if (!need_transpose) return 0;
   transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, pl->d_Tt.p, nullptr, pl->d_Wt.p);
   SB_LAUNCH_CHECK_N("transpose_scale_kernel");
   return 0;
@@ -945,6 +981,14 @@ static int psdframeit_core(sb200_psd_plan *pl, const double *lab_dev, double *x_
 int sb200_psdframeit_dev(sb200_psd_plan *pl, const double *lab_dev, const double *frms_dev, double *x_dev) {
   SB_TRY(ensure_init());
   if (pl->nblk == 0) return 0;
+  if (pl->maxn <= PSD_SMALL_MAX && !pl->wy && !pl->wy_rows) {
+    // small blocks: Q by the per-column kernel, then ONE fused congruence  X = Q' diag(lab) Q  (lower triangle mirrored)
+    SB_TRY(build_q(pl, frms_dev, false));
+    CongArgs A{pl->d_Tt.p, nullptr, lab_dev, nullptr, nullptr, 0, 0, 0, 0, 0, 1};
+    SB_TRY(small_congruence(pl, A, x_dev));
+    SB_LAUNCH_CHECK_N("small_congruence_kernel");
+    return 0;
+  }
   SB_TRY(build_q(pl, frms_dev));
   return psdframeit_core(pl, lab_dev, x_dev);
 }
@@ -967,6 +1011,17 @@ static int psdinvjmul_core(sb200_psd_plan *pl, const double *xlab_dev, const dou
 int sb200_psdinvjmul_dev(sb200_psd_plan *pl, const double *xlab_dev, const double *frms_dev, const double *y_dev, double *z_dev) {
   SB_TRY(ensure_init());
   if (pl->nblk == 0) return 0;
+  if (pl->maxn <= PSD_SMALL_MAX && !pl->wy && !pl->wy_rows) {
+    // small blocks: two fused congruences.  M = Qb Ys Qb' with the jdiv scaling in its epilogue, then Z = Qb' M Qb
+    SB_TRY(build_q(pl, frms_dev, false));
+    CongArgs A1{pl->d_Tt.p, y_dev, nullptr, xlab_dev, nullptr, 0, 1, 1, 0, 0, 1};
+    SB_TRY(small_congruence(pl, A1, pl->d_Y.p));
+    SB_LAUNCH_CHECK_N("small_congruence_kernel");
+    CongArgs A2{pl->d_Tt.p, pl->d_Y.p, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 1};
+    SB_TRY(small_congruence(pl, A2, z_dev));
+    SB_LAUNCH_CHECK_N("small_congruence_kernel");
+    return 0;
+  }
   SB_TRY(build_q(pl, frms_dev));                                      // Q = d_Tt, Q' = d_Wt
   return psdinvjmul_core(pl, xlab_dev, y_dev, z_dev);
 }
