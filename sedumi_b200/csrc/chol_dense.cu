@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256)
 dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, const double *scal, double maxu,
                  int *flag, double *sval, const double *diagX, double *vscratch, double *dinv, unsigned *bar, long long *tdbg) {
   __shared__ double A[PB][PB + 1];
-  __shared__ double s_lb[PB], z[PB], dloc[PB], Lk[PB];
+  __shared__ double s_lb[PB], z[PB], dloc[PB];
   __shared__ int skipped[PB];
   __shared__ ArgMaxD sh_am[32];
   __shared__ double s_x;

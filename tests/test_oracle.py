@@ -120,3 +120,82 @@ def test_reference_diag_add_reads_element_after_first_max():
     LL, d, skip, add = ref.blkchol(dense_L(m), full_pattern(X), pars, np.diag(X).copy(), nlhs=4)
     assert add.indices.tolist() == [0]
     assert abs(d.ravel()[0] - 1e-3 / 10.0) <= 1e-18       # |x[imax+1]|/maxu, not |x[imax]|/maxu = 3e-4
+
+
+@needs_ref
+def test_getada_m_restatement_equals_reference_getada12_on_nb():
+    """getada.m (the M path for sum(K.s)==0, sedumi.m:446-448) restated in numpy against the reference's own
+    getada1 + getada2 MEX chain on nb.mat: two independent routes to the same Schur complement."""
+    At, b, c, K = cones.pretransfo(*problems.load_fixture("nb"))[:4]
+    S = setup.build_setup(At, b, c, K)
+    d = problems.scaling(K, "S1", seed=3)
+    R = refpath.RefHotPath(S)
+    _, ADA, absd = R.assemble(d)                               # numpy restatement (no PSD block)
+    A1 = ref.getada1(R.ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], {"l": d["l"], "det": d["det"]}, S.K["qblkstart"].reshape(1, -1))
+    A2 = ref.getada2(A1, {"q": R.DAtq(d)}, S.Aord, R.Km)
+    A3, _ = ref.getada3(A2, S.At, S.Ablkjc[:, 2], S.Aord, np.zeros(0), R.Km, nlhs=2)
+    assert relerr(ADA.toarray(), A3.toarray()) <= 1e-13
+    assert relerr(absd.ravel(), A3.diagonal()) <= 1e-13
+
+
+@needs_ref
+def test_reference_getada3_hermitian_matches_dense_formula():
+    """Pins the conventions of Hermitian blocks ([Re lower; Im strictly lower] rows, udsqr = [Re D; Im D]) against
+    ADA(i,j) = Re tr(H_i^H D H_j D) with H = (tril + tril^H)/2 evaluated densely in numpy."""
+    At, b, c, K = problems.synth_hermitian_mixed()
+    S = setup.build_setup(At, b, c, K)
+    d = problems.scaling_hermitian(K, 3)
+    udsqr, ADA, absd = refpath.RefHotPath(S).assemble(d)
+    m, l = S.m, int(K["l"])
+    A = At.toarray()
+    M = A[:l, :].T @ np.diag(d["l"]) @ A[:l, :]
+    ud = udsqr.ravel()
+    s, nr = K["s"].astype(int), K["rsdpN"]
+    off, uo = l, 0
+    for i, n in enumerate(s):
+        cplx = i >= nr
+        span = (2 if cplx else 1) * n * n
+        D = ud[uo:uo + n * n].reshape(n, n, order="F").astype(complex)
+        if cplx:
+            D = D + 1j * ud[uo + n * n:uo + 2 * n * n].reshape(n, n, order="F")
+        Hs = []
+        for j in range(m):
+            col = A[off:off + span, j]
+            X = col[:n * n].reshape(n, n, order="F").astype(complex)
+            if cplx:
+                X = X + 1j * col[n * n:].reshape(n, n, order="F")
+            Lw = np.tril(X)
+            Hs.append((Lw + Lw.conj().T) / 2.0)
+        for a in range(m):
+            for bb in range(m):
+                M[a, bb] += np.real(np.trace(Hs[a].conj().T @ D @ Hs[bb] @ D))
+        off += span
+        uo += span
+    assert relerr(ADA.toarray(), M) <= 1e-13
+
+
+@needs_ref
+def test_synth_frames_are_orthogonal_product_forms():
+    """problems.synth_frames (inputs of the bench's psdframeit / psdinvjmul calls) through the reference's psdframeit:
+    X = Qb' diag(lab) Qb must have exactly the eigenvalues lab."""
+    K = cones.finish_K({"l": 0.0, "q": np.zeros(0), "s": np.array([7.0, 4.0])})
+    lab, frms = problems.synth_frames(K["s"])
+    x = ref.psdframeit(lab, frms, cones.K_for_mex(K)).ravel()
+    X = x[:49].reshape(7, 7, order="F")
+    assert np.abs(np.sort(np.linalg.eigvalsh((X + X.T) / 2)) - np.sort(lab[:7])).max() <= 1e-13
+
+
+def test_restated_psdscale_hermitian_block_against_direct_formula():
+    rng = np.random.default_rng(5)
+    n = 5
+    K = cones.finish_K({"l": 1.0, "q": np.zeros(0), "s": np.array([float(n)]), "rsdpN": 0})
+    U = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    X = X + X.conj().T
+    u = np.r_[U.real.ravel(order="F"), U.imag.ravel(order="F")]
+    x = np.r_[X.real.ravel(order="F"), X.imag.ravel(order="F")]
+    y = restate.psdscale(u, x, K, True)
+    Y = U.conj().T @ X @ U
+    Yi = Y.imag.copy()
+    Yi[np.diag_indices(n)] = 0.0
+    assert relerr(y, np.r_[Y.real.ravel(order="F"), Yi.ravel(order="F")]) <= 1e-14
