@@ -273,6 +273,10 @@ def main():
         config["parallelism"] = (f"PSD blocks sharded over {world} ranks (owner computes: invcholfac, getada3, psdscale, frames, "
                                  "rotations), 1 all-reduce(ADA,absd)/iteration, factor+solves replicated")
     hp = sbdev.HotPath(S, device=local_rank)
+    if shard_dist is not None and len(np.asarray(S.L["xsuper"]).ravel()) - 1 > 2:
+        info = hp.shard_factor_setup(world, rank)           # elimination-tree subtrees per rank, replicated top
+        config["parallelism"] = (f"PSD blocks and etree subtrees sharded over {world} ranks (owner computes); collectives per iteration: "
+                                 f"all-reduce(ADA,absd), all-reduce(top fronts, {info['top_len']} doubles), 2 small all-reduces per solve")
     lib = sbdev.lib()
     stream = hp.stream()
     dev = hp.dev

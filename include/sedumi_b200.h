@@ -98,6 +98,23 @@ int sb200_blkchol(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *L
 
 /* y = L \ b(perm,:)  and  y(perm,:) = L' \ b   (dense right-hand sides, m x nrhs).
  * *_dev: Lrect_dev in internal layout; b_dev/y_dev column-major m x nrhs.  */
+/* ---- subtree sharding of the factor over ranks (multi-supernode factors).  Supernodes >= t0 form a
+ * replicated top, the forest below is dealt to the ranks.  Call order on every rank (all on the library stream):
+ *   sb200_blkchol_shard_local_dev ; all-reduce(sum) rect[top_rect_off, +top_rect_len) ; sb200_blkchol_shard_top_dev
+ *   sb200_fw_shard_local_dev ; all-reduce(sum) y[top_col0 .. m) per rhs ; sb200_solve_shard_top_dev (in place: ./d and the
+ *   backward pass, foreign columns zeroed) ; all-reduce(sum) y ; sb200_bw_shard_finish_dev (back to the original order).
+ * d/flag/sval are complete for a rank's own columns and the top; colmask_dev marks the columns a rank answers for. */
+int sb200_chol_shard_create(sb200_chol_plan *plan, sb_idx world, sb_idx rank);
+int sb200_chol_shard_info(const sb200_chol_plan *plan, sb_idx *t0, sb_idx *top_rect_off, sb_idx *top_rect_len,
+                          sb_idx *top_col0, const int **colmask_dev);
+int sb200_blkchol_shard_local_dev(sb200_chol_plan *plan, const double *Xpr_dev, const double *absd_dev,
+                                  sb200_chol_pars pars, double *Lrect_dev, double *d_dev, int *flag_dev, double *sval_dev);
+int sb200_blkchol_shard_top_dev(sb200_chol_plan *plan, sb200_chol_pars pars, double *Lrect_dev, double *d_dev,
+                                int *flag_dev, double *sval_dev);
+int sb200_fw_shard_local_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev, double *y_dev, sb_idx nrhs);
+int sb200_solve_shard_top_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev, const int *flag_dev,
+                              double *y_dev, sb_idx nrhs);
+int sb200_bw_shard_finish_dev(sb200_chol_plan *plan, const double *z_dev, double *y_dev, sb_idx nrhs);
 int sb200_fwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
                        double *y_dev, sb_idx nrhs);
 int sb200_bwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,

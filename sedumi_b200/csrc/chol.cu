@@ -428,7 +428,7 @@ __global__ void csc_to_rect_kernel(const Sn *sn, const int *snode, const long lo
 // Forward: one CTA per (supernode of the level, rhs).  y has length m per rhs, already = b(perm).
 __global__ void __launch_bounds__(512)
 fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair_beg, const int *rel,
-               const double *rect, double *y, int m) {
+               const double *rect, double *y, int m, int solve) {
   extern __shared__ double sm[];             // s[n]
   Sn sj = sn[list[blockIdx.x]];
   double *yy = y + (long long)blockIdx.y * m;
@@ -450,10 +450,11 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
     }
     __syncthreads();
   }
-  // dense unit-lower solve of the n x n diagonal block, 32 columns at a time
+  // dense unit-lower solve of the n x n diagonal block, 32 columns at a time (solve = 0: pull only, used by the
+  // sharded forward pass to collect the contributions of a rank's subtrees in the replicated top rows)
   const double *P = rect + sj.poff;
   const int ld = sj.m;
-  for (int k0 = 0; k0 < n; k0 += 32) {
+  for (int k0 = 0; solve && k0 < n; k0 += 32) {
     int w = min(32, n - k0);
     if (threadIdx.x < 32) {
       int lane = threadIdx.x;
@@ -777,7 +778,7 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   for (int lv = 0; lv < pl->nlevels; lv++) {
     dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
     fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pairs.p,
-                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m);
+                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
@@ -822,6 +823,302 @@ int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
     SB_LAUNCH_CHECK_N("bwsolve_kernel");
   }
   scatter_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, pl->d_y.p, y);
+  SB_LAUNCH_CHECK_N("scatter_perm_kernel");
+  return 0;
+}
+
+
+// ======================================================================= subtree sharding (multi-GPU)
+// Supernodes are postordered, so any suffix [t0, nsuper) is closed under "parent of": it is the replicated TOP; the
+// supernodes below form a forest whose trees are dealt to the ranks (largest first).  A rank factors its trees, adds
+// their Schur contributions into the top panels (which start from the ADA values on rank 0 and from zero elsewhere);
+// one all-reduce(sum) of the top panels -- done by the caller between sb200_blkchol_shard_local_dev and
+// sb200_blkchol_shard_top_dev -- completes them, and every rank factors the top redundantly.  Solves: forward =
+// own trees + pull of their contributions into the top rows, all-reduce of the top segment, top; backward = top, own
+// trees; entries of foreign trees are zeroed so that a final all-reduce(sum) assembles the solution.
+__global__ void shard_mask_kernel(int m, int nrhs, const int *colmask, double *z) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < (long long)m * nrhs && !colmask[i % m]) z[i] = 0.0;
+}
+__global__ void shard_scale_kernel(int m, int nrhs, const int *colmask, int top_col0, const double *d, const int *flag, const double *lb, double *w) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)m * nrhs) return;
+  const int c = (int)(i % m);
+  if (!colmask[c] && c < top_col0) { w[i] = 0.0; return; }       // foreign tree; the replicated top is kept on every rank
+  double dk = d[c];
+  if (flag && flag[c] == 1 && dk <= lb[c]) dk = 1.0;
+  w[i] /= dk;
+}
+
+int sb200_chol_shard_create(sb200_chol_plan *pl, sb_idx world64, sb_idx rank64) {
+  SB_TRY(ensure_init());
+  SB_CHECK(!pl->dense_fast, "subtree sharding needs a multi-supernode factor (this one is a single dense supernode)");
+  const int world = (int)world64, rank = (int)rank64, ns = pl->nsuper;
+  SB_CHECK(world >= 1 && rank >= 0 && rank < world, "shard: rank/world out of range");
+  delete pl->shard;
+  auto *sh = new sb200_chol_plan::Shard();
+  pl->shard = sh;
+  sh->world = world; sh->rank = rank;
+  // parent of a supernode = supernode of its first off-diagonal row
+  std::vector<int> lindx((size_t)0);
+  std::vector<Pair> pairs(pl->pair_beg[ns]);
+  SB_CUDA(cudaMemcpy(pairs.data(), pl->d_pairs.p, sizeof(Pair) * pairs.size(), cudaMemcpyDeviceToHost));
+  std::vector<int> parent(ns, -1);
+  for (auto &p : pairs) if (parent[p.K] < 0 || p.J < parent[p.K]) parent[p.K] = p.J;
+  std::vector<double> cost(ns, 0.0), sub(ns, 0.0);
+  for (int s = 0; s < ns; s++) { cost[s] = (double)pl->sn[s].n * pl->sn[s].m * pl->sn[s].m; sub[s] += cost[s]; if (parent[s] >= 0) sub[parent[s]] += sub[s]; }
+  double total = 0.0; for (int s = 0; s < ns; s++) total += cost[s];
+  // grow the top from the end until the forest below has enough, small enough trees
+  int t0 = ns;
+  auto forest_ok = [&](int t) {
+    int ntrees = 0; double mx = 0.0;
+    for (int s = 0; s < t; s++) if (parent[s] < 0 || parent[s] >= t) { ntrees++; mx = std::max(mx, sub[s]); }
+    return ntrees >= 2 * world && mx <= 1.25 * total / world;
+  };
+  while (t0 > 0 && !forest_ok(t0)) t0--;
+  if (t0 == 0) { t0 = ns; while (t0 > 0 && !(([&] { int c = 0; for (int s = 0; s < t0; s++) if (parent[s] < 0 || parent[s] >= t0) c++; return c >= world; })())) t0--; }
+  sh->t0 = t0;
+  // deal the trees (roots: parent outside the forest) to the ranks, heaviest first
+  std::vector<int> roots;
+  for (int s = 0; s < t0; s++) if (parent[s] < 0 || parent[s] >= t0) roots.push_back(s);
+  std::sort(roots.begin(), roots.end(), [&](int a, int b) { return sub[a] != sub[b] ? sub[a] > sub[b] : a < b; });
+  std::vector<double> load(world, 0.0);
+  std::vector<int> root_owner(ns, -1);
+  for (int r : roots) { int w = (int)(std::min_element(load.begin(), load.end()) - load.begin()); root_owner[r] = w; load[w] += sub[r]; }
+  sh->owner.assign(ns, -1);
+  for (int s = t0 - 1; s >= 0; s--) sh->owner[s] = (parent[s] < 0 || parent[s] >= t0) ? root_owner[s] : sh->owner[parent[s]];
+  // top region of rect / of the column space
+  sh->top_col0 = t0 < ns ? pl->sn[t0].first : pl->m;
+  sh->top_rect_off = t0 < ns ? pl->sn[t0].poff : pl->rect;
+  sh->top_rect_len = pl->rect - sh->top_rect_off;
+  // filtered pair lists for the top: A = owned descendants below t0, B = descendants inside the top
+  std::vector<Pair> pA, pB;
+  std::vector<int> begA(ns + 1, 0), begB(ns + 1, 0);
+  for (int J = 0; J < ns; J++) {
+    begA[J] = (int)pA.size(); begB[J] = (int)pB.size();
+    if (J < t0) continue;
+    for (int e = pl->pair_beg[J]; e < pl->pair_beg[J + 1]; e++) {
+      const Pair &p = pairs[e];
+      if (p.K >= t0) pB.push_back(p);
+      else if (sh->owner[p.K] == rank) pA.push_back(p);
+    }
+  }
+  begA[ns] = (int)pA.size(); begB[ns] = (int)pB.size();
+  // schedules
+  const int nlev = pl->nlevels;
+  sh->own_small.assign(nlev, {}); sh->own_big.assign(nlev, {}); sh->own_all.assign(nlev, {});
+  sh->top_small.assign(nlev, {}); sh->top_big.assign(nlev, {}); sh->top_all.assign(nlev, {});
+  std::vector<int> lists;
+  std::vector<UTile> tiles;
+  std::vector<std::vector<UTile>> own_tiles(nlev), top_tiles(nlev);
+  std::vector<UTile> topA_tiles;
+  auto add_tiles = [&](std::vector<UTile> &v, int s2) {
+    const Sn &S = pl->sn[s2];
+    for (int c0 = 0; c0 < S.n; c0 += UT_C)
+      for (int r0 = (c0 / UT_R) * UT_R; r0 < S.m; r0 += UT_R) v.push_back(UTile{s2, r0, c0});
+  };
+  for (int s2 = 0; s2 < ns; s2++) {
+    const int lv = pl->level_of[s2];
+    const bool small = pl->sn[s2].n <= SMALL_N;
+    if (s2 < t0) {
+      if (sh->owner[s2] != rank) continue;
+      (small ? sh->own_small : sh->own_big)[lv].push_back(s2); sh->own_all[lv].push_back(s2);
+      if (pl->pair_beg[s2 + 1] > pl->pair_beg[s2]) add_tiles(own_tiles[lv], s2);
+    } else {
+      (small ? sh->top_small : sh->top_big)[lv].push_back(s2); sh->top_all[lv].push_back(s2);
+      if (begB[s2 + 1] > begB[s2]) add_tiles(top_tiles[lv], s2);
+      if (begA[s2 + 1] > begA[s2]) add_tiles(topA_tiles, s2);
+    }
+  }
+  for (int lv = 0; lv < nlev; lv++) {
+    sh->own_small_off.push_back((int)lists.size()); for (int v : sh->own_small[lv]) lists.push_back(v);
+    sh->own_all_off.push_back((int)lists.size()); for (int v : sh->own_all[lv]) lists.push_back(v);
+    sh->top_small_off.push_back((int)lists.size()); for (int v : sh->top_small[lv]) lists.push_back(v);
+    sh->top_all_off.push_back((int)lists.size()); for (int v : sh->top_all[lv]) lists.push_back(v);
+    sh->own_tile_off.push_back((int)tiles.size()); sh->own_tile_cnt.push_back((int)own_tiles[lv].size());
+    tiles.insert(tiles.end(), own_tiles[lv].begin(), own_tiles[lv].end());
+    sh->top_tile_off.push_back((int)tiles.size()); sh->top_tile_cnt.push_back((int)top_tiles[lv].size());
+    tiles.insert(tiles.end(), top_tiles[lv].begin(), top_tiles[lv].end());
+  }
+  sh->topA_tile_off = (int)tiles.size(); sh->topA_tile_cnt = (int)topA_tiles.size();
+  tiles.insert(tiles.end(), topA_tiles.begin(), topA_tiles.end());
+  sh->top_list_off = (int)lists.size();
+  for (int s2 = t0; s2 < ns; s2++) lists.push_back(s2);
+  sh->top_list_cnt = ns - t0;
+  std::vector<int> colmask(pl->m, 0);
+  for (int s2 = 0; s2 < ns; s2++) {
+    const bool mine = s2 < t0 ? sh->owner[s2] == rank : rank == 0;
+    for (int c = 0; c < pl->sn[s2].n; c++) colmask[pl->sn[s2].first + c] = mine ? 1 : 0;
+  }
+  if (lists.empty()) lists.push_back(0);
+  if (tiles.empty()) tiles.push_back(UTile{0, 0, 0});
+  if (pA.empty()) pA.push_back(Pair{});
+  if (pB.empty()) pB.push_back(Pair{});
+  SB_TRY(sh->d_lists.upload(lists)); SB_TRY(sh->d_tiles.upload(tiles));
+  SB_TRY(sh->d_pairsA.upload(pA)); SB_TRY(sh->d_pairsB.upload(pB));
+  SB_TRY(sh->d_pair_begA.upload(begA)); SB_TRY(sh->d_pair_begB.upload(begB));
+  SB_TRY(sh->d_colmask.upload(colmask));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+// t0: first top supernode; the top occupies rect[top_rect_off, +top_rect_len) and columns [top_col0, m) of the
+// permuted index space; colmask_dev[c] = 1 for the columns this rank answers for (its trees; the top on rank 0).
+int sb200_chol_shard_info(const sb200_chol_plan *pl, sb_idx *t0, sb_idx *top_rect_off, sb_idx *top_rect_len, sb_idx *top_col0,
+                          const int **colmask_dev) {
+  SB_CHECK(pl->shard, "shard: sb200_chol_shard_create has not been called");
+  *t0 = pl->shard->t0; *top_rect_off = pl->shard->top_rect_off; *top_rect_len = pl->shard->top_rect_len;
+  *top_col0 = pl->shard->top_col0; *colmask_dev = pl->shard->d_colmask.p;
+  return 0;
+}
+
+static int shard_factor_levels(sb200_chol_plan *pl, bool top, sb200_chol_pars pars, double *rect, double *d, int *flag, double *sval) {
+  auto *sh = pl->shard;
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  for (int lv = 0; lv < pl->nlevels; lv++) {
+    const int ntile = top ? sh->top_tile_cnt[lv] : sh->own_tile_cnt[lv];
+    if (ntile) {
+      update_kernel<<<ntile, 256, 0, st>>>(sh->d_tiles.p + (top ? sh->top_tile_off[lv] : sh->own_tile_off[lv]), pl->d_sn.p,
+                                            top ? sh->d_pairsB.p : pl->d_pairs.p, top ? sh->d_pair_begB.p : pl->d_pair_beg.p, pl->d_rel.p, d, rect);
+      SB_LAUNCH_CHECK_N("update_kernel");
+    }
+    const auto &small = top ? sh->top_small[lv] : sh->own_small[lv];
+    if (!small.empty()) {
+      factor_small_kernel<<<(unsigned)small.size(), 512, 0, st>>>(sh->d_lists.p + (top ? sh->top_small_off[lv] : sh->own_small_off[lv]), pl->d_sn.p, rect, d,
+                                                                   pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m);
+      SB_LAUNCH_CHECK_N("factor_small_kernel");
+    }
+    for (int s2 : (top ? sh->top_big[lv] : sh->own_big[lv])) {
+      const Sn &S = pl->sn[s2];
+      for (int p0 = 0; p0 < S.n; p0 += NB) {
+        int w = std::min(NB, S.n - p0);
+        diag_kernel<<<1, 256, 0, st>>>(S, p0, w, rect, d, pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m, pl->d_vscratch.p);
+        SB_LAUNCH_CHECK_N("diag_kernel");
+        int nrow = S.m - (p0 + w);
+        if (nrow > 0) {
+          trsm_kernel<<<(nrow + 127) / 128, 128, 0, st>>>(S, p0, w, rect, d);
+          SB_LAUNCH_CHECK_N("trsm_kernel");
+          int ncol = S.n - (p0 + w);
+          if (ncol > 0) {
+            dim3 g((nrow + 63) / 64, (ncol + 63) / 64);
+            trail_kernel<<<g, 256, 0, st>>>(S, p0, w, rect, d);
+            SB_LAUNCH_CHECK_N("trail_kernel");
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// Phase 1: this rank's trees + their contributions to the top panels.  Afterwards the caller sums
+// rect[top_rect_off, +top_rect_len) over the ranks (one all-reduce).
+int sb200_blkchol_shard_local_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb200_chol_pars pars,
+                                  double *rect, double *d, int *flag, double *sval) {
+  SB_TRY(ensure_init());
+  SB_CHECK(pl->shard, "shard: sb200_chol_shard_create has not been called");
+  auto *sh = pl->shard;
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  SB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * m, st));
+  SB_CUDA(cudaMemsetAsync(sval, 0, sizeof(double) * m, st));
+  SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * m, st));
+  permuteP_kernel<<<m, 256, 0, st>>>(pl->d_sn.p, pl->d_snode.p, pl->d_lindx.p, pl->d_perm.p, pl->d_Xjc.p, pl->d_Xir.p, Xpr, rect, pl->d_diagX.p);
+  SB_LAUNCH_CHECK_N("permuteP_kernel");
+  bounds_kernel<<<1, 1024, 0, st>>>(m, pl->d_diagX.p, absd, pl->d_perm.p, pars.abstol, pars.canceltol, pars.maxu, pl->d_lb.p, pl->d_scal.p);
+  SB_LAUNCH_CHECK_N("bounds_kernel");
+  if (sh->rank != 0 && sh->top_rect_len) SB_CUDA(cudaMemsetAsync(rect + sh->top_rect_off, 0, sizeof(double) * sh->top_rect_len, st));
+  SB_TRY(shard_factor_levels(pl, false, pars, rect, d, flag, sval));
+  if (sh->topA_tile_cnt) {
+    update_kernel<<<sh->topA_tile_cnt, 256, 0, st>>>(sh->d_tiles.p + sh->topA_tile_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, d, rect);
+    SB_LAUNCH_CHECK_N("update_kernel");
+  }
+  return 0;
+}
+// Phase 2 (after the all-reduce of the top panels): the top, redundantly on every rank.
+int sb200_blkchol_shard_top_dev(sb200_chol_plan *pl, sb200_chol_pars pars, double *rect, double *d, int *flag, double *sval) {
+  SB_TRY(ensure_init());
+  SB_CHECK(pl->shard, "shard: sb200_chol_shard_create has not been called");
+  return shard_factor_levels(pl, true, pars, rect, d, flag, sval);
+}
+
+static size_t shard_solve_shm(sb200_chol_plan *pl) { return sizeof(double) * (size_t)pl->max_sn_n; }
+// Forward, phase 1: y = b(perm) (top rows zeroed off rank 0), own trees, pull into the top rows.  Then all-reduce
+// y[top_col0 .. m) per right-hand side.
+int sb200_fw_shard_local_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  SB_CHECK(pl->shard, "shard: sb200_chol_shard_create has not been called");
+  auto *sh = pl->shard;
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  if (m == 0 || nrhs == 0) return 0;
+  const long long tot = (long long)m * nrhs;
+  gather_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, b, y);
+  SB_LAUNCH_CHECK_N("gather_perm_kernel");
+  if (sh->rank != 0 && sh->top_col0 < m)
+    for (sb_idx r = 0; r < nrhs; r++) SB_CUDA(cudaMemsetAsync(y + r * m + sh->top_col0, 0, sizeof(double) * (m - sh->top_col0), st));
+  const size_t shm = shard_solve_shm(pl);
+  SB_CHECK(shm <= 200 * 1024, "fwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
+  if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(fwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  for (int lv = 0; lv < pl->nlevels; lv++) {
+    if (sh->own_all[lv].empty()) continue;
+    dim3 g((unsigned)sh->own_all[lv].size(), (unsigned)nrhs);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_pairs.p, pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1);
+    SB_LAUNCH_CHECK_N("fwsolve_kernel");
+  }
+  if (sh->top_list_cnt) {
+    dim3 g((unsigned)sh->top_list_cnt, (unsigned)nrhs);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_list_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, rect, y, m, 0);
+    SB_LAUNCH_CHECK_N("fwsolve_kernel");
+  }
+  return 0;
+}
+// Forward, phase 2 (after the all-reduce of the top segment), ./d on this rank's columns, backward over the top and the
+// own trees; foreign columns of z end up zero, so that all-reduce(sum) of z followed by sb200_bw_shard_finish_dev
+// gives y = L' \ ((L \ b(perm)) ./ d) in the original order.  z: m x nrhs scratch (the permuted solution).
+int sb200_solve_shard_top_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag, double *y, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  SB_CHECK(pl->shard, "shard: sb200_chol_shard_create has not been called");
+  auto *sh = pl->shard;
+  cudaStream_t st = ctx().stream;
+  const int m = pl->m;
+  if (m == 0 || nrhs == 0) return 0;
+  const size_t shm = shard_solve_shm(pl);
+  if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(bwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  for (int lv = 0; lv < pl->nlevels; lv++) {
+    if (sh->top_all[lv].empty()) continue;
+    dim3 g((unsigned)sh->top_all[lv].size(), (unsigned)nrhs);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, sh->d_pairsB.p, sh->d_pair_begB.p, pl->d_rel.p, rect, y, m, 1);
+    SB_LAUNCH_CHECK_N("fwsolve_kernel");
+  }
+  const long long tot = (long long)m * nrhs;
+  // ./d: the top columns on every rank (needed by the backward pass), own columns; foreign columns become 0
+  {
+    shard_scale_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, sh->d_colmask.p, sh->top_col0, d, flag, pl->d_lb.p, y);
+    SB_LAUNCH_CHECK_N("shard_scale_kernel");
+  }
+  for (int lv = pl->nlevels - 1; lv >= 0; lv--) {
+    if (sh->top_all[lv].empty()) continue;
+    dim3 g((unsigned)sh->top_all[lv].size(), (unsigned)nrhs);
+    bwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, pl->d_lindx.p, rect, y, m);
+    SB_LAUNCH_CHECK_N("bwsolve_kernel");
+  }
+  for (int lv = pl->nlevels - 1; lv >= 0; lv--) {
+    if (sh->own_all[lv].empty()) continue;
+    dim3 g((unsigned)sh->own_all[lv].size(), (unsigned)nrhs);
+    bwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_lindx.p, rect, y, m);
+    SB_LAUNCH_CHECK_N("bwsolve_kernel");
+  }
+  shard_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, sh->d_colmask.p, y);
+  SB_LAUNCH_CHECK_N("shard_mask_kernel");
+  return 0;
+}
+// After the all-reduce of z: back to the original order.
+int sb200_bw_shard_finish_dev(sb200_chol_plan *pl, const double *z, double *y, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  const long long tot = (long long)pl->m * nrhs;
+  if (tot == 0) return 0;
+  scatter_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx().stream>>>(pl->m, (int)nrhs, pl->d_perm.p, z, y);
   SB_LAUNCH_CHECK_N("scatter_perm_kernel");
   return 0;
 }

@@ -57,6 +57,20 @@ struct sb200_chol_plan {
   sb::DevBuf<unsigned> d_bar;
   sb::DevBuf<int> d_ready;
   int solve_epoch = 0;
+  // ---- subtree sharding: supernodes >= t0 form the replicated "top", the forest below is split over ranks
+  struct Shard {
+    int world = 1, rank = 0, t0 = 0, top_col0 = 0;
+    long long top_rect_off = 0, top_rect_len = 0;
+    std::vector<int> owner;                                    // per supernode < t0
+    std::vector<std::vector<int>> own_small, own_big, own_all, top_small, top_big, top_all;   // per level
+    std::vector<int> own_small_off, own_all_off, top_small_off, top_all_off, own_tile_off, own_tile_cnt, top_tile_off, top_tile_cnt;
+    int topA_tile_off = 0, topA_tile_cnt = 0;                  // partial update of the top by owned descendants
+    int top_list_off = 0, top_list_cnt = 0;                    // all top supernodes (pull-only forward pass)
+    sb::DevBuf<int> d_lists, d_pair_begA, d_pair_begB, d_colmask;
+    sb::DevBuf<sb::UTile> d_tiles;
+    sb::DevBuf<sb::Pair> d_pairsA, d_pairsB;
+  };
+  Shard *shard = nullptr;
   // MEX-level solves: device copy of the last L.L (internal layout) keyed by a hash of its values
   sb::DevBuf<double> d_rect_cache;
   uint64_t Lcache_hash = 0;

@@ -73,7 +73,9 @@ EXPORTS = [
     "sb200_kernel_launches", "sb200_dev_alloc", "sb200_dev_free", "sb200_h2d", "sb200_d2h",
     "sb200_chol_plan_create", "sb200_chol_plan_destroy", "sb200_chol_plan_nnzL", "sb200_chol_plan_rect_size",
     "sb200_blkchol_dev", "sb200_chol_rect_to_csc_dev", "sb200_chol_csc_to_rect_dev", "sb200_blkchol",
-    "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
+    "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_chol_shard_create", "sb200_chol_shard_info",
+    "sb200_blkchol_shard_local_dev", "sb200_blkchol_shard_top_dev", "sb200_fw_shard_local_dev", "sb200_solve_shard_top_dev",
+    "sb200_bw_shard_finish_dev", "sb200_fwblkslv", "sb200_bwblkslv", "sb200_fwblkslv_sparse",
     "sb200_psd_plan_get", "sb200_psd_plan_lenud", "sb200_psd_plan_sumn", "sb200_invcholfac_dev", "sb200_psdscale_dev",
     "sb200_invcholfac", "sb200_psdscale", "sb200_invcholfac_h", "sb200_psdscale_h", "sb200_psdframeit_h", "sb200_psdinvjmul_h", "sb200_urotorder_h", "sb200_givensrot_h", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
     "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_urotorder_dev", "sb200_givensrot_dev", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
@@ -154,6 +156,7 @@ class HotPath:
         self.flag = torch.zeros(max(m, 1), dtype=torch.int32, device=self.dev)
         self.psd_x, self.psd_y = z(self.lenud), z(self.lenud)
         self.rhs = self.y = self.w = None
+        self.shard = None
         # scaling update (updtransfo.m:99-108): frames of the PSD iterate, re-ordered factor, rotation list
         sumn = int(s.sum())
         self.sumn = sumn
@@ -219,6 +222,58 @@ class HotPath:
         check(lib().sb200_ldl_solve_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.rhs),
                                         _p(self.w), _p(self.y), I64(self.nrhs)), "ldl_solve")
 
+    # ------------------------------------------------------------------ subtree-sharded factor / solve
+    def shard_factor_setup(self, world: int, rank: int):
+        """Deal the elimination-tree subtrees below a replicated top to `world` ranks (this object is rank `rank`)."""
+        L = lib()
+        check(L.sb200_chol_shard_create(self.chol, I64(world), I64(rank)), "chol_shard_create")
+        t0, off, ln, col0, cm = I64(0), I64(0), I64(0), I64(0), C.c_void_p()
+        check(L.sb200_chol_shard_info(self.chol, C.byref(t0), C.byref(off), C.byref(ln), C.byref(col0), C.byref(cm)), "chol_shard_info")
+        self.shard = dict(world=world, rank=rank, t0=int(t0.value), top_off=int(off.value), top_len=int(ln.value), col0=int(col0.value))
+        return self.shard
+
+    def blkchol_shard_local(self):
+        check(lib().sb200_blkchol_shard_local_dev(self.chol, _p(self.ADA), _p(self.absd), self.pars, _p(self.Lrect), _p(self.dvec),
+                                                  _p(self.flag), _p(self.sval)), "blkchol_shard_local")
+
+    def blkchol_shard_top(self):
+        check(lib().sb200_blkchol_shard_top_dev(self.chol, self.pars, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.sval)),
+              "blkchol_shard_top")
+
+    def top_panels(self):
+        sh = self.shard
+        return self.Lrect[sh["top_off"]:sh["top_off"] + sh["top_len"]]
+
+    def blkchol_sharded(self, dist):
+        """Own subtrees, ONE all-reduce of the top panels, top (replicated)."""
+        self.blkchol_shard_local()
+        if self.shard["top_len"]:
+            with self.torch.cuda.stream(self.stream()):
+                dist.all_reduce(self.top_panels())
+        self.blkchol_shard_top()
+
+    def solve_shard_local(self):
+        check(lib().sb200_fw_shard_local_dev(self.chol, _p(self.Lrect), _p(self.rhs), _p(self.w), I64(self.nrhs)), "fw_shard_local")
+
+    def solve_shard_top(self):
+        check(lib().sb200_solve_shard_top_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.w), I64(self.nrhs)),
+              "solve_shard_top")
+
+    def solve_shard_finish(self):
+        check(lib().sb200_bw_shard_finish_dev(self.chol, _p(self.w), _p(self.y), I64(self.nrhs)), "bw_shard_finish")
+
+    def solve_sharded(self, dist):
+        """Forward over the own subtrees, all-reduce of the top segment, top + backward, all-reduce of the solution."""
+        self.solve_shard_local()
+        col0 = self.shard["col0"]
+        with self.torch.cuda.stream(self.stream()):
+            if col0 < self.m:
+                dist.all_reduce(self.w[:, col0:])
+        self.solve_shard_top()
+        with self.torch.cuda.stream(self.stream()):
+            dist.all_reduce(self.w)
+        self.solve_shard_finish()
+
     def psdscale(self, transp: int):
         check(lib().sb200_psdscale_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
                                        _p(self.psd_x), C.c_int(transp), _p(self.psd_y)), "psdscale")
@@ -283,9 +338,14 @@ class HotPath:
         self.getada()
         if dist is not None:
             self.allreduce_ada(dist)
-        self.blkchol()
-        for _ in range(nsolve):
-            self.solve()
+        if dist is not None and getattr(self, "shard", None):
+            self.blkchol_sharded(dist)
+            for _ in range(nsolve):
+                self.solve_sharded(dist)
+        else:
+            self.blkchol()
+            for _ in range(nsolve):
+                self.solve()
         if self.lenud:
             for i in range(npsdscale):
                 self.psdscale(i & 1)
