@@ -209,7 +209,7 @@ def run_reference(S, d, rhs, psd_x, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="control07")
@@ -389,7 +389,7 @@ def main():
     if not args.no_e2e and shard_dist is None:
         if world > 1:
             dist.barrier()
-        e2e = run_e2e(S, d, rhs, psd_x, max(3, args.steps // 3), 1)
+        e2e = run_e2e(S, d, rhs, psd_x, min(40, max(3, args.steps // 3)), 1)
         if world > 1:
             tt = torch.tensor([e2e["seconds"]], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
