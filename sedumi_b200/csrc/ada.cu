@@ -231,46 +231,28 @@ __device__ __forceinline__ void build_slots(int *slot, const int *rows, int coll
   __syncthreads();
 }
 
+struct DotsCtx {
+  AdaPair P; int c, ipc, first, multi, warp, lane, nw;
+  long long colbeg;
+  ColSlots cs;
+  const int *eidx; const double *Wp;
+  const int *blkp_beg; const BlkPartner *blkp; const int *invperm;
+  const double *Atpr; const int *ent_src; const double *ent_scale;
+  double *ws, *ada, *absd;
+};
+// The partner loop with G lanes per partner; G is chosen PER BLOCK from the average number of entries of its pairs
+// (control07: 161 entries per pair in the 70x70 block, exactly 1 in the 35x35 block).
 template <int G>
-__global__ void __launch_bounds__(256)
-ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *invperm, int first,
-                 const int *cpair_beg, const AdaPair *pairs, const int *blk_n, const int *ublk_off,
-                 const int *blkp_beg, const BlkPartner *blkp,
-                 const int *ent_lin, const int *ent_pk, const int *ent_src, const double *Atpr, const double *ent_scale,
-                 double *ws, double *ada, double *absd, int wcap, int use_map, int m) {
-  extern __shared__ double dots_sm[];
-  double *Wsm = dots_sm;
-  int *slot = (int *)(dots_sm + wcap);
-  const AdaPair P = pairs[p0 + blockIdx.x];
-  const int c = P.j;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  const bool multi = cpair_beg[c + 1] - cpair_beg[c] > 1;
-  const int ipc = invperm[c];
-  const long long colbeg = adajc[c];
-  ColSlots cs{adair + colbeg, (int)(adajc[c + 1] - colbeg), nullptr};
-  if (!multi) {
-    if (use_map) { build_slots(slot, cs.rows, cs.collen, m); cs.slot = slot; }
-    if (tid == 0) {
-      const int sd = ipc >= first ? cs.find(c) : -1;
-      absd[c] = sd >= 0 ? ada[colbeg + sd] : 0.0;
-    }
-  }
-  const int n = blk_n[P.k];
-  const double *Wg = ws + P.w_off;
-  const int wsize = P.sparse ? (ublk_off[P.k + 1] - ublk_off[P.k]) : n * (n + 1) / 2;
-  const bool stage = wsize <= wcap;
-  if (stage) {
-    if (P.sparse) for (int t = tid; t < wsize; t += blockDim.x) Wsm[t] = Wg[t];
-    else
-      for (int q = warp; q < n; q += nw) {
-        const double *src = Wg + (long long)q * n;
-        double *dst = Wsm + ((long long)q * (2 * n - q + 1)) / 2 - q;       // packed column q, indexed by row p >= q
-        for (int pp = q + lane; pp < n; pp += 32) dst[pp] = src[pp];
-      }
-  }
-  __syncthreads();
-  const int *eidx = stage ? ent_pk : ent_lin;
-  const double *Wp = stage ? Wsm : Wg;
+__device__ __forceinline__ void dots_partners(const DotsCtx &X) {
+  const AdaPair &P = X.P;
+  const int c = X.c, ipc = X.ipc, first = X.first, warp = X.warp, lane = X.lane, nw = X.nw;
+  const bool multi = X.multi;
+  const long long colbeg = X.colbeg;
+  const ColSlots &cs = X.cs;
+  const int *eidx = X.eidx; const double *Wp = X.Wp;
+  const int *blkp_beg = X.blkp_beg; const BlkPartner *blkp = X.blkp; const int *invperm = X.invperm;
+  const double *Atpr = X.Atpr; const int *ent_src = X.ent_src; const double *ent_scale = X.ent_scale;
+  double *ws = X.ws, *ada = X.ada, *absd = X.absd;
   constexpr int GPW = 32 / G;                      // partner groups per warp
   const int grp = lane / G, gl = lane % G;
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));   // groups diverge: sync only the group
@@ -330,6 +312,57 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
         }
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *invperm, int first,
+                 const int *cpair_beg, const AdaPair *pairs, const int *blk_n, const int *ublk_off,
+                 const int *blkp_beg, const BlkPartner *blkp,
+                 const int *ent_lin, const int *ent_pk, const int *ent_src, const double *Atpr, const double *ent_scale,
+                 double *ws, double *ada, double *absd, int wcap, int use_map, int m, const int *blk_group) {
+  extern __shared__ double dots_sm[];
+  double *Wsm = dots_sm;
+  int *slot = (int *)(dots_sm + wcap);
+  const AdaPair P = pairs[p0 + blockIdx.x];
+  const int c = P.j;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const bool multi = cpair_beg[c + 1] - cpair_beg[c] > 1;
+  const int ipc = invperm[c];
+  const long long colbeg = adajc[c];
+  ColSlots cs{adair + colbeg, (int)(adajc[c + 1] - colbeg), nullptr};
+  if (!multi) {
+    if (use_map) { build_slots(slot, cs.rows, cs.collen, m); cs.slot = slot; }
+    if (tid == 0) {
+      const int sd = ipc >= first ? cs.find(c) : -1;
+      absd[c] = sd >= 0 ? ada[colbeg + sd] : 0.0;
+    }
+  }
+  const int n = blk_n[P.k];
+  const double *Wg = ws + P.w_off;
+  const int wsize = P.sparse ? (ublk_off[P.k + 1] - ublk_off[P.k]) : n * (n + 1) / 2;
+  const bool stage = wsize <= wcap;
+  if (stage) {
+    if (P.sparse) for (int t = tid; t < wsize; t += blockDim.x) Wsm[t] = Wg[t];
+    else
+      for (int q = warp; q < n; q += nw) {
+        const double *src = Wg + (long long)q * n;
+        double *dst = Wsm + ((long long)q * (2 * n - q + 1)) / 2 - q;       // packed column q, indexed by row p >= q
+        for (int pp = q + lane; pp < n; pp += 32) dst[pp] = src[pp];
+      }
+  }
+  __syncthreads();
+  const int *eidx = stage ? ent_pk : ent_lin;
+  const double *Wp = stage ? Wsm : Wg;
+  DotsCtx X;
+  X.P = P; X.c = c; X.ipc = ipc; X.first = first; X.multi = multi ? 1 : 0; X.warp = warp; X.lane = lane; X.nw = nw;
+  X.colbeg = colbeg; X.cs = cs; X.eidx = eidx; X.Wp = Wp; X.blkp_beg = blkp_beg; X.blkp = blkp; X.invperm = invperm;
+  X.Atpr = Atpr; X.ent_src = ent_src; X.ent_scale = ent_scale; X.ws = ws; X.ada = ada; X.absd = absd;
+  switch (blk_group[P.k]) {
+    case 4: dots_partners<4>(X); break;
+    case 8: dots_partners<8>(X); break;
+    case 16: dots_partners<16>(X); break;
+    default: dots_partners<32>(X); break;
   }
 }
 
@@ -420,6 +453,7 @@ struct sb200_ada_plan {
   DevBuf<int> d_ublk_off, d_u_p, d_u_q, d_blkp_beg, d_ent_pk;
   DevBuf<BlkPartner> d_blkp;
   int wcap = 0, use_map = 0, dots_group = 32;
+  DevBuf<int> d_blk_group;
   size_t dots_smem = 0;
   std::vector<int> blk_sparse;
   int max_nu = 0;
@@ -590,6 +624,14 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     pl->dots_smem = (size_t)(wc * 8 + mapb);
     const double avg = pl->pairs.empty() ? 0.0 : (double)ent_lin.size() / (double)pl->pairs.size();
     pl->dots_group = avg <= 6.0 ? 4 : (avg <= 12.0 ? 8 : (avg <= 24.0 ? 16 : 32));
+    std::vector<double> bent(nblk, 0.0), bcnt(nblk, 0.0);
+    for (auto &P : pl->pairs) { bent[P.k] += P.e1 - P.e0; bcnt[P.k] += 1.0; }
+    std::vector<int> bgrp(std::max<sb_idx>(nblk, 1), 32);
+    for (sb_idx k = 0; k < nblk; k++) {
+      const double a2 = bcnt[k] > 0 ? bent[k] / bcnt[k] : 0.0;
+      bgrp[k] = a2 <= 6.0 ? 4 : (a2 <= 12.0 ? 8 : (a2 <= 24.0 ? 16 : 32));
+    }
+    SB_TRY(pl->d_blk_group.upload(bgrp));
   }
   // ---- batches of whole constraints, workspace bounded
   const long long BUDGET = (long long)96 << 20;     // doubles (768 MB)
@@ -936,21 +978,12 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
       SB_LAUNCH_CHECK_N("sparse_w_kernel");
     }
     {
-#define SB_DOTS(G)                                                                                                       \
-  do {                                                                                                                   \
-    static bool attr_done = false;                                                                                       \
-    if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(ada3_dots_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_done = true; } \
-    ada3_dots_kernel<G><<<B.p1 - B.p0, 256, pl->dots_smem, st>>>(B.p0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p, \
-        pl->d_pairs.p, pl->d_blk_n.p, pl->d_ublk_off.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ent_lin.p, pl->d_ent_pk.p,  \
-        pl->d_ent_src.p, pl->d_Atpr.p, pl->herm ? pl->d_ent_scale.p : nullptr, pl->d_ws.p, ada_dev, absd_dev, pl->wcap, pl->use_map, pl->m); \
-  } while (0)
-      switch (pl->dots_group) {
-        case 4: SB_DOTS(4); break;
-        case 8: SB_DOTS(8); break;
-        case 16: SB_DOTS(16); break;
-        default: SB_DOTS(32); break;
-      }
-#undef SB_DOTS
+      static bool attr_done = false;
+      if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(ada3_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_done = true; }
+      ada3_dots_kernel<<<B.p1 - B.p0, 256, pl->dots_smem, st>>>(B.p0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first, pl->d_cpair_beg.p,
+          pl->d_pairs.p, pl->d_blk_n.p, pl->d_ublk_off.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ent_lin.p, pl->d_ent_pk.p,
+          pl->d_ent_src.p, pl->d_Atpr.p, pl->herm ? pl->d_ent_scale.p : nullptr, pl->d_ws.p, ada_dev, absd_dev, pl->wcap, pl->use_map, pl->m,
+          pl->d_blk_group.p);
     }
     SB_LAUNCH_CHECK_N("ada3_dots_kernel");
     if (B.nmulti) {
