@@ -21,7 +21,7 @@ sedumi_b200/csrc/%.o: sedumi_b200/csrc/%.cu $(wildcard sedumi_b200/csrc/*.h sedu
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
 $(LIB): $(COBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(COBJ) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(COBJ) -lcudart -ldl
 
 sedumi_b200/mex/%.so: sedumi_b200/mex/%.cpp sedumi_b200/mex/mex_common.h include/sedumi_b200.h $(LIB) | shim
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Imxshim -Iinclude -o $@ $< -Lsedumi_b200 -lsedumi_b200 -Lmxshim -lmxshim \

@@ -39,6 +39,7 @@ int         sb200_device_count(void);
 int         sb200_sync(void);                     /* cudaStreamSynchronize(library stream) */
 void       *sb200_stream(void);                   /* cudaStream_t of the library */
 int64_t     sb200_kernel_launches(void);          /* kernels launched by this library so far */
+int         sb200_xfer_bytes(int64_t *h2d, int64_t *d2h);   /* bytes this library copied host->device / device->host so far */
 /* per-kernel timing with CUDA events on the library stream: begin, run, end -> text report
  * "kernel_name launches total_ms" per line */
 int         sb200_prof_begin(void);
@@ -52,6 +53,20 @@ int         sb200_dev_alloc(void **p, int64_t bytes);
 int         sb200_dev_free(void *p);
 int         sb200_h2d(void *dst, const void *src, int64_t bytes);
 int         sb200_d2h(void *dst, const void *src, int64_t bytes);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * One process per GPU.  Rank 0 calls sb200_comm_unique_id and hands the 128 bytes to every rank (any host channel);
+ * all ranks call sb200_comm_init_rank after sb200_init(device).  The all-reduce is in place, on the library stream,
+ * and may be captured into a CUDA graph with the kernels around it.  NCCL (libnccl.so.2) is loaded on first use. */
+int sb200_comm_unique_id(void *id128);
+int sb200_comm_init_rank(int nranks, int rank, const void *id128);
+int sb200_comm_size(void);
+int sb200_comm_rank(void);
+int sb200_comm_nccl_version(void);
+int sb200_comm_stats(int64_t *calls, int64_t *bytes);
+int sb200_allreduce_sum_dev(double *buf_dev, int64_t count);
+int sb200_allreduce_sum2_dev(double *a_dev, int64_t na, double *b_dev, int64_t nb);
+int sb200_comm_destroy(void);
 
 /* ------------------------------------------------------------------ supernodal LDL'
  * blkchol.c:239-440 (mexFunction), blkchol2.c:96-167 (cholonBlk), :346-420 (precorrect),
@@ -115,6 +130,11 @@ int sb200_fw_shard_local_dev(sb200_chol_plan *plan, const double *Lrect_dev, con
 int sb200_solve_shard_top_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev, const int *flag_dev,
                               double *y_dev, sb_idx nrhs);
 int sb200_bw_shard_finish_dev(sb200_chol_plan *plan, const double *z_dev, double *y_dev, sb_idx nrhs);
+/* The same sequences with the collectives issued by the library (sb200_comm_*, below): call on every rank. */
+int sb200_blkchol_sharded_dev(sb200_chol_plan *plan, const double *Xpr_dev, const double *absd_dev, sb200_chol_pars pars,
+                              double *Lrect_dev, double *d_dev, int *flag_dev, double *sval_dev);
+int sb200_ldl_solve_sharded_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev, const int *flag_dev,
+                                const double *b_dev, double *w_dev, double *y_dev, sb_idx nrhs);
 int sb200_fwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
                        double *y_dev, sb_idx nrhs);
 int sb200_bwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *b_dev,
@@ -211,6 +231,10 @@ int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx
                          const sb_idx *Ajc1, sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal,
                          const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair);
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *plan);
+/* sb200_ada_plan_get hands out plans of a bounded cache; a caller that keeps the pointer beyond one call (device-resident
+ * chains, captured CUDA graphs) retains it, which exempts it from eviction until the matching release. */
+int sb200_ada_plan_retain(sb200_ada_plan *plan);
+int sb200_ada_plan_release(sb200_ada_plan *plan);
 int sb200_ada_set_At_values(sb200_ada_plan *plan, const double *Atpr);
 /* device-resident variants: invperm_dev = inverse of the ordering (int32) or NULL = natural */
 int sb200_getada1_dev(sb200_ada_plan *plan, const double *dl_dev, const double *ddet_dev,

@@ -444,7 +444,9 @@ struct sb200_ada_plan {
   struct Batch { int p0, p1, c0, c1; long long ws; int tile0, ntiles; int nsparse; int nmulti; };
   std::vector<Batch> batches;
   long long ws_max = 0;
-  uint64_t key = 0, val_hash = 0;
+  Hash128 key, val_hash;
+  int pins = 0;                   // device-resident owners (sb200_ada_plan_retain); pinned plans are never evicted
+  uint64_t cache_stamp = 0;
   bool have_vals = false;
   // device
   DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
@@ -475,7 +477,8 @@ struct sb200_ada_plan {
   DevBuf<int> d_invperm, d_ident;
 };
 
-static std::map<uint64_t, sb200_ada_plan *> g_ada_plans;
+static std::map<Hash128, sb200_ada_plan *> g_ada_plans;
+static uint64_t g_ada_clock = 0;
 
 static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, const sb_idx *Air, const sb_idx *Ajc1,
                      sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal, const sb_idx *blkstart, const sb_idx *blkn,
@@ -775,7 +778,7 @@ int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx
                          const sb_idx *blkstart, const sb_idx *blkn, const sb_idx *adajc, const sb_idx *adair) {
   SB_TRY(ensure_init());
   SB_CHECK(nreal >= 0 && nreal <= nblk, "number of real PSD blocks out of range");
-  uint64_t h = fnv1a(&N, sizeof N); h = fnv1a(&m, sizeof m, h);
+  Hash128 h = fnv1a(&N, sizeof N); h = fnv1a(&m, sizeof m, h);
   h = fnv1a(Ajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(Air, sizeof(sb_idx) * Ajc[m], h);
   h = fnv1a(Ajc1, sizeof(sb_idx) * m, h); h = fnv1a(&lpN, sizeof lpN, h); h = fnv1a(&nq, sizeof nq, h);
   if (nq) h = fnv1a(qstart, sizeof(sb_idx) * (nq + 1), h);
@@ -783,12 +786,27 @@ int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx
   if (nblk) { h = fnv1a(blkstart, sizeof(sb_idx) * nblk, h); h = fnv1a(blkn, sizeof(sb_idx) * nblk, h); }
   h = fnv1a(adajc, sizeof(sb_idx) * (m + 1), h); h = fnv1a(adair, sizeof(sb_idx) * adajc[m], h);
   auto it = g_ada_plans.find(h);
-  if (it != g_ada_plans.end()) { *plan = it->second; return 0; }
+  if (it != g_ada_plans.end()) { it->second->cache_stamp = ++g_ada_clock; *plan = it->second; return 0; }
   sb200_ada_plan *pl = new sb200_ada_plan();
   int rc = ada_build(pl, N, m, Ajc, Air, Ajc1, lpN, nq, qstart, nblk, nreal, blkstart, blkn, adajc, adair);
   if (rc) { delete pl; return rc; }
   pl->key = h;
-  if (g_ada_plans.size() >= 8) { for (auto &kv : g_ada_plans) delete kv.second; g_ada_plans.clear(); }
+  // bounded cache: evict the least-recently-used plan that no device-resident owner has pinned (a HotPath, and the
+  // CUDA graphs it captured, keep using a plan's device buffers for their whole lifetime)
+  for (;;) {
+    size_t unpinned = 0;
+    auto lru = g_ada_plans.end();
+    for (auto i2 = g_ada_plans.begin(); i2 != g_ada_plans.end(); ++i2) {
+      if (i2->second->pins > 0) continue;
+      unpinned++;
+      if (lru == g_ada_plans.end() || i2->second->cache_stamp < lru->second->cache_stamp) lru = i2;
+    }
+    if (unpinned < 8) break;
+    cudaStreamSynchronize(ctx().stream);
+    delete lru->second;
+    g_ada_plans.erase(lru);
+  }
+  pl->cache_stamp = ++g_ada_clock;
   g_ada_plans[h] = pl;
   *plan = pl;
   return 0;
@@ -796,7 +814,7 @@ int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx
 
 // Values of At (host) -> device copy held by the plan (skipped when unchanged).
 int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
-  uint64_t h = fnv1a(Atpr, sizeof(double) * pl->nnzA);
+  Hash128 h = fnv1a(Atpr, sizeof(double) * pl->nnzA);
   if (pl->have_vals && h == pl->val_hash) return 0;
   SB_CUDA(cudaMemcpyAsync(pl->d_Atpr.p, Atpr, sizeof(double) * pl->nnzA, cudaMemcpyHostToDevice, ctx().stream));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -804,6 +822,9 @@ int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
   return 0;
 }
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *pl) { return pl->nnzADA; }
+// Ownership for device-resident callers: a retained plan is exempt from cache eviction until released.
+int sb200_ada_plan_retain(sb200_ada_plan *pl) { if (pl) pl->pins++; return 0; }
+int sb200_ada_plan_release(sb200_ada_plan *pl) { if (pl && pl->pins > 0) pl->pins--; return 0; }
 
 static int set_invperm(sb200_ada_plan *pl, const sb_idx *perm, const int **out) {
   if (!perm) { *out = pl->d_ident.p; return 0; }

@@ -1123,19 +1123,39 @@ int sb200_bw_shard_finish_dev(sb200_chol_plan *pl, const double *z, double *y, s
   return 0;
 }
 
+// The whole sharded factorisation / solve with the collectives issued by the library itself (comm.cu) on the library
+// stream: a host calls these like the unsharded entries, on every rank, and the sequence is capturable as one graph.
+int sb200_blkchol_sharded_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd, sb200_chol_pars pars,
+                              double *rect, double *d, int *flag, double *sval) {
+  SB_TRY(sb200_blkchol_shard_local_dev(pl, Xpr, absd, pars, rect, d, flag, sval));
+  if (pl->shard->top_rect_len) SB_TRY(sb200_allreduce_sum_dev(rect + pl->shard->top_rect_off, pl->shard->top_rect_len));
+  return sb200_blkchol_shard_top_dev(pl, pars, rect, d, flag, sval);
+}
+int sb200_ldl_solve_sharded_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag,
+                                const double *b, double *w, double *y, sb_idx nrhs) {
+  SB_TRY(sb200_fw_shard_local_dev(pl, rect, b, w, nrhs));
+  const int m = pl->m, c0 = pl->shard->top_col0;
+  if (c0 < m)                      // only the top segment of each right-hand side is a sum over ranks
+    for (sb_idx r = 0; r < nrhs; r++) SB_TRY(sb200_allreduce_sum_dev(w + r * m + c0, m - c0));
+  SB_TRY(sb200_solve_shard_top_dev(pl, rect, d, flag, w, nrhs));
+  SB_TRY(sb200_allreduce_sum_dev(w, (sb_idx)m * nrhs));
+  return sb200_bw_shard_finish_dev(pl, w, y, nrhs);
+}
+
 }  // extern "C"
 
 // --------------------------------------------------------------------------- plan cache
 namespace sb {
 struct PlanCache {
-  std::map<uint64_t, sb200_chol_plan *> plans;
+  std::map<Hash128, sb200_chol_plan *> plans;
+  uint64_t clock = 0;
   ~PlanCache() { /* plans leak at process exit on purpose: the CUDA context may be gone */ }
 };
 static PlanCache g_cache;
 
-static uint64_t structure_key(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
+static Hash128 structure_key(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc, const sb_idx *Lir,
                               const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir) {
-  uint64_t h = fnv1a(&m, sizeof m);
+  Hash128 h = fnv1a(&m, sizeof m);
   h = fnv1a(&nsuper, sizeof nsuper, h);
   h = fnv1a(xsuper, sizeof(sb_idx) * (nsuper + 1), h);
   h = fnv1a(Ljc, sizeof(sb_idx) * (m + 1), h);
@@ -1150,18 +1170,26 @@ static uint64_t structure_key(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, con
 int get_plan(sb200_chol_plan **out, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
              const sb_idx *Lir, const sb_idx *perm, const sb_idx *Xjc, const sb_idx *Xir) {
   SB_TRY(ensure_init());
-  uint64_t key = structure_key(m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir);
+  Hash128 key = structure_key(m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir);
   auto it = g_cache.plans.find(key);
-  if (it != g_cache.plans.end()) { *out = it->second; return 0; }
+  if (it != g_cache.plans.end()) { it->second->cache_stamp = ++g_cache.clock; *out = it->second; return 0; }
   std::vector<sb_idx> zjc;
   if (!Xjc) { zjc.assign(m + 1, 0); Xjc = zjc.data(); Xir = zjc.data(); }
   sb200_chol_plan *pl = nullptr;
   SB_TRY(sb200_chol_plan_create(&pl, m, nsuper, xsuper, Ljc, Lir, perm, Xjc, Xir));
   pl->key = key;
-  if (g_cache.plans.size() >= 16) {            // bounded: drop everything, rebuild on demand
-    for (auto &kv : g_cache.plans) sb200_chol_plan_destroy(kv.second);
-    g_cache.plans.clear();
+  // bounded, least-recently-used first.  Plans of this cache are only ever borrowed for the duration of one host
+  // entry (device-resident callers own theirs through sb200_chol_plan_create), and destroying a plan frees device
+  // memory, which waits for the kernels still using it.
+  while (g_cache.plans.size() >= 16) {
+    auto lru = g_cache.plans.begin();
+    for (auto i2 = g_cache.plans.begin(); i2 != g_cache.plans.end(); ++i2)
+      if (i2->second->cache_stamp < lru->second->cache_stamp) lru = i2;
+    cudaStreamSynchronize(ctx().stream);
+    sb200_chol_plan_destroy(lru->second);
+    g_cache.plans.erase(lru);
   }
+  pl->cache_stamp = ++g_cache.clock;
   g_cache.plans[key] = pl;
   *out = pl;
   return 0;
@@ -1225,7 +1253,7 @@ static int solve_host(bool fw, sb_idx m, sb_idx nsuper, const sb_idx *xsuper, co
   cudaStream_t st = ctx().stream;
   // The factor values usually repeat over many solves (3-4 solves x fw/bw per IPM iteration): keep the
   // device copy in the internal layout (+ inverted diagonal blocks, L') under a content hash.
-  const uint64_t hL = hash64(Lpr, sizeof(double) * pl->nnzL);
+  const Hash128 hL = hash128(Lpr, sizeof(double) * pl->nnzL);
   if (!(pl->Lcache_valid && pl->Lcache_hash == hL)) {
     double *dL = arena<double>((size_t)pl->nnzL);
     SB_CHECK(dL, "solve: out of device memory");

@@ -30,7 +30,8 @@ struct UTile { int J, r0, c0; };
 struct sb200_chol_plan {
   int m = 0, nsuper = 0, nlevels = 0;
   long long nnzL = 0, rect = 0;
-  uint64_t key = 0;
+  sb::Hash128 key;
+  uint64_t cache_stamp = 0;      // LRU clock of the host-entry plan cache
   std::vector<sb::Sn> sn;
   std::vector<int> snode, level_of;
   std::vector<std::vector<int>> level_small, level_big;      // supernodes per level
@@ -73,7 +74,7 @@ struct sb200_chol_plan {
   Shard *shard = nullptr;
   // MEX-level solves: device copy of the last L.L (internal layout) keyed by a hash of its values
   sb::DevBuf<double> d_rect_cache;
-  uint64_t Lcache_hash = 0;
+  sb::Hash128 Lcache_hash;
   bool Lcache_valid = false;
 };
 

@@ -16,45 +16,55 @@ static thread_local char g_err[1024] = "";
 Context &ctx() { return g_ctx; }
 
 // ---------------------------------------------------------------- chunked, multi-threaded content hash
-// hash64(data) = hash64_st(data)                                    for up to HASH_PAR_MIN bytes
-//              = hash64_st(array of hash64_st(chunk_i), seed)       above, chunks of HASH_CHUNK bytes,
+// hash128(data) = hash128_st(data)                                   for up to HASH_PAR_MIN bytes
+//               = hash128_st(array of hash128_st(chunk_i), seed)     above, chunks of HASH_CHUNK bytes,
 // so the value depends on the bytes only.  Workers are created on first use and sleep on a condition variable
 // between jobs (after a short spin, so that back-to-back plugin calls do not pay the wake-up).
+//
+// Job hand-over.  The submitter publishes a job (parameters + generation g) under `mu`; a worker copies the
+// parameters under the same mutex and may claim chunk i only by a compare-and-swap on `next` = (g << 32 | i):
+// a worker that is late (still holding an older generation) sees a foreign tag, claims nothing and writes nothing.
+// Every claimed chunk bumps `done` after its result is stored and the submitter waits for done == nchunks, so no
+// write to `out` can be outstanding when the next job resizes it.
 static const size_t HASH_PAR_MIN = 512 * 1024, HASH_CHUNK = 256 * 1024;
 namespace {
+struct HashJob { const unsigned char *data; size_t bytes, nchunks; Hash128 seed; Hash128 *out; uint64_t gen; };
 struct HashPool {
   std::vector<std::thread> th;
   std::mutex mu;
   std::condition_variable cv;
-  const unsigned char *data = nullptr;
-  size_t bytes = 0, nchunks = 0;
-  uint64_t seed = 0;
-  std::vector<uint64_t> out;
-  std::atomic<size_t> next{0}, done{0};
+  HashJob job{nullptr, 0, 0, HASH_SEED, nullptr, 0};
+  std::vector<Hash128> out;
+  std::atomic<uint64_t> next{0};           // (generation << 32) | next unclaimed chunk
+  std::atomic<size_t> done{0};
   std::atomic<uint64_t> gen{0};
   bool stop = false;
-  void work() {
+  void work(const HashJob &J) {
     for (;;) {
-      const size_t i = next.fetch_add(1);
-      if (i >= nchunks) break;
-      const size_t off = i * HASH_CHUNK, len = std::min(HASH_CHUNK, bytes - off);
-      out[i] = hash64_st(data + off, len, seed);
+      uint64_t cur = next.load(std::memory_order_acquire);
+      if ((cur >> 32) != (J.gen & 0xffffffffull)) return;          // the counter belongs to another job
+      const size_t i = (size_t)(cur & 0xffffffffull);
+      if (i >= J.nchunks) return;
+      if (!next.compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel)) continue;
+      const size_t off = i * HASH_CHUNK, len = std::min(HASH_CHUNK, J.bytes - off);
+      J.out[i] = hash128_st(J.data + off, len, J.seed);
       done.fetch_add(1, std::memory_order_release);
     }
   }
   void loop() {
     uint64_t seen = 0;
     for (;;) {
-      // spin briefly for the next job, then sleep
-      bool got = false;
+      bool got = false;                   // spin briefly for the next job, then sleep
       for (int s = 0; s < 20000 && !got; s++) got = gen.load(std::memory_order_acquire) != seen;
-      if (!got) {
+      HashJob J;
+      {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return stop || gen.load() != seen; });
+        if (!got) cv.wait(lk, [&] { return stop || gen.load() != seen; });
         if (stop) return;
+        J = job;                          // a consistent snapshot: jobs are published under `mu`
       }
-      seen = gen.load(std::memory_order_acquire);
-      work();
+      seen = J.gen;
+      work(J);
     }
   }
   void start() {
@@ -73,21 +83,28 @@ HashPool *g_pool = nullptr;
 std::mutex g_pool_mu;
 }  // namespace
 
-uint64_t hash64(const void *data, size_t bytes, uint64_t seed) {
-  if (bytes <= HASH_PAR_MIN) return hash64_st(data, bytes, seed);
-  std::lock_guard<std::mutex> job(g_pool_mu);          // one job at a time
+Hash128 hash128(const void *data, size_t bytes, Hash128 seed) {
+  if (bytes <= HASH_PAR_MIN) return hash128_st(data, bytes, seed);
+  std::lock_guard<std::mutex> one(g_pool_mu);          // one job at a time
   if (!g_pool) { g_pool = new HashPool(); g_pool->start(); }
   HashPool &P = *g_pool;
-  P.data = (const unsigned char *)data; P.bytes = bytes; P.seed = seed;
-  P.nchunks = (bytes + HASH_CHUNK - 1) / HASH_CHUNK;
-  P.out.assign(P.nchunks, 0);
-  P.done.store(0); P.next.store(0);
-  { std::lock_guard<std::mutex> lk(P.mu); P.gen.fetch_add(1, std::memory_order_release); }
+  HashJob J;
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    const size_t nchunks = (bytes + HASH_CHUNK - 1) / HASH_CHUNK;
+    if (P.out.size() < nchunks) P.out.resize(nchunks);  // the previous job has fully drained (done == nchunks)
+    const uint64_t g = P.gen.load() + 1;
+    P.job = HashJob{(const unsigned char *)data, bytes, nchunks, seed, P.out.data(), g};
+    P.done.store(0);
+    P.next.store((g & 0xffffffffull) << 32, std::memory_order_release);
+    P.gen.store(g, std::memory_order_release);
+    J = P.job;
+  }
   P.cv.notify_all();
-  P.work();                                             // the calling thread takes its share
-  while (P.done.load(std::memory_order_acquire) < P.nchunks) { }
-  // late workers may still be inside work() probing `next`: they only read nchunks/next, which stay valid
-  return hash64_st(P.out.data(), sizeof(uint64_t) * P.nchunks, seed ^ (uint64_t)bytes);
+  P.work(J);                                            // the calling thread takes its share
+  while (P.done.load(std::memory_order_acquire) < J.nchunks) { }
+  Hash128 s2{seed.a ^ (uint64_t)bytes, seed.b + (uint64_t)bytes};
+  return hash128_st(J.out, sizeof(Hash128) * J.nchunks, s2);
 }
 
 void set_error(const char *fmt, ...) {
@@ -171,11 +188,11 @@ static MirrorSlot *mirror_victim(size_t bytes) {
     if (cudaMalloc(&best->dev, cap) != cudaSuccess) { cudaGetLastError(); set_error("mirror: cudaMalloc(%zu) failed", cap); return nullptr; }
     best->cap = cap;
   }
-  best->hash = 0; best->bytes = 0; best->stamp = ++g_mirror_clock;
+  best->hash = Hash128{}; best->bytes = 0; best->stamp = ++g_mirror_clock;
   return best;
 }
-void *mirror_input(const void *host, size_t bytes, uint64_t *hash_out, bool *hit) {
-  const uint64_t h = hash64(host, bytes);
+void *mirror_input(const void *host, size_t bytes, Hash128 *hash_out, bool *hit) {
+  const Hash128 h = hash128(host, bytes);
   if (hash_out) *hash_out = h;
   for (auto &s : g_mirror)
     if (s.dev && s.bytes == bytes && s.hash == h) { s.stamp = ++g_mirror_clock; if (hit) *hit = true; return s.dev; }
@@ -192,7 +209,7 @@ void *mirror_output_slot(size_t bytes) {
 }
 void mirror_publish(void *slot_dev, const void *host, size_t bytes) {
   for (auto &s : g_mirror)
-    if (s.dev == slot_dev) { s.hash = hash64(host, bytes); s.bytes = bytes; s.stamp = ++g_mirror_clock; return; }
+    if (s.dev == slot_dev) { s.hash = hash128(host, bytes); s.bytes = bytes; s.stamp = ++g_mirror_clock; return; }
 }
 
 int ensure_init() {
@@ -242,6 +259,11 @@ int sb200_sync(void) {
   return 0;
 }
 
+int sb200_xfer_bytes(int64_t *h2d, int64_t *d2h) {
+  if (h2d) *h2d = sb::ctx().h2d_bytes;
+  if (d2h) *d2h = sb::ctx().d2h_bytes;
+  return 0;
+}
 void *sb200_stream(void) { return sb::ensure_init() ? nullptr : (void *)sb::ctx().stream; }
 int64_t sb200_kernel_launches(void) { return sb::ctx().launches; }
 

@@ -366,12 +366,12 @@ static int make_blocks(sb_idx nblk, const sb_idx *n, std::vector<UrotBlk> &blks,
 
 // Block descriptors on the device, worst-case rotation layout; cached per block-size list so that the
 // *_dev entries can be recorded into a CUDA graph (no allocation or copy at call time after the first).
-static std::map<uint64_t, UrotBlk *> g_blk_cache;
+static std::map<Hash128, UrotBlk *> g_blk_cache;
 static int device_blocks(sb_idx nblk, const sb_idx *n, UrotBlk **out, long long &lenud, long long &sumn, long long &gtot, int &maxn) {
   std::vector<UrotBlk> blks;
   SB_TRY(make_blocks(nblk, n, blks, lenud, sumn, gtot));
   maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
-  uint64_t h = fnv1a(&nblk, sizeof nblk); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
+  Hash128 h = fnv1a(&nblk, sizeof nblk); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
   auto it = g_blk_cache.find(h);
   if (it != g_blk_cache.end()) { *out = it->second; return 0; }
   UrotBlk *d = nullptr;

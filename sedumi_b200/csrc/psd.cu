@@ -653,7 +653,7 @@ __global__ void herm_frames_kernel(const HermBlk *blks, const long long *fr_off,
   }
 }
 
-static std::map<uint64_t, sb200_psd_plan *> g_psd_plans;
+static std::map<Hash128, sb200_psd_plan *> g_psd_plans;
 
 }  // namespace sb
 
@@ -778,7 +778,7 @@ extern "C" {
 
 int sb200_psd_plan_get(sb200_psd_plan **plan, sb_idx nblk, const sb_idx *n) {
   SB_TRY(ensure_init());
-  uint64_t key = fnv1a(n, sizeof(sb_idx) * nblk, fnv1a(&nblk, sizeof nblk));
+  Hash128 key = fnv1a(n, sizeof(sb_idx) * nblk, fnv1a(&nblk, sizeof nblk));
   auto it = g_psd_plans.find(key);
   if (it != g_psd_plans.end()) { *plan = it->second; return 0; }
   sb200_psd_plan *pl = new sb200_psd_plan();
@@ -1093,11 +1093,11 @@ struct HermCtx {
   int sumn = 0, maxn = 0, nblk = 0;
   int *d_perm = nullptr;
 };
-static std::map<uint64_t, HermCtx *> g_herm;
+static std::map<Hash128, HermCtx *> g_herm;
 static int herm_get(sb_idx nblk, sb_idx nreal, const sb_idx *n, HermCtx **out) {
   SB_TRY(ensure_init());
   SB_CHECK(nreal >= 0 && nreal <= nblk, "number of real PSD blocks out of range");
-  uint64_t h = fnv1a(&nblk, sizeof nblk); h = fnv1a(&nreal, sizeof nreal, h); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
+  Hash128 h = fnv1a(&nblk, sizeof nblk); h = fnv1a(&nreal, sizeof nreal, h); h = fnv1a(n, sizeof(sb_idx) * nblk, h);
   auto it = g_herm.find(h);
   if (it != g_herm.end()) { *out = it->second; return 0; }
   HermCtx *c = new HermCtx();

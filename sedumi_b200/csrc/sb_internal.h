@@ -17,6 +17,7 @@ struct Context {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this library (every cudaMemcpyAsync, counted below)
   bool profiling = false;
   // bump arena for per-call scratch (reset at the start of each public entry point)
   std::vector<std::pair<char *, size_t>> arena_chunks;
@@ -30,6 +31,15 @@ template <typename T> inline T *arena(size_t count) { return (T *)arena_alloc(co
 Context &ctx();
 void set_error(const char *fmt, ...);
 int  ensure_init();
+
+// Every asynchronous copy of this library goes through here so that the host<->device traffic of a plugin call is
+// COUNTED, not estimated (sb200_xfer_bytes; bench.py prints these as e2e.h2d/d2h_bytes_per_step).
+inline cudaError_t counted_memcpy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  if (kind == cudaMemcpyHostToDevice) ctx().h2d_bytes += (int64_t)bytes;
+  else if (kind == cudaMemcpyDeviceToHost) ctx().d2h_bytes += (int64_t)bytes;
+  return ::cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+#define cudaMemcpyAsync(...) sb::counted_memcpy_async(__VA_ARGS__)
 
 #define SB_CUDA(call)                                                                 \
   do {                                                                                \
@@ -104,17 +114,27 @@ struct DevBuf {
   }
 };
 
-// Content hash of a host buffer.  Buffers above 512 KB are hashed in 256 KB chunks by a small pool of host threads
-// (the plugin boundary hashes ~65 MB per IPM iteration to recognise plans and device mirrors; one core does
-// 15 GB/s); the result is a function of the bytes only, independent of the number of threads.
-uint64_t hash64(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull);
+// Content hash of a host buffer: 128 bits.  Word `a` comes from four independent multiply-xorshift lanes over
+// 32-byte blocks (the dependent multiply chain of a single-lane hash limits it to ~2 GB/s; four lanes run at memory
+// speed); word `b` is an independent rotate-add chain over the same blocks with its own finaliser, so two buffers
+// are taken for equal only when both 64-bit functions agree (plans and device mirrors are keyed by these values).
+// Buffers above 512 KB are hashed in 256 KB chunks by a small pool of host threads (the plugin boundary hashes
+// tens of MB per IPM iteration); the result is a function of the bytes only, independent of the number of threads.
+struct Hash128 {
+  uint64_t a = 0, b = 0;
+  bool operator==(const Hash128 &o) const { return a == o.a && b == o.b; }
+  bool operator!=(const Hash128 &o) const { return !(*this == o); }
+  bool operator<(const Hash128 &o) const { return a != o.a ? a < o.a : b < o.b; }
+};
+static const Hash128 HASH_SEED{0x9E3779B97F4A7C15ull, 0xD6E8FEB86659FD93ull};
+Hash128 hash128(const void *data, size_t bytes, Hash128 seed = HASH_SEED);
 
-// Fast 64-bit content hash: four independent multiply-xorshift lanes over 32-byte blocks
-// (the dependent multiply chain of a single-lane hash limits it to ~2 GB/s; this runs at memory speed).
-inline uint64_t hash64_st(const void *data, size_t bytes, uint64_t seed = 0x9E3779B97F4A7C15ull) {
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline Hash128 hash128_st(const void *data, size_t bytes, Hash128 seed = HASH_SEED) {
   const unsigned char *p = (const unsigned char *)data;
   const uint64_t M = 0xFF51AFD7ED558CCDull;
-  uint64_t a = seed ^ bytes, b = seed * 3, c = seed * 5, d = seed * 7;
+  uint64_t a = seed.a ^ bytes, b = seed.a * 3, c = seed.a * 5, d = seed.a * 7;
+  uint64_t t = seed.b ^ (bytes * 0x9FB21C651E98DF25ull);
   size_t nblk = bytes / 32;
   const uint64_t *w = (const uint64_t *)p;
   for (size_t i = 0; i < nblk; i++, w += 4) {
@@ -122,37 +142,29 @@ inline uint64_t hash64_st(const void *data, size_t bytes, uint64_t seed = 0x9E37
     b = (b ^ w[1]) * M; b ^= b >> 32;
     c = (c ^ w[2]) * M; c ^= c >> 32;
     d = (d ^ w[3]) * M; d ^= d >> 32;
+    t = rotl64(t, 7) + (w[0] ^ rotl64(w[1], 13) ^ rotl64(w[2], 29) ^ rotl64(w[3], 43));
   }
   uint64_t h = a ^ (b * 0xC4CEB9FE1A85EC53ull) ^ (c << 1) ^ (d * M);
-  for (size_t i = nblk * 32; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  for (size_t i = nblk * 32; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; t = rotl64(t, 9) + p[i]; }
   h ^= h >> 33; h *= M; h ^= h >> 33;
-  return h;
+  t ^= t >> 31; t *= 0xC4CEB9FE1A85EC53ull; t ^= t >> 29; t *= M; t ^= t >> 32;
+  return Hash128{h, t};
 }
 
 // ---- device mirrors of host arrays, keyed by content: a host entry asks for the
 // device copy of an input; if an array with the same size and hash is already resident (typically
 // the output of the previous plugin call: ADA travelling getada1 -> 2 -> 3 -> blkchol, or L.L used by
 // eight solves) the upload is skipped.  Semantically invisible: same bytes in, same result out.
-struct MirrorSlot { uint64_t hash = 0; size_t bytes = 0, cap = 0; void *dev = nullptr; uint64_t stamp = 0; int tag = 0; };
+struct MirrorSlot { Hash128 hash; size_t bytes = 0, cap = 0; void *dev = nullptr; uint64_t stamp = 0; int tag = 0; };
 // Returns the device copy of (host, bytes); *hit tells whether an upload was avoided.
-void *mirror_input(const void *host, size_t bytes, uint64_t *hash_out = nullptr, bool *hit = nullptr);
+void *mirror_input(const void *host, size_t bytes, Hash128 *hash_out = nullptr, bool *hit = nullptr);
 // A device buffer (persistent slot) to write an output into; after the D2H copy call
 // mirror_publish(slot_dev, host, bytes) so that the next call can find it.
 void *mirror_output_slot(size_t bytes);
 void mirror_publish(void *slot_dev, const void *host, size_t bytes);
 
-inline uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
-  return hash64(data, bytes, h);
-}
-inline uint64_t fnv1a_old(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
-  const unsigned char *p = (const unsigned char *)data;
-  // word-at-a-time variant (not the canonical byte FNV, just a fast content hash)
-  size_t nw = bytes / 8;
-  const uint64_t *w = (const uint64_t *)p;
-  for (size_t i = 0; i < nw; i++) { h ^= w[i]; h *= 1099511628211ull; h ^= h >> 29; }
-  for (size_t i = nw * 8; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
-  return h;
-}
+// chained key of several arrays: each call folds the previous value in as the seed
+inline Hash128 fnv1a(const void *data, size_t bytes, Hash128 h = HASH_SEED) { return hash128(data, bytes, h); }
 
 inline int to_i32(const sb_idx *src, size_t n, std::vector<int> &dst, const char *what) {
   dst.resize(n);

@@ -70,7 +70,7 @@ def _p(a):
 
 EXPORTS = [
     "sb200_init", "sb200_shutdown", "sb200_last_error", "sb200_device_count", "sb200_sync", "sb200_stream",
-    "sb200_kernel_launches", "sb200_dev_alloc", "sb200_dev_free", "sb200_h2d", "sb200_d2h",
+    "sb200_kernel_launches", "sb200_xfer_bytes", "sb200_dev_alloc", "sb200_dev_free", "sb200_h2d", "sb200_d2h",
     "sb200_chol_plan_create", "sb200_chol_plan_destroy", "sb200_chol_plan_nnzL", "sb200_chol_plan_rect_size",
     "sb200_blkchol_dev", "sb200_chol_rect_to_csc_dev", "sb200_chol_csc_to_rect_dev", "sb200_blkchol",
     "sb200_fwblkslv_dev", "sb200_bwblkslv_dev", "sb200_ldl_solve_dev", "sb200_chol_shard_create", "sb200_chol_shard_info",
@@ -80,11 +80,34 @@ EXPORTS = [
     "sb200_invcholfac", "sb200_psdscale", "sb200_invcholfac_h", "sb200_psdscale_h", "sb200_psdframeit_h", "sb200_psdinvjmul_h", "sb200_urotorder_h", "sb200_givensrot_h", "sb200_psdframeit_dev", "sb200_psdinvjmul_dev", "sb200_psdframeit",
     "sb200_psdinvjmul", "sb200_urotorder", "sb200_givensrot", "sb200_urotorder_dev", "sb200_givensrot_dev", "sb200_dpr1fact", "sb200_dpr1solve", "sb200_prof_begin", "sb200_prof_end", "sb200_graph_begin", "sb200_graph_end", "sb200_graph_launch",
     "sb200_graph_destroy",
-    "sb200_ada_plan_get", "sb200_ada_plan_get_h", "sb200_ada_plan_nnz", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
+    "sb200_ada_plan_get", "sb200_ada_plan_get_h", "sb200_ada_plan_nnz", "sb200_ada_plan_retain", "sb200_ada_plan_release", "sb200_ada_set_At_values", "sb200_getada1_dev", "sb200_getada2_dev",
     "sb200_getada3_dev", "sb200_getada1", "sb200_getada2", "sb200_getada3", "sb200_getdatm_dev", "sb200_ada_plan_datq",
     "sb200_ddot_dense_dev", "sb200_qblkmul_dev", "sb200_quadadd_dev", "sb200_ddot_dense", "sb200_ddot_sparse",
     "sb200_qblkmul", "sb200_quadadd", "sb200_adendotd",
+    "sb200_comm_unique_id", "sb200_comm_init_rank", "sb200_comm_size", "sb200_comm_rank", "sb200_comm_nccl_version",
+    "sb200_comm_stats", "sb200_allreduce_sum_dev", "sb200_allreduce_sum2_dev", "sb200_comm_destroy",
+    "sb200_blkchol_sharded_dev", "sb200_ldl_solve_sharded_dev",
 ]
+
+
+def comm_init(rank: int, world: int, device: int, bcast) -> None:
+    """Join the library's own NCCL communicator (include/sedumi_b200.h "multi-GPU"): rank 0 draws the unique id,
+    `bcast(bytearray(128)) -> bytes` moves it to every rank over whatever channel the host has (bench.py: a
+    torch.distributed broadcast), then all ranks call sb200_comm_init_rank.  Collective."""
+    L = lib()
+    check(L.sb200_init(C.c_int(device)), "init")
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        check(L.sb200_comm_unique_id(buf), "comm_unique_id")
+    raw = bcast(bytes(buf.raw))
+    buf2 = (C.c_char * 128).from_buffer_copy(raw)
+    check(L.sb200_comm_init_rank(C.c_int(world), C.c_int(rank), buf2), "comm_init_rank")
+
+
+def comm_stats():
+    calls, nbytes = I64(0), I64(0)
+    lib().sb200_comm_stats(C.byref(calls), C.byref(nbytes))
+    return int(calls.value), int(nbytes.value)
 
 
 class _CholPars(C.Structure):
@@ -122,6 +145,7 @@ class HotPath:
         check(L.sb200_ada_plan_get(C.byref(self.ada), I64(At.shape[0]), I64(m), _p(Ajc), _p(Air), _p(Ajc1),
                                    I64(self.lpN), I64(self.nq), _p(qstart), I64(len(s)), _p(bs), _p(_i64(s)),
                                    _p(adajc), _p(adair)), "ada_plan")
+        L.sb200_ada_plan_retain(self.ada)          # the cache may not evict a plan this object (and its graphs) uses
         check(L.sb200_ada_set_At_values(self.ada, _p(np.ascontiguousarray(At.data, dtype=np.float64))), "At values")
         self.psd = VP()
         check(L.sb200_psd_plan_get(C.byref(self.psd), I64(len(s)), _p(_i64(s))), "psd_plan")
@@ -151,7 +175,9 @@ class HotPath:
         self.d_u, self.udsqr = z(self.lenud), z(self.lenud)
         self.d_perm = torch.zeros(max(int(s.sum()), 1), dtype=torch.int32, device=self.dev)
         self.has_perm = False
-        self.ADA, self.absd = z(self.nnzADA), z(m)
+        # ADA values and absd share one allocation: the sharded path reduces both at the Schur-assembly boundary
+        self._ada_absd = z(self.nnzADA + m + 8)
+        self.ADA, self.absd = self._ada_absd[:max(self.nnzADA, 1)], self._ada_absd[self.nnzADA:self.nnzADA + max(m, 1)]
         self.Lrect, self.dvec, self.sval = z(self.rect), z(m), z(m)
         self.flag = torch.zeros(max(m, 1), dtype=torch.int32, device=self.dev)
         self.psd_x, self.psd_y = z(self.lenud), z(self.lenud)
@@ -168,6 +194,14 @@ class HotPath:
         self.perm_new = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
         self.gjc = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
         self.maxu_urot = 1.1                        # updtransfo.m:100
+
+    def __del__(self):
+        try:
+            if getattr(self, "ada", None) and _lib is not None:
+                _lib.sb200_ada_plan_release(self.ada)
+                self.ada = None
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ data movement
     def set_scaling(self, d: dict, non_blocking=False) -> int:
@@ -244,13 +278,10 @@ class HotPath:
         sh = self.shard
         return self.Lrect[sh["top_off"]:sh["top_off"] + sh["top_len"]]
 
-    def blkchol_sharded(self, dist):
-        """Own subtrees, ONE all-reduce of the top panels, top (replicated)."""
-        self.blkchol_shard_local()
-        if self.shard["top_len"]:
-            with self.torch.cuda.stream(self.stream()):
-                dist.all_reduce(self.top_panels())
-        self.blkchol_shard_top()
+    def blkchol_sharded(self):
+        """Own subtrees, ONE all-reduce of the top panels, top (replicated) -- collectives inside the library."""
+        check(lib().sb200_blkchol_sharded_dev(self.chol, _p(self.ADA), _p(self.absd), self.pars, _p(self.Lrect), _p(self.dvec),
+                                              _p(self.flag), _p(self.sval)), "blkchol_sharded")
 
     def solve_shard_local(self):
         check(lib().sb200_fw_shard_local_dev(self.chol, _p(self.Lrect), _p(self.rhs), _p(self.w), I64(self.nrhs)), "fw_shard_local")
@@ -262,17 +293,10 @@ class HotPath:
     def solve_shard_finish(self):
         check(lib().sb200_bw_shard_finish_dev(self.chol, _p(self.w), _p(self.y), I64(self.nrhs)), "bw_shard_finish")
 
-    def solve_sharded(self, dist):
+    def solve_sharded(self):
         """Forward over the own subtrees, all-reduce of the top segment, top + backward, all-reduce of the solution."""
-        self.solve_shard_local()
-        col0 = self.shard["col0"]
-        with self.torch.cuda.stream(self.stream()):
-            if col0 < self.m:
-                dist.all_reduce(self.w[:, col0:])
-        self.solve_shard_top()
-        with self.torch.cuda.stream(self.stream()):
-            dist.all_reduce(self.w)
-        self.solve_shard_finish()
+        check(lib().sb200_ldl_solve_sharded_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.rhs),
+                                                _p(self.w), _p(self.y), I64(self.nrhs)), "ldl_solve_sharded")
 
     def psdscale(self, transp: int):
         check(lib().sb200_psdscale_dev(self.psd, _p(self.d_u), _p(self.d_perm) if self.has_perm else None,
@@ -326,22 +350,20 @@ class HotPath:
         self.urotorder()
         self.givensrot()
 
-    def allreduce_ada(self, dist):
-        """The one collective of the sharded path: sum the per-rank partial ADA values
-        and absd over NCCL, enqueued on the library stream right behind getada3."""
-        with self.torch.cuda.stream(self.stream()):
-            dist.all_reduce(self.ADA[:self.nnzADA])
-            dist.all_reduce(self.absd[:self.m])
+    def allreduce_ada(self):
+        """The collective at the Schur-assembly boundary: sum the per-rank partial ADA values and absd
+        (one contiguous buffer, one NCCL call) on the library stream right behind getada3."""
+        check(lib().sb200_allreduce_sum_dev(_p(self._ada_absd), I64(self.nnzADA + self.m)), "allreduce(ADA,absd)")
 
-    def iteration(self, nsolve=4, npsdscale=12, dist=None):
+    def iteration(self, nsolve=4, npsdscale=12, sharded=False):
         self.invcholfac()
         self.getada()
-        if dist is not None:
-            self.allreduce_ada(dist)
-        if dist is not None and getattr(self, "shard", None):
-            self.blkchol_sharded(dist)
+        if sharded:
+            self.allreduce_ada()
+        if sharded and getattr(self, "shard", None):
+            self.blkchol_sharded()
             for _ in range(nsolve):
-                self.solve_sharded(dist)
+                self.solve_sharded()
         else:
             self.blkchol()
             for _ in range(nsolve):
@@ -353,15 +375,16 @@ class HotPath:
         else:
             self.lorentz_streams()
 
-    def capture(self, nsolve=4, npsdscale=12):
-        """Record one iteration into a CUDA graph; returns a callable that replays it."""
+    def capture(self, nsolve=4, npsdscale=12, sharded=False):
+        """Record one iteration -- kernels AND, when sharded, the library's NCCL collectives -- into a CUDA graph;
+        returns a callable that replays it."""
         L = lib()
-        self.iteration(nsolve, npsdscale)          # warm: lazy allocations / attribute changes happen here
+        self.iteration(nsolve, npsdscale, sharded)          # warm: lazy allocations / attribute changes happen here
         self.sync()
         l0 = L.sb200_kernel_launches()
         check(L.sb200_graph_begin(), "graph_begin")
         try:
-            self.iteration(nsolve, npsdscale)
+            self.iteration(nsolve, npsdscale, sharded)
         finally:
             g = VP()
             rc = L.sb200_graph_end(C.byref(g))

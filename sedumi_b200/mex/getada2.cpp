@@ -11,10 +11,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   MEX_REQUIRE(mxGetN(ADA) == m, "Size mismatch ADA.");
   MEX_REQUIRE(mxIsSparse(ADA), "ADA should be sparse.");
   plhs[0] = sparse_with_pattern(m, m, mxGetJc(ADA), mxGetIr(ADA));
-  if (K.lorN <= 0) {                                        // ready if no Lorentz blocks (getada2.c:151-152)
-    memcpy(mxGetPr(plhs[0]), mxGetPr(ADA), mxGetJc(ADA)[m] * sizeof(double));
-    return;
-  }
+  // ADA_OUT starts as a duplicate of ADA_IN (getada2.c:153 mxDuplicateArray): every early exit below returns the
+  // input values unchanged -- sparse_with_pattern leaves the value array uninitialised on purpose
+  memcpy(mxGetPr(plhs[0]), mxGetPr(ADA), mxGetJc(ADA)[m] * sizeof(double));
+  if (K.lorN <= 0) return;                                  // ready if no Lorentz blocks (getada2.c:151-152)
   MEX_REQUIRE(mxIsStruct(DAT), "DAt should be a structure.");
   const mxArray *Q = need_field(DAT, "q", "Missing field DAt.q.");
   MEX_REQUIRE(mxGetM(Q) == (mwSize)K.lorN && mxGetN(Q) == m, "Size mismatch DAt.q");
@@ -22,7 +22,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   MEX_REQUIRE(mxIsStruct(AORD), "Aord should be a structure.");
   const mxArray *QP = need_field(AORD, "qperm", "Missing field Aord.qperm.");
   MEX_REQUIRE(numel(QP) == m, "Size mismatch Aord.qperm.");
-  if (mxGetJc(Q)[m] == 0) return;                           // nothing to add
+  if (mxGetJc(Q)[m] == 0) return;                           // DAt.q empty (all Lorentz cones dense, getDAtm.m:44): ADA unchanged
   std::vector<sb_idx> perm;
   idx_from_double(QP, perm, 1, "Aord.qperm");
   const mwIndex *adajc = mxGetJc(ADA), *adair = mxGetIr(ADA);

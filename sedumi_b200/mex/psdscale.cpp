@@ -19,14 +19,29 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   sb_idx N = K.rDim + K.hDim;
   MEX_REQUIRE(numel(ufield) >= (mwSize)N, "ud.u size mismatch");
   MEX_REQUIRE(numel(prhs[1]) >= (mwSize)N, "x size mismatch");
-  MEX_REQUIRE(!mxIsSparse(prhs[1]), "x must be full");
   std::vector<sb_idx> perm;
   bool isperm = pfield && numel(pfield) > 0;
   if (isperm) {
     MEX_REQUIRE(numel(pfield) >= (mwSize)(K.rLen + K.hLen), "ud.perm size mismatch");
     idx_from_double(pfield, perm, 1, "ud.perm");
   }
-  const double *x = mxGetPr(prhs[1]) + (numel(prhs[1]) - (mwSize)N);     // PSD part is the tail (psdscale.m:58)
+  // PSD part is the tail (psdscale.m:58).  psdscale.m takes any x, sparse included (it even sparsifies blocks
+  // itself, :100-102): a sparse vector is scattered into a dense tail here.
+  const mwSize tail0 = numel(prhs[1]) - (mwSize)N;
+  std::vector<double> xdense;
+  const double *x;
+  if (mxIsSparse(prhs[1])) {
+    xdense.assign((size_t)N, 0.0);
+    const mwIndex *xjc = mxGetJc(prhs[1]), *xir = mxGetIr(prhs[1]);
+    const double *xpr = mxGetPr(prhs[1]);
+    const mwSize xm = mxGetM(prhs[1]), xn = mxGetN(prhs[1]);
+    for (mwSize c = 0; c < xn; c++)
+      for (mwIndex p = xjc[c]; p < xjc[c + 1]; p++) {
+        const mwSize lin = c * xm + xir[p];
+        if (lin >= tail0) xdense[lin - tail0] = xpr[p];
+      }
+    x = xdense.data();
+  } else x = mxGetPr(prhs[1]) + tail0;
   plhs[0] = mxCreateDoubleMatrix((mwSize)N, 1, mxREAL);
   int rc = herm ? sb200_psdscale_h(K.sdpN, K.rsdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]))
                 : sb200_psdscale(K.sdpN, K.s.data(), mxGetPr(ufield), isperm ? perm.data() : NULL, x, transp ? 1 : 0, mxGetPr(plhs[0]));

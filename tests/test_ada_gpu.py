@@ -125,3 +125,32 @@ def test_invcholfac_empty_perm_and_identity():
     Km = cones.K_for_mex(K)
     assert relerr(gpu.invcholfac(d["u"], Km), ref.invcholfac(d["u"], Km)) <= 1e-12
     assert relerr(gpu.invcholfac(d["u"], Km, np.zeros((0, 0))), ref.invcholfac(d["u"], Km, np.zeros((0, 0)))) <= 1e-12
+
+
+def test_getada2_empty_DAtq_returns_input():
+    """K.q non-empty but DAt.q without nonzeros (every Lorentz cone dense, getDAtm.m:44): the reference returns
+    mxDuplicateArray(ADA_IN) (getada2.c:150-153) -- the plugin must return the input VALUES, not scratch."""
+    S = _problem("small_mixed")
+    d = problems.scaling(S.K, "S1", seed=4)
+    Km = S.Kmex()
+    ADA0 = sp.csc_matrix((np.zeros(S.ADA.nnz), S.ADA.indices, S.ADA.indptr), shape=S.ADA.shape)
+    A1 = ref.getada1(ADA0, S.At, S.Ablkjc[:, 2], S.Aord["lqperm"], {"l": d["l"], "det": d["det"]},
+                     S.K["qblkstart"].reshape(1, -1))
+    empty = {"q": sp.csc_matrix((len(S.K["q"]), S.m))}
+    Ar = ref.getada2(A1, empty, S.Aord, Km)
+    Ag = gpu.getada2(A1, empty, S.Aord, Km)
+    assert np.array_equal(Ag.indptr, Ar.indptr) and np.array_equal(Ag.indices, Ar.indices)
+    assert np.array_equal(Ag.data, Ar.data) and np.array_equal(Ag.data, A1.data)
+
+
+def test_psdscale_sparse_x():
+    """psdscale.m accepts a sparse x (it sparsifies blocks itself, psdscale.m:100-102); so does the plugin."""
+    s = (7, 4)
+    K = cones.finish_K({"l": 1, "q": np.zeros(0), "s": np.array(s, dtype=float)})
+    d = problems.scaling(K, "S1", seed=11)
+    rng = np.random.default_rng(5)
+    lenud = int(sum(n * n for n in s))
+    x = rng.standard_normal(1 + lenud) * (rng.random(1 + lenud) < 0.2)
+    yr = restate.psdscale({"u": d["u"], "perm": d["perm"]}, x, K, 0)
+    yg = gpu.psdscale({"u": d["u"], "perm": d["perm"]}, sp.csc_matrix(x.reshape(-1, 1)), cones.K_for_mex(K), 0.0)
+    assert relerr(yg.ravel(), yr) <= 1e-10

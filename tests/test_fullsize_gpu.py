@@ -49,3 +49,49 @@ def test_invcholfac_n1000_matches_numpy():
     u = (U + np.triu(U, 1).T).ravel(order="F")
     D = gpu.invcholfac(u, K).reshape(n, n, order="F")
     assert relerr(D, U.T @ U) <= 1e-12 and np.array_equal(D, D.T)
+
+
+# ---- oracle parity at BASELINE.json's full sizes: the device-resident pipeline against one reference iteration
+# (oracle/gates.py: ADA/absd/L/d 1e-10, identical skip/add sets, search direction 1e-8, PSD tail 1e-10 / bit-exact).
+# The reference needs about half a minute (blockdiag64) / a minute (maxcut4000) of one host core for it.
+def _gated_iteration(name, nsolve=2, npsd=2, tail=True):
+    import os
+    import sys
+    import torch
+    from helpers import ROOT
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bench
+    import gates
+    from sedumi_b200 import device
+    W = bench.load_workload(name)
+    hp = device.HotPath(W.S)
+    st = hp.stream()
+    with torch.cuda.stream(st):
+        hp.set_scaling(W.d)
+        hp.set_rhs(W.rhs)
+        hp.psd_x[:W.psd_x.size].copy_(torch.from_numpy(W.psd_x))
+        hp.set_frames(*W.frames)
+        st.synchronize()
+        hp.iteration(nsolve, npsd)
+        hp.sync()
+        return gates.run_gates(hp, W.S, W.d, W.rhs, W.psd_x, W.frames, nsolve, npsd, tail=tail), W
+
+
+def test_blockdiag64_full_size_oracle_parity():
+    """BASELINE configs[3]: 64 PSD blocks of order 200, m = 5000, arrow ADA with 65 supernodes."""
+    g, W = _gated_iteration("blockdiag64")
+    assert len(W.S.L["xsuper"].ravel()) - 1 == 65 and W.S.m == 5000
+    assert g["ok"], g
+    assert g["skip_equal"] and g["add_equal"] and g["urotorder_bit_exact"]
+    for k, v in g["err"].items():
+        assert v <= g["tol"][k], (k, v)
+
+
+def test_maxcut4000_full_size_oracle_parity():
+    """BASELINE configs[4]: one PSD block n = 4000, m = 4000 (getada3's sparse-W mode, one dense supernode)."""
+    g, W = _gated_iteration("maxcut4000", nsolve=1, npsd=2)
+    assert W.S.m == 4000
+    assert g["ok"], g
+    for k, v in g["err"].items():
+        assert v <= g["tol"][k], (k, v)
