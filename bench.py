@@ -397,21 +397,15 @@ def device_run(W, args, rank, world, local_rank, sharded, dist, steps, warmup, w
 
         # ---- per-kernel timing pass (CUDA events after every launch on the library stream); every rank takes part
         # because the sharded iteration contains collectives
-        import ctypes as C
-        nprof = min(steps, 20)
-        lib.sb200_prof_begin()
+        nprof = 1
         cs0 = sbdev.comm_stats()
-        for _ in range(nprof):
-            hp.iteration(NSOLVE, NPSD, sharded)
+        hp.iteration(NSOLVE, NPSD, sharded)
         cs1 = sbdev.comm_stats()
-        buf = C.create_string_buffer(1 << 16)
-        lib.sb200_prof_end(buf, C.c_int64(len(buf)))
-        out.comm["collectives_per_iteration"] = (cs1[0] - cs0[0]) / nprof
-        out.comm["allreduce_bytes_per_iteration"] = (cs1[1] - cs0[1]) / nprof
-        prof = {}
-        for ln_ in buf.value.decode().splitlines():
-            nm, cnt, tot = ln_.split()
-            prof[nm] = (int(cnt), float(tot))
+        out.comm["collectives_per_iteration"] = cs1[0] - cs0[0]
+        out.comm["allreduce_bytes_per_iteration"] = cs1[1] - cs0[1]
+        barrier()
+        prof = hp.profile(NSOLVE, NPSD, sharded, graph=not args.no_graph)      # one replay of an event-instrumented graph
+        barrier()
         out.roof = None
         if rank == 0 and prof:
             tot_ms = sum(v[1] for v in prof.values())

@@ -34,6 +34,7 @@ struct AdaPair {      // one (constraint, PSD block) with nonzeros
   int sparse;         // 1: W is only evaluated on U_k, the union pattern of block k
   int pad_;
   long long part_off; // constraints with several blocks: offset of this pair's partial sums (npartners(k)+1)
+  long long fpart_off; // the same in the compact workspace of the fused path (no T / W there)
 };
 
 // --------------------------------------------------------------------- sparse A'WA on a pattern
@@ -370,7 +371,7 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
 __global__ void __launch_bounds__(256)
 ada3_reduce_kernel(int c0, const long long *adajc, const int *adair, const int *invperm, int first,
                    const int *cpair_beg, const AdaPair *pairs, const int *blkp_beg, const BlkPartner *blkp,
-                   const double *ws, double *ada, double *absd, int use_map, int m) {
+                   const double *ws, double *ada, double *absd, int use_map, int m, int fused) {
   extern __shared__ int red_slot[];
   const int c = c0 + blockIdx.x;
   const int pcb = cpair_beg[c], pce = cpair_beg[c + 1];
@@ -386,7 +387,7 @@ ada3_reduce_kernel(int c0, const long long *adajc, const int *adair, const int *
   for (int pc = pcb; pc < pce; pc++) {
     __syncthreads();                               // two blocks can feed the same entry: keep them in order
     const int k = pairs[pc].k;
-    const double *part = ws + pairs[pc].part_off;
+    const double *part = ws + (fused ? pairs[pc].fpart_off : pairs[pc].part_off);
     const int tb = blkp_beg[k], te = blkp_beg[k + 1];
     for (int t = tb + threadIdx.x; t < te; t += blockDim.x) {
       const int i = blkp[t].j;
@@ -426,7 +427,15 @@ __global__ void makesym_kernel(int m, const long long *jc, const int *ir, double
   }
 }
 
+// tt_val[t] = weight * value of the At entry it comes from (refreshed whenever the values of At change)
+__global__ void tt_val_kernel(long long n, const double *tt_w, const int *tt_src, const double *Atpr, double *tt_val) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    tt_val[t] = tt_w[t] * Atpr[tt_src[t]];
+}
+
 }  // namespace sb
+
+#include "ada_fused.cuh"
 
 using namespace sb;
 
@@ -475,6 +484,15 @@ struct sb200_ada_plan {
   DevBuf<GemmTile> d_tiles;
   DevBuf<double> d_Atpr, d_dsqr, d_ws;
   DevBuf<int> d_invperm, d_ident;
+  // fused path (ada_fused.cuh): every block in dense mode and of order <= FUSED_MAX_N, no Hermitian block
+  bool fused_ok = false, tt_val_valid = false;
+  int fused_threads = 0, fused_grid = 0, fused_wcap = 0, fused_ldmax = 0, fused_small = 0;
+  size_t fused_smem = 0;
+  long long fused_scratch_stride = 0, fws = 0, n_tt = 0;
+  int any_multi = 0;
+  DevBuf<double> d_tt_val, d_fscratch, d_fws;
+  DevBuf<int> d_fcounter, d_fitem_beg;
+  DevBuf<int2> d_fitems;
 };
 
 static std::map<Hash128, sb200_ada_plan *> g_ada_plans;
@@ -568,6 +586,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     }
   }
   pl->cpair_beg[m] = (int)pl->pairs.size();
+  pl->n_tt = (long long)tt_col.size();
   // ---- union pattern U_k per block; blocks that use less than a quarter of their lower triangle
   // evaluate W only there ("sparse mode"), and their entries index into U_k instead of the n x n array
   std::vector<std::vector<int>> ulin(nblk);
@@ -747,6 +766,60 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(pl->d_ublk_off.upload(ublk_off)); SB_TRY(pl->d_u_p.upload(u_p)); SB_TRY(pl->d_u_q.upload(u_q));
   SB_TRY(pl->d_blkp_beg.upload(blkp_beg)); SB_TRY(pl->d_blkp.upload(blkp)); SB_TRY(pl->d_ent_pk.upload(ent_pk));
   SB_TRY(pl->d_Rlist.upload(Rlist));
+  // ---- fused path: compact partial-sum workspace, scratch slot per resident CTA
+  {
+    bool ok = !pl->herm && !pl->pairs.empty() && !getenv("SB200_NO_FUSED_ADA3");
+    int maxn = 0; long long max_tt = 1;
+    for (auto &P : pl->pairs) {
+      if (P.sparse || pl->blk_n[P.k] > FUSED_MAX_N) ok = false;
+      maxn = std::max(maxn, pl->blk_n[P.k]);
+      max_tt = std::max(max_tt, (long long)pl->blk_n[P.k] * P.r);
+    }
+    long long fws = 0;
+    for (sb_idx c2 = 0; c2 < m; c2++) {
+      const bool multi = pl->cpair_beg[c2 + 1] - pl->cpair_beg[c2] > 1;
+      for (int p = pl->cpair_beg[c2]; p < pl->cpair_beg[c2 + 1]; p++) {
+        pl->pairs[p].fpart_off = fws;
+        if (multi) { fws += blkp_beg[pl->pairs[p].k + 1] - blkp_beg[pl->pairs[p].k] + 1; pl->any_multi = 1; }
+      }
+    }
+    pl->fused_ok = ok;
+    if (ok) {
+      const int nst = (maxn + 31) / 32, items = nst * (nst + 1) / 2;
+      pl->fused_small = items <= 8;
+      pl->fused_threads = pl->fused_small ? 256 : 512;
+      // per block: lower supertiles sorted by their number of fragments (a round costs what its dearest item costs)
+      std::vector<int> ibeg(nblk + 1, 0);
+      std::vector<int2> its;
+      for (sb_idx k = 0; k < nblk; k++) {
+        ibeg[k] = (int)its.size();
+        const int nk = pl->blk_n[k], nt = (nk + 7) / 8, ns = (nk + 31) / 32;
+        std::vector<std::pair<int, int2>> v;
+        for (int I = 0; I < ns; I++)
+          for (int J = 0; J <= I; J++) {
+            const int nra = std::min(4, nt - 4 * I), ncb = std::min(4, nt - 4 * J);
+            int cost = 0;
+            for (int a2 = 0; a2 < nra; a2++) for (int b2 = 0; b2 < ncb; b2++) if (I != J || a2 >= b2) cost++;
+            v.push_back({-cost, make_int2(I, J)});
+          }
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first < y.first; });
+        for (auto &e : v) its.push_back(e.second);
+      }
+      ibeg[nblk] = (int)its.size();
+      SB_TRY(pl->d_fitem_beg.upload(ibeg)); SB_TRY(pl->d_fitems.upload(its));
+      pl->fused_wcap = (maxn * (maxn + 1) / 2 + 1) & ~1;
+      pl->fused_ldmax = ((maxn + 7) & ~7) + 4;
+      pl->fused_smem = sizeof(double) * ((size_t)pl->fused_wcap + 4 * FKC * pl->fused_ldmax);
+      const int per_sm = pl->fused_small ? (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / pl->fused_smem)) : 1;
+      pl->fused_grid = (int)std::min<long long>((long long)pl->pairs.size(), (long long)ctx().sm_count * per_sm);
+      pl->fused_scratch_stride = (max_tt + 1) & ~1LL;
+      pl->fws = fws;
+      SB_TRY(pl->d_tt_val.alloc((size_t)std::max<long long>(pl->n_tt, 1)));
+      SB_TRY(pl->d_fscratch.alloc((size_t)(pl->fused_scratch_stride * pl->fused_grid)));
+      SB_TRY(pl->d_fws.alloc((size_t)std::max<long long>(fws, 1)));
+      SB_TRY(pl->d_fcounter.alloc(1));
+    }
+  }
   SB_TRY(pl->d_pairs.upload(pl->pairs));
   SB_TRY(pl->d_descs.upload(descs)); SB_TRY(pl->d_tiles.upload(tiles));
   SB_TRY(pl->d_Atpr.alloc((size_t)std::max<long long>(pl->nnzA, 1)));
@@ -818,7 +891,7 @@ int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
   if (pl->have_vals && h == pl->val_hash) return 0;
   SB_CUDA(cudaMemcpyAsync(pl->d_Atpr.p, Atpr, sizeof(double) * pl->nnzA, cudaMemcpyHostToDevice, ctx().stream));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));
-  pl->val_hash = h; pl->have_vals = true; pl->lq_dense_valid = false;
+  pl->val_hash = h; pl->have_vals = true; pl->lq_dense_valid = false; pl->tt_val_valid = false;
   return 0;
 }
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *pl) { return pl->nnzADA; }
@@ -983,6 +1056,35 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     SB_LAUNCH_CHECK_N("ada_embed_d_kernel");
     udsqr_dev = pl->d_De.p;
   }
+  if (pl->fused_ok) {
+    if (!pl->tt_val_valid) {
+      tt_val_kernel<<<(unsigned)std::min<long long>((pl->n_tt + 255) / 256, 2048), 256, 0, st>>>(pl->n_tt, pl->d_tt_w.p, pl->d_tt_src.p, pl->d_Atpr.p, pl->d_tt_val.p);
+      SB_LAUNCH_CHECK_N("tt_val_kernel");
+      if (!ctx().capturing) pl->tt_val_valid = true;      // inside a graph capture the launch must stay part of every replay
+    }
+    SB_CUDA(cudaMemsetAsync(pl->d_fcounter.p, 0, sizeof(int), st));
+    FusedArgs FA;
+    FA.pairs = pl->d_pairs.p; FA.npairs = (int)pl->pairs.size(); FA.counter = pl->d_fcounter.p;
+    FA.blk_n = pl->d_blk_n.p; FA.blk_off = pl->d_blk_off.p; FA.tt_ptr = pl->d_tt_ptr.p; FA.tt_col = pl->d_tt_col.p; FA.tt_val = pl->d_tt_val.p;
+    FA.Rlist = pl->d_Rlist.p; FA.udsqr = udsqr_dev; FA.scratch = pl->d_fscratch.p; FA.scratch_stride = pl->fused_scratch_stride;
+    FA.adajc = pl->d_adajc.p; FA.adair = pl->d_adair.p; FA.invperm = ip; FA.first = (int)first; FA.cpair_beg = pl->d_cpair_beg.p;
+    FA.blkp_beg = pl->d_blkp_beg.p; FA.blkp = pl->d_blkp.p; FA.ent_pk = pl->d_ent_pk.p; FA.ent_src = pl->d_ent_src.p; FA.Atpr = pl->d_Atpr.p;
+    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax;
+    static bool attr_done = false;
+    if (!attr_done) {
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done = true;
+    }
+    if (pl->fused_small) ada3_fused_kernel<256, 2><<<pl->fused_grid, pl->fused_threads, pl->fused_smem, st>>>(FA);
+    else ada3_fused_kernel<512, 1><<<pl->fused_grid, pl->fused_threads, pl->fused_smem, st>>>(FA);
+    SB_LAUNCH_CHECK_N("ada3_fused_kernel");
+    if (pl->any_multi) {
+      ada3_reduce_kernel<<<pl->m, 256, pl->use_map ? (size_t)pl->m * 4 : 0, st>>>(0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
+          pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_fws.p, ada_dev, absd_dev, pl->use_map, pl->m, 1);
+      SB_LAUNCH_CHECK_N("ada3_reduce_kernel");
+    }
+  } else
   for (auto &B : pl->batches) {
     if (B.p1 == B.p0) continue;
     build_tt_kernel<<<B.p1 - B.p0, 256, 0, st>>>(pl->d_pairs.p, B.p0, pl->d_blk_n.p, pl->d_blk_off.p, pl->d_tt_ptr.p, pl->d_tt_col.p,
@@ -1009,7 +1111,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     SB_LAUNCH_CHECK_N("ada3_dots_kernel");
     if (B.nmulti) {
       ada3_reduce_kernel<<<B.c1 - B.c0, 256, pl->use_map ? (size_t)pl->m * 4 : 0, st>>>(B.c0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
-          pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ws.p, ada_dev, absd_dev, pl->use_map, pl->m);
+          pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_ws.p, ada_dev, absd_dev, pl->use_map, pl->m, 0);
       SB_LAUNCH_CHECK_N("ada3_reduce_kernel");
     }
   }

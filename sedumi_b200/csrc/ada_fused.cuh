@@ -1,0 +1,201 @@
+// ada_fused.cuh -- getada3 for PSD blocks up to order 208: W_jk never leaves the SM.
+//
+// One CTA works on one (constraint j, PSD block k) pair at a time (pairs are handed out by an atomic counter):
+//   1. T = sym(A_jk)(R,:) D_k, r x n, written to this CTA's private scratch slot (global memory, but the slot is
+//      re-used for every pair the CTA processes, so it lives in L2 and is never streamed from HBM);
+//   2. W = D_k(:,R) T on the FP64 tensor pipe (DMMA m8n8k4): a warp owns one 32x32 supertile of the LOWER triangle
+//      per round (4x4 fragments, clipped at the diagonal and at n; n = 200 needs two rounds of 16 warps), operands
+//      staged through a two-stage cp.async ring of 8-deep k-slabs; the accumulators go to shared memory as the
+//      packed lower triangle of W;
+//   3. every constraint i of block k that precedes j in the ordering takes <A_ik, W> from shared memory
+//      (dots_partners, the same code the unfused kernel uses), writes ADA(i,j) / per-pair partial sums and absd.
+// The unfused path materialised W (n^2 doubles per pair) in HBM between a GEMM launch and a dots launch: 7x the
+// algorithmic traffic of getada3 (profiles/traffic_r01.json).  Reference: getada3.c:305-351, spscale.c:249-305.
+#pragma once
+
+namespace sb {
+
+static const int FUSED_MAX_N = 208;                 // 7 x 7 supertiles -> 28 warps; W (packed) + the staging ring fit 227 KB
+static const int FKC = 8;                            // k-slab depth (two DMMA k-steps)
+static const int FUSED_GEMM_WARPS = 16;              // warps that hold a 32x32 accumulator tile in one round
+
+struct FusedArgs {
+  const AdaPair *pairs; int npairs;
+  int *counter;
+  const int *blk_n; const long long *blk_off;
+  const int *tt_ptr, *tt_col; const double *tt_val;  // per (pair, row of R): entries (column, weight*value)
+  const int *Rlist;
+  const double *udsqr;
+  double *scratch; long long scratch_stride;         // per-CTA T slot
+  // dots
+  const long long *adajc; const int *adair; const int *invperm; int first;
+  const int *cpair_beg; const int *blkp_beg; const BlkPartner *blkp;
+  const int *ent_pk; const int *ent_src; const double *Atpr;
+  double *ws, *ada, *absd;
+  const int *blk_group;
+  const int *blk_item_beg; const int2 *items;        // per block: its lower supertiles (I, J), most expensive first
+  int wcap, ldmax;
+};
+
+__device__ __forceinline__ int fused_ld(int n) { return ((n + 7) & ~7) + 4; }   // == 4 (mod 8): conflict-free fragment loads
+
+// one k-slab of both operands, global -> shared:  As[kk][p] = D[p + R[k0+kk] n],  Bs[kk][q] = Tt[q + (k0+kk) n]
+__device__ __forceinline__ void fused_stage(double *As, double *Bs, int ld, const double *D, const double *Tt, const int *R,
+                                            int n, int r, int k0, bool vec) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (vec) {                                         // n even, 16-byte aligned bases
+    const int half = n >> 1, tot = FKC * half;
+    for (int idx = tid; idx < 2 * tot; idx += nt) {
+      const int which = idx >= tot, e = which ? idx - tot : idx;
+      const int kk = e / half, p = (e - kk * half) * 2, k = k0 + kk;
+      if (k < r) {
+        const double *src = which ? (Tt + p + (long long)k * n) : (D + p + (long long)R[k] * n);
+        cp_async_16((which ? Bs : As) + kk * ld + p, src);
+      } else { double *dst = (which ? Bs : As) + kk * ld + p; dst[0] = 0.0; dst[1] = 0.0; }
+    }
+  } else {
+    const int tot = FKC * n;
+    for (int idx = tid; idx < 2 * tot; idx += nt) {
+      const int which = idx >= tot, e = which ? idx - tot : idx;
+      const int kk = e / n, p = e - kk * n, k = k0 + kk;
+      const bool nz = k < r;
+      const double *src = !nz ? D : (which ? (Tt + p + (long long)k * n) : (D + p + (long long)R[k] * n));
+      cp_async_8((which ? Bs : As) + kk * ld + p, src, nz ? 8 : 0);
+    }
+  }
+}
+
+template <int NTHREADS, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedArgs A) {
+  extern __shared__ __align__(16) double fsm[];
+  double *Wp = fsm;                                             // packed lower triangle of W, wcap doubles
+  double *stA = fsm + A.wcap;                                   // [2][FKC][ldmax]
+  double *stB = stA + 2 * FKC * A.ldmax;
+  __shared__ int s_pair;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int qr = lane >> 2, qc = lane & 3;
+  double *Tt = A.scratch + (long long)blockIdx.x * A.scratch_stride;
+  for (;;) {
+    if (tid == 0) s_pair = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int pi = s_pair;
+    if (pi >= A.npairs) break;
+    const AdaPair P = A.pairs[pi];
+    const int n = A.blk_n[P.k], r = P.r, ld = fused_ld(n);
+    const double *D = A.udsqr + A.blk_off[P.k];
+    const int *R = A.Rlist + P.r0;
+    // ---------------- 1. T (as Tt: n x r, column rho = row R[rho] of sym(A) D): one warp per row, lanes over columns
+    {
+      const int *ptr = A.tt_ptr + P.r0;
+      for (int rho = warp; rho < r; rho += nw) {
+        double acc[(FUSED_MAX_N + 31) / 32];
+#pragma unroll
+        for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) acc[ch] = 0.0;
+        const int t0 = ptr[rho], t1 = ptr[rho + 1];
+        for (int t = t0; t < t1; t++) {
+          const double v = A.tt_val[t];
+          const double *Dc = D + (long long)A.tt_col[t] * n;
+#pragma unroll
+          for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) {
+            const int c = lane + 32 * ch;
+            if (c < n) acc[ch] += v * Dc[c];
+          }
+        }
+        double *dst = Tt + (long long)rho * n;
+#pragma unroll
+        for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) {
+          const int c = lane + 32 * ch;
+          if (c < n) dst[c] = acc[ch];
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- 2. W = D(:,R) T on the lower supertiles, in rounds of at most FUSED_GEMM_WARPS items
+    // (the accumulators of the whole lower triangle -- 325 fragments at n = 200 -- do not fit the register file next to
+    // anything else; the planner sorts the items of a block by cost, so a round costs what its first item costs)
+    {
+      const int ib = A.blk_item_beg[P.k], ie = A.blk_item_beg[P.k + 1];
+      const int nwg = min(nw, FUSED_GEMM_WARPS);
+      const bool vec = ((n & 1) == 0) && ((((unsigned long long)D) & 15) == 0) && ((((unsigned long long)Tt) & 15) == 0);
+      const int nslab = (r + FKC - 1) / FKC;
+      for (int it0 = ib; it0 < ie; it0 += nwg) {
+        const bool have = warp < nwg && it0 + warp < ie;
+        const int2 IJ = have ? A.items[it0 + warp] : make_int2(0, 0);
+        const int rb = 32 * IJ.x, cb = 32 * IJ.y;
+        const int nra = have ? min(4, (n - rb + 7) >> 3) : 0;       // fragment rows / columns inside n
+        const int ncb = have ? min(4, (n - cb + 7) >> 3) : 0;
+        const bool diag = (IJ.x == IJ.y);
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        if (nslab > 0) fused_stage(stA, stB, ld, D, Tt, R, n, r, 0, vec);
+        cp_async_commit();
+        for (int s = 0; s < nslab; s++) {
+          const int buf = s & 1;
+          cp_async_wait_all();
+          __syncthreads();                                        // slab s visible; everyone is done with slab s-1
+          if (s + 1 < nslab) fused_stage(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
+          cp_async_commit();
+          const double *As = stA + buf * FKC * A.ldmax + rb + qr, *Bs = stB + buf * FKC * A.ldmax + cb + qr;
+#pragma unroll
+          for (int k4 = 0; k4 < FKC; k4 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int b = 0; b < 4; b++)
+                if (a < nra && b < ncb && (!diag || a >= b)) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          }
+        }
+        cp_async_wait_all();
+        // accumulators -> packed lower triangle: (p, q), p >= q, at q (2n - q + 1)/2 - q + p
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int p = rb + 8 * a + qr, q = cb + 8 * b + 2 * qc + e;
+              if (a < nra && b < ncb && p < n && q < n && p >= q) Wp[(q * (2 * n - q + 1)) / 2 - q + p] = acc[a][b][e];
+            }
+        __syncthreads();                                          // the ring is re-used by the next round
+      }
+    }
+    __syncthreads();
+    // ---------------- 3. inner products with the partners of block k
+    {
+      const int c = P.j;
+      const bool multi = A.cpair_beg[c + 1] - A.cpair_beg[c] > 1;
+      const int ipc = A.invperm[c];
+      const long long colbeg = A.adajc[c];
+      ColSlots cs{A.adair + colbeg, (int)(A.adajc[c + 1] - colbeg), nullptr};
+      if (!multi) {
+        if (tid == 0) {
+          const int sd = ipc >= A.first ? cs.find(c) : -1;
+          A.absd[c] = sd >= 0 ? A.ada[colbeg + sd] : 0.0;
+        }
+        __syncthreads();
+      }
+      DotsCtx X;
+      X.P = P; X.P.part_off = P.fpart_off; X.c = c; X.ipc = ipc; X.first = A.first; X.multi = multi ? 1 : 0;
+      X.warp = warp; X.lane = lane; X.nw = nw; X.colbeg = colbeg; X.cs = cs; X.eidx = A.ent_pk; X.Wp = Wp;
+      X.blkp_beg = A.blkp_beg; X.blkp = A.blkp; X.invperm = A.invperm; X.Atpr = A.Atpr; X.ent_src = A.ent_src;
+      X.ent_scale = nullptr; X.ws = A.ws; X.ada = A.ada; X.absd = A.absd;
+      switch (A.blk_group[P.k]) {
+        case 4: dots_partners<4>(X); break;
+        case 8: dots_partners<8>(X); break;
+        case 16: dots_partners<16>(X); break;
+        default: dots_partners<32>(X); break;
+      }
+    }
+    __syncthreads();                                            // Wp, s_pair and the scratch slot are re-used by the next pair
+  }
+}
+
+}  // namespace sb

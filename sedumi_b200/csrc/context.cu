@@ -307,10 +307,15 @@ int sb200_graph_begin(void) {
   SB_TRY(sb::ensure_init());
   SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
   SB_CUDA(cudaStreamBeginCapture(sb::ctx().stream, cudaStreamCaptureModeThreadLocal));
+  sb::ctx().capturing = true;
+  // profiling a captured iteration: the event records become graph nodes, so the intervals measured after a replay
+  // are pure device time (no host launch gaps); the first marker opens the first interval
+  if (sb::ctx().profiling) { sb::g_prof.used = 0; sb::prof_mark("__begin__"); }
   return 0;
 }
 int sb200_graph_end(void **graph_exec) {
   cudaGraph_t g = nullptr;
+  sb::ctx().capturing = false;
   SB_CUDA(cudaStreamEndCapture(sb::ctx().stream, &g));
   cudaGraphExec_t ge = nullptr;
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);

@@ -19,6 +19,7 @@ struct Context {
   int64_t launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by this library (every cudaMemcpyAsync, counted below)
   bool profiling = false;
+  bool capturing = false;                  // between sb200_graph_begin and sb200_graph_end
   // bump arena for per-call scratch (reset at the start of each public entry point)
   std::vector<std::pair<char *, size_t>> arena_chunks;
   size_t arena_cur = 0, arena_off = 0;

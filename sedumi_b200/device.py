@@ -393,6 +393,29 @@ class HotPath:
         self._graph = g
         return lambda: check(L.sb200_graph_launch(g), "graph_launch")
 
+    def profile(self, nsolve=4, npsdscale=12, sharded=False, graph=True):
+        """Per-kernel device time of ONE iteration: {kernel name: (launches, ms)}.  With graph=True the iteration is
+        captured with an event record after every launch and replayed once, so host launch gaps do not count."""
+        L = lib()
+        self.iteration(nsolve, npsdscale, sharded)
+        self.sync()
+        check(L.sb200_prof_begin(), "prof_begin")
+        if graph:
+            run = self.capture(nsolve, npsdscale, sharded)
+            run()
+            g = self._graph
+        else:
+            self.iteration(nsolve, npsdscale, sharded)
+        buf = C.create_string_buffer(1 << 16)
+        check(L.sb200_prof_end(buf, I64(len(buf))), "prof_end")
+        if graph:
+            L.sb200_graph_destroy(g)
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            nm, cnt, tot = ln.split()
+            out[nm] = (int(cnt), float(tot))
+        return out
+
     def sync(self):
         check(lib().sb200_sync(), "sync")
 
