@@ -1072,8 +1072,8 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax;
     static bool attr_done = false;
     if (!attr_done) {
-      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));   // + static
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
       attr_done = true;
     }
     if (pl->fused_small) ada3_fused_kernel<256, 2><<<pl->fused_grid, pl->fused_threads, pl->fused_smem, st>>>(FA);

@@ -123,7 +123,7 @@ __global__ void bounds_kernel(int m, const double *diagX, const double *absd, co
 // CTA = one UT_R x UT_C tile of ancestor panel J; loops over J's descendants in order.
 __global__ void __launch_bounds__(256)
 update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pair_beg,
-              const int *rel, const double *d, double *rect) {
+              const int *rel, const double *U, double *rect) {
   UTile tl = tiles[blockIdx.x];
   Sn sj = sn[tl.J];
   double *PJ = rect + sj.poff;
@@ -151,31 +151,87 @@ update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pa
     int nr = b - a, nc = cB - cA;
     if (nr <= 0 || nc <= 0) continue;
     Sn sk = sn[p.K];
-    const double *PK = rect + sk.poff + p.koff;       // row koff of K's panel
-    const double *dk = d + sk.first;
+    const int mk = sk.m - sk.n, u0 = p.koff - sk.n;   // U_K is indexed by K's rows below its diagonal block
+    const double *UK = U + sk.uoff;
     for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
       int t1 = a + idx % nr, t2 = cA + idx / nr;
       if (t1 < t2) continue;                           // strictly above the diagonal of J
-      double acc = 0.0;
-      const double *x1 = PK + t1, *x2 = PK + t2;
-      for (int kk = 0; kk < sk.n; kk++) {
-        double dkk = dk[kk];
-        acc += x1[(long long)kk * sk.m] * (dkk * x2[(long long)kk * sk.m]);
-      }
-      PJ[rl[t1] + (long long)rl[t2] * sj.m] -= acc;
+      PJ[rl[t1] + (long long)rl[t2] * sj.m] -= UK[(u0 + t1) + (long long)(u0 + t2) * mk];
+    }
+  }
+}
+
+// ======================================================================= Schur contributions
+// U_K = L21 D L21' (lower triangle) for every supernode of a list: blockIdx.x = supernode, blockIdx.y = lower 64x64
+// tile.  Skipped pivots have d = 0 and drop out (blkchol2.c:375,389).
+__global__ void __launch_bounds__(256)
+schur_kernel(const int *list, const Sn *sn, const double *rect, const double *d, double *U) {
+  const Sn s = sn[list[blockIdx.x]];
+  const int mk = s.m - s.n;
+  if (mk <= 0) return;
+  const int nt = (mk + 63) / 64;
+  int t = blockIdx.y;
+  if (t >= nt * (nt + 1) / 2) return;
+  int ti = 0;
+  while (t > ti) { t -= ti + 1; ti++; }
+  const int r0 = ti * 64, c0 = t * 64;
+  __shared__ double As[16][64 + 1], Bs[16][64 + 1];
+  const double *P = rect + s.poff + s.n;
+  const double *dk = d + s.first;
+  const int ld = s.m;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < s.n; k0 += 16) {
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += blockDim.x) {
+      const int i = idx % 64, j = idx / 64, kk = k0 + j;
+      const bool in = kk < s.n;
+      As[j][i] = (in && r0 + i < mk) ? P[(long long)kk * ld + r0 + i] : 0.0;
+      Bs[j][i] = (in && c0 + i < mk) ? P[(long long)kk * ld + c0 + i] * dk[kk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { av[i] = As[j][tx + 16 * i]; bv[i] = Bs[j][ty + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[i][q] += av[i] * bv[q];
+    }
+    __syncthreads();
+  }
+  double *UK = U + s.uoff;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int c = c0 + ty + 16 * q;
+    if (c >= mk) continue;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = r0 + tx + 16 * i;
+      if (r < mk && r >= c) UK[r + (long long)c * mk] = acc[i][q];
     }
   }
 }
 
 // ======================================================================= small supernodes
-// One CTA factors one whole supernode panel (m x n, in global/L2), column by column.
+// One CTA factors one whole supernode panel (m x n), column by column; the panel is staged in shared memory when it
+// fits (cap doubles), otherwise worked on in place (L2).
 __global__ void __launch_bounds__(512)
 factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, const double *lb,
                     const double *scal, double maxu, int *flag, double *sval,
-                    const double *diagX, int mtot) {
+                    const double *diagX, int mtot, int cap) {
+  extern __shared__ double pan[];
   Sn s = sn[list[blockIdx.x]];
-  double *P = rect + s.poff;
+  double *Pg = rect + s.poff;
   const int ld = s.m, n = s.n, m = s.m;
+  const bool insm = (long long)m * n <= cap;
+  double *P = Pg;
+  if (insm) {
+    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) pan[idx] = Pg[idx];
+    P = pan;
+    __syncthreads();
+  }
   const double ub = scal[0];
   __shared__ ArgMax sh_am[32];
   __shared__ double s_x;
@@ -223,6 +279,10 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
     for (int r = k + 1 + threadIdx.x; r < m; r += blockDim.x) ck[r] /= xkk;
     if (threadIdx.x == 0) { d[gk] = xkk; ck[k] = 1.0; }
     __syncthreads();
+  }
+  if (insm) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) Pg[idx] = pan[idx];
   }
 }
 
@@ -428,26 +488,22 @@ __global__ void csc_to_rect_kernel(const Sn *sn, const int *snode, const long lo
 // Forward: one CTA per (supernode of the level, rhs).  y has length m per rhs, already = b(perm).
 __global__ void __launch_bounds__(512)
 fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair_beg, const int *rel,
-               const double *rect, double *y, int m, int solve) {
+               const double *rect, double *y, int m, int solve, double *cvec, long long ctot) {
   extern __shared__ double sm[];             // s[n]
   Sn sj = sn[list[blockIdx.x]];
   double *yy = y + (long long)blockIdx.y * m;
+  double *cv = cvec + (long long)blockIdx.y * ctot;
   const int n = sj.n;
   double *s = sm;
   for (int c = threadIdx.x; c < n; c += blockDim.x) s[c] = yy[sj.first + c];
   __syncthreads();
-  // pull contributions of descendants:  s[col] -= L_K[row, :] * y_K
+  // pull the contributions c_K = L21_K y_K of the descendants, in list order:  s[col] -= c_K[row]
   for (int e = pair_beg[list[blockIdx.x]]; e < pair_beg[list[blockIdx.x] + 1]; e++) {
     Pair p = pairs[e];
     Sn sk = sn[p.K];
-    const double *PK = rect + sk.poff + p.koff;
-    const double *yk = yy + sk.first;
+    const double *ck = cv + sk.cvoff + (p.koff - sk.n);
     const int *rl = rel + p.rel;
-    for (int t = threadIdx.x; t < p.ncolup; t += blockDim.x) {
-      double acc = 0.0;
-      for (int kk = 0; kk < sk.n; kk++) acc += PK[(long long)kk * sk.m + t] * yk[kk];
-      s[rl[t]] -= acc;                       // rl[t] < n: distinct per t inside one pair
-    }
+    for (int t = threadIdx.x; t < p.ncolup; t += blockDim.x) s[rl[t]] -= ck[t];     // rl[t] < n: distinct per t inside one pair
     __syncthreads();
   }
   // dense unit-lower solve of the n x n diagonal block, 32 columns at a time (solve = 0: pull only, used by the
@@ -474,6 +530,34 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
     __syncthreads();
   }
   for (int c = threadIdx.x; c < n; c += blockDim.x) yy[sj.first + c] = s[c];
+  // this supernode's own contribution to its ancestors: c_J = L21 y_J
+  const int mk = sj.m - n;
+  if (solve && mk > 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double *cj = cv + sj.cvoff;
+    if (mk >= 256) {                                      // long tails: one thread per row (coalesced over rows)
+      for (int t = threadIdx.x; t < mk; t += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < n; k++) acc += P[(long long)k * ld + n + t] * s[k];
+        cj[t] = acc;
+      }
+    } else {                                              // short tails: 32 rows per warp pass, columns split over warps
+      __syncthreads();
+      double *part = sm + n;                              // [nw][mk] partial sums (the launcher sizes shared memory for it)
+      for (int t0 = 0; t0 < mk; t0 += 32) {
+        const int t = t0 + lane;
+        double acc = 0.0;
+        if (t < mk) for (int k = warp; k < n; k += nw) acc += P[(long long)k * ld + n + t] * s[k];
+        if (t < mk) part[warp * mk + t] = acc;
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < mk; t += blockDim.x) {
+        double acc = 0.0;
+        for (int w = 0; w < nw; w++) acc += part[w * mk + t];
+        cj[t] = acc;
+      }
+    }
+  }
 }
 
 // Backward: z = L'^-1 b in permuted order, levels descending.
@@ -548,6 +632,52 @@ __global__ void scatter_perm_kernel(int m, int nrhs, const int *perm, const doub
 // =========================================================================== host side
 using namespace sb;
 
+// one CTA factors the whole panel: narrow supernodes, or any panel that fits the CTA's shared memory
+static inline bool sn_is_small(const sb200_chol_plan *pl, const Sn &S) {
+  return S.n <= SMALL_N || (size_t)S.m * S.n <= pl->small_cap;
+}
+static inline size_t small_shm(const sb200_chol_plan *pl, const std::vector<int> &list) {
+  size_t need = 0;
+  for (int s : list) { const size_t e = (size_t)pl->sn[s].m * pl->sn[s].n; if (e <= pl->small_cap) need = std::max(need, e); }
+  return need * sizeof(double);
+}
+static inline int schur_tiles(const sb200_chol_plan *pl, const std::vector<int> &list) {
+  int mx = 0;
+  for (int s : list) { const int nt = (pl->sn[s].m - pl->sn[s].n + 63) / 64; mx = std::max(mx, nt * (nt + 1) / 2); }
+  return mx;
+}
+static int launch_factor_small(sb200_chol_plan *pl, const std::vector<int> &list, const int *list_dev, sb200_chol_pars pars, double *rect,
+                               double *d, int *flag, double *sval) {
+  if (list.empty()) return 0;
+  const size_t shm = small_shm(pl, list);
+  static size_t attr = 0;
+  if (shm > attr) { SB_CUDA(cudaFuncSetAttribute(factor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pl->small_cap * sizeof(double)))); attr = pl->small_cap * sizeof(double); }
+  factor_small_kernel<<<(unsigned)list.size(), 512, shm, ctx().stream>>>(list_dev, pl->d_sn.p, rect, d, pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval,
+                                                                          pl->d_diagX.p, pl->m, (int)pl->small_cap);
+  SB_LAUNCH_CHECK_N("factor_small_kernel");
+  return 0;
+}
+static int launch_schur(sb200_chol_plan *pl, const std::vector<int> &list, const int *list_dev, const double *rect, const double *d) {
+  const int nt = schur_tiles(pl, list);
+  if (list.empty() || nt == 0) return 0;
+  schur_kernel<<<dim3((unsigned)list.size(), (unsigned)nt), 256, 0, ctx().stream>>>(list_dev, pl->d_sn.p, rect, d, pl->d_U.p);
+  SB_LAUNCH_CHECK_N("schur_kernel");
+  return 0;
+}
+// shared memory of a forward-solve CTA: the supernode's part of y + the per-warp partial sums of its contribution
+static inline size_t fw_shm(const sb200_chol_plan *pl) {
+  size_t need = 0;
+  for (auto &S : pl->sn) { const int mk = S.m - S.n; need = std::max(need, (size_t)S.n + (mk < 256 ? (size_t)16 * mk : 0)); }
+  return need * sizeof(double);
+}
+static int ensure_cvec(sb200_chol_plan *pl, int nrhs) {
+  if (pl->cvec_nrhs >= nrhs && pl->d_cvec.p) return 0;
+  SB_CHECK(!ctx().capturing, "solve: the contribution workspace must be sized before graph capture (run one solve first)");
+  SB_TRY(pl->d_cvec.alloc((size_t)std::max<long long>(pl->ctot, 1) * nrhs));
+  pl->cvec_nrhs = nrhs;
+  return 0;
+}
+
 static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb_idx *xsuper,
                       const sb_idx *Ljc, const sb_idx *Lir, const sb_idx *perm,
                       const sb_idx *Xjc, const sb_idx *Xir) {
@@ -586,6 +716,21 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
     pl->max_sn_m = std::max(pl->max_sn_m, S.m);
   }
   pl->rect = poff;
+  // contribution blocks (Schur complement of every supernode on its rows below the diagonal block, and its share of
+  // the forward solve): offsets
+  {
+    long long uo = 0, co = 0;
+    for (int s = 0; s < nsuper; s++) {
+      Sn &S = pl->sn[s];
+      const long long mk = S.m - S.n;
+      S.uoff = uo; S.cvoff = (int)co; S.pad_ = 0;
+      uo += mk * mk; co += mk;
+      pl->max_mk = std::max(pl->max_mk, (int)mk);
+    }
+    SB_CHECK(co < 2147483647LL, "blkchol: factor too large for 32-bit contribution offsets");
+    pl->utot = uo; pl->ctot = co;
+    pl->small_cap = 27000;                               // 216 KB of shared memory for a factor CTA's panel
+  }
   // update pairs
   std::vector<std::vector<Pair>> byJ(nsuper);
   std::vector<int> rel;
@@ -626,7 +771,7 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
   pl->level_all.assign(nlev, {});
   for (int s = 0; s < nsuper; s++) {
     int lv = pl->level_of[s];
-    (pl->sn[s].n <= SMALL_N ? pl->level_small : pl->level_big)[lv].push_back(s);
+    (sn_is_small(pl, pl->sn[s]) ? pl->level_small : pl->level_big)[lv].push_back(s);
     pl->level_all[lv].push_back(s);
     if (pl->pair_beg[s + 1] > pl->pair_beg[s]) {
       const Sn &S = pl->sn[s];
@@ -666,6 +811,7 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
   SB_TRY(pl->d_lb.alloc(m));
   SB_TRY(pl->d_scal.alloc(8));
   SB_TRY(pl->d_vscratch.alloc(std::max(pl->max_sn_m, 1)));
+  if (nsuper > 1) SB_TRY(pl->d_U.alloc((size_t)std::max<long long>(pl->utot, 1)));
   pl->dense_fast = (nsuper == 1 && m >= 1 && pl->sn[0].m == m && pl->sn[0].n == m &&
                     (size_t)m * 8 + 8 * 2 * 1024 * 8 + 8192 <= 200 * 1024);   // shared memory of the dataflow solves
   if (pl->dense_fast) SB_TRY(dense_factor_prepare(pl));
@@ -715,15 +861,10 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
     int ntile = (int)pl->level_tiles[lv].size();
     if (ntile) {
       update_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_pairs.p,
-                                            pl->d_pair_beg.p, pl->d_rel.p, d, rect);
+                                            pl->d_pair_beg.p, pl->d_rel.p, pl->d_U.p, rect);
       SB_LAUNCH_CHECK_N("update_kernel");
     }
-    int nsmall = (int)pl->level_small[lv].size();
-    if (nsmall) {
-      factor_small_kernel<<<nsmall, 512, 0, st>>>(pl->d_level_list.p + pl->level_small_off[lv], pl->d_sn.p, rect, d,
-                                                   pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m);
-      SB_LAUNCH_CHECK_N("factor_small_kernel");
-    }
+    SB_TRY(launch_factor_small(pl, pl->level_small[lv], pl->d_level_list.p + pl->level_small_off[lv], pars, rect, d, flag, sval));
     for (int s : pl->level_big[lv]) {
       const Sn &S = pl->sn[s];
       for (int p0 = 0; p0 < S.n; p0 += NB) {
@@ -744,6 +885,7 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
         }
       }
     }
+    if (lv + 1 < pl->nlevels) SB_TRY(launch_schur(pl, pl->level_all[lv], pl->d_level_all.p + pl->level_all_off[lv], rect, d));
   }
   return 0;
 }
@@ -772,13 +914,14 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   long long tot = (long long)m * nrhs;
   gather_perm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(m, (int)nrhs, pl->d_perm.p, b, y);
   SB_LAUNCH_CHECK_N("gather_perm_kernel");
-  size_t shm = sizeof(double) * (size_t)pl->max_sn_n;
+  size_t shm = fw_shm(pl);
   SB_CHECK(shm <= 200 * 1024, "fwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
   if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(fwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  SB_TRY(ensure_cvec(pl, (int)nrhs));
   for (int lv = 0; lv < pl->nlevels; lv++) {
     dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
     fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pairs.p,
-                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1);
+                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
@@ -919,7 +1062,7 @@ int sb200_chol_shard_create(sb200_chol_plan *pl, sb_idx world64, sb_idx rank64) 
   };
   for (int s2 = 0; s2 < ns; s2++) {
     const int lv = pl->level_of[s2];
-    const bool small = pl->sn[s2].n <= SMALL_N;
+    const bool small = sn_is_small(pl, pl->sn[s2]);
     if (s2 < t0) {
       if (sh->owner[s2] != rank) continue;
       (small ? sh->own_small : sh->own_big)[lv].push_back(s2); sh->own_all[lv].push_back(s2);
@@ -979,15 +1122,11 @@ static int shard_factor_levels(sb200_chol_plan *pl, bool top, sb200_chol_pars pa
     const int ntile = top ? sh->top_tile_cnt[lv] : sh->own_tile_cnt[lv];
     if (ntile) {
       update_kernel<<<ntile, 256, 0, st>>>(sh->d_tiles.p + (top ? sh->top_tile_off[lv] : sh->own_tile_off[lv]), pl->d_sn.p,
-                                            top ? sh->d_pairsB.p : pl->d_pairs.p, top ? sh->d_pair_begB.p : pl->d_pair_beg.p, pl->d_rel.p, d, rect);
+                                            top ? sh->d_pairsB.p : pl->d_pairs.p, top ? sh->d_pair_begB.p : pl->d_pair_beg.p, pl->d_rel.p, pl->d_U.p, rect);
       SB_LAUNCH_CHECK_N("update_kernel");
     }
     const auto &small = top ? sh->top_small[lv] : sh->own_small[lv];
-    if (!small.empty()) {
-      factor_small_kernel<<<(unsigned)small.size(), 512, 0, st>>>(sh->d_lists.p + (top ? sh->top_small_off[lv] : sh->own_small_off[lv]), pl->d_sn.p, rect, d,
-                                                                   pl->d_lb.p, pl->d_scal.p, pars.maxu, flag, sval, pl->d_diagX.p, m);
-      SB_LAUNCH_CHECK_N("factor_small_kernel");
-    }
+    SB_TRY(launch_factor_small(pl, small, sh->d_lists.p + (top ? sh->top_small_off[lv] : sh->own_small_off[lv]), pars, rect, d, flag, sval));
     for (int s2 : (top ? sh->top_big[lv] : sh->own_big[lv])) {
       const Sn &S = pl->sn[s2];
       for (int p0 = 0; p0 < S.n; p0 += NB) {
@@ -1006,6 +1145,11 @@ static int shard_factor_levels(sb200_chol_plan *pl, bool top, sb200_chol_pars pa
           }
         }
       }
+    }
+    // contributions of this level's supernodes (own trees: they feed later own levels and the top; top: later top levels)
+    {
+      const auto &all = top ? sh->top_all[lv] : sh->own_all[lv];
+      SB_TRY(launch_schur(pl, all, sh->d_lists.p + (top ? sh->top_all_off[lv] : sh->own_all_off[lv]), rect, d));
     }
   }
   return 0;
@@ -1030,7 +1174,7 @@ int sb200_blkchol_shard_local_dev(sb200_chol_plan *pl, const double *Xpr, const 
   if (sh->rank != 0 && sh->top_rect_len) SB_CUDA(cudaMemsetAsync(rect + sh->top_rect_off, 0, sizeof(double) * sh->top_rect_len, st));
   SB_TRY(shard_factor_levels(pl, false, pars, rect, d, flag, sval));
   if (sh->topA_tile_cnt) {
-    update_kernel<<<sh->topA_tile_cnt, 256, 0, st>>>(sh->d_tiles.p + sh->topA_tile_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, d, rect);
+    update_kernel<<<sh->topA_tile_cnt, 256, 0, st>>>(sh->d_tiles.p + sh->topA_tile_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, pl->d_U.p, rect);
     SB_LAUNCH_CHECK_N("update_kernel");
   }
   return 0;
@@ -1042,7 +1186,7 @@ int sb200_blkchol_shard_top_dev(sb200_chol_plan *pl, sb200_chol_pars pars, doubl
   return shard_factor_levels(pl, true, pars, rect, d, flag, sval);
 }
 
-static size_t shard_solve_shm(sb200_chol_plan *pl) { return sizeof(double) * (size_t)pl->max_sn_n; }
+static size_t shard_solve_shm(sb200_chol_plan *pl) { return std::max(fw_shm(pl), sizeof(double) * (size_t)pl->max_sn_n); }
 // Forward, phase 1: y = b(perm) (top rows zeroed off rank 0), own trees, pull into the top rows.  Then all-reduce
 // y[top_col0 .. m) per right-hand side.
 int sb200_fw_shard_local_dev(sb200_chol_plan *pl, const double *rect, const double *b, double *y, sb_idx nrhs) {
@@ -1060,15 +1204,16 @@ int sb200_fw_shard_local_dev(sb200_chol_plan *pl, const double *rect, const doub
   const size_t shm = shard_solve_shm(pl);
   SB_CHECK(shm <= 200 * 1024, "fwblkslv: supernode wider than the shared-memory solve supports (%d)", pl->max_sn_n);
   if (shm > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(fwsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  SB_TRY(ensure_cvec(pl, (int)nrhs));
   for (int lv = 0; lv < pl->nlevels; lv++) {
     if (sh->own_all[lv].empty()) continue;
     dim3 g((unsigned)sh->own_all[lv].size(), (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_pairs.p, pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_pairs.p, pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   if (sh->top_list_cnt) {
     dim3 g((unsigned)sh->top_list_cnt, (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_list_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, rect, y, m, 0);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_list_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, rect, y, m, 0, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
@@ -1088,7 +1233,7 @@ int sb200_solve_shard_top_dev(sb200_chol_plan *pl, const double *rect, const dou
   for (int lv = 0; lv < pl->nlevels; lv++) {
     if (sh->top_all[lv].empty()) continue;
     dim3 g((unsigned)sh->top_all[lv].size(), (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, sh->d_pairsB.p, sh->d_pair_begB.p, pl->d_rel.p, rect, y, m, 1);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, sh->d_pairsB.p, sh->d_pair_begB.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   const long long tot = (long long)m * nrhs;

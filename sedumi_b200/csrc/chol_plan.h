@@ -15,6 +15,9 @@ struct Sn {        // one supernode
   int lindx;       // offset of its row list in lindx[]
   long long poff;  // offset of its m x n panel in the rect layout (ld = m)
   long long coff;  // offset of its first column in the packed CSC value array (= Ljc[first])
+  long long uoff;  // offset of its Schur contribution U = L21 D L21' ((m-n) x (m-n), lower triangle, ld = m-n)
+  int cvoff;       // offset of its forward-solve contribution L21 y ((m-n) doubles)
+  int pad_;
 };
 struct Pair {      // update of ancestor J by descendant K
   int K, J;
@@ -50,6 +53,13 @@ struct sb200_chol_plan {
   sb::DevBuf<long long> d_Ljc;
   // numeric scratch
   sb::DevBuf<double> d_diagX, d_lb, d_scal, d_vscratch, d_y;
+  // contribution blocks of the multi-supernode path: every supernode K forms U_K = L21 D L21' right after it is
+  // factored (all supernodes of a level in one launch); its ancestors then only ADD entries of U_K, in list order.
+  // The forward solve does the same with the vectors c_K = L21 y_K.
+  sb::DevBuf<double> d_U, d_cvec;
+  long long utot = 0, ctot = 0;
+  int cvec_nrhs = 0, max_mk = 0;
+  size_t small_cap = 0;          // doubles of shared memory a factor CTA may use for its panel
   // dense fast path (one supernode spanning the whole matrix): working copy, inverted diagonal
   // blocks (32x32 each, column-major), grid-barrier counter, solve flags
   bool dense_fast = false;
