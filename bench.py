@@ -404,7 +404,7 @@ def device_run(W, args, rank, world, local_rank, sharded, dist, steps, warmup, w
         out.comm["collectives_per_iteration"] = cs1[0] - cs0[0]
         out.comm["allreduce_bytes_per_iteration"] = cs1[1] - cs0[1]
         barrier()
-        prof = hp.profile(NSOLVE, NPSD, sharded, graph=not args.no_graph)      # one replay of an event-instrumented graph
+        prof = hp.profile(NSOLVE, NPSD, sharded)
         barrier()
         out.roof = None
         if rank == 0 and prof:

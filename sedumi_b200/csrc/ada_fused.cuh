@@ -39,29 +39,28 @@ struct FusedArgs {
 
 __device__ __forceinline__ int fused_ld(int n) { return ((n + 7) & ~7) + 4; }   // == 4 (mod 8): conflict-free fragment loads
 
-// one k-slab of both operands, global -> shared:  As[kk][p] = D[p + R[k0+kk] n],  Bs[kk][q] = Tt[q + (k0+kk) n]
+// one k-slab of both operands, global -> shared:  As[kk][p] = D[p + R[k0+kk] n],  Bs[kk][q] = Tt[q + (k0+kk) n].
+// Thread t serves k-row kk = t / TPR with TPR = blockDim / 8 threads per row (no divisions: TPR is a power of two).
+template <int TPR_LOG2>
 __device__ __forceinline__ void fused_stage(double *As, double *Bs, int ld, const double *D, const double *Tt, const int *R,
                                             int n, int r, int k0, bool vec) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (vec) {                                         // n even, 16-byte aligned bases
-    const int half = n >> 1, tot = FKC * half;
-    for (int idx = tid; idx < 2 * tot; idx += nt) {
-      const int which = idx >= tot, e = which ? idx - tot : idx;
-      const int kk = e / half, p = (e - kk * half) * 2, k = k0 + kk;
-      if (k < r) {
-        const double *src = which ? (Tt + p + (long long)k * n) : (D + p + (long long)R[k] * n);
-        cp_async_16((which ? Bs : As) + kk * ld + p, src);
-      } else { double *dst = (which ? Bs : As) + kk * ld + p; dst[0] = 0.0; dst[1] = 0.0; }
+  const int kk = threadIdx.x >> TPR_LOG2, l = threadIdx.x & ((1 << TPR_LOG2) - 1), k = k0 + kk;
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(As + kk * ld), sb = (unsigned)__cvta_generic_to_shared(Bs + kk * ld);
+  if (k < r) {
+    const double *srcA = D + (long long)R[k] * n, *srcB = Tt + (long long)k * n;
+    if (vec) {                                       // n even, 16-byte aligned bases
+      for (int p = 2 * l; p < n; p += 2 << TPR_LOG2) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa + 8u * p), "l"(srcA + p) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sb + 8u * p), "l"(srcB + p) : "memory");
+      }
+    } else {
+      for (int p = l; p < n; p += 1 << TPR_LOG2) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa + 8u * p), "l"(srcA + p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sb + 8u * p), "l"(srcB + p) : "memory");
+      }
     }
-  } else {
-    const int tot = FKC * n;
-    for (int idx = tid; idx < 2 * tot; idx += nt) {
-      const int which = idx >= tot, e = which ? idx - tot : idx;
-      const int kk = e / n, p = e - kk * n, k = k0 + kk;
-      const bool nz = k < r;
-      const double *src = !nz ? D : (which ? (Tt + p + (long long)k * n) : (D + p + (long long)R[k] * n));
-      cp_async_8((which ? Bs : As) + kk * ld + p, src, nz ? 8 : 0);
-    }
+  } else {                                           // beyond K: zero rows
+    for (int p = l; p < n; p += 1 << TPR_LOG2) { As[kk * ld + p] = 0.0; Bs[kk * ld + p] = 0.0; }
   }
 }
 
@@ -87,25 +86,53 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
     // ---------------- 1. T (as Tt: n x r, column rho = row R[rho] of sym(A) D): one warp per row, lanes over columns
     {
       const int *ptr = A.tt_ptr + P.r0;
-      for (int rho = warp; rho < r; rho += nw) {
-        double acc[(FUSED_MAX_N + 31) / 32];
+      const bool vec2 = ((n & 1) == 0) && ((((unsigned long long)D) & 15) == 0) && ((((unsigned long long)Tt) & 15) == 0);
+      if (vec2) {                                                // two columns per lane and load
+        constexpr int NCH = (FUSED_MAX_N / 2 + 31) / 32;
+        const int half = n >> 1;
+        for (int rho = warp; rho < r; rho += nw) {
+          double2 acc[NCH];
 #pragma unroll
-        for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) acc[ch] = 0.0;
-        const int t0 = ptr[rho], t1 = ptr[rho + 1];
-        for (int t = t0; t < t1; t++) {
-          const double v = A.tt_val[t];
-          const double *Dc = D + (long long)A.tt_col[t] * n;
+          for (int ch = 0; ch < NCH; ch++) acc[ch] = make_double2(0.0, 0.0);
+          const int t0 = ptr[rho], t1 = ptr[rho + 1];
+          for (int t = t0; t < t1; t++) {
+            const double v = A.tt_val[t];
+            const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)A.tt_col[t] * n);
 #pragma unroll
-          for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) {
+            for (int ch = 0; ch < NCH; ch++) {
+              const int c = lane + 32 * ch;
+              if (c < half) { const double2 x = Dc[c]; acc[ch].x += v * x.x; acc[ch].y += v * x.y; }
+            }
+          }
+          double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * n);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++) {
             const int c = lane + 32 * ch;
-            if (c < n) acc[ch] += v * Dc[c];
+            if (c < half) dst[c] = acc[ch];
           }
         }
-        double *dst = Tt + (long long)rho * n;
+      } else {
+        constexpr int NCH = (FUSED_MAX_N + 31) / 32;
+        for (int rho = warp; rho < r; rho += nw) {
+          double acc[NCH];
 #pragma unroll
-        for (int ch = 0; ch < (FUSED_MAX_N + 31) / 32; ch++) {
-          const int c = lane + 32 * ch;
-          if (c < n) dst[c] = acc[ch];
+          for (int ch = 0; ch < NCH; ch++) acc[ch] = 0.0;
+          const int t0 = ptr[rho], t1 = ptr[rho + 1];
+          for (int t = t0; t < t1; t++) {
+            const double v = A.tt_val[t];
+            const double *Dc = D + (long long)A.tt_col[t] * n;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+              const int c = lane + 32 * ch;
+              if (c < n) acc[ch] += v * Dc[c];
+            }
+          }
+          double *dst = Tt + (long long)rho * n;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ch++) {
+            const int c = lane + 32 * ch;
+            if (c < n) dst[c] = acc[ch];
+          }
         }
       }
     }
@@ -125,32 +152,54 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         const int nra = have ? min(4, (n - rb + 7) >> 3) : 0;       // fragment rows / columns inside n
         const int ncb = have ? min(4, (n - cb + 7) >> 3) : 0;
         const bool diag = (IJ.x == IJ.y);
+        const bool full = have && !diag && nra == 4 && ncb == 4;
+        unsigned tmask = 0;                                         // fragments of a clipped / diagonal supertile
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) if (a < nra && b < ncb && (!diag || a >= b)) tmask |= 1u << (a * 4 + b);
         double acc[4][4][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
           for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-        if (nslab > 0) fused_stage(stA, stB, ld, D, Tt, R, n, r, 0, vec);
+        constexpr int TPR_LOG2 = (NTHREADS == 512) ? 6 : 5;       // 8 k-rows x TPR threads = blockDim
+        if (nslab > 0) fused_stage<TPR_LOG2>(stA, stB, ld, D, Tt, R, n, r, 0, vec);
         cp_async_commit();
         for (int s = 0; s < nslab; s++) {
           const int buf = s & 1;
           cp_async_wait_all();
           __syncthreads();                                        // slab s visible; everyone is done with slab s-1
-          if (s + 1 < nslab) fused_stage(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
+          if (s + 1 < nslab) fused_stage<TPR_LOG2>(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
           cp_async_commit();
           const double *As = stA + buf * FKC * A.ldmax + rb + qr, *Bs = stB + buf * FKC * A.ldmax + cb + qr;
+          if (full) {                                             // interior supertile: no predicates in the inner loop
 #pragma unroll
-          for (int k4 = 0; k4 < FKC; k4 += 4) {
-            double af[4], bf[4];
+            for (int k4 = 0; k4 < FKC; k4 += 4) {
+              double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
+              for (int a = 0; a < 4; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
 #pragma unroll
-            for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
+              for (int b = 0; b < 4; b++) bf[b] = Bs[(k4 + qc) * ld + 8 * b];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+              for (int a = 0; a < 4; a++)
 #pragma unroll
-              for (int b = 0; b < 4; b++)
-                if (a < nra && b < ncb && (!diag || a >= b)) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+          } else if (have) {
+#pragma unroll
+            for (int k4 = 0; k4 < FKC; k4 += 4) {
+              double af[4], bf[4];
+#pragma unroll
+              for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
+#pragma unroll
+              for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
+#pragma unroll
+              for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                  if (tmask & (1u << (a * 4 + b))) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
           }
         }
         cp_async_wait_all();

@@ -212,6 +212,13 @@ void mirror_publish(void *slot_dev, const void *host, size_t bytes) {
     if (s.dev == slot_dev) { s.hash = hash128(host, bytes); s.bytes = bytes; s.stamp = ++g_mirror_clock; return; }
 }
 
+// keeps the stream busy for a few milliseconds so that the host can enqueue a whole iteration behind it: the event
+// intervals of the per-kernel profile are then pure device time, free of host launch gaps
+__global__ void prof_spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) { }
+}
+
 int ensure_init() {
   if (g_ctx.inited) return 0;
   return sb200_init(0);
@@ -274,6 +281,7 @@ int sb200_prof_begin(void) {
   SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
   sb::g_prof.used = 0;
   sb::ctx().profiling = true;
+  sb::prof_spin_kernel<<<1, 1, 0, sb::ctx().stream>>>(6000000LL);      // about 3 ms
   sb::prof_mark("__begin__");
   return 0;
 }
@@ -308,9 +316,6 @@ int sb200_graph_begin(void) {
   SB_CUDA(cudaStreamSynchronize(sb::ctx().stream));
   SB_CUDA(cudaStreamBeginCapture(sb::ctx().stream, cudaStreamCaptureModeThreadLocal));
   sb::ctx().capturing = true;
-  // profiling a captured iteration: the event records become graph nodes, so the intervals measured after a replay
-  // are pure device time (no host launch gaps); the first marker opens the first interval
-  if (sb::ctx().profiling) { sb::g_prof.used = 0; sb::prof_mark("__begin__"); }
   return 0;
 }
 int sb200_graph_end(void **graph_exec) {

@@ -3,7 +3,7 @@
 //
 // Reference semantics:
 //   dpr1fact.c:97-135    first pass over a column: pivot j is accepted while the implied multipliers
-//                        stay below maxu, otherwise postponed (fi, d, t recurrences)
+//                        stay below maxu, otherwise postponed
 //   dpr1fact.c:224-240   second pass over the postponed rows, sorted by decreasing p^2
 //   dpr1fact.c:280-477   dodpr1fact: dependent rows (d = 0), removal of one dependency when t > 0
 //   dpr1fact.c:495-512   findnewdep after a subtraction (smult < 0, Lorentz trace columns)
@@ -11,172 +11,79 @@
 //                        later columns that overlap it (auxfwdpr1.c:44-122)
 //   fwdpr1.c:70-90, bwdpr1.c:65-162   product-form forward / backward solves
 //
-// These are scalar recurrences with data-dependent pivot decisions; only the work across the
-// dense columns that follow (forward solves) and across right-hand sides is independent.  The kernels
-// keep the decision chain on one thread of a CTA and spread the independent pieces over the rest:
-// this keeps the factor on the device between blkchol and the solves, it is not a throughput kernel
-// (SURVEY.md section 8d lists it as latency-bound; it only runs when getdense finds dense columns).
+// GPU formulation.  The reference's loops are first-order recurrences, and first-order recurrences are scans:
+//   * factor:  t_{j+1} = t_j + x_j / d_j over the ACCEPTED pivots (x = p.^2): an exclusive prefix sum gives every
+//     t_j at once, from which fi_j = x_j + t_j d_j, the new d_j = fi_j / t_j and beta_j = p_j / fi_j follow
+//     elementwise.  Which pivots are accepted depends on t, so the stability test is evaluated speculatively for all
+//     rows under the current postponed set; the FIRST failing row is final (it only depends on earlier rows), it
+//     joins the postponed set and the scan is repeated -- (number of postponed rows + 1) block-wide passes, 1 pass
+//     in the common case.  Suffix maxima (mu), the running maximum over postponed rows, the stream compaction of
+//     the accepted pivots and the partition around dependent rows are scans as well; the postponed rows are ranked
+//     by a parallel counting sort and finished with one more prefix sum.
+//   * solves:  t_{i+1} = (1 - beta_i p_i) t_i + beta_i y_i  -- an affine map per row, composed by a block-wide
+//     scan of (a, b) pairs; the backward solve is the same recurrence run from the other end.
+// One CTA of 1024 threads per column (factor) / per (right-hand side) or per later column (solves).  Only the
+// bookkeeping of the short list of dependent rows (dpr1fact.c:362-376,495-512) is done by a single thread.
 #include <algorithm>
 #include "sb_internal.h"
 
 namespace sb {
 
 struct KD { double r; int k; };
+static const int DT = 1024;
 
-// forward solve with L(p,beta) = I + tril(p beta', -1), natural order (auxfwdpr1.c:44-77)
-__device__ void d_fwipr1(double *y, const double *p, const double *beta, int m, int n) {
-  if (n < 1) return;
-  double yi = y[0], betai = beta[0], t = 0.0;
-  int i = 1;
-  for (; i < n; i++) {
-    t += yi * betai;
-    yi = (y[i] -= t * p[i]);
-    betai = beta[i];
-  }
-  if (n < m) {
-    t += yi * betai;
-    for (; i < m; i++) y[i] -= t * p[i];
-  }
-}
-// ordered variant (auxfwdpr1.c:79-122)
-__device__ void d_fwipr1o(double *y, const int *perm, const double *p, const double *beta, int m, int n) {
-  if (n < 1) return;
-  double yi = y[perm[0]], betai = beta[0], t = 0.0;
-  int i = 1;
-  for (; i < n; i++) {
-    t += yi * betai;
-    const int pi = perm[i];
-    yi = (y[pi] -= t * p[pi]);
-    betai = beta[i];
-  }
-  if (n < m) {
-    t += yi * betai;
-    for (; i < m; i++) { const int pi = perm[i]; y[pi] -= t * p[pi]; }
-  }
-}
-// backward solves (bwdpr1.c:65-113)
-__device__ void d_bwipr1(double *y, const double *p, const double *beta, int m, int n) {
-  if (n < 1) return;
-  double t = 0.0;
-  for (int i = n; i < m; i++) t += p[i] * y[i];
-  for (int i = n; i > 0; i--) {
-    const double yi = (y[i - 1] -= t * beta[i - 1]);
-    t += p[i - 1] * yi;
-  }
-}
-__device__ void d_bwipr1o(double *y, const int *perm, const double *p, const double *beta, int m, int n) {
-  if (n < 1) return;
-  double t = 0.0;
-  for (int i = m - 1; i >= n; i--) { const int pi = perm[i]; t += p[pi] * y[pi]; }
-  for (int i = n; i > 0; i--) {
-    const int pi = perm[i - 1];
-    const double yi = (y[pi] -= t * beta[i - 1]);
-    t += p[pi] * yi;
-  }
-}
+struct Aff { double a, b; };                         // t -> a t + b
+__device__ __forceinline__ double shfl_up_t(double v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ int shfl_up_t(int v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ Aff shfl_up_t(Aff v, int o) { return Aff{__shfl_up_sync(0xffffffffu, v.a, o), __shfl_up_sync(0xffffffffu, v.b, o)}; }
+struct OpSum { __device__ double operator()(double e, double l) const { return e + l; } };
+struct OpMax { __device__ double operator()(double e, double l) const { return fmax(e, l); } };
+struct OpAddI { __device__ int operator()(int e, int l) const { return e + l; } };
+struct OpAff { __device__ Aff operator()(Aff e, Aff l) const { return Aff{l.a * e.a, l.a * e.b + l.b}; } };   // earlier, then later
 
-// One rank-1 step: (D + smult p p')(perm) = L diag(d_new(perm)) L', L = I + tril(p(perm) beta', -1).
-// Runs on ONE thread.  Returns 1 if rows were re-ordered (perm written), 0 for the natural order.
-__device__ int d_rank1_factor(double *beta, int *perm, double *d, double smult, const double *p, int m, int *pn,
-                              int *dep, int *pndep, double maxu, double *fi, double *mu, KD *kd) {
-  if (smult == 0.0) { *pn = 0; return 0; }
-  double t = 1.0 / smult;
-  int ndep = *pndep;
-  for (int i = 0; i < m; i++) fi[i] = p[i] * p[i];
-  const double maxusq_scale = maxu;            // compared as (maxu*fij)^2 like the reference
-  if (dep[0] >= m) {
-    // ---- no dependent row among the first m: natural order first, postponed rows afterwards
-    *pn = m;
-    double h = 0.0;
-    for (int i = m; i > 0; i--) { mu[i - 1] = h; h = fmax(h, fi[i - 1]); }
-    int nph2 = 0;
-    double muph2 = 0.0;
-    for (int j = 0; j < m; j++) {
-      const double dj = d[j], x = fi[j];
-      const double fij = x + t * dj;
-      const double lim = maxusq_scale * fij;
-      if (x * fmax(muph2, mu[j]) <= lim * lim) { fi[j] = fij; d[j] = fij / t; t = fij / dj; }
-      else { kd[nph2].r = x; kd[nph2].k = j; nph2++; muph2 = fmax(muph2, x); }
-    }
-    if (nph2 == 0) {
-      for (int i = 0; i < m; i++) beta[i] = p[i] / fi[i];
-      return 0;
-    }
-    int w = 0, q = 0;                          // accepted rows keep their order
-    for (int j = 0; j < m; j++) {
-      if (q < nph2 && kd[q].k == j) { q++; continue; }
-      perm[w] = j; beta[w] = p[j] / fi[j]; w++;
-    }
-    // postponed rows by decreasing p^2 (insertion sort; ties keep ascending row order)
-    for (int a = 1; a < nph2; a++) {
-      KD key = kd[a]; int b = a - 1;
-      while (b >= 0 && kd[b].r < key.r) { kd[b + 1] = kd[b]; b--; }
-      kd[b + 1] = key;
-    }
-    for (int a = 0; a < nph2; a++) {
-      const int j = kd[a].k;
-      const double dj = d[j];
-      const double fij = (kd[a].r += t * dj);
-      d[j] = fij / t; t = fij / dj;
-      perm[w + a] = j; beta[w + a] = p[j] / fij;
-    }
-    return 1;
+// Block-wide EXCLUSIVE scan of one value per thread, in thread order; *total (optional) = reduction over the block.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_exscan(T v, Op op, T ident, T *sh, T *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { T u = shfl_up_t(inc, o); if (lane >= o) inc = op(u, inc); }
+  __syncthreads();
+  if (lane == 31) sh[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < nw ? sh[lane] : ident;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T u = shfl_up_t(w, o); if (lane >= o) w = op(u, w); }
+    sh[lane] = w;
   }
-  // ---- some d(i) = 0 among the first m rows
-  double psqrdep = 0.0;
-  int jd = 0, i;
-  for (i = 0; dep[i] < m; i++)
-    if (fi[dep[i]] > psqrdep) { jd = i; psqrdep = fi[dep[i]]; }
-  int idep, deldep = 0;
-  double h;
-  if (psqrdep > 0.0) {
-    idep = dep[jd];
-    if (t > 0.0) {
-      deldep = 1;
-      for (int a = jd; a < ndep; a++) dep[a] = dep[a + 1];      // shifts the tail entry too
-      h = maxu * maxu * psqrdep;
-      dep[ndep] = idep;
-      *pndep = --ndep;
-    } else { h = psqrdep; deldep = 0; }
-  } else { idep = dep[0]; h = 0.0; deldep = 0; }
-  int j = 0, back = m;
-  for (i = 0; i < idep; i++) { if (fi[i] > h) perm[j++] = i; else perm[--back] = i; }
-  for (++i; i < m; i++) { if (fi[i] > h) perm[j++] = i; else perm[--back] = i; }
-  perm[j] = idep;
-  int n = j;
-  *pn = j + deldep;
-  for (i = n; i > 0; i--) { mu[i - 1] = h; h = fmax(h, fi[perm[i - 1]]); }
-  int nph2 = 0, jnz = 0;
-  double muph2 = 0.0;
-  for (i = 0; i < n; i++) {
-    const int k = perm[i];
-    const double dj = d[k], x = fi[k];
-    const double fij = x + t * dj;
-    const double lim = maxu * fij;
-    if (x * fmax(muph2, mu[i]) <= lim * lim) { fi[k] = fij; perm[jnz++] = k; d[k] = fij / t; t = fij / dj; }
-    else { kd[nph2].r = x; kd[nph2].k = k; nph2++; muph2 = fmax(muph2, x); }
-  }
-  n -= nph2;
-  for (i = 0; i < n; i++) beta[i] = p[perm[i]] / fi[perm[i]];
-  if (nph2) {
-    for (int a = 1; a < nph2; a++) {
-      KD key = kd[a]; int b = a - 1;
-      while (b >= 0 && kd[b].r < key.r) { kd[b + 1] = kd[b]; b--; }
-      kd[b + 1] = key;
-    }
-    for (int a = 0; a < nph2; a++) {
-      const int k = kd[a].k;
-      const double dj = d[k];
-      const double fij = (kd[a].r += t * dj);
-      d[k] = fij / t; t = fij / dj;
-      perm[n + a] = k; beta[n + a] = p[k] / fij;
-    }
-  }
-  if (deldep) { d[idep] = fi[idep] / t; beta[n + nph2] = 1.0 / p[idep]; }
-  return 1;
+  __syncthreads();
+  T ex = shfl_up_t(inc, 1);
+  if (lane == 0) ex = ident;
+  const T pre = warp > 0 ? op(sh[warp - 1], ex) : ex;
+  if (total) *total = sh[nw - 1];
+  __syncthreads();
+  return pre;
 }
+__device__ __forceinline__ int block_min_int(int v, int *sh) {
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) sh[0] = v;
+  }
+  __syncthreads();
+  v = sh[0];
+  __syncthreads();
+  return v;
+}
+#define DPR1_CHUNK(n, lo, hi) const int _c = ((n) + (int)blockDim.x - 1) / (int)blockDim.x; \
+  const int lo = min((n), (int)threadIdx.x * _c), hi = min((n), lo + _c)
 
-// dep(0:ndep) sorted + previously removed dependencies behind it (dpr1fact.c:495-512)
+// dependent-row bookkeeping (a short sorted list with a tail sentinel; dpr1fact.c:362-376 and :495-512)
 __device__ int d_findnewdep(int *dep, int ndep, int maxndep, const double *d) {
   int i;
   for (i = ndep + 1; i <= maxndep; i++) if (d[dep[i]] <= 0.0) break;
@@ -189,74 +96,263 @@ __device__ int d_findnewdep(int *dep, int ndep, int maxndep, const double *d) {
   return 1;
 }
 
-// The whole product-form factorisation, one CTA.  xs[k] = number of rows of column k (dz.jc[k+1]);
-// p holds the columns back to back (column k starts at sum_{j<=k-1} xs[j] ... see poff[]).
-__global__ void __launch_bounds__(256)
-prodform_kernel(int n, const int *xs, const long long *poff, double *p, int *pivperm, double *beta, int *betajc,
-                double *d, int *ordered, const int *colperm, const int *firstpiv, const double *smult, int *dep,
-                int *ndep_io, double maxu, double *fi, double *mu, KD *kd, long long *permoff_out) {
-  __shared__ int s_useperm, s_nk, s_inz;
-  __shared__ long long s_permoff;
-  if (threadIdx.x == 0) { s_inz = 0; s_permoff = 0; }
+struct Dpr1Work {         // scratch of one factorisation, each array at least max_k xs[k] long
+  double *x, *mu, *tq;    // p.^2 ; suffix maxima in candidate order ; t at each candidate position
+  int *ord, *post, *slot; // candidate order ; postponed flags ; output slot of each candidate
+  KD *kd;                 // postponed rows (row, p^2)
+  int *cursor;            // [0] = next free entry of beta, [1] = next free entry of pivperm, [2] = ndep, [3] = maxndep
+  int *permoffs;          // per column: where its pivot order starts in pivperm (valid when ordered[k])
+};
+
+// One dense column k: factor diag(d) + smult p p' in product form (dodpr1fact, dpr1fact.c:280-477).
+__global__ void __launch_bounds__(DT)
+dpr1_column_kernel(int k, const int *xs, const long long *poff, const double *p, int *pivperm, double *beta, int *betajc,
+                   double *d, int *ordered, const int *colperm, const double *smult, int *dep, double maxu, Dpr1Work W) {
+  __shared__ double shd[33];
+  __shared__ int shi[33];
+  __shared__ int s_idep, s_deldep, s_case;
+  __shared__ double s_h, s_t0;
+  const int tid = threadIdx.x;
+  const int mk = xs[k];
+  const double *pk = p + poff[k];
+  const double sm = smult[colperm[k]];
+  const int inz = W.cursor[0];
+  double *betak = beta + inz;
+  int *permk = pivperm + W.cursor[1];
+  if (tid == 0) { betajc[k] = inz; W.permoffs[k] = W.cursor[1]; }
+  if (sm == 0.0) {                                   // diag(d) + 0 p p' = I diag(d) I  (dpr1fact.c:291-294)
+    if (tid == 0) { ordered[k] = 0; betajc[k + 1] = inz; }
+    return;
+  }
+  for (int i = tid; i < mk; i += blockDim.x) { W.x[i] = pk[i] * pk[i]; W.post[i] = 0; }
+  // ---- dependent rows inside this column
+  if (tid == 0) {
+    int ndep = W.cursor[2];
+    double t0 = 1.0 / sm;
+    s_t0 = t0; s_idep = -1; s_deldep = 0; s_h = 0.0; s_case = 0;
+    if (dep[0] < mk) {                               // case B (dpr1fact.c:352-410); the list is short
+      s_case = 1;
+      double psqrdep = 0.0; int j = 0;
+      for (int i = 0; dep[i] < mk; i++) { const double v = pk[dep[i]] * pk[dep[i]]; if (v > psqrdep) { j = i; psqrdep = v; } }
+      if (psqrdep > 0.0) {
+        const int idep = dep[j];
+        s_idep = idep;
+        if (t0 > 0.0) {
+          s_deldep = 1;
+          for (int a = j; a < ndep; a++) dep[a] = dep[a + 1];
+          s_h = maxu * maxu * psqrdep;
+          dep[ndep] = idep;
+          W.cursor[2] = --ndep;
+        } else s_h = psqrdep;
+      } else s_idep = dep[0];
+    }
+  }
   __syncthreads();
-  const int maxndep = *ndep_io;
-  for (int k = 0; k < n; k++) {
-    const int colk = colperm[k];
-    const int mk = xs[k];
-    double *pk = p + poff[k];
-    if (threadIdx.x == 0) {
-      betajc[k] = s_inz;
-      int nk = 0, ndep = *ndep_io;
-      int up = d_rank1_factor(beta + s_inz, pivperm + s_permoff, d, smult[colk], pk, mk, &nk, dep, &ndep, maxu, fi, mu, kd);
-      ordered[k] = up;
-      if (smult[colk] < 0.0) ndep += d_findnewdep(dep, ndep, maxndep, d);
-      *ndep_io = ndep;
-      s_useperm = up; s_nk = nk;
-    }
+  const double t0 = s_t0, h = s_h;
+  const int idep = s_idep, deldep = s_deldep, caseB = s_case;
+  // ---- candidate order: case A = 0..mk-1; case B = [rows with x > h (ascending), idep, the rest (descending)]
+  int n;
+  if (!caseB) {
+    for (int i = tid; i < mk; i += blockDim.x) W.ord[i] = i;
+    n = mk;
     __syncthreads();
-    if (smult[colk] != 0.0) {
-      const double *betak = beta + s_inz;
-      const int *permk = pivperm + s_permoff;
-      for (int j = k + 1 + threadIdx.x; j < n; j += blockDim.x) {
-        if (firstpiv[colperm[j]] <= k) {
-          double *pj = p + poff[j];
-          if (s_useperm) d_fwipr1o(pj, permk, pk, betak, mk, s_nk);
-          else d_fwipr1(pj, pk, betak, mk, s_nk);
-        }
+  } else {
+    DPR1_CHUNK(mk, lo, hi);
+    int cf = 0, cr = 0;
+    for (int i = lo; i < hi; i++) { if (i == idep) continue; if (W.x[i] > h) cf++; else cr++; }
+    int totf = 0;
+    const int pf = block_exscan(cf, OpAddI(), 0, shi, &totf);
+    const int pr = block_exscan(cr, OpAddI(), 0, shi, (int *)nullptr);
+    int a = pf, r = pr;
+    for (int i = lo; i < hi; i++) {
+      if (i == idep) continue;
+      if (W.x[i] > h) { W.ord[a] = i; permk[a] = i; a++; } else { permk[mk - 1 - r] = i; r++; }
+    }
+    n = totf;
+    if (tid == 0) permk[n] = idep;
+    __syncthreads();
+  }
+  // ---- mu[i] = max(h, max x[ord[i+1 .. n-1]])   (dpr1fact.c:316-319,416-419): reverse exclusive max-scan
+  {
+    DPR1_CHUNK(n, lo, hi);
+    double mx = 0.0;
+    for (int i = lo; i < hi; i++) mx = fmax(mx, W.x[W.ord[n - 1 - i]]);
+    double run = fmax(h, block_exscan(mx, OpMax(), 0.0, shd, (double *)nullptr));
+    for (int i = lo; i < hi; i++) { const int pos = n - 1 - i; W.mu[pos] = run; run = fmax(run, W.x[W.ord[pos]]); }
+    __syncthreads();
+  }
+  // ---- first pass with speculation: under the current postponed set every t is a prefix sum; the first row that
+  // fails the stability test is final and joins the set (dpr1fact.c:97-135,168-202)
+  {
+    DPR1_CHUNK(n, lo, hi);
+    for (;;) {
+      double sacc = 0.0, mpost = 0.0;
+      for (int i = lo; i < hi; i++) { const int r = W.ord[i]; if (W.post[i]) mpost = fmax(mpost, W.x[r]); else sacc += W.x[r] / d[r]; }
+      const double tpre = block_exscan(sacc, OpSum(), 0.0, shd, (double *)nullptr);
+      const double mpre = block_exscan(mpost, OpMax(), 0.0, shd, (double *)nullptr);
+      double t = t0 + tpre, muph2 = mpre;
+      int fail = 0x7fffffff;
+      for (int i = lo; i < hi; i++) {
+        const int r = W.ord[i];
+        if (W.post[i]) { muph2 = fmax(muph2, W.x[r]); continue; }
+        const double dj = d[r], xr = W.x[r], fij = xr + t * dj, lim = maxu * fij;
+        if (!(xr * fmax(muph2, W.mu[i]) <= lim * lim)) { fail = i; break; }
+        W.tq[i] = t;
+        t = fij / dj;
       }
+      const int f = block_min_int(fail, shi);
+      if (f == 0x7fffffff) break;
+      if (tid == 0) W.post[f] = 1;
+      __syncthreads();
+    }
+  }
+  // ---- accepted pivots: slots by stream compaction; d, beta; postponed rows collected in order
+  int nacc = 0, nph2 = 0;
+  double tend;
+  {
+    DPR1_CHUNK(n, lo, hi);
+    int ca = 0, cp = 0; double sacc = 0.0;
+    for (int i = lo; i < hi; i++) { if (W.post[i]) cp++; else { ca++; const int r = W.ord[i]; sacc += W.x[r] / d[r]; } }
+    double stot = 0.0;
+    const int pa = block_exscan(ca, OpAddI(), 0, shi, &nacc);
+    const int pp = block_exscan(cp, OpAddI(), 0, shi, &nph2);
+    block_exscan(sacc, OpSum(), 0.0, shd, &stot);
+    tend = t0 + stot;
+    int a = pa, q = pp;
+    for (int i = lo; i < hi; i++) {
+      const int r = W.ord[i];
+      if (W.post[i]) { W.kd[q].k = r; W.kd[q].r = W.x[r]; q++; }
+      else { W.slot[i] = a; a++; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      if (smult[colk] != 0.0 && s_useperm) s_permoff += mk;
-      s_inz += s_nk;
+    for (int i = lo; i < hi; i++) {
+      if (W.post[i]) continue;
+      const int r = W.ord[i];
+      const double t = W.tq[i], fij = W.x[r] + t * d[r];
+      d[r] = fij / t;                                 // d_new = d + p^2 / t
+      betak[W.slot[i]] = pk[r] / fij;
+      if (caseB || nph2) permk[W.slot[i]] = r;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { betajc[n] = s_inz; *permoff_out = s_permoff; }
+  // ---- second pass: postponed rows by decreasing p^2 (ties: smaller row first), one more prefix sum (dpr1fact.c:224-240)
+  if (nph2) {
+    for (int e = tid; e < nph2; e += blockDim.x) {
+      const double xe = W.kd[e].r; const int re = W.kd[e].k;
+      int rank = 0;
+      for (int o = 0; o < nph2; o++) { const double xo = W.kd[o].r; rank += (xo > xe) || (xo == xe && W.kd[o].k < re); }
+      W.slot[e] = rank;                               // slot[] is free again: accepted slots were consumed above
+    }
+    __syncthreads();
+    for (int e = tid; e < nph2; e += blockDim.x) W.ord[W.slot[e]] = W.kd[e].k;      // sorted rows
+    __syncthreads();
+    DPR1_CHUNK(nph2, lo, hi);
+    double sacc = 0.0;
+    for (int i = lo; i < hi; i++) { const int r = W.ord[i]; sacc += W.x[r] / d[r]; }
+    double stot = 0.0;
+    const double tpre = block_exscan(sacc, OpSum(), 0.0, shd, &stot);
+    double t = tend + tpre;
+    for (int i = lo; i < hi; i++) {
+      const int r = W.ord[i];
+      const double dj = d[r], fij = W.x[r] + t * dj;
+      d[r] = fij / t;
+      betak[nacc + i] = pk[r] / fij;
+      permk[nacc + i] = r;
+      t = fij / dj;
+    }
+    tend += stot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int nk = caseB ? n + deldep : mk;
+    if (caseB && deldep) {                            // finish by pivoting on idep (dpr1fact.c:468-475)
+      d[idep] = W.x[idep] / tend;
+      betak[nacc + nph2] = 1.0 / pk[idep];
+    }
+    const int useperm = caseB || nph2 > 0;
+    ordered[k] = useperm;
+    W.cursor[0] = inz + nk;
+    betajc[k + 1] = inz + nk;
+    if (useperm) W.cursor[1] += mk;
+    if (sm < 0.0) W.cursor[2] += d_findnewdep(dep, W.cursor[2], W.cursor[3], d);
+  }
 }
 
-// product-form solves: one thread per right-hand side (columns of y are independent)
-__global__ void prodform_solve_kernel(int backward, int nrhs, int m, int nden, int dznnz, const int *dzir, const int *xs,
-                                      const long long *poff, const long long *permoff, const double *p, const int *pivperm,
-                                      const double *beta, const int *betajc, const int *ordered, double *y, double *fwork) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= nrhs) return;
-  double *yy = y + (long long)col * m, *f = fwork + (long long)col * dznnz;
-  for (int i = 0; i < dznnz; i++) f[i] = yy[dzir[i]];
-  if (!backward) {
-    for (int k = 0; k < nden; k++) {
-      const int nk = betajc[k + 1] - betajc[k];
-      if (ordered[k]) d_fwipr1o(f, pivperm + permoff[k], p + poff[k], beta + betajc[k], xs[k], nk);
-      else d_fwipr1(f, p + poff[k], beta + betajc[k], xs[k], nk);
-    }
-  } else {
-    for (int k = nden - 1; k >= 0; k--) {
-      const int nk = betajc[k + 1] - betajc[k];
-      if (ordered[k]) d_bwipr1o(f, pivperm + permoff[k], p + poff[k], beta + betajc[k], xs[k], nk);
-      else d_bwipr1(f, p + poff[k], beta + betajc[k], xs[k], nk);
-    }
+// L(p_k, beta_k) yNEW = yOLD for one vector y (auxfwdpr1.c:44-122) as a block-wide scan of affine maps.
+// rows: pivot order (perm) or nullptr = natural; beta has nk entries (beta_i = 0 beyond); all mk rows are updated.
+__device__ __forceinline__ void d_fw_scan(double *y, const int *perm, const double *p, const double *beta, int mk, int nk, Aff *sh) {
+  if (nk < 1) return;
+  DPR1_CHUNK(mk, lo, hi);
+  Aff loc{1.0, 0.0};
+  for (int i = lo; i < hi; i++) {
+    const int r = perm ? perm[i] : i;
+    const double b = i < nk ? beta[i] : 0.0;
+    loc = OpAff()(loc, Aff{1.0 - b * p[r], b * y[r]});
   }
-  for (int i = 0; i < dznnz; i++) yy[dzir[i]] = f[i];
+  const Aff pre = block_exscan(loc, OpAff(), Aff{1.0, 0.0}, sh, (Aff *)nullptr);
+  double t = pre.b;                                    // t starts at 0
+  for (int i = lo; i < hi; i++) {
+    const int r = perm ? perm[i] : i;
+    const double yi = y[r] - t * p[r];
+    y[r] = yi;
+    if (i < nk) t += yi * beta[i];
+  }
+  __syncthreads();
+}
+// L(p_k, beta_k)' yNEW = yOLD (bwdpr1.c:65-162): t starts as p(n:m-1)'y and runs from row n-1 down to 0.
+__device__ __forceinline__ void d_bw_scan(double *y, const int *perm, const double *p, const double *beta, int mk, int nk, Aff *sh, double *shd) {
+  if (nk < 1) return;
+  double tail = 0.0;
+  for (int i = nk + threadIdx.x; i < mk; i += blockDim.x) { const int r = perm ? perm[i] : i; tail += p[r] * y[r]; }
+  double t0 = 0.0;
+  block_exscan(tail, OpSum(), 0.0, shd, &t0);
+  DPR1_CHUNK(nk, lo, hi);                              // positions in REVERSE order: q = nk-1-i
+  Aff loc{1.0, 0.0};
+  for (int q = lo; q < hi; q++) {
+    const int i = nk - 1 - q, r = perm ? perm[i] : i;
+    loc = OpAff()(loc, Aff{1.0 - p[r] * beta[i], p[r] * y[r]});
+  }
+  const Aff pre = block_exscan(loc, OpAff(), Aff{1.0, 0.0}, sh, (Aff *)nullptr);
+  double t = pre.a * t0 + pre.b;
+  for (int q = lo; q < hi; q++) {
+    const int i = nk - 1 - q, r = perm ? perm[i] : i;
+    const double yi = y[r] - t * beta[i];
+    y[r] = yi;
+    t += p[r] * yi;
+  }
+  __syncthreads();
+}
+
+// Forward solve of the later columns j > k that overlap column k (dpr1fact.c:578-596): one CTA per column j.
+__global__ void __launch_bounds__(DT)
+dpr1_fwcols_kernel(int k, int n, const int *xs, const long long *poff, double *p, const int *pivperm, const double *beta,
+                   const int *betajc, const int *ordered, const int *colperm, const int *firstpiv, const double *smult,
+                   const int *permoffs) {
+  __shared__ Aff sha[33];
+  const int j = k + 1 + blockIdx.x;
+  if (j >= n || smult[colperm[k]] == 0.0 || firstpiv[colperm[j]] > k) return;
+  const int nk = betajc[k + 1] - betajc[k];
+  d_fw_scan(p + poff[j], ordered[k] ? pivperm + permoffs[k] : nullptr, p + poff[k], beta + betajc[k], xs[k], nk, sha);
+}
+
+// Product-form solves over all dense columns, one CTA per right-hand side (fwdpr1.c:70-90, bwdpr1.c:131-162).
+__global__ void __launch_bounds__(DT)
+dpr1_solve_kernel(int backward, int m, int nden, int dznnz, const int *dzir, const int *xs, const long long *poff,
+                  const long long *permoff, const double *p, const int *pivperm, const double *beta, const int *betajc,
+                  const int *ordered, double *y, double *fwork) {
+  __shared__ Aff sha[33];
+  __shared__ double shd[33];
+  double *yy = y + (long long)blockIdx.x * m, *f = fwork + (long long)blockIdx.x * dznnz;
+  for (int i = threadIdx.x; i < dznnz; i += blockDim.x) f[i] = yy[dzir[i]];
+  __syncthreads();
+  if (!backward) {
+    for (int k = 0; k < nden; k++)
+      d_fw_scan(f, ordered[k] ? pivperm + permoff[k] : nullptr, p + poff[k], beta + betajc[k], xs[k], betajc[k + 1] - betajc[k], sha);
+  } else {
+    for (int k = nden - 1; k >= 0; k--)
+      d_bw_scan(f, ordered[k] ? pivperm + permoff[k] : nullptr, p + poff[k], beta + betajc[k], xs[k], betajc[k + 1] - betajc[k], sha, shd);
+  }
+  for (int i = threadIdx.x; i < dznnz; i += blockDim.x) yy[dzir[i]] = f[i];
 }
 
 }  // namespace sb
@@ -307,13 +403,18 @@ int sb200_dpr1fact(sb_idx m, sb_idx n, const sb_idx *xjc, const sb_idx *xir, con
   arena_reset();
   cudaStream_t st = ctx().stream;
   int *d_xs = arena<int>(n), *d_colp = arena<int>(n), *d_first = arena<int>(n), *d_pivperm = arena<int>(std::max<sb_idx>(pnnz, 1)),
-      *d_betajc = arena<int>(n + 1), *d_ordered = arena<int>(n), *d_dep = arena<int>(m + 2), *d_ndep = arena<int>(1);
-  long long *d_poff = arena<long long>(n + 1), *d_permoff = arena<long long>(1);
-  double *d_p = arena<double>(std::max<sb_idx>(pnnz, 1)), *d_beta = arena<double>(std::max<sb_idx>(pnnz, 1)), *d_d = arena<double>(std::max<sb_idx>(dznnz, 1)),
-         *d_smult = arena<double>(n), *d_fi = arena<double>(std::max<sb_idx>(dznnz, 1)), *d_mu = arena<double>(std::max<sb_idx>(dznnz, 1));
-  KD *d_kd = arena<KD>(std::max<sb_idx>(dznnz, 1));
-  SB_CHECK(d_xs && d_colp && d_first && d_pivperm && d_betajc && d_ordered && d_dep && d_ndep && d_poff && d_permoff && d_p && d_beta &&
-           d_d && d_smult && d_fi && d_mu && d_kd, "dpr1fact: out of device memory");
+      *d_betajc = arena<int>(n + 1), *d_ordered = arena<int>(n), *d_dep = arena<int>(m + 2), *d_cursor = arena<int>(4), *d_permoffs = arena<int>(n);
+  long long *d_poff = arena<long long>(n + 1);
+  const size_t wl = (size_t)std::max<sb_idx>(dznnz, 1);
+  double *d_p = arena<double>(std::max<sb_idx>(pnnz, 1)), *d_beta = arena<double>(std::max<sb_idx>(pnnz, 1)), *d_d = arena<double>(wl),
+         *d_smult = arena<double>(n);
+  Dpr1Work W;
+  W.x = arena<double>(wl); W.mu = arena<double>(wl); W.tq = arena<double>(wl);
+  W.ord = arena<int>(wl); W.post = arena<int>(wl); W.slot = arena<int>(wl); W.kd = arena<KD>(wl);
+  W.cursor = d_cursor; W.permoffs = d_permoffs;
+  SB_CHECK(d_xs && d_colp && d_first && d_pivperm && d_betajc && d_ordered && d_dep && d_cursor && d_permoffs && d_poff && d_p && d_beta &&
+           d_d && d_smult && W.x && W.mu && W.tq && W.ord && W.post && W.slot && W.kd, "dpr1fact: out of device memory");
+  const int cursor0[4] = {0, 0, ndep, ndep};
   SB_CUDA(cudaMemcpyAsync(d_xs, xs.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(d_colp, colp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(d_first, firstp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
@@ -322,21 +423,26 @@ int sb200_dpr1fact(sb_idx m, sb_idx n, const sb_idx *xjc, const sb_idx *xir, con
   SB_CUDA(cudaMemcpyAsync(d_d, dd.data(), sizeof(double) * dd.size(), cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(d_smult, smult, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(d_dep, dep.data(), sizeof(int) * (m + 2), cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemcpyAsync(d_ndep, &ndep, sizeof(int), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(d_cursor, cursor0, sizeof(cursor0), cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(double) * std::max<sb_idx>(pnnz, 1), st));
-  prodform_kernel<<<1, 256, 0, st>>>((int)n, d_xs, d_poff, d_p, d_pivperm, d_beta, d_betajc, d_d, d_ordered, d_colp, d_first,
-                                     d_smult, d_dep, d_ndep, maxu, d_fi, d_mu, d_kd, d_permoff);
-  SB_LAUNCH_CHECK_N("prodform_kernel");
+  SB_CUDA(cudaMemsetAsync(d_betajc, 0, sizeof(int) * (n + 1), st));
+  for (sb_idx k = 0; k < n; k++) {
+    dpr1_column_kernel<<<1, DT, 0, st>>>((int)k, d_xs, d_poff, d_p, d_pivperm, d_beta, d_betajc, d_d, d_ordered, d_colp, d_smult, d_dep, maxu, W);
+    SB_LAUNCH_CHECK_N("dpr1_column_kernel");
+    if (k + 1 < n) {
+      dpr1_fwcols_kernel<<<(unsigned)(n - k - 1), DT, 0, st>>>((int)k, (int)n, d_xs, d_poff, d_p, d_pivperm, d_beta, d_betajc, d_ordered, d_colp,
+                                                               d_first, d_smult, d_permoffs);
+      SB_LAUNCH_CHECK_N("dpr1_fwcols_kernel");
+    }
+  }
   std::vector<int> h_betajc(n + 1), h_ordered(n), h_pivperm((size_t)std::max<sb_idx>(pnnz, 1));
   std::vector<double> h_beta((size_t)std::max<sb_idx>(pnnz, 1));
-  long long permoff = 0;
   SB_CUDA(cudaMemcpyAsync(h_betajc.data(), d_betajc, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(h_ordered.data(), d_ordered, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(h_pivperm.data(), d_pivperm, sizeof(int) * h_pivperm.size(), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(h_beta.data(), d_beta, sizeof(double) * h_beta.size(), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(p_out, d_p, sizeof(double) * pnnz, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(dd.data(), d_d, sizeof(double) * dd.size(), cudaMemcpyDeviceToHost, st));
-  SB_CUDA(cudaMemcpyAsync(&permoff, d_permoff, sizeof(long long), cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   for (sb_idx i = 0; i < dznnz; i++) d_out[dzir[i]] = dd[i];            // lab(dz.ir) = d
   for (sb_idx k = 0; k <= n; k++) betajc_out[k] = h_betajc[k];
@@ -347,7 +453,6 @@ int sb200_dpr1fact(sb_idx m, sb_idx n, const sb_idx *xjc, const sb_idx *xir, con
   // the reference advances its perm cursor only for re-ordered columns with smult != 0 (dpr1fact.c:588-596)
   for (sb_idx i = 0; i < permnnz && i < (sb_idx)h_pivperm.size(); i++) pivperm_out[i] = h_pivperm[i];
   *npivperm = permnnz;
-  (void)permoff;
   return 0;
 }
 
@@ -387,9 +492,9 @@ int sb200_dpr1solve(int backward, sb_idx m, sb_idx nrhs, sb_idx nden, const sb_i
   if (pnnz) SB_CUDA(cudaMemcpyAsync(d_p, p, sizeof(double) * pnnz, cudaMemcpyHostToDevice, st));
   if (bj[nden]) SB_CUDA(cudaMemcpyAsync(d_beta, beta, sizeof(double) * bj[nden], cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(d_y, y, sizeof(double) * m * nrhs, cudaMemcpyHostToDevice, st));
-  prodform_solve_kernel<<<(unsigned)((nrhs + 63) / 64), 64, 0, st>>>(backward, (int)nrhs, (int)m, (int)nden, (int)dznnz, d_ir, d_xs, d_poff,
-                                                                      d_permoff, d_p, d_pp, d_beta, d_bj, d_ord, d_y, d_f);
-  SB_LAUNCH_CHECK_N("prodform_solve_kernel");
+  dpr1_solve_kernel<<<(unsigned)nrhs, DT, 0, st>>>(backward, (int)m, (int)nden, (int)dznnz, d_ir, d_xs, d_poff, d_permoff, d_p, d_pp, d_beta,
+                                                    d_bj, d_ord, d_y, d_f);
+  SB_LAUNCH_CHECK_N("dpr1_solve_kernel");
   SB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(double) * m * nrhs, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;

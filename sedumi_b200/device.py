@@ -393,28 +393,24 @@ class HotPath:
         self._graph = g
         return lambda: check(L.sb200_graph_launch(g), "graph_launch")
 
-    def profile(self, nsolve=4, npsdscale=12, sharded=False, graph=True):
-        """Per-kernel device time of ONE iteration: {kernel name: (launches, ms)}.  With graph=True the iteration is
-        captured with an event record after every launch and replayed once, so host launch gaps do not count."""
+    def profile(self, nsolve=4, npsdscale=12, sharded=False, reps=3):
+        """Per-kernel device time of one iteration, averaged over `reps`: {kernel name: (launches, ms)}.  An event is
+        recorded after every launch; sb200_prof_begin parks a ~3 ms spin kernel on the stream first, so the host has
+        enqueued the iteration before the GPU starts on it and the intervals contain no host launch gaps."""
         L = lib()
         self.iteration(nsolve, npsdscale, sharded)
         self.sync()
-        check(L.sb200_prof_begin(), "prof_begin")
-        if graph:
-            run = self.capture(nsolve, npsdscale, sharded)
-            run()
-            g = self._graph
-        else:
-            self.iteration(nsolve, npsdscale, sharded)
-        buf = C.create_string_buffer(1 << 16)
-        check(L.sb200_prof_end(buf, I64(len(buf))), "prof_end")
-        if graph:
-            L.sb200_graph_destroy(g)
         out = {}
-        for ln in buf.value.decode().splitlines():
-            nm, cnt, tot = ln.split()
-            out[nm] = (int(cnt), float(tot))
-        return out
+        for _ in range(reps):
+            check(L.sb200_prof_begin(), "prof_begin")
+            self.iteration(nsolve, npsdscale, sharded)
+            buf = C.create_string_buffer(1 << 16)
+            check(L.sb200_prof_end(buf, I64(len(buf))), "prof_end")
+            for ln in buf.value.decode().splitlines():
+                nm, cnt, tot = ln.split()
+                c0, t0 = out.get(nm, (0, 0.0))
+                out[nm] = (c0 + int(cnt), t0 + float(tot))
+        return {k: (v[0] // reps, v[1] / reps) for k, v in out.items()}
 
     def sync(self):
         check(lib().sb200_sync(), "sync")
