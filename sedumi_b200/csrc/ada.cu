@@ -32,9 +32,15 @@ struct AdaPair {      // one (constraint, PSD block) with nonzeros
   long long tt_off;   // offset of Tt (n x r) in the batch workspace
   long long w_off;    // offset of W in the batch workspace: n x n (dense mode) or |U_k| values (sparse mode)
   int sparse;         // 1: W is only evaluated on U_k, the union pattern of block k
-  int pad_;
+  int rank;           // position of this pair in its block's partner list (sparsest constraint first)
   long long part_off; // constraints with several blocks: offset of this pair's partial sums (npartners(k)+1)
   long long fpart_off; // the same in the compact workspace of the fused path (no T / W there)
+  // fused path: how W_jk is evaluated.  A pair only needs W on the union of the patterns of the partners that precede
+  // it in its block's list (the observation behind the reference's incremental `dz`, getada3.c:305-326): when that
+  // set is small, W is evaluated entry by entry there (mode 1: through T, mode 2: directly from the few entries of
+  // A_jk) instead of as a dense DMMA product (mode 0).
+  int mode, need_cnt;
+  long long need_off;
 };
 
 // --------------------------------------------------------------------- sparse A'WA on a pattern
@@ -234,6 +240,7 @@ __device__ __forceinline__ void build_slots(int *slot, const int *rows, int coll
 
 struct DotsCtx {
   AdaPair P; int c, ipc, first, multi, warp, lane, nw;
+  int rank_limit;     // >= 0: the partners are the first rank_limit+1 entries of the block's list; < 0: filter by invperm
   long long colbeg;
   ColSlots cs;
   const int *eidx; const double *Wp;
@@ -258,20 +265,22 @@ __device__ __forceinline__ void dots_partners(const DotsCtx &X) {
   const int grp = lane / G, gl = lane % G;
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));   // groups diverge: sync only the group
   const int tb = blkp_beg[P.k], te = blkp_beg[P.k + 1];
+  const bool by_rank = X.rank_limit >= 0;
+  const int tl = by_rank ? tb + X.rank_limit + 1 : te;      // end of the partner loop
   double *part = ws + P.part_off;                 // multi: one partial per partner, then the |.| sum of the diagonal
   // the descriptor and the order of the NEXT partner are fetched while the current one is worked on: the chain
   // descriptor -> invperm -> entries -> W is four dependent loads, which bounded this loop
   int t = tb + warp * GPW + grp;
-  BlkPartner Qn = t < te ? blkp[t] : BlkPartner{0, 0, 0, 0};
-  int ipn = t < te ? invperm[Qn.j] : 0;
-  for (; t < te; t += nw * GPW) {
+  BlkPartner Qn = t < tl ? blkp[t] : BlkPartner{0, 0, 0, 0};
+  int ipn = (t < tl && !by_rank) ? invperm[Qn.j] : 0;
+  for (; t < tl; t += nw * GPW) {
     const BlkPartner Q = Qn;
     const int ipi = ipn;
     {
       const int tn = t + nw * GPW;
-      if (tn < te) { Qn = blkp[tn]; ipn = invperm[Qn.j]; }
+      if (tn < tl) { Qn = blkp[tn]; ipn = by_rank ? 0 : invperm[Qn.j]; }
     }
-    if (ipi > ipc) continue;
+    if (!by_rank && ipi > ipc) continue;
     const double *av = Atpr + Q.src0 - Q.e0;            // the entries of one pair are consecutive in At.pr ...
     double acc = 0.0, aabs = 0.0;
     int e = Q.e0 + gl;
@@ -357,6 +366,7 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
   const double *Wp = stage ? Wsm : Wg;
   DotsCtx X;
   X.P = P; X.c = c; X.ipc = ipc; X.first = first; X.multi = multi ? 1 : 0; X.warp = warp; X.lane = lane; X.nw = nw;
+  X.rank_limit = -1;
   X.colbeg = colbeg; X.cs = cs; X.eidx = eidx; X.Wp = Wp; X.blkp_beg = blkp_beg; X.blkp = blkp; X.invperm = invperm;
   X.Atpr = Atpr; X.ent_src = ent_src; X.ent_scale = ent_scale; X.ws = ws; X.ada = ada; X.absd = absd;
   switch (blk_group[P.k]) {
@@ -389,9 +399,10 @@ ada3_reduce_kernel(int c0, const long long *adajc, const int *adair, const int *
     const int k = pairs[pc].k;
     const double *part = ws + (fused ? pairs[pc].fpart_off : pairs[pc].part_off);
     const int tb = blkp_beg[k], te = blkp_beg[k + 1];
-    for (int t = tb + threadIdx.x; t < te; t += blockDim.x) {
+    const int tl = fused ? tb + pairs[pc].rank + 1 : te;     // fused path: the partners are a prefix of the block's list
+    for (int t = tb + threadIdx.x; t < tl; t += blockDim.x) {
       const int i = blkp[t].j;
-      if (invperm[i] > ipc) continue;
+      if (!fused && invperm[i] > ipc) continue;
       const int sl = cs.find(i);
       if (sl < 0) continue;
       ada[colbeg + sl] += part[t - tb];
@@ -491,8 +502,9 @@ struct sb200_ada_plan {
   long long fused_scratch_stride = 0, fws = 0, n_tt = 0;
   int any_multi = 0;
   DevBuf<double> d_tt_val, d_fscratch, d_fws;
-  DevBuf<int> d_fcounter, d_fitem_beg;
+  DevBuf<int> d_fcounter, d_fitem_beg, d_fneed, d_forder;
   DevBuf<int2> d_fitems;
+  long long fused_ndense = 0;
 };
 
 static std::map<Hash128, sb200_ada_plan *> g_ada_plans;
@@ -620,10 +632,26 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   for (auto &P : pl->pairs) blkp_beg[P.k + 1]++;
   for (sb_idx k = 0; k < nblk; k++) blkp_beg[k + 1] += blkp_beg[k];
   std::vector<BlkPartner> blkp(pl->pairs.size());
+  std::vector<int> blkp_pair(pl->pairs.size());        // pair index of every list entry
   {
-    std::vector<int> fill(blkp_beg.begin(), blkp_beg.end() - 1);
+    // the partner list of a block, sparsest constraint first (ties: constraint number): a pair's partners in the
+    // fused path are the entries up to and including its own position
+    std::vector<std::vector<int>> byblk(nblk);
+    for (size_t pi = 0; pi < pl->pairs.size(); pi++) byblk[pl->pairs[pi].k].push_back((int)pi);
+    for (sb_idx k = 0; k < nblk; k++) {
+      auto &v = byblk[k];
+      std::stable_sort(v.begin(), v.end(), [&](int a, int b) {
+        const int ea = pl->pairs[a].e1 - pl->pairs[a].e0, eb = pl->pairs[b].e1 - pl->pairs[b].e0;
+        return ea != eb ? ea < eb : pl->pairs[a].j < pl->pairs[b].j;
+      });
+      for (size_t t = 0; t < v.size(); t++) {
+        AdaPair &P = pl->pairs[v[t]];
+        P.rank = (int)t;
+        blkp[blkp_beg[k] + t] = BlkPartner{P.j, P.e0, P.e1, ent_src[P.e0]};
+        blkp_pair[blkp_beg[k] + t] = v[t];
+      }
+    }
     for (auto &P : pl->pairs) {
-      blkp[fill[P.k]++] = BlkPartner{P.j, P.e0, P.e1, ent_src[P.e0]};
       const long long n = pl->blk_n[P.k];
       for (int e = P.e0; e < P.e1; e++) {
         if (P.sparse) ent_pk[e] = ent_lin[e];
@@ -807,6 +835,44 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       }
       ibeg[nblk] = (int)its.size();
       SB_TRY(pl->d_fitem_beg.upload(ibeg)); SB_TRY(pl->d_fitems.upload(its));
+      // evaluation mode of every pair: walk each block's list in order, keep the union of the patterns seen so far
+      std::vector<int> need_pq;
+      std::vector<char> seen;
+      std::vector<double> cost(pl->pairs.size(), 0.0);
+      long long ndense = 0;
+      for (sb_idx k = 0; k < nblk; k++) {
+        const long long nk = pl->blk_n[k], tri = nk * (nk + 1) / 2;
+        seen.assign((size_t)tri, 0);
+        std::vector<int> uni;                           // packed indices of the union, in order of first appearance
+        for (int t = blkp_beg[k]; t < blkp_beg[k + 1]; t++) {
+          AdaPair &P = pl->pairs[blkp_pair[t]];
+          for (int e = P.e0; e < P.e1; e++) if (!seen[ent_pk[e]]) { seen[ent_pk[e]] = 1; uni.push_back(ent_pk[e]); }
+          long long nfull = 0;                          // nonzeros of sym(A_jk)
+          for (int rho = 0; rho < P.r; rho++) nfull += tt_ptr[P.r0 + rho + 1] - tt_ptr[P.r0 + rho];
+          const long long nu = (long long)uni.size();
+          if (nu * 16 <= tri && !getenv("SB200_ADA3_DENSE_ONLY")) {
+            P.mode = (nfull <= 2 * nk) ? 2 : 1;
+            P.need_off = (long long)need_pq.size(); P.need_cnt = (int)nu;
+            for (int pk : uni) {                         // packed index -> (p, q): column q starts at q(2n-q+1)/2 - q
+              long long q = 0;
+              { long long lo = 0, hi = nk - 1; while (lo < hi) { long long mid = (lo + hi + 1) >> 1; if ((mid * (2 * nk - mid + 1)) / 2 <= pk) lo = mid; else hi = mid - 1; } q = lo; }
+              const long long pp = pk - ((q * (2 * nk - q + 1)) / 2 - q);
+              need_pq.push_back((int)(pp | (q << 16)));
+            }
+            cost[blkp_pair[t]] = (double)nu * (P.mode == 2 ? (double)nfull : (double)P.r) * 8.0 + (P.mode == 1 ? (double)nk * P.r * 4.0 : 0.0);
+          } else {
+            P.mode = 0; P.need_off = 0; P.need_cnt = 0; ndense++;
+            cost[blkp_pair[t]] = (double)tri * P.r + (double)nk * P.r * 4.0;
+          }
+        }
+      }
+      pl->fused_ndense = ndense;
+      // pairs are handed out most expensive first (dense products, then the entry-wise ones)
+      std::vector<int> order(pl->pairs.size());
+      for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      if (need_pq.empty()) need_pq.push_back(0);
+      SB_TRY(pl->d_fneed.upload(need_pq)); SB_TRY(pl->d_forder.upload(order));
       pl->fused_wcap = (maxn * (maxn + 1) / 2 + 1) & ~1;
       pl->fused_ldmax = ((maxn + 7) & ~7) + 4;
       pl->fused_smem = sizeof(double) * ((size_t)pl->fused_wcap + 4 * FKC * pl->fused_ldmax);
@@ -1069,7 +1135,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     FA.Rlist = pl->d_Rlist.p; FA.udsqr = udsqr_dev; FA.scratch = pl->d_fscratch.p; FA.scratch_stride = pl->fused_scratch_stride;
     FA.adajc = pl->d_adajc.p; FA.adair = pl->d_adair.p; FA.invperm = ip; FA.first = (int)first; FA.cpair_beg = pl->d_cpair_beg.p;
     FA.blkp_beg = pl->d_blkp_beg.p; FA.blkp = pl->d_blkp.p; FA.ent_pk = pl->d_ent_pk.p; FA.ent_src = pl->d_ent_src.p; FA.Atpr = pl->d_Atpr.p;
-    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax;
+    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.need_pq = pl->d_fneed.p; FA.order = pl->d_forder.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax;
     static bool attr_done = false;
     if (!attr_done) {
       SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));   // + static

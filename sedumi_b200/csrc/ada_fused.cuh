@@ -34,6 +34,7 @@ struct FusedArgs {
   double *ws, *ada, *absd;
   const int *blk_group;
   const int *blk_item_beg; const int2 *items;        // per block: its lower supertiles (I, J), most expensive first
+  const int *need_pq; const int *order;              // entry-wise pairs: their (p | q << 16) lists; processing order of the pairs
   int wcap, ldmax;
 };
 
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
   for (;;) {
     if (tid == 0) s_pair = atomicAdd(A.counter, 1);
     __syncthreads();
-    const int pi = s_pair;
-    if (pi >= A.npairs) break;
+    if (s_pair >= A.npairs) break;
+    const int pi = A.order[s_pair];
     const AdaPair P = A.pairs[pi];
     const int n = A.blk_n[P.k], r = P.r, ld = fused_ld(n);
     const double *D = A.udsqr + A.blk_off[P.k];
     const int *R = A.Rlist + P.r0;
     // ---------------- 1. T (as Tt: n x r, column rho = row R[rho] of sym(A) D): one warp per row, lanes over columns
-    {
+    if (P.mode != 2) {
       const int *ptr = A.tt_ptr + P.r0;
       const bool vec2 = ((n & 1) == 0) && ((((unsigned long long)D) & 15) == 0) && ((((unsigned long long)Tt) & 15) == 0);
       if (vec2) {                                                // two columns per lane and load
@@ -95,13 +96,25 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++) acc[ch] = make_double2(0.0, 0.0);
           const int t0 = ptr[rho], t1 = ptr[rho + 1];
-          for (int t = t0; t < t1; t++) {
-            const double v = A.tt_val[t];
-            const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)A.tt_col[t] * n);
+          // four entries per trip: their (column, value) loads go out together, then the 4 x NCH loads of D
+          for (int t = t0; t < t1; t += 4) {
+            double v[4]; const double2 *Dc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const bool ok = t + u < t1;
+              v[u] = ok ? A.tt_val[t + u] : 0.0;
+              Dc[u] = reinterpret_cast<const double2 *>(D + (long long)A.tt_col[ok ? t + u : t0] * n);
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
               const int c = lane + 32 * ch;
-              if (c < half) { const double2 x = Dc[c]; acc[ch].x += v * x.x; acc[ch].y += v * x.y; }
+              if (c < half) {
+                const double2 x0 = Dc[0][c], x1 = Dc[1][c], x2 = Dc[2][c], x3 = Dc[3][c];
+                acc[ch].x += v[0] * x0.x; acc[ch].y += v[0] * x0.y;
+                acc[ch].x += v[1] * x1.x; acc[ch].y += v[1] * x1.y;
+                acc[ch].x += v[2] * x2.x; acc[ch].y += v[2] * x2.y;
+                acc[ch].x += v[3] * x3.x; acc[ch].y += v[3] * x3.y;
+              }
             }
           }
           double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * n);
@@ -137,7 +150,27 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
       }
     }
     __syncthreads();
-    // ---------------- 2. W = D(:,R) T on the lower supertiles, in rounds of at most FUSED_GEMM_WARPS items
+    // ---------------- 2a. entry-wise evaluation on the needed set (pairs early in their block's list)
+    if (P.mode != 0) {
+      const int *pq = A.need_pq + P.need_off;
+      const int *ptr = A.tt_ptr + P.r0;
+      for (int u = tid; u < P.need_cnt; u += blockDim.x) {
+        const int v = pq[u], pp = v & 0xffff, qq = v >> 16;
+        double acc = 0.0;
+        if (P.mode == 1) {
+          for (int rho = 0; rho < r; rho++) acc += D[pp + (long long)R[rho] * n] * Tt[qq + (long long)rho * n];
+        } else {                                                 // W(p,q) = sum_rho D(p,R[rho]) sum_t v_t D(c_t,q), D symmetric
+          for (int rho = 0; rho < r; rho++) {
+            const double dp = D[pp + (long long)R[rho] * n];
+            double in = 0.0;
+            for (int t = ptr[rho]; t < ptr[rho + 1]; t++) in += A.tt_val[t] * D[qq + (long long)A.tt_col[t] * n];
+            acc += dp * in;
+          }
+        }
+        Wp[(qq * (2 * n - qq + 1)) / 2 - qq + pp] = acc;
+      }
+    } else
+    // ---------------- 2b. W = D(:,R) T on the lower supertiles, in rounds of at most FUSED_GEMM_WARPS items
     // (the accumulators of the whole lower triangle -- 325 fragments at n = 200 -- do not fit the register file next to
     // anything else; the planner sorts the items of a block by cost, so a round costs what its first item costs)
     {
@@ -232,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         __syncthreads();
       }
       DotsCtx X;
+      X.rank_limit = P.rank;
       X.P = P; X.P.part_off = P.fpart_off; X.c = c; X.ipc = ipc; X.first = A.first; X.multi = multi ? 1 : 0;
       X.warp = warp; X.lane = lane; X.nw = nw; X.colbeg = colbeg; X.cs = cs; X.eidx = A.ent_pk; X.Wp = Wp;
       X.blkp_beg = A.blkp_beg; X.blkp = A.blkp; X.invperm = A.invperm; X.Atpr = A.Atpr; X.ent_src = A.ent_src;

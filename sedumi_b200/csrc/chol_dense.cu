@@ -106,39 +106,45 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       if (tid < PB) s_lb[tid] = (tid < w) ? lb[p0 + tid] : 0.0;
       __syncthreads();
       int k_resume = 0, resolved_k = -1;
-      // All 8 warps cooperate on each pivot step: the lower triangle below/right of the pivot is at most
-      // 31*32/2 elements, one per thread; the step is then bounded by the reciprocal + two block barriers
-      // instead of one warp issuing the whole rank-1 update (measured: 930 cycles/step -> see profiles/).
+      // The 32 pivots of the block are a dependent chain; with the block spread over 8 warps every step paid two block
+      // barriers and shared-memory round trips (670 cycles per pivot, profiles/ncu_r01_top_kernels.txt).  Here ONE warp
+      // keeps the block in registers -- lane r holds row r -- and exchanges the pivot column by shuffles: a step is a
+      // reciprocal, 31-k shuffle + FMA pairs and no barrier.  The pivot rules are evaluated on the broadcast pivot, so
+      // every lane takes the same branch.
       while (true) {
-        {
-        int k = k_resume;
-        for (; k < w; k++) {
-          const int gk = p0 + k;
-          double xkk = A[k][k];
-          const bool resolved = (k == resolved_k);
-          if (resolved) xkk = s_x;
-          const bool skip = !(xkk > s_lb[k]);
-          if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) break;          // stability test needed (uniform)
-          if (skip) {
-            if (tid == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
-            continue;
+        if (warp == 0) {
+          double a[PB];
+#pragma unroll
+          for (int c = 0; c < PB; c++) a[c] = A[lane][c];
+          int kstop = w;
+          bool stop = false;
+#pragma unroll
+          for (int k = 0; k < PB; k++) {
+            if (!stop && k >= k_resume && k < w) {
+              const int gk = p0 + k;
+              double xkk = __shfl_sync(0xffffffffu, a[k], k);
+              const bool resolved = (k == resolved_k);
+              if (resolved) xkk = s_x;
+              const bool skip = !(xkk > s_lb[k]);
+              if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) { stop = true; kstop = k; }      // stability test needed
+              else if (skip) { if (lane == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; } }
+              else {
+                const double rinv = 1.0 / xkk;
+                const double xr = (lane > k) ? a[k] : 0.0;
+                // element (r,c), k < c <= r: A[r][c] -= (A[c][k]/xkk) * A[r][k]
+#pragma unroll
+                for (int c = k + 1; c < PB; c++) {
+                  const double ack = __shfl_sync(0xffffffffu, a[k], c);
+                  if (lane >= c) a[c] -= (ack * rinv) * xr;
+                }
+                if (lane > k) a[k] *= rinv;
+                if (lane == k) { a[k] = 1.0; dloc[k] = xkk; }
+              }
+            }
           }
-          const double rinv = 1.0 / xkk;
-          // element (r,c), k < c <= r < w: A[r][c] -= (A[c][k]/xkk) * A[r][k]
-          {
-            const int r = lane;                                   // warp wq handles columns k+1+wq, +8, ...
-            const double xr = (r > k && r < w) ? A[r][k] : 0.0;
-            for (int c = k + 1 + warp; c < w; c += 8)
-              if (r >= c && r < w) A[r][c] -= (A[c][k] * rinv) * xr;
-          }
-          __syncthreads();
-          // (scaling the column one step later, in the shadow of the next update, saves a barrier but
-          // measured 17 % slower: the extra loop-carried state lengthens the dependent chain)
-          if (tid > k && tid < w) A[tid][k] *= rinv;
-          if (tid == 0) { dloc[k] = xkk; A[k][k] = 1.0; }
-          __syncthreads();
-        }
-        if (tid == 0) s_state = k;
+#pragma unroll
+          for (int c = 0; c < PB; c++) A[lane][c] = a[c];
+          if (lane == 0) s_state = kstop;
         }
         __syncthreads();
         const int k = s_state;
@@ -428,6 +434,30 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 static const int SOLVE_WARPS = 8;
 static const int SOLVE_CLUSTER = 8;
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;\n" ::: "memory"); }
+// Hand-over of a solved block row inside the cluster: the producer writes y_b into every CTA's shared memory with
+// st.async, which also counts the bytes on an mbarrier of the RECEIVING CTA; consumers sleep on their local mbarrier
+// (try_wait is a hardware wait, not a poll).  One DSMEM hop (~215 cycles) + wake-up (~60) per dependent block row,
+// instead of store + cluster fence + flag + polling.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }\n"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(unsigned remote_addr, double v, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n"
+               :: "r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
 
 template <bool BACKWARD, int CL>
 __device__ __forceinline__ void
@@ -437,6 +467,7 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
   double *ys = smem;                                    // m doubles (rounded up to even)
   double *ring = smem + ((m + 1) & ~1);                 // SOLVE_WARPS x 2 x 1024 doubles
   volatile int *ready = (volatile int *)(ring + SOLVE_WARPS * 2 * PB * PB);
+  unsigned long long *bars = (unsigned long long *)(ring + SOLVE_WARPS * 2 * PB * PB + ((nb + 1) >> 1));   // one mbarrier per block row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   namespace cg = cooperative_groups;
   unsigned crank = 0;
@@ -448,9 +479,16 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
   double *myring = ring + warp * 2 * PB * PB;
   auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   if (tdbg && threadIdx.x == 0 && blockIdx.x == 0) tdbg[nb] = gtime();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) ready[i] = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    ready[i] = 0;
+    if (CL > 1) {                                       // block row i arrives as min(PB, m - i*PB) doubles from its owner
+      mbar_init(smem_u32(bars + i), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      mbar_expect_tx(smem_u32(bars + i), 8u * (unsigned)min(PB, m - i * PB));
+    }
+  }
   __syncthreads();
-  if (CL > 1) cg::this_cluster().sync();                // nobody writes a remote flag before it is cleared
+  if (CL > 1) cg::this_cluster().sync();                // nobody signals a remote barrier before it is armed
   if (tdbg && threadIdx.x == 0 && blockIdx.x == 0) tdbg[nb + 1] = gtime();
   for (int step = warp * CL + (int)crank; step < nb; step += SOLVE_WARPS * CL) {
     const int br = BACKWARD ? (nb - 1 - step) : step;
@@ -487,8 +525,11 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
     for (int t = 0; t < nprev; t++) {
       const int j = BACKWARD ? (nb - 1 - t) : t;
       cp_async_wait<1>();                                // group t has landed (only t+1 may be in flight)
-      while (ready[j] == 0) { __nanosleep(20); }          // back off: spinning warps starve the shared-memory pipe
-      if (CL > 1) fence_cluster(); else __threadfence_block();
+      if (CL > 1) mbar_wait(smem_u32(bars + j), 0);       // y_j has been delivered into this CTA's shared memory
+      else {
+        while (ready[j] == 0) { __nanosleep(20); }        // back off: spinning warps starve the shared-memory pipe
+        __threadfence_block();
+      }
       __syncwarp();
       const volatile double *yv = ys + j * PB;
       const double *lv = myring + (t & 1) * PB * PB + lane;
@@ -523,14 +564,13 @@ dense_solve_body(int m, const double *L, const double *dinv, const int *perm, co
     const double yv = (y0 + y1) + (y2 + y3);
     if (lane < w) {
       if (CL > 1) {
+        const unsigned ya = smem_u32(ys + k0 + lane), ba = smem_u32(bars + br);
 #pragma unroll
-        for (int r = 0; r < CL; r++) cg::this_cluster().map_shared_rank(ys, r)[k0 + lane] = yv;
+        for (int r = 0; r < CL; r++) st_async_f64(mapa_u32(ya, (unsigned)r), yv, mapa_u32(ba, (unsigned)r));
       } else ys[k0 + lane] = yv;
     }
     if (CL > 1) {
-      fence_cluster();
       __syncwarp();
-      if (lane < CL) ((volatile int *)cg::this_cluster().map_shared_rank((int *)ready, lane))[br] = 1;
     } else {
       __threadfence_block();
       __syncwarp();
@@ -667,7 +707,7 @@ int dense_make_transpose(sb200_chol_plan *pl, const double *rect) {
 static int solve_launch(bool backward, sb200_chol_plan *pl, const double *rect, const double *b, double *y, int nrhs,
                         const double *dscale, const int *flag) {
   const int m = pl->m, nb = (m + PB - 1) / PB;
-  size_t shm = sizeof(double) * (((m + 1) & ~1) + SOLVE_WARPS * 2 * PB * PB) + sizeof(int) * nb;
+  size_t shm = sizeof(double) * (((m + 1) & ~1) + SOLVE_WARPS * 2 * PB * PB + ((nb + 1) >> 1) + nb);      // y, rings, flags, mbarriers
   SB_CHECK(shm <= 200 * 1024, "dense solve: m=%d too large for the shared-memory dataflow kernel", m);
   cudaStream_t st = ctx().stream;
   static const bool use_cluster = !(getenv("SB200_SOLVE_CLUSTER") && atoi(getenv("SB200_SOLVE_CLUSTER")) == 0);

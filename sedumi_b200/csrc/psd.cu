@@ -903,11 +903,13 @@ int sb200_invcholfac(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx
   SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
   if (pl->lenud == 0) return 0;
   arena_reset();
-  double *du = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud);
+  // d.u is the same array for invcholfac, the psdscale calls and urotorder of one IPM iteration: its device copy is
+  // found again by content (mirror_input), only the first of those calls pays the upload
+  const double *du = (const double *)mirror_input(u, sizeof(double) * pl->lenud);
+  double *dy = arena<double>((size_t)pl->lenud);
   SB_CHECK(du && dy, "invcholfac: out of device memory");
   const int *dperm;
   SB_TRY(upload_perm(pl, perm, &dperm));
-  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
   SB_TRY(sb200_invcholfac_dev(pl, du, dperm, dy));
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, ctx().stream));
   SB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -919,11 +921,11 @@ int sb200_psdscale(sb_idx nblk, const sb_idx *n, const double *u, const sb_idx *
   SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
   if (pl->lenud == 0) return 0;
   arena_reset();
-  double *du = arena<double>((size_t)pl->lenud), *dx = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud);
+  const double *du = (const double *)mirror_input(u, sizeof(double) * pl->lenud);
+  double *dx = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud);
   SB_CHECK(du && dx && dy, "psdscale: out of device memory");
   const int *dperm;
   SB_TRY(upload_perm(pl, perm, &dperm));
-  SB_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
   SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, ctx().stream));
   SB_TRY(sb200_psdscale_dev(pl, du, dperm, dx, transp, dy));
   SB_CUDA(cudaMemcpyAsync(y, dy, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1053,11 +1055,11 @@ int sb200_psdframeit(sb_idx nblk, const sb_idx *n, const double *lab, const doub
   SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
   if (pl->lenud == 0) return 0;
   arena_reset();
-  double *dl = arena<double>((size_t)pl->sumn), *df = arena<double>((size_t)pl->lenud), *dx = arena<double>((size_t)pl->lenud);
+  double *dl = arena<double>((size_t)pl->sumn), *dx = arena<double>((size_t)pl->lenud);
+  const double *df = (const double *)mirror_input(frms, sizeof(double) * pl->lenud);      // the frame travels psdinvjmul -> psdframeit x2
   SB_CHECK(dl && df && dx, "psdframeit: out of device memory");
   cudaStream_t st = ctx().stream;
   SB_CUDA(cudaMemcpyAsync(dl, lab, sizeof(double) * pl->sumn, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
   SB_TRY(sb200_psdframeit_dev(pl, dl, df, dx));
   SB_CUDA(cudaMemcpyAsync(x, dx, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
@@ -1069,12 +1071,11 @@ int sb200_psdinvjmul(sb_idx nblk, const sb_idx *n, const double *xlab, const dou
   SB_TRY(sb200_psd_plan_get(&pl, nblk, n));
   if (pl->lenud == 0) return 0;
   arena_reset();
-  double *dl = arena<double>((size_t)pl->sumn), *df = arena<double>((size_t)pl->lenud), *dy = arena<double>((size_t)pl->lenud),
-         *dz = arena<double>((size_t)pl->lenud);
+  double *dl = arena<double>((size_t)pl->sumn), *dy = arena<double>((size_t)pl->lenud), *dz = arena<double>((size_t)pl->lenud);
+  const double *df = (const double *)mirror_input(frms, sizeof(double) * pl->lenud);
   SB_CHECK(dl && df && dy && dz, "psdinvjmul: out of device memory");
   cudaStream_t st = ctx().stream;
   SB_CUDA(cudaMemcpyAsync(dl, xlab, sizeof(double) * pl->sumn, cudaMemcpyHostToDevice, st));
-  SB_CUDA(cudaMemcpyAsync(df, frms, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * pl->lenud, cudaMemcpyHostToDevice, st));
   SB_TRY(sb200_psdinvjmul_dev(pl, dl, df, dy, dz));
   SB_CUDA(cudaMemcpyAsync(z, dz, sizeof(double) * pl->lenud, cudaMemcpyDeviceToHost, st));
