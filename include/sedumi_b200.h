@@ -143,6 +143,8 @@ int sb200_bwblkslv_dev(sb200_chol_plan *plan, const double *Lrect_dev, const dou
  * pivots get d=1 like deninfac.m:88-93 when flag_dev is given.  w_dev: m*nrhs scratch. */
 int sb200_ldl_solve_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev,
                         const int *flag_dev, const double *b_dev, double *w_dev, double *y_dev, sb_idx nrhs);
+int sb200_ldl_solve2_dev(sb200_chol_plan *plan, const double *Lrect_dev, const double *d_dev, const int *flag_dev,
+                         const double *b_dev, double *w_dev, double *y_dev, sb_idx nrhs, double *ssqr_dev);
 int sb200_fwblkslv(sb_idx m, sb_idx nsuper, const sb_idx *xsuper, const sb_idx *Ljc,
                    const sb_idx *Lir, const double *Lpr, const sb_idx *perm,
                    const double *b, double *y, sb_idx nrhs);
@@ -256,6 +258,21 @@ int sb200_getada2(sb200_ada_plan *plan, sb_idx nq, const sb_idx *Qjc, const sb_i
                   const sb_idx *perm, const double *ada_in, double *ada_out);
 int sb200_getada3(sb200_ada_plan *plan, const double *Atpr, const double *udsqr, sb_idx lenud,
                   const sb_idx *perm, sb_idx first, const double *ada_in, double *ada_out, double *absd_out);
+
+/* ------------------------------------------------------------------ search direction
+ * The direct step of wrapPcg.m:42-97 on device-resident data, LP + PSD cones without dense columns:
+ *   dx = D'rv ; r = A dx + rb ; p = L'\((L\r)./d) ; x = vecsym(At p) ; alpha = (p'(p./d)) / |D x|^2 ;
+ *   y = alpha p ; dx = rv - alpha D x ; r = A D'dx + rb ; normr = |r|_inf      (Amul.m:42-56, vecsym.c, psdscale.m).
+ * rv_dev: N = K.l + sum(K.s.^2) doubles; rb_dev: m doubles or NULL; outputs y (m), dx (N), r (m);
+ * scal_dev[0..3] = ssqrNew, ssqrdx, alpha, normr (device); work_dev: 3 N + 2 m + 600 doubles.  Nothing synchronises. */
+int sb200_wrappcg_dev(sb200_ada_plan *ada, sb200_psd_plan *psd, sb200_chol_plan *chol, const double *dl_dev,
+                      const double *u_dev, const int *perm_dev, const double *Lrect_dev, const double *Ld_dev,
+                      const int *flag_dev, const double *rv_dev, const double *rb_dev, double *y_dev, double *dx_dev,
+                      double *r_dev, double *scal_dev, double *work_dev);
+int sb200_ada_plan_csr(sb200_ada_plan *plan, const long long **Ajc, const int **Air, const double **Apr,
+                       const long long **rowptr, const int **rowcol, const int **rowsrc, sb_idx *N, sb_idx *m,
+                       sb_idx *lpN, sb_idx *nq);
+int sb200_psd_plan_blocks(sb200_psd_plan *plan, const int **n_dev, const long long **off_dev, int *nblk, int *maxn);
 
 /* ------------------------------------------------------------------ Lorentz streams
  * ddot.c:165-308, qblkmul.c:57-116, quadadd.c:89-130.

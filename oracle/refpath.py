@@ -147,3 +147,41 @@ class DenseColumnRef:
         smult = d["l"][dense.cols[:dense.l].astype(int) - 1]
         LAD = self.mex.fwblkslv(self.Lm, Ad, self.sym["LAD"])
         return LAD, Ld, self.sym, smult.reshape(-1, 1)
+
+
+def wrappcg_direct(R: "RefHotPath", L: dict, d: dict, rv, rb=None):
+    """The direct step of wrapPcg.m:42-97 (no dense columns, no Lorentz cones) driven through the reference's own
+    MEX solves and vecsym, with numpy for the M-only glue (Amul.m:42-56, psdscale.m) -- the parity point of the
+    search direction.  Returns dict(y, dx, r, ssqrNew, ssqrdx, alpha, normr)."""
+    S = R.S
+    K = S.K
+    l = int(K["l"])
+    At = S.At
+    rv = np.asarray(rv, dtype=float).ravel()
+    sl = np.sqrt(np.asarray(d["l"], dtype=float).ravel())
+
+    def D(x, transp):
+        return np.r_[sl * x[:l], restate.psdscale({"u": d["u"], "perm": d["perm"]}, x, K, transp)]
+
+    Lm = hsetup.L_for_mex({k: L[k] for k in ("perm", "L", "xsuper", "tmpsiz")})
+    Ld = np.asarray(L["d"], dtype=float).reshape(-1, 1)
+    dx = D(rv, 1)
+    r = np.asarray(At.T @ dx).ravel()
+    if rb is not None:
+        r = r + np.asarray(rb, dtype=float).ravel()
+    p = R.mex.fwblkslv(Lm, r.reshape(-1, 1))
+    y = p / Ld
+    ssq = float((p * y).sum())
+    p = np.asarray(R.mex.bwblkslv(Lm, y)).ravel()
+    x = np.asarray(At @ p).ravel()
+    x = np.asarray(R.mex.vecsym(x.reshape(-1, 1), R.Km)).ravel()
+    dx2 = D(x, 0)
+    ssqrdx = float(dx2 @ dx2)
+    alpha = ssq / ssqrdx
+    yout = alpha * p
+    dxo = rv - alpha * dx2
+    x = D(dxo, 1)
+    r = np.asarray(At.T @ x).ravel()
+    if rb is not None:
+        r = r + np.asarray(rb, dtype=float).ravel()
+    return dict(y=yout, dx=dxo, r=r, ssqrNew=ssq, ssqrdx=ssqrdx, alpha=alpha, normr=float(np.abs(r).max()))

@@ -470,7 +470,7 @@ struct sb200_ada_plan {
   bool have_vals = false;
   // device
   DevBuf<long long> d_Ajc, d_Ajc1, d_Ajcend, d_adajc, d_qstart, d_blk_off;
-  DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_lin, d_ent_src, d_Rlist, d_tt_ptr, d_tt_col, d_tt_src;
+  DevBuf<int> d_Air, d_adair, d_blk_n, d_cpair_beg, d_ent_lin, d_ent_src, d_Rlist, d_tt_ptr, d_tt_col, d_tt_src, d_tt_row;
   DevBuf<double> d_tt_w;
   DevBuf<int> d_ublk_off, d_u_p, d_u_q, d_blkp_beg, d_ent_pk;
   DevBuf<BlkPartner> d_blkp;
@@ -503,6 +503,10 @@ struct sb200_ada_plan {
   int any_multi = 0;
   DevBuf<double> d_tt_val, d_fscratch, d_fws;
   DevBuf<int> d_fcounter, d_fitem_beg, d_fneed, d_forder;
+  // row-wise (CSR) view of the pattern of At for products At*p without atomics (pcg.cu)
+  DevBuf<long long> d_rowptr; DevBuf<int> d_rowcol, d_rowsrc;
+  std::vector<long long> h_Ajc; std::vector<int> h_Air;
+  bool csr_built = false;
   DevBuf<int2> d_fitems;
   long long fused_ndense = 0;
 };
@@ -514,6 +518,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
                      sb_idx lpN, sb_idx nq, const sb_idx *qstart, sb_idx nblk, sb_idx nreal, const sb_idx *blkstart, const sb_idx *blkn,
                      const sb_idx *adajc, const sb_idx *adair) {
   pl->m = (int)m; pl->N = N; pl->nnzA = Ajc[m]; pl->nnzADA = adajc[m];
+  pl->h_Ajc.assign(Ajc, Ajc + m + 1);
   pl->lpN = (int)lpN; pl->nq = (int)nq; pl->nblk = (int)nblk;
   SB_CHECK(pl->nnzA < 2147483647LL, "At has too many nonzeros for 32-bit entry indices");
   // Hermitian blocks (k >= nreal) are handled through the real embedding E(Z) = [[Re Z, -Im Z],[Im Z, Re Z]] of
@@ -532,7 +537,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   const long long psd0 = nblk ? blkstart[0] : N;
   pl->lq_rows = nq ? qstart[nq] : lpN;
   // ---- pairs
-  std::vector<int> ent_p, ent_q, ent_lin, ent_src, Rlist, tt_ptr, tt_col, tt_src;
+  std::vector<int> ent_p, ent_q, ent_lin, ent_src, Rlist, tt_ptr, tt_col, tt_row, tt_src;
   std::vector<double> ent_sgn;
   std::vector<double> tt_w;
   std::vector<std::vector<std::pair<int, std::pair<int, double>>>> percol;
@@ -591,7 +596,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       }
       for (size_t rho = 0; rho < tmpR.size(); rho++) {
         tt_ptr.push_back((int)tt_col.size());
-        for (auto &t : percol[rho]) { tt_col.push_back(t.first); tt_src.push_back(t.second.first); tt_w.push_back(t.second.second); }
+        for (auto &t : percol[rho]) { tt_col.push_back(t.first); tt_row.push_back(tmpR[rho]); tt_src.push_back(t.second.first); tt_w.push_back(t.second.second); }
       }
       tt_ptr.push_back((int)tt_col.size());
       pl->pairs.push_back(P);
@@ -776,6 +781,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
   SB_TRY(up64(pl->d_adajc, adajc, m + 1));
   if (nq) SB_TRY(up64(pl->d_qstart, qstart, nq + 1)); else SB_TRY(pl->d_qstart.alloc(1));
   SB_TRY(to_i32(Air, (size_t)Ajc[m], v32, "At.ir")); SB_TRY(pl->d_Air.upload(v32));
+  pl->h_Air = v32;
   SB_TRY(to_i32(adair, (size_t)adajc[m], v32, "ADA.ir")); SB_TRY(pl->d_adair.upload(v32));
   SB_TRY(pl->d_blk_n.upload(pl->blk_n)); SB_TRY(pl->d_blk_off.upload(pl->blk_off));
   SB_TRY(pl->d_cpair_beg.upload(pl->cpair_beg));
@@ -790,6 +796,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     SB_TRY(pl->d_De.alloc((size_t)std::max<long long>(pl->lenud_emb, 1)));
   }
   SB_TRY(pl->d_tt_ptr.upload(tt_ptr)); SB_TRY(pl->d_tt_col.upload(tt_col)); SB_TRY(pl->d_tt_src.upload(tt_src));
+  SB_TRY(pl->d_tt_row.upload(tt_row));
   SB_TRY(pl->d_tt_w.upload(tt_w));
   SB_TRY(pl->d_ublk_off.upload(ublk_off)); SB_TRY(pl->d_u_p.upload(u_p)); SB_TRY(pl->d_u_q.upload(u_q));
   SB_TRY(pl->d_blkp_beg.upload(blkp_beg)); SB_TRY(pl->d_blkp.upload(blkp)); SB_TRY(pl->d_ent_pk.upload(ent_pk));
@@ -961,6 +968,27 @@ int sb200_ada_set_At_values(sb200_ada_plan *pl, const double *Atpr) {
   return 0;
 }
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *pl) { return pl->nnzADA; }
+// Device arrays of At (CSC as given, and a CSR view built on first use) for the matrix-vector products of pcg.cu.
+int sb200_ada_plan_csr(sb200_ada_plan *pl, const long long **Ajc, const int **Air, const double **Apr, const long long **rowptr,
+                       const int **rowcol, const int **rowsrc, sb_idx *N, sb_idx *m, sb_idx *lpN, sb_idx *nq) {
+  if (!pl->csr_built) {
+    SB_CHECK(!ctx().capturing, "At's row-wise view must be built before graph capture (call once outside)");
+    const long long N2 = pl->N; const int m2 = pl->m;
+    std::vector<long long> rp((size_t)N2 + 1, 0);
+    for (long long p = 0; p < pl->nnzA; p++) rp[pl->h_Air[p] + 1]++;
+    for (long long r = 0; r < N2; r++) rp[r + 1] += rp[r];
+    std::vector<int> rc((size_t)std::max<long long>(pl->nnzA, 1)), rs((size_t)std::max<long long>(pl->nnzA, 1));
+    std::vector<long long> fill(rp.begin(), rp.end() - 1);
+    for (int j = 0; j < m2; j++)
+      for (long long p = pl->h_Ajc[j]; p < pl->h_Ajc[j + 1]; p++) { const long long t = fill[pl->h_Air[p]]++; rc[t] = j; rs[t] = (int)p; }
+    SB_TRY(pl->d_rowptr.upload(rp)); SB_TRY(pl->d_rowcol.upload(rc)); SB_TRY(pl->d_rowsrc.upload(rs));
+    SB_CUDA(cudaStreamSynchronize(ctx().stream));
+    pl->csr_built = true;
+  }
+  *Ajc = pl->d_Ajc.p; *Air = pl->d_Air.p; *Apr = pl->d_Atpr.p; *rowptr = pl->d_rowptr.p; *rowcol = pl->d_rowcol.p; *rowsrc = pl->d_rowsrc.p;
+  *N = pl->N; *m = pl->m; *lpN = pl->lpN; *nq = pl->nq;
+  return 0;
+}
 // Ownership for device-resident callers: a retained plan is exempt from cache eviction until released.
 int sb200_ada_plan_retain(sb200_ada_plan *pl) { if (pl) pl->pins++; return 0; }
 int sb200_ada_plan_release(sb200_ada_plan *pl) { if (pl && pl->pins > 0) pl->pins--; return 0; }
@@ -1131,7 +1159,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     SB_CUDA(cudaMemsetAsync(pl->d_fcounter.p, 0, sizeof(int), st));
     FusedArgs FA;
     FA.pairs = pl->d_pairs.p; FA.npairs = (int)pl->pairs.size(); FA.counter = pl->d_fcounter.p;
-    FA.blk_n = pl->d_blk_n.p; FA.blk_off = pl->d_blk_off.p; FA.tt_ptr = pl->d_tt_ptr.p; FA.tt_col = pl->d_tt_col.p; FA.tt_val = pl->d_tt_val.p;
+    FA.blk_n = pl->d_blk_n.p; FA.blk_off = pl->d_blk_off.p; FA.tt_ptr = pl->d_tt_ptr.p; FA.tt_col = pl->d_tt_col.p; FA.tt_row = pl->d_tt_row.p; FA.tt_val = pl->d_tt_val.p;
     FA.Rlist = pl->d_Rlist.p; FA.udsqr = udsqr_dev; FA.scratch = pl->d_fscratch.p; FA.scratch_stride = pl->fused_scratch_stride;
     FA.adajc = pl->d_adajc.p; FA.adair = pl->d_adair.p; FA.invperm = ip; FA.first = (int)first; FA.cpair_beg = pl->d_cpair_beg.p;
     FA.blkp_beg = pl->d_blkp_beg.p; FA.blkp = pl->d_blkp.p; FA.ent_pk = pl->d_ent_pk.p; FA.ent_src = pl->d_ent_src.p; FA.Atpr = pl->d_Atpr.p;

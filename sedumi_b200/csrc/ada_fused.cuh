@@ -23,7 +23,7 @@ struct FusedArgs {
   const AdaPair *pairs; int npairs;
   int *counter;
   const int *blk_n; const long long *blk_off;
-  const int *tt_ptr, *tt_col; const double *tt_val;  // per (pair, row of R): entries (column, weight*value)
+  const int *tt_ptr, *tt_col, *tt_row; const double *tt_val;  // per (pair, row of R): entries (column, row, weight*value)
   const int *Rlist;
   const double *udsqr;
   double *scratch; long long scratch_stride;         // per-CTA T slot
@@ -152,22 +152,30 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
     __syncthreads();
     // ---------------- 2a. entry-wise evaluation on the needed set (pairs early in their block's list)
     if (P.mode != 0) {
+      // four lanes share one needed entry (p, q) and split the sum; eight terms per lane are in flight at a time
       const int *pq = A.need_pq + P.need_off;
-      const int *ptr = A.tt_ptr + P.r0;
-      for (int u = tid; u < P.need_cnt; u += blockDim.x) {
-        const int v = pq[u], pp = v & 0xffff, qq = v >> 16;
+      const int g = tid & 3;
+      const int e0 = A.tt_ptr[P.r0], e1 = A.tt_ptr[P.r0 + r];
+      for (int u0 = 0; u0 < P.need_cnt; u0 += (int)(blockDim.x >> 2)) {
+        const int u = u0 + (tid >> 2);
+        const bool live = u < P.need_cnt;
+        const int v = live ? pq[u] : 0, pp = v & 0xffff, qq = v >> 16;
         double acc = 0.0;
-        if (P.mode == 1) {
-          for (int rho = 0; rho < r; rho++) acc += D[pp + (long long)R[rho] * n] * Tt[qq + (long long)rho * n];
-        } else {                                                 // W(p,q) = sum_rho D(p,R[rho]) sum_t v_t D(c_t,q), D symmetric
-          for (int rho = 0; rho < r; rho++) {
-            const double dp = D[pp + (long long)R[rho] * n];
-            double in = 0.0;
-            for (int t = ptr[rho]; t < ptr[rho + 1]; t++) in += A.tt_val[t] * D[qq + (long long)A.tt_col[t] * n];
-            acc += dp * in;
+        if (P.mode == 1) {                                        // through T: sum_rho D(p,R[rho]) T(rho,q)
+          if (live) {
+#pragma unroll 8
+            for (int rho = g; rho < r; rho += 4) acc += D[pp + (long long)R[rho] * n] * Tt[qq + (long long)rho * n];
+          }
+        } else {                                                  // few entries in A_jk: sum_t v_t D(p,row_t) D(col_t,q), D symmetric
+          if (live) {
+#pragma unroll 8
+            for (int t = e0 + g; t < e1; t += 4)
+              acc += A.tt_val[t] * (D[pp + (long long)A.tt_row[t] * n] * D[qq + (long long)A.tt_col[t] * n]);
           }
         }
-        Wp[(qq * (2 * n - qq + 1)) / 2 - qq + pp] = acc;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (live && g == 0) Wp[(qq * (2 * n - qq + 1)) / 2 - qq + pp] = acc;
       }
     } else
     // ---------------- 2b. W = D(:,R) T on the lower supertiles, in rounds of at most FUSED_GEMM_WARPS items

@@ -614,6 +614,21 @@ __global__ void scale_by_d_kernel(int m, int nrhs, const double *d, const int *f
   w[i] /= dk;
 }
 
+// ssqr = sum_i w_i^2 d_i with deninfac's repaired pivots (one block: m is at most a few thousand)
+__global__ void __launch_bounds__(1024) ssqr_kernel(int m, const double *d, const int *flag, const double *lb, const double *w, double *out) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    double dk = d[k];
+    if (flag && flag[k] == 1 && dk <= lb[k]) dk = 1.0;
+    a += w[k] * w[k] * dk;
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 32; i++) t += sh[i]; *out = t; }
+}
+
 __global__ void gather_perm_kernel(int m, int nrhs, const int *perm, const double *b, double *y) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)m * nrhs) return;
@@ -934,16 +949,26 @@ int sb200_bwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
 // from the last sb200_blkchol_dev call).
 int sb200_ldl_solve_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag,
                         const double *b, double *w, double *y, sb_idx nrhs) {
-  if (pl->dense_fast) {
-    SB_TRY(dense_fwsolve(pl, rect, b, w, (int)nrhs, d, flag));
-    return dense_bwsolve(pl, rect, w, y, (int)nrhs);
+  return sb200_ldl_solve2_dev(pl, rect, d, flag, b, w, y, nrhs, nullptr);
+}
+// The same, also returning ssqr = p' (p ./ d) with p = L \ b(perm) (wrapPcg.m:56-58, first right-hand side), computed
+// from w = p ./ d as sum w_i^2 d_i with the repaired pivots.
+int sb200_ldl_solve2_dev(sb200_chol_plan *pl, const double *rect, const double *d, const int *flag,
+                         const double *b, double *w, double *y, sb_idx nrhs, double *ssqr_dev) {
+  if (pl->dense_fast) SB_TRY(dense_fwsolve(pl, rect, b, w, (int)nrhs, d, flag));
+  else {
+    SB_TRY(sb200_fwblkslv_dev(pl, rect, b, w, nrhs));
+    long long tot = (long long)pl->m * nrhs;
+    if (tot > 0) {
+      scale_by_d_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx().stream>>>(pl->m, (int)nrhs, d, flag, pl->d_lb.p, w);
+      SB_LAUNCH_CHECK_N("scale_by_d_kernel");
+    }
   }
-  SB_TRY(sb200_fwblkslv_dev(pl, rect, b, w, nrhs));
-  long long tot = (long long)pl->m * nrhs;
-  if (tot > 0) {
-    scale_by_d_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx().stream>>>(pl->m, (int)nrhs, d, flag, pl->d_lb.p, w);
-    SB_LAUNCH_CHECK_N("scale_by_d_kernel");
+  if (ssqr_dev && pl->m > 0) {
+    ssqr_kernel<<<1, 1024, 0, ctx().stream>>>(pl->m, d, flag, pl->d_lb.p, w, ssqr_dev);
+    SB_LAUNCH_CHECK_N("ssqr_kernel");
   }
+  if (pl->dense_fast) return dense_bwsolve(pl, rect, w, y, (int)nrhs);
   return sb200_bwblkslv_dev(pl, rect, w, y, nrhs);
 }
 

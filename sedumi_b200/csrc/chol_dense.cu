@@ -74,6 +74,48 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
   __syncthreads();
 }
 
+// The 32 x 32 diagonal block, factored by ONE warp with the block in registers (lane r = row r); the pivot column
+// travels by shuffles, a step has no barrier.  A separate, non-inlined function so that its 32 doubles per lane get
+// registers of their own (inlined into the 250-register panel kernel they were demoted to local memory and the
+// factorisation ran 2.3x slower than the shared-memory version).  Returns the first pivot that needs the reference's
+// stability test (w if none); the state up to there is written back to A / dloc / skipped.
+__device__ __noinline__ int warp_factor_block(double (*A)[PB + 1], const double *s_lb, double *dloc, int *skipped, int *flag,
+                                              double *sval, int p0, int w, int m, double ub, int k_resume, int resolved_k, double s_x) {
+  const int lane = threadIdx.x & 31;
+  double a[PB];
+#pragma unroll
+  for (int c = 0; c < PB; c++) a[c] = A[lane][c];
+  int kstop = w;
+  bool stop = false;
+#pragma unroll
+  for (int k = 0; k < PB; k++) {
+    if (!stop && k >= k_resume && k < w) {
+      const int gk = p0 + k;
+      double xkk = __shfl_sync(0xffffffffu, a[k], k);
+      const bool resolved = (k == resolved_k);
+      if (resolved) xkk = s_x;
+      const bool skip = !(xkk > s_lb[k]);
+      if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) { stop = true; kstop = k; }      // stability test needed
+      else if (skip) { if (lane == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; } }
+      else {
+        const double rinv = 1.0 / xkk;
+        const double xr = (lane > k) ? a[k] : 0.0;
+        // element (r,c), k < c <= r: A[r][c] -= (A[c][k]/xkk) * A[r][k]
+#pragma unroll
+        for (int c = k + 1; c < PB; c++) {
+          const double ack = __shfl_sync(0xffffffffu, a[k], c);
+          if (lane >= c) a[c] -= (ack * rinv) * xr;
+        }
+        if (lane > k) a[k] *= rinv;
+        if (lane == k) { a[k] = 1.0; dloc[k] = xkk; }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < PB; c++) A[lane][c] = a[c];
+  return kstop;
+}
+
 // W: working matrix (m x m, ld = m, lower triangle live); Lo: output factor (same layout).
 __global__ void __launch_bounds__(256)
 dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, const double *scal, double maxu,
@@ -107,43 +149,11 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       __syncthreads();
       int k_resume = 0, resolved_k = -1;
       // The 32 pivots of the block are a dependent chain; with the block spread over 8 warps every step paid two block
-      // barriers and shared-memory round trips (670 cycles per pivot, profiles/ncu_r01_top_kernels.txt).  Here ONE warp
-      // keeps the block in registers -- lane r holds row r -- and exchanges the pivot column by shuffles: a step is a
-      // reciprocal, 31-k shuffle + FMA pairs and no barrier.  The pivot rules are evaluated on the broadcast pivot, so
-      // every lane takes the same branch.
+      // barriers and shared-memory round trips (670 cycles per pivot, profiles/ncu_r01_top_kernels.txt): one warp does
+      // it in registers instead (warp_factor_block).
       while (true) {
         if (warp == 0) {
-          double a[PB];
-#pragma unroll
-          for (int c = 0; c < PB; c++) a[c] = A[lane][c];
-          int kstop = w;
-          bool stop = false;
-#pragma unroll
-          for (int k = 0; k < PB; k++) {
-            if (!stop && k >= k_resume && k < w) {
-              const int gk = p0 + k;
-              double xkk = __shfl_sync(0xffffffffu, a[k], k);
-              const bool resolved = (k == resolved_k);
-              if (resolved) xkk = s_x;
-              const bool skip = !(xkk > s_lb[k]);
-              if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) { stop = true; kstop = k; }      // stability test needed
-              else if (skip) { if (lane == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; } }
-              else {
-                const double rinv = 1.0 / xkk;
-                const double xr = (lane > k) ? a[k] : 0.0;
-                // element (r,c), k < c <= r: A[r][c] -= (A[c][k]/xkk) * A[r][k]
-#pragma unroll
-                for (int c = k + 1; c < PB; c++) {
-                  const double ack = __shfl_sync(0xffffffffu, a[k], c);
-                  if (lane >= c) a[c] -= (ack * rinv) * xr;
-                }
-                if (lane > k) a[k] *= rinv;
-                if (lane == k) { a[k] = 1.0; dloc[k] = xkk; }
-              }
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < PB; c++) A[lane][c] = a[c];
+          const int kstop = warp_factor_block(A, s_lb, dloc, skipped, flag, sval, p0, w, m, ub, k_resume, resolved_k, s_x);
           if (lane == 0) s_state = kstop;
         }
         __syncthreads();

@@ -789,6 +789,11 @@ int sb200_psd_plan_get(sb200_psd_plan **plan, sb_idx nblk, const sb_idx *n) {
   return 0;
 }
 sb_idx sb200_psd_plan_lenud(const sb200_psd_plan *pl) { return pl->lenud; }
+// device-side block table (orders, offsets in a lenud vector) for kernels of other translation units
+int sb200_psd_plan_blocks(sb200_psd_plan *pl, const int **n_dev, const long long **off_dev, int *nblk, int *maxn) {
+  *n_dev = pl->d_n.p; *off_dev = pl->d_off.p; *nblk = pl->nblk; *maxn = pl->maxn;
+  return 0;
+}
 sb_idx sb200_psd_plan_sumn(const sb200_psd_plan *pl) { return pl->sumn; }
 
 static dim3 blk_grid(const sb200_psd_plan *pl, int per) {

@@ -87,6 +87,7 @@ EXPORTS = [
     "sb200_comm_unique_id", "sb200_comm_init_rank", "sb200_comm_size", "sb200_comm_rank", "sb200_comm_nccl_version",
     "sb200_comm_stats", "sb200_allreduce_sum_dev", "sb200_allreduce_sum2_dev", "sb200_comm_destroy",
     "sb200_blkchol_sharded_dev", "sb200_ldl_solve_sharded_dev",
+    "sb200_wrappcg_dev", "sb200_ldl_solve2_dev", "sb200_ada_plan_csr", "sb200_psd_plan_blocks",
 ]
 
 
@@ -392,6 +393,32 @@ class HotPath:
         self.launches_per_iteration = int(L.sb200_kernel_launches() - l0)
         self._graph = g
         return lambda: check(L.sb200_graph_launch(g), "graph_launch")
+
+    def wrappcg(self, rv: np.ndarray, rb: np.ndarray | None = None):
+        """The direct step of wrapPcg.m:42-97 on the device (factor and scaling already resident: call after blkchol).
+        rv: N = K.l + sum(K.s.^2) right-hand side in x-space, rb: m or None.  Returns dict(y, dx, r, ssqrNew, ssqrdx,
+        alpha, normr) as host arrays / floats (one D2H at the end)."""
+        t = self.torch
+        N = self.lpN + self.lenud
+        rv = np.ascontiguousarray(np.asarray(rv, dtype=np.float64).ravel())
+        assert rv.size == N, (rv.size, N)
+        with t.cuda.stream(self.stream()):
+            if getattr(self, "_pcg", None) is None:
+                f64 = dict(dtype=t.float64, device=self.dev)
+                self._pcg = dict(work=t.zeros(3 * N + 2 * self.m + 600, **f64), y=t.zeros(self.m, **f64), dx=t.zeros(N, **f64),
+                                 r=t.zeros(self.m, **f64), scal=t.zeros(4, **f64), rv=t.zeros(N, **f64), rb=t.zeros(self.m, **f64))
+            P = self._pcg
+            P["rv"].copy_(t.from_numpy(rv))
+            if rb is not None:
+                P["rb"].copy_(t.from_numpy(np.ascontiguousarray(np.asarray(rb, dtype=np.float64).ravel())))
+            check(lib().sb200_wrappcg_dev(self.ada, self.psd, self.chol, _p(self.d_l), _p(self.d_u),
+                                          _p(self.d_perm) if self.has_perm else None, _p(self.Lrect), _p(self.dvec), _p(self.flag),
+                                          _p(P["rv"]), _p(P["rb"]) if rb is not None else None, _p(P["y"]), _p(P["dx"]), _p(P["r"]),
+                                          _p(P["scal"]), _p(P["work"])), "wrappcg")
+            self.sync()
+            sc = P["scal"].cpu().numpy()
+            return dict(y=P["y"].cpu().numpy(), dx=P["dx"].cpu().numpy(), r=P["r"].cpu().numpy(), ssqrNew=float(sc[0]),
+                        ssqrdx=float(sc[1]), alpha=float(sc[2]), normr=float(sc[3]))
 
     def profile(self, nsolve=4, npsdscale=12, sharded=False, reps=3):
         """Per-kernel device time of one iteration, averaged over `reps`: {kernel name: (launches, ms)}.  An event is
