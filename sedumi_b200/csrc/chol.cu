@@ -221,16 +221,32 @@ __global__ void __launch_bounds__(512)
 factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, const double *lb,
                     const double *scal, double maxu, int *flag, double *sval,
                     const double *diagX, int mtot, int cap) {
-  extern __shared__ double pan[];
+  extern __shared__ __align__(16) double pan[];
+  __shared__ __align__(8) unsigned long long pan_bar;
   Sn s = sn[list[blockIdx.x]];
   double *Pg = rect + s.poff;
   const int ld = s.m, n = s.n, m = s.m;
   const bool insm = (long long)m * n <= cap;
   double *P = Pg;
+  // The panel is one contiguous, 16-byte aligned run of m*n doubles (padded to an even count): it is staged into shared
+  // memory by the TMA unit as 1-D bulk copies that complete on an mbarrier, and written back the same way.
+  const unsigned pan_bytes = (unsigned)((((long long)m * n + 1) & ~1LL) * 8);
   if (insm) {
-    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) pan[idx] = Pg[idx];
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&pan_bar), dst = (unsigned)__cvta_generic_to_shared(pan);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(pan_bytes) : "memory");
+      for (unsigned off = 0; off < pan_bytes; off += 65536u) {
+        const unsigned len = min(65536u, pan_bytes - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     :: "r"(dst + off), "l"((const char *)Pg + off), "r"(len), "r"(bar) : "memory");
+      }
+    }
+    __syncthreads();                                   // the barrier is initialised before anybody waits on it
+    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }\n"
+                 :: "r"(bar) : "memory");
     P = pan;
-    __syncthreads();
   }
   const double ub = scal[0];
   __shared__ ArgMax sh_am[32];
@@ -282,7 +298,16 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
   }
   if (insm) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) Pg[idx] = pan[idx];
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy writes of the panel -> visible to the bulk store
+      const unsigned src = (unsigned)__cvta_generic_to_shared(pan);
+      for (unsigned off = 0; off < pan_bytes; off += 65536u) {
+        const unsigned len = min(65536u, pan_bytes - off);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" :: "l"((char *)Pg + off), "r"(src + off), "r"(len) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    }
   }
 }
 
@@ -717,6 +742,7 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
     S.poff = poff;
     S.coff = Ljc[S.first];
     poff += (long long)S.m * S.n;
+    poff = (poff + 1) & ~1LL;                 // panels start on 16-byte boundaries: they move through the TMA unit as bulk copies
     for (int t = 0; t < S.m; t++) {
       sb_idx r = Lir[Ljc[S.first] + t];
       SB_CHECK(r >= 0 && r < m, "blkchol: L.L row index out of range");
