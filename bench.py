@@ -73,10 +73,12 @@ def load_workload(name):
         raw = problems.synth_blockdiag_sdp(nblk=8, n=60, m=400, nlink=16, density=0.03)
     elif name == "dense1000":
         raw = problems.synth_dense_sdp()
+    elif name == "densecol":
+        raw = problems.synth_blockdiag_sdp(dense_lp=8)
     else:
         raise SystemExit(f"unknown workload {name}")
     At, b, c, K = cones.pretransfo(*raw)[:4]
-    perm = np.arange(At.shape[1]) if name.startswith("blockdiag") else None
+    perm = np.arange(At.shape[1]) if name.startswith("blockdiag") or name == "densecol" else None
     S = setup.build_setup(At, b, c, K, perm=perm)
     d = problems.scaling(K, "S1", seed=problems.SEED0 + 2)
     rng = np.random.default_rng(problems.SEED0)
@@ -612,7 +614,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--secondary", default="control07,nb,arch0,maxcut4000")
+    ap.add_argument("--secondary", default="control07,nb,arch0,maxcut4000,densecol")
     ap.add_argument("--full-secondary", dest="quick_secondary", action="store_false",
                     help="also run the oracle gates of the large secondary workloads (maxcut4000: about a minute of CPU)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
@@ -722,9 +724,12 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-        if sharded:
-            sbdev.lib().sb200_comm_destroy()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # The communicators (torch's and the library's) are torn down by process exit: destroying an NCCL communicator
+        # whose collectives live in instantiated CUDA graphs blocked for minutes on the B200 box (round-2 N=2 run).
+        os._exit(0)
 
 
 if __name__ == "__main__":

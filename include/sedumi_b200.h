@@ -305,6 +305,20 @@ int sb200_dpr1solve(int backward, sb_idx m, sb_idx nrhs, sb_idx nden, const sb_i
                     const double *p, const sb_idx *pivperm, sb_idx permnnz, const double *beta,
                     const sb_idx *betajc, const double *dopiv, double *y);
 
+/* device-resident product form: plan from Lsymb (dz, perm, first; 0-based), factor from the dense block L\Ad (m x n,
+ * column-major, rows in the factor's permuted order) and L.d, then in-place solves on m x nrhs device data */
+typedef struct sb200_dpr1_plan sb200_dpr1_plan;
+int  sb200_dpr1_plan_create(sb200_dpr1_plan **plan, sb_idx m, sb_idx n, const sb_idx *dzjc, const sb_idx *dzir,
+                            const sb_idx *colperm, const sb_idx *firstpiv);
+void sb200_dpr1_plan_destroy(sb200_dpr1_plan *plan);
+int  sb200_dpr1fact_dev(sb200_dpr1_plan *plan, const double *LAD_dev, const double *smult_dev, double maxu,
+                        const double *d_in_dev, double *d_out_dev);
+int  sb200_dpr1solve_dev(sb200_dpr1_plan *plan, int backward, double *y_dev, sb_idx nrhs);
+int  sb200_gather_dev(sb_idx n, const int *idx_dev, const double *src_dev, double *dst_dev);
+int  sb200_scale_by_d_dev(sb_idx m, sb_idx nrhs, const double *d_dev, const int *flag_dev, const double *lb_dev, double *y_dev);
+const double *sb200_chol_plan_lb_dev(const sb200_chol_plan *plan);   /* lb_k = max(abstol, canceltol*absd(perm_k)) of the last factorisation */
+int  sb200_dpr1_plan_download(sb200_dpr1_plan *plan, double *p, double *beta, int *betajc, int *pivperm, int *ordered);
+
 #ifdef __cplusplus
 }
 #endif

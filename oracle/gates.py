@@ -22,7 +22,7 @@ import numpy as np
 
 import refpath
 
-TOL = {"ADA": 1e-10, "absd": 1e-10, "L": 1e-10, "d": 1e-10, "y": 1e-8, "udsqr": 1e-10, "psdscale": 1e-10,
+TOL = {"d_dense": 1e-10, "ADA": 1e-10, "absd": 1e-10, "L": 1e-10, "d": 1e-10, "y": 1e-8, "udsqr": 1e-10, "psdscale": 1e-10,
        "frame": 1e-10, "givensrot": 1e-10}
 
 
@@ -71,8 +71,19 @@ def run_gates(hp, S, d, rhs, psd_x, frames, nsolve, npsd, *, S_local=None, d_loc
     LL, Ld, skip, add = R.mex.blkchol(hsetup.L_for_mex(dict(S.L)), ADA, R.pars, absd, nlhs=4)
     Lref = R.factor(ADA, absd)
     y = None
-    for _ in range(nsolve):
-        y = R.solve(Lref, rhs)
+    dense = getattr(S, "dense", None)
+    Lden = dden = None
+    if dense is not None and len(dense.cols):            # deninfac.m:57-79 on the reference's own MEX files
+        DC = refpath.DenseColumnRef(S, Lref)
+        LAD, Ld0, sym, smult = DC.inputs(d, np.asarray(Ld, dtype=float).ravel().copy())
+        Lden, dden = R.mex.dpr1fact(LAD, Ld0.reshape(-1, 1), sym, smult, 5e2, nlhs=2)
+        Lden.update(dz=sym["dz"], first=sym["first"], perm=sym["perm"])
+        Lm = hsetup.L_for_mex({k: Lref[k] for k in ("perm", "L", "xsuper", "tmpsiz")})
+        for _ in range(nsolve):
+            y = R.mex.bwblkslv(Lm, R.mex.bwdpr1(Lden, R.mex.fwdpr1(Lden, R.mex.fwblkslv(Lm, rhs)) / np.asarray(dden).reshape(-1, 1)))
+    else:
+        for _ in range(nsolve):
+            y = R.solve(Lref, rhs)
     err, info = {}, {}
     err["ADA"] = _rel(dev["ADA"], ADA.data)
     err["absd"] = _rel(dev["absd"], absd)
@@ -93,6 +104,8 @@ def run_gates(hp, S, d, rhs, psd_x, frames, nsolve, npsd, *, S_local=None, d_loc
         info["add_equal"] = bool(np.array_equal(np.flatnonzero(dev["flag"][cols] == 2), np.flatnonzero(np.isin(cols, add.indices))))
         info["factor_scope"] = f"{cols.size} of {S.m} columns (this rank's subtrees + replicated top)"
     err["y"] = _rel(dev["y"], y)
+    if dden is not None:
+        err["d_dense"] = _rel(hp.dvec_den.cpu().numpy()[:S.m], np.asarray(dden).ravel(), np.inf)
     info["nskip"], info["nadd"] = int(skip.nnz), int(add.nnz)
     if hp.lenud:
         Rl = R if Sl is S else refpath.RefHotPath(Sl)

@@ -36,6 +36,7 @@
 #include "sb_internal.h"
 
 #include "chol_plan.h"
+#include "ldl_block.cuh"
 
 namespace sb {
 
@@ -128,36 +129,31 @@ update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pa
   Sn sj = sn[tl.J];
   double *PJ = rect + sj.poff;
   int r0 = tl.r0, r1 = min(tl.r0 + UT_R, sj.m), c0 = tl.c0, c1 = min(tl.c0 + UT_C, sj.n);
-  __shared__ int s_rng[4];
-  for (int e = pair_beg[tl.J]; e < pair_beg[tl.J + 1]; e++) {
-    Pair p = pairs[e];
-    const int *rl = rel + p.rel;
-    if (threadIdx.x == 0) {
-      // rows t1 in [a,b): rel in [r0,r1) ; cols t2 in [cA,cB) (t2 < ncolup): rel in [c0,c1)
-      int lo = 0, hi = p.mk;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r0) lo = mid + 1; else hi = mid; }
-      s_rng[0] = lo; hi = p.mk;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r1) lo = mid + 1; else hi = mid; }
-      s_rng[1] = lo;
-      lo = 0; hi = p.ncolup;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c0) lo = mid + 1; else hi = mid; }
-      s_rng[2] = lo; hi = p.ncolup;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c1) lo = mid + 1; else hi = mid; }
-      s_rng[3] = lo;
+  // Every thread OWNS entries (r, c) of the tile and walks the descendants in list order (deterministic sums, no
+  // barrier between descendants: the 63 subtrees that feed the border supernode of the arrow used to cost 63 block
+  // barriers and as many dependent descriptor loads per tile).  The position of (r, c) inside a descendant's row list is
+  // found by bisection of its (ascending) relative-index list.
+  const int pb = pair_beg[tl.J], pe = pair_beg[tl.J + 1];
+  const int nr = r1 - r0, nc = c1 - c0;
+  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+    const int r = r0 + idx % nr, c = c0 + idx / nr;
+    if (r < c) continue;                               // strictly above the diagonal of J
+    double acc = 0.0;
+    for (int e = pb; e < pe; e++) {
+      const Pair p = pairs[e];
+      const int *rl = rel + p.rel;
+      int lo = 0, hi = p.ncolup;                       // column position t2: rl[t2] == c, t2 < ncolup
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c) lo = mid + 1; else hi = mid; }
+      if (lo >= p.ncolup || rl[lo] != c) continue;
+      const int t2 = lo;
+      hi = p.mk;                                       // row position t1 >= t2: rl[t1] == r
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < r) lo = mid + 1; else hi = mid; }
+      if (lo >= p.mk || rl[lo] != r) continue;
+      const Sn sk = sn[p.K];
+      const int mk = sk.m - sk.n, u0 = p.koff - sk.n;  // U_K is indexed by K's rows below its diagonal block
+      acc += U[sk.uoff + (u0 + lo) + (long long)(u0 + t2) * mk];
     }
-    __syncthreads();
-    int a = s_rng[0], b = s_rng[1], cA = s_rng[2], cB = s_rng[3];
-    __syncthreads();
-    int nr = b - a, nc = cB - cA;
-    if (nr <= 0 || nc <= 0) continue;
-    Sn sk = sn[p.K];
-    const int mk = sk.m - sk.n, u0 = p.koff - sk.n;   // U_K is indexed by K's rows below its diagonal block
-    const double *UK = U + sk.uoff;
-    for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
-      int t1 = a + idx % nr, t2 = cA + idx / nr;
-      if (t1 < t2) continue;                           // strictly above the diagonal of J
-      PJ[rl[t1] + (long long)rl[t2] * sj.m] -= UK[(u0 + t1) + (long long)(u0 + t2) * mk];
-    }
+    PJ[r + (long long)c * sj.m] -= acc;
   }
 }
 
@@ -251,7 +247,77 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
   const double ub = scal[0];
   __shared__ ArgMax sh_am[32];
   __shared__ double s_x;
-  for (int k = 0; k < n; k++) {
+  // ---- blocked pass: 32 columns at a time.  The diagonal block is factored by one warp in registers (ldl_block.cuh),
+  // every row below it is brought up to date by its own thread (a 32-step substitution in registers) and the rest of
+  // the panel takes the rank-32 update.  A pivot that needs the reference's stability test (rare) ends the blocked
+  // pass: the remaining columns, starting with this block, go through the column-by-column code below, which
+  // evaluates the test on the fully updated column exactly like cholonBlk.
+  __shared__ double Ab[LDLB][LDLB + 1];
+  __shared__ double b_lb[LDLB], b_d[LDLB], b_rd[LDLB];
+  __shared__ int b_skip[LDLB], b_stop;
+  int kleg = 0;                                        // first column left to the column-by-column code
+  for (int p0 = 0; p0 < n; p0 += LDLB) {
+    const int w = min(LDLB, n - p0);
+    for (int idx = threadIdx.x; idx < LDLB * LDLB; idx += blockDim.x) {
+      const int r = idx % LDLB, c = idx / LDLB;
+      Ab[r][c] = (r < w && c < w && r >= c) ? P[(long long)(p0 + c) * ld + p0 + r] : 0.0;
+    }
+    if (threadIdx.x < LDLB) { b_skip[threadIdx.x] = 0; b_d[threadIdx.x] = 0.0; b_lb[threadIdx.x] = threadIdx.x < w ? lb[s.first + p0 + threadIdx.x] : 0.0; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // global column = s.first + p0 + k; "column longer than 1" <=> (s.first + m) - (s.first + p0 + k) > 1
+      const int ks = warp_factor_block(Ab, b_lb, b_d, b_skip, flag, sval, s.first + p0, w, s.first + m, ub, 0, -1, 0.0);
+      if (threadIdx.x == 0) b_stop = ks;
+    }
+    __syncthreads();
+    if (b_stop < w) {                                  // undo the marks of this block and leave the rest to the column code
+      if (threadIdx.x < w && b_skip[threadIdx.x]) { flag[s.first + p0 + threadIdx.x] = 0; sval[s.first + p0 + threadIdx.x] = 0.0; }
+      kleg = p0;
+      break;
+    }
+    kleg = p0 + w;
+    if (threadIdx.x < LDLB) b_rd[threadIdx.x] = (threadIdx.x < w && b_d[threadIdx.x] > 0.0) ? 1.0 / b_d[threadIdx.x] : 0.0;
+    if (threadIdx.x < w) d[s.first + p0 + threadIdx.x] = b_d[threadIdx.x];
+    // L11 back into the panel (unit lower; a skipped column keeps no entries below its diagonal)
+    for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+      const int r = idx % w, c = idx / w;
+      if (r >= c) P[(long long)(p0 + c) * ld + p0 + r] = (r == c) ? 1.0 : (b_skip[c] ? 0.0 : Ab[r][c]);
+    }
+    __syncthreads();
+    // rows below the block: L21 = A21 L11^-T D^-1, one thread per row
+    for (int r = p0 + w + threadIdx.x; r < m; r += blockDim.x) {
+      double a[LDLB];
+#pragma unroll
+      for (int j = 0; j < LDLB; j++) a[j] = (j < w) ? P[(long long)(p0 + j) * ld + r] : 0.0;
+#pragma unroll
+      for (int j = 0; j < LDLB; j++) {
+        const double rj = b_rd[j];
+        const double xj = a[j];
+        if (rj > 0.0) {
+#pragma unroll
+          for (int j2 = j + 1; j2 < LDLB; j2++) a[j2] -= xj * Ab[j2][j];
+          a[j] = xj * rj;
+        } else a[j] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < LDLB; j++) if (j < w) P[(long long)(p0 + j) * ld + r] = a[j];
+    }
+    __syncthreads();
+    // rank-w update of the remaining columns of the panel: P(r,c) -= sum_j L(r,j) d_j L(c,j), r >= c > last block column
+    {
+      const int c0 = p0 + w, ncol = n - c0, nrow = m - c0;
+      for (long long idx = threadIdx.x; idx < (long long)ncol * nrow; idx += blockDim.x) {
+        const int r = c0 + (int)(idx % nrow), c = c0 + (int)(idx / nrow);
+        if (r < c) continue;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < LDLB; j++) acc += P[(long long)(p0 + j) * ld + r] * (b_d[j] * P[(long long)(p0 + j) * ld + c]);
+        P[(long long)c * ld + r] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = kleg; k < n; k++) {
     const int gk = s.first + k;
     double *ck = P + (long long)k * ld;
     double xkk = ck[k];
@@ -523,12 +589,20 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
   for (int c = threadIdx.x; c < n; c += blockDim.x) s[c] = yy[sj.first + c];
   __syncthreads();
   // pull the contributions c_K = L21_K y_K of the descendants, in list order:  s[col] -= c_K[row]
-  for (int e = pair_beg[list[blockIdx.x]]; e < pair_beg[list[blockIdx.x] + 1]; e++) {
-    Pair p = pairs[e];
-    Sn sk = sn[p.K];
-    const double *ck = cv + sk.cvoff + (p.koff - sk.n);
-    const int *rl = rel + p.rel;
-    for (int t = threadIdx.x; t < p.ncolup; t += blockDim.x) s[rl[t]] -= ck[t];     // rl[t] < n: distinct per t inside one pair
+  // (thread c owns s[c] and walks the descendants itself: no barrier per descendant)
+  {
+    const int pb = pair_beg[list[blockIdx.x]], pe = pair_beg[list[blockIdx.x] + 1];
+    for (int c = threadIdx.x; c < n && pb < pe; c += blockDim.x) {
+      double acc = 0.0;
+      for (int e = pb; e < pe; e++) {
+        const Pair p = pairs[e];
+        const int *rl = rel + p.rel;
+        int lo = 0, hi = p.ncolup;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c) lo = mid + 1; else hi = mid; }
+        if (lo < p.ncolup && rl[lo] == c) { const Sn sk = sn[p.K]; acc += cv[sk.cvoff + (p.koff - sk.n) + lo]; }
+      }
+      s[c] -= acc;
+    }
     __syncthreads();
   }
   // dense unit-lower solve of the n x n diagonal block, 32 columns at a time (solve = 0: pull only, used by the
@@ -540,9 +614,13 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
     if (threadIdx.x < 32) {
       int lane = threadIdx.x;
       double v = (lane < w) ? s[k0 + lane] : 0.0;
-      for (int k = 0; k < w; k++) {
+      double lr[32];                                    // row `lane` of the diagonal block: all loads in flight before the chain starts
+#pragma unroll
+      for (int k = 0; k < 32; k++) lr[k] = (k < w && lane > k && lane < w) ? P[(long long)(k0 + k) * ld + k0 + lane] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
         double yk = __shfl_sync(0xffffffffu, v, k);
-        if (lane > k && lane < w) v -= P[(long long)(k0 + k) * ld + k0 + lane] * yk;
+        v -= lr[k] * yk;
       }
       if (lane < w) s[k0 + lane] = v;
     }
@@ -609,10 +687,14 @@ bwsolve_kernel(const int *list, const Sn *sn, const int *lindx, const double *re
     int k0 = max(0, k1 - 32), w = k1 - k0;
     if (threadIdx.x < 32) {
       double v = (lane < w) ? s[k0 + lane] : 0.0;
-      for (int k = w - 1; k >= 0; k--) {
+      double lc[32];                                    // column `lane` of the diagonal block, fetched before the chain starts
+#pragma unroll
+      for (int k = 0; k < 32; k++) lc[k] = (k < w && lane < k) ? P[(long long)(k0 + lane) * ld + k0 + k] : 0.0;
+#pragma unroll
+      for (int k = 31; k >= 0; k--) {
         double zk = __shfl_sync(0xffffffffu, v, k);
         // z_c -= L[k, c] * z_k for c < k
-        if (lane < k) v -= P[(long long)(k0 + lane) * ld + k0 + k] * zk;
+        v -= lc[k] * zk;
       }
       if (lane < w) s[k0 + lane] = v;
     }
@@ -874,6 +956,7 @@ int sb200_chol_plan_create(sb200_chol_plan **plan, sb_idx m, sb_idx nsuper, cons
 }
 void sb200_chol_plan_destroy(sb200_chol_plan *plan) { delete plan; }
 sb_idx sb200_chol_plan_nnzL(const sb200_chol_plan *plan) { return plan->nnzL; }
+const double *sb200_chol_plan_lb_dev(const sb200_chol_plan *plan) { return plan->d_lb.p; }
 sb_idx sb200_chol_plan_rect_size(const sb200_chol_plan *plan) { return plan->rect; }
 
 static void launch_bounds_cb(sb200_chol_plan *pl, const double *absd, sb200_chol_pars pars) {

@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "chol_plan.h"
+#include "ldl_block.cuh"
 
 namespace sb {
 
@@ -72,52 +73,6 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
     __threadfence();
   }
   __syncthreads();
-}
-
-// The 32 x 32 diagonal block, factored by ONE warp with the block in registers: lane r holds row r as a window a[j] =
-// A[r][k+j] that slides one column per pivot, so every register index is static while the pivot loop itself stays a
-// loop (fully unrolled, the 496 shuffle/FMA pairs were 20 000 instructions -- more than the instruction cache -- and
-// ran slower than the shared-memory version).  The pivot column travels by shuffles; a step has no barrier.
-// A separate, non-inlined function so that the window gets registers of its own.  Returns the first pivot that needs
-// the reference's stability test (w if none); the state up to there is written back to A / dloc / skipped.
-__device__ __noinline__ int warp_factor_block(double (*A)[PB + 1], const double *s_lb, double *dloc, int *skipped, int *flag,
-                                              double *sval, int p0, int w, int m, double ub, int k_resume, int resolved_k, double s_x) {
-  const int lane = threadIdx.x & 31;
-  double a[PB];
-#pragma unroll
-  for (int j = 0; j < PB; j++) a[j] = (k_resume + j < PB) ? A[lane][k_resume + j] : 0.0;
-  int k = k_resume;
-  for (; k < w; k++) {
-    const int gk = p0 + k;
-    double xkk = __shfl_sync(0xffffffffu, a[0], k);
-    const bool resolved = (k == resolved_k);
-    if (resolved) xkk = s_x;
-    const bool skip = !(xkk > s_lb[k]);
-    if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) break;        // stability test needed (uniform)
-    if (skip) {
-      if (lane == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
-      if (lane >= k) A[lane][k] = a[0];                                 // the column is left as it is
-    } else {
-      const double rinv = 1.0 / xkk;
-      const double xr = (lane > k) ? a[0] : 0.0;
-      // element (r, c = k+j), k < c <= r: A[r][c] -= (A[c][k]/xkk) * A[r][k]
-#pragma unroll
-      for (int j = 1; j < PB; j++) {
-        const double ack = __shfl_sync(0xffffffffu, a[0], min(k + j, PB - 1));
-        if (k + j < PB && lane >= k + j) a[j] -= (ack * rinv) * xr;
-      }
-      if (lane > k) A[lane][k] = a[0] * rinv;
-      if (lane == k) { A[k][k] = 1.0; dloc[k] = xkk; }
-    }
-#pragma unroll
-    for (int j = 0; j + 1 < PB; j++) a[j] = a[j + 1];
-    a[PB - 1] = 0.0;
-  }
-  if (k < w) {                                                           // stopped: hand the updated columns back
-#pragma unroll
-    for (int j = 0; j < PB; j++) if (k + j < PB) A[lane][k + j] = a[j];
-  }
-  return k;
 }
 
 // W: working matrix (m x m, ld = m, lower triangle live); Lo: output factor (same layout).

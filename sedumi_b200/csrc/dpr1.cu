@@ -355,6 +355,63 @@ dpr1_solve_kernel(int backward, int m, int nden, int dznnz, const int *dzir, con
   for (int i = threadIdx.x; i < dznnz; i += blockDim.x) yy[dzir[i]] = f[i];
 }
 
+__global__ void __launch_bounds__(DT)
+dpr1_solve_dev_kernel(int backward, int m, int nden, int dznnz, const int *dzir, const int *xs, const long long *poff,
+                      const int *permoffs, const double *p, const int *pivperm, const double *beta, const int *betajc,
+                      const int *ordered, double *y, double *fwork) {
+  __shared__ Aff sha[33];
+  __shared__ double shd[33];
+  double *yy = y + (long long)blockIdx.x * m, *f = fwork + (long long)blockIdx.x * dznnz;
+  for (int i = threadIdx.x; i < dznnz; i += blockDim.x) f[i] = yy[dzir[i]];
+  __syncthreads();
+  if (!backward) {
+    for (int k = 0; k < nden; k++)
+      d_fw_scan(f, ordered[k] ? pivperm + permoffs[k] : nullptr, p + poff[k], beta + betajc[k], xs[k], betajc[k + 1] - betajc[k], sha);
+  } else {
+    for (int k = nden - 1; k >= 0; k--)
+      d_bw_scan(f, ordered[k] ? pivperm + permoffs[k] : nullptr, p + poff[k], beta + betajc[k], xs[k], betajc[k + 1] - betajc[k], sha, shd);
+  }
+  for (int i = threadIdx.x; i < dznnz; i += blockDim.x) yy[dzir[i]] = f[i];
+}
+
+__global__ void gather_idx_kernel(int n, const int *idx, const double *src, double *dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void dscale_kernel(int m, long long tot, const double *d, const int *flag, const double *lb, double *y) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= tot) return;
+  const int k = (int)(i % m);
+  double dk = d[k];
+  if (flag && lb && flag[k] == 1 && dk <= lb[k]) dk = 1.0;
+  y[i] /= dk;
+}
+
+// ---- device-resident chain: p from the dense block of L\Ad, d in the dz order, the list of dependent rows
+__global__ void dpr1_gather_kernel(int m, int n, const int *xs, const long long *poff, const int *colperm, const int *dzir,
+                                   const double *LAD, double *p) {
+  const int k = blockIdx.y;
+  const double *col = LAD + (long long)colperm[k] * m;
+  double *pk = p + poff[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < xs[k]; i += gridDim.x * blockDim.x) pk[i] = col[dzir[i]];
+}
+// dd = d_in(dz.ir); dep = ascending positions with dd <= 0, tail sentinel m; cursor = {0, 0, ndep, ndep}
+__global__ void __launch_bounds__(DT) dpr1_prepare_kernel(int m, int dznnz, const int *dzir, const double *d_in, double *dd, int *dep, int *cursor) {
+  __shared__ int shi[33];
+  DPR1_CHUNK(dznnz, lo, hi);
+  int c = 0;
+  for (int i = lo; i < hi; i++) { const double v = d_in[dzir[i]]; dd[i] = v; c += (v <= 0.0); }
+  int ndep = 0;
+  int pos = block_exscan(c, OpAddI(), 0, shi, &ndep);
+  for (int i = lo; i < hi; i++) if (dd[i] <= 0.0) dep[pos++] = i;
+  if (threadIdx.x == 0) { dep[ndep] = m; cursor[0] = 0; cursor[1] = 0; cursor[2] = ndep; cursor[3] = ndep; }
+}
+__global__ void dpr1_scatter_d_kernel(int m, int dznnz, const int *dzir, const double *d_in, const double *dd, double *d_out, int phase) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase == 0) { if (i < m) d_out[i] = d_in[i]; }
+  else if (i < dznnz) d_out[dzir[i]] = dd[i];
+}
+
 }  // namespace sb
 using namespace sb;
 
@@ -496,6 +553,123 @@ int sb200_dpr1solve(int backward, sb_idx m, sb_idx nrhs, sb_idx nden, const sb_i
                                                     d_bj, d_ord, d_y, d_f);
   SB_LAUNCH_CHECK_N("dpr1_solve_kernel");
   SB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(double) * m * nrhs, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ device-resident product form (HotPath chain)
+struct sb200_dpr1_plan {
+  int m = 0, n = 0, dznnz = 0;
+  long long pnnz = 0;
+  int solve_nrhs = 0;
+  sb::DevBuf<int> d_xs, d_colp, d_first, d_dzir, d_pivperm, d_betajc, d_ordered, d_dep, d_cursor, d_permoffs, d_ord, d_post, d_slot;
+  sb::DevBuf<long long> d_poff, d_permoff64;
+  sb::DevBuf<double> d_p, d_beta, d_d, d_x, d_mu, d_tq, d_f;
+  sb::DevBuf<sb::KD> d_kd;
+};
+
+extern "C" {
+
+// Lsymb of the dense columns (symbcholden.m:45-62): dz (m x n pattern, jc/ir), perm (column order), first -- all 0-based.
+int sb200_dpr1_plan_create(sb200_dpr1_plan **plan, sb_idx m, sb_idx n, const sb_idx *dzjc, const sb_idx *dzir, const sb_idx *colperm,
+                           const sb_idx *firstpiv) {
+  SB_TRY(ensure_init());
+  sb200_dpr1_plan *pl = new sb200_dpr1_plan();
+  pl->m = (int)m; pl->n = (int)n; pl->dznnz = (int)dzjc[n];
+  std::vector<int> xs(n), colp(n), firstp(n), ir32((size_t)std::max<sb_idx>(dzjc[n], 1));
+  std::vector<long long> poff(n + 1, 0);
+  long long pnnz = 0;
+  for (sb_idx k = 0; k < n; k++) { xs[k] = (int)dzjc[k + 1]; poff[k] = pnnz; pnnz += dzjc[k + 1]; colp[k] = (int)colperm[k]; firstp[k] = (int)firstpiv[k]; }
+  poff[n] = pnnz; pl->pnnz = pnnz;
+  for (sb_idx i = 0; i < dzjc[n]; i++) ir32[i] = (int)dzir[i];
+  const size_t wl = (size_t)std::max(pl->dznnz, 1), pl1 = (size_t)std::max<long long>(pnnz, 1);
+  int rc = pl->d_xs.upload(xs) || pl->d_colp.upload(colp) || pl->d_first.upload(firstp) || pl->d_dzir.upload(ir32) || pl->d_poff.upload(poff) ||
+           pl->d_pivperm.alloc(pl1) || pl->d_betajc.alloc(n + 1) || pl->d_ordered.alloc(n) || pl->d_dep.alloc(m + 2) || pl->d_cursor.alloc(4) ||
+           pl->d_permoffs.alloc(n) || pl->d_permoff64.alloc(n + 1) || pl->d_ord.alloc(wl) || pl->d_post.alloc(wl) || pl->d_slot.alloc(wl) || pl->d_p.alloc(pl1) ||
+           pl->d_beta.alloc(pl1) || pl->d_d.alloc(wl) || pl->d_x.alloc(wl) || pl->d_mu.alloc(wl) || pl->d_tq.alloc(wl) || pl->d_kd.alloc(wl);
+  if (rc) { delete pl; return 1; }
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *plan = pl;
+  return 0;
+}
+void sb200_dpr1_plan_destroy(sb200_dpr1_plan *pl) { delete pl; }
+
+// [Lden, d] = dpr1fact(L\Ad, L.d, Lsymb, smult, maxu) on device data (deninfac.m:67-72).  LAD_dev: m x n, column-major,
+// rows in the factor's permuted order (what sb200_fwblkslv_dev returns for the dense columns); d_in/d_out: m doubles.
+int sb200_dpr1fact_dev(sb200_dpr1_plan *pl, const double *LAD_dev, const double *smult_dev, double maxu, const double *d_in_dev,
+                       double *d_out_dev) {
+  SB_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  const int n = pl->n, m = pl->m;
+  if (n == 0) return 0;
+  int maxx = pl->dznnz;
+  dpr1_gather_kernel<<<dim3((unsigned)std::max(1, std::min((maxx + 255) / 256, 64)), (unsigned)n), 256, 0, st>>>(m, n, pl->d_xs.p, pl->d_poff.p, pl->d_colp.p,
+                                                                                                     pl->d_dzir.p, LAD_dev, pl->d_p.p);
+  SB_LAUNCH_CHECK_N("dpr1_gather_kernel");
+  dpr1_prepare_kernel<<<1, DT, 0, st>>>(m, pl->dznnz, pl->d_dzir.p, d_in_dev, pl->d_d.p, pl->d_dep.p, pl->d_cursor.p);
+  SB_LAUNCH_CHECK_N("dpr1_prepare_kernel");
+  SB_CUDA(cudaMemsetAsync(pl->d_beta.p, 0, sizeof(double) * std::max<long long>(pl->pnnz, 1), st));
+  Dpr1Work W;
+  W.x = pl->d_x.p; W.mu = pl->d_mu.p; W.tq = pl->d_tq.p; W.ord = pl->d_ord.p; W.post = pl->d_post.p; W.slot = pl->d_slot.p; W.kd = pl->d_kd.p;
+  W.cursor = pl->d_cursor.p; W.permoffs = pl->d_permoffs.p;
+  for (int k = 0; k < n; k++) {
+    dpr1_column_kernel<<<1, DT, 0, st>>>(k, pl->d_xs.p, pl->d_poff.p, pl->d_p.p, pl->d_pivperm.p, pl->d_beta.p, pl->d_betajc.p, pl->d_d.p,
+                                         pl->d_ordered.p, pl->d_colp.p, smult_dev, pl->d_dep.p, maxu, W);
+    SB_LAUNCH_CHECK_N("dpr1_column_kernel");
+    if (k + 1 < n) {
+      dpr1_fwcols_kernel<<<(unsigned)(n - k - 1), DT, 0, st>>>(k, n, pl->d_xs.p, pl->d_poff.p, pl->d_p.p, pl->d_pivperm.p, pl->d_beta.p, pl->d_betajc.p,
+                                                               pl->d_ordered.p, pl->d_colp.p, pl->d_first.p, smult_dev, pl->d_permoffs.p);
+      SB_LAUNCH_CHECK_N("dpr1_fwcols_kernel");
+    }
+  }
+  dpr1_scatter_d_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, pl->dznnz, pl->d_dzir.p, d_in_dev, pl->d_d.p, d_out_dev, 0);
+  SB_LAUNCH_CHECK_N("dpr1_scatter_d_kernel");
+  dpr1_scatter_d_kernel<<<(unsigned)((std::max(pl->dznnz, 1) + 255) / 256), 256, 0, st>>>(m, pl->dznnz, pl->d_dzir.p, d_in_dev, pl->d_d.p, d_out_dev, 1);
+  SB_LAUNCH_CHECK_N("dpr1_scatter_d_kernel");
+  return 0;
+}
+
+// y = fwdpr1(Lden, y) / bwdpr1(Lden, y) in place on m x nrhs device data, with the factor the plan holds.
+int sb200_dpr1solve_dev(sb200_dpr1_plan *pl, int backward, double *y_dev, sb_idx nrhs) {
+  SB_TRY(ensure_init());
+  if (pl->n == 0 || nrhs == 0) return 0;
+  if (pl->solve_nrhs < nrhs) {
+    SB_CHECK(!ctx().capturing, "dpr1 solve: workspace must be sized before graph capture");
+    SB_TRY(pl->d_f.alloc((size_t)std::max(pl->dznnz, 1) * nrhs));
+    pl->solve_nrhs = (int)nrhs;
+  }
+  dpr1_solve_dev_kernel<<<(unsigned)nrhs, DT, 0, ctx().stream>>>(backward, pl->m, pl->n, pl->dznnz, pl->d_dzir.p, pl->d_xs.p, pl->d_poff.p, pl->d_permoffs.p,
+                                                                 pl->d_p.p, pl->d_pivperm.p, pl->d_beta.p, pl->d_betajc.p, pl->d_ordered.p, y_dev, pl->d_f.p);
+  SB_LAUNCH_CHECK_N("dpr1_solve_kernel");
+  return 0;
+}
+// smult = d.l(dense.cols) (deninfac.m:61): dst[i] = src[idx[i]]
+int sb200_gather_dev(sb_idx n, const int *idx_dev, const double *src_dev, double *dst_dev) {
+  SB_TRY(ensure_init());
+  if (n <= 0) return 0;
+  gather_idx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>((int)n, idx_dev, src_dev, dst_dev);
+  SB_LAUNCH_CHECK_N("gather_idx_kernel");
+  return 0;
+}
+// y ./= d with deninfac's repair of the pivots that are still zero (deninfac.m:88-93): d <= lb on a skipped pivot -> 1
+int sb200_scale_by_d_dev(sb_idx m, sb_idx nrhs, const double *d_dev, const int *flag_dev, const double *lb_dev, double *y_dev) {
+  SB_TRY(ensure_init());
+  const long long tot = (long long)m * nrhs;
+  if (tot <= 0) return 0;
+  dscale_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx().stream>>>((int)m, tot, d_dev, flag_dev, lb_dev, y_dev);
+  SB_LAUNCH_CHECK_N("dscale_kernel");
+  return 0;
+}
+// the factor as the MEX interface carries it (for tests): sizes first (p, beta, pivperm lengths), then the arrays
+int sb200_dpr1_plan_download(sb200_dpr1_plan *pl, double *p, double *beta, int *betajc, int *pivperm, int *ordered) {
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(p, pl->d_p.p, sizeof(double) * pl->pnnz, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(beta, pl->d_beta.p, sizeof(double) * pl->pnnz, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(betajc, pl->d_betajc.p, sizeof(int) * (pl->n + 1), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(pivperm, pl->d_pivperm.p, sizeof(int) * pl->pnnz, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(ordered, pl->d_ordered.p, sizeof(int) * pl->n, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

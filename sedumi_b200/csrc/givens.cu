@@ -53,6 +53,39 @@ __device__ void d_givensrotuj(double *z, const double *g, int n) {
 
 struct UrotBlk { int n; long long uoff; int poff; long long goff; };   // goff: in doubles, worst-case layout
 
+// ---- speculative "nothing to rotate" pre-pass for large blocks.  The column-pivoting loop below is n dependent steps
+// (17 ms at n = 4000) even when no pivot is ever exchanged, which is the common case.  If no exchange happens, every
+// decision of the loop depends on the ORIGINAL factor only: d0(i) = sum_{t<=i} u(t,i)^2 (computed once, at k = 0) and
+// rowmax(k) = max_{j>k} u(k,j)^2.  Both are computed here in parallel -- d0 with the reference's summation order, so
+// the comparisons are the reference's bit for bit -- and the loop is skipped when every test comes out "keep".
+static const int UROT_PRECHECK_MIN_N = 128;
+__global__ void urot_colnorm_kernel(const UrotBlk *blks, const double *W, double *d_all) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < UROT_PRECHECK_MIN_N || i >= n) return;
+  const double *x = W + B.uoff + (long long)i * n;
+  double sacc = 0.0;
+  for (int t = 0; t <= i; t++) sacc = add_(sacc, mul_(x[t], x[t]));
+  d_all[B.poff + i] = sacc;
+}
+__global__ void __launch_bounds__(256) urot_rowmax_kernel(const UrotBlk *blks, const double *W, double *g_all) {
+  const UrotBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  if (n < UROT_PRECHECK_MIN_N || blockIdx.x * 32 >= n) return;
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, k = blockIdx.x * 32 + lane;
+  const double *u = W + B.uoff;
+  double mx = 0.0;
+  for (int j = blockIdx.x * 32 + 1 + warp; j < n; j += 8)
+    if (k < n && j > k) { const double v = u[k + (long long)j * n]; mx = fmax(mx, mul_(v, v)); }
+  sh[warp][lane] = mx;
+  __syncthreads();
+  if (warp == 0 && k < n) {
+    for (int w = 1; w < 8; w++) mx = fmax(mx, sh[w][lane]);
+    g_all[B.goff + k] = mx;                            // parked in the (still unused) rotation area
+  }
+}
+
 __global__ void __launch_bounds__(256)
 urotorder_kernel(const UrotBlk *blks, double *W, int *perm_all, int *gjc_all, double *g_all, double *d_all,
                  double maxusqr) {
@@ -66,6 +99,22 @@ urotorder_kernel(const UrotBlk *blks, double *W, int *perm_all, int *gjc_all, do
   __shared__ int s_flag, s_pivk, s_inz, s_redi[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   for (int j = tid; j < n; j += blockDim.x) perm[j] = j;
+  if (n >= UROT_PRECHECK_MIN_N) {                      // the pre-pass left d0 in d and rowmax in g
+    const double h0 = mul_(d[0], DRELTOL);
+    int keep = 1;
+    for (int k = tid; k < n - 1; k += blockDim.x) {
+      const double dk = d[k];
+      if (k >= 1 && dk <= h0) keep = 0;                 // the loop would recompute the norms here
+      if (g[k] > mul_(maxusqr, dk)) keep = 0;           // the loop would exchange a pivot here
+    }
+    keep = __syncthreads_and(keep);
+    if (keep) {
+      for (int k = tid; k < n; k += blockDim.x) { gjc[k] = 0; g[k] = 0.0; }       // (un-park rowmax: the rotation area stays clean)
+      return;
+    }
+  }
+  if (n >= UROT_PRECHECK_MIN_N) for (int k = tid; k < n; k += blockDim.x) g[k] = 0.0;
+  __syncthreads();
   if (tid == 0) { d[0] = 0.0; s_h = 1.0; s_pivk = 0; s_inz = 0; }
   __syncthreads();
   for (int k = 0; k < n - 1; k++) {
@@ -398,6 +447,12 @@ int sb200_urotorder_dev(sb_idx nblk, const sb_idx *n, const double *u_dev, doubl
   SB_CUDA(cudaMemcpyAsync(W, u_dev, sizeof(double) * lenud, cudaMemcpyDeviceToDevice, st));
   if (gtot) SB_CUDA(cudaMemsetAsync(g_dev, 0, sizeof(double) * gtot, st));
   SB_CUDA(cudaMemsetAsync(gjc_dev, 0, sizeof(int) * sumn, st));
+  if (maxn >= UROT_PRECHECK_MIN_N) {
+    urot_colnorm_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nblk), 128, 0, st>>>(db, W, d);
+    SB_LAUNCH_CHECK_N("urot_colnorm_kernel");
+    urot_rowmax_kernel<<<dim3((unsigned)((maxn + 31) / 32), (unsigned)nblk), 256, 0, st>>>(db, W, g_dev);
+    SB_LAUNCH_CHECK_N("urot_rowmax_kernel");
+  }
   urotorder_kernel<<<(unsigned)nblk, 256, 0, st>>>(db, W, perm_dev, gjc_dev, g_dev, d, maxu * maxu);
   SB_LAUNCH_CHECK_N("urotorder_kernel");
   uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, W, perm_dev, u_out_dev);
@@ -440,9 +495,15 @@ int sb200_urotorder(sb_idx nblk, const sb_idx *n, const double *u, double maxu, 
   SB_CUDA(cudaMemcpyAsync(W, u, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
   SB_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * std::max<long long>(gtot, 1), st));
   SB_CUDA(cudaMemsetAsync(gjc, 0, sizeof(int) * sumn, st));
+  int maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
+  if (maxn >= UROT_PRECHECK_MIN_N) {
+    urot_colnorm_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nblk), 128, 0, st>>>(db, W, d);
+    SB_LAUNCH_CHECK_N("urot_colnorm_kernel");
+    urot_rowmax_kernel<<<dim3((unsigned)((maxn + 31) / 32), (unsigned)nblk), 256, 0, st>>>(db, W, g);
+    SB_LAUNCH_CHECK_N("urot_rowmax_kernel");
+  }
   urotorder_kernel<<<(unsigned)nblk, 256, 0, st>>>(db, W, perm, gjc, g, d, maxu * maxu);
   SB_LAUNCH_CHECK_N("urotorder_kernel");
-  int maxn = 0; for (auto &b : blks) maxn = std::max(maxn, b.n);
   uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, W, perm, uo);
   SB_LAUNCH_CHECK_N("uperm_sym_kernel");
   std::vector<int> hp(sumn), hg(sumn);
@@ -530,6 +591,13 @@ int sb200_urotorder_h(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *
   int maxr = 0, maxc = 0;
   for (sb_idx k = 0; k < nblk; k++) (k < nreal ? maxr : maxc) = std::max(k < nreal ? maxr : maxc, (int)n[k]);
   if (nreal > 0) {
+    int maxn = 0; for (sb_idx k2 = 0; k2 < nreal; k2++) maxn = std::max(maxn, blks[k2].n);
+    if (maxn >= UROT_PRECHECK_MIN_N) {
+      urot_colnorm_kernel<<<dim3((unsigned)((maxn + 127) / 128), (unsigned)nreal), 128, 0, st>>>(db, W, d);
+      SB_LAUNCH_CHECK_N("urot_colnorm_kernel");
+      urot_rowmax_kernel<<<dim3((unsigned)((maxn + 31) / 32), (unsigned)nreal), 256, 0, st>>>(db, W, g);
+      SB_LAUNCH_CHECK_N("urot_rowmax_kernel");
+    }
     urotorder_kernel<<<(unsigned)nreal, 256, 0, st>>>(db, W, perm, gjc, g, d, maxu * maxu);
     SB_LAUNCH_CHECK_N("urotorder_kernel");
     uperm_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxr * maxr + 255) / 256, 1024), (unsigned)nreal), 256, 0, st>>>(db, W, perm, uo);

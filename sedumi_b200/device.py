@@ -46,6 +46,7 @@ def lib() -> C.CDLL:
         L.sb200_chol_plan_rect_size.restype = I64
         L.sb200_ada_plan_nnz.restype = I64
         L.sb200_psd_plan_lenud.restype = I64
+        L.sb200_chol_plan_lb_dev.restype = VP
         _lib = L
     return _lib
 
@@ -88,6 +89,8 @@ EXPORTS = [
     "sb200_comm_stats", "sb200_allreduce_sum_dev", "sb200_allreduce_sum2_dev", "sb200_comm_destroy",
     "sb200_blkchol_sharded_dev", "sb200_ldl_solve_sharded_dev",
     "sb200_wrappcg_dev", "sb200_ldl_solve2_dev", "sb200_ada_plan_csr", "sb200_psd_plan_blocks",
+    "sb200_dpr1_plan_create", "sb200_dpr1_plan_destroy", "sb200_dpr1fact_dev", "sb200_dpr1solve_dev", "sb200_dpr1_plan_download",
+    "sb200_gather_dev", "sb200_scale_by_d_dev", "sb200_chol_plan_lb_dev",
 ]
 
 
@@ -195,6 +198,24 @@ class HotPath:
         self.perm_new = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
         self.gjc = torch.zeros(max(sumn, 1), dtype=torch.int32, device=self.dev)
         self.maxu_urot = 1.1                        # updtransfo.m:100
+        # ---- dense columns (getdense.m): product-form factor on top of the sparse one (deninfac.m:57-79)
+        self.nden = len(S.dense.cols) if getattr(S, "dense", None) is not None else 0
+        self.dpr1 = None
+        if self.nden:
+            from .host import symbolic
+            assert len(S.dense.q) == 0, "dense Lorentz blocks are not wired into the device chain"
+            self.symLden = symbolic.symbcholden(S.L, S.dense)
+            dz = self.symLden["dz"]
+            self.dpr1 = VP()
+            check(L.sb200_dpr1_plan_create(C.byref(self.dpr1), I64(m), I64(self.nden), _p(_i64(dz.indptr)), _p(_i64(dz.indices)),
+                                           _p(_i64(self.symLden["perm"].ravel() - 1)), _p(_i64(self.symLden["first"].ravel() - 1))), "dpr1_plan")
+            Ad = np.asfortranarray(np.asarray(S.dense.A.todense(), dtype=np.float64))          # m x nden, deninfac.m:59 (LP columns)
+            self.Ad = torch.from_numpy(np.ascontiguousarray(Ad.T)).to(self.dev)                 # rows = columns of Ad (column-major m x nden)
+            self.LAD = torch.zeros_like(self.Ad)
+            self.den_idx = torch.from_numpy((S.dense.cols[:S.dense.l].astype(np.int64) - 1).astype(np.int32)).to(self.dev)
+            self.smult = z(self.nden)
+            self.dvec_den = z(m)
+            self.maxuden = 5e2                       # checkpars.m:158-166
 
     def __del__(self):
         try:
@@ -253,9 +274,28 @@ class HotPath:
                                       _p(self.flag), _p(self.sval)), "blkchol")
 
     def solve(self):
-        """y = L' \\ ((L \\ r(perm)) ./ d), all right-hand sides (wrapPcg.m:56-59 without dense columns)."""
-        check(lib().sb200_ldl_solve_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.rhs),
+        """y = L' \\ ((L \\ r(perm)) ./ d), all right-hand sides (wrapPcg.m:56-59); with dense columns the product-form
+        factor sits in the middle: fwblkslv -> fwdpr1 -> ./d -> bwdpr1 -> bwblkslv."""
+        L = lib()
+        if self.dpr1 is None:
+            check(L.sb200_ldl_solve_dev(self.chol, _p(self.Lrect), _p(self.dvec), _p(self.flag), _p(self.rhs),
                                         _p(self.w), _p(self.y), I64(self.nrhs)), "ldl_solve")
+            return
+        check(L.sb200_fwblkslv_dev(self.chol, _p(self.Lrect), _p(self.rhs), _p(self.w), I64(self.nrhs)), "fwblkslv")
+        check(L.sb200_dpr1solve_dev(self.dpr1, C.c_int(0), _p(self.w), I64(self.nrhs)), "fwdpr1")
+        check(L.sb200_scale_by_d_dev(I64(self.m), I64(self.nrhs), _p(self.dvec_den), _p(self.flag), VP(L.sb200_chol_plan_lb_dev(self.chol)),
+                                     _p(self.w)), "./d")
+        check(L.sb200_dpr1solve_dev(self.dpr1, C.c_int(1), _p(self.w), I64(self.nrhs)), "bwdpr1")
+        check(L.sb200_bwblkslv_dev(self.chol, _p(self.Lrect), _p(self.w), _p(self.y), I64(self.nrhs)), "bwblkslv")
+
+    def deninfac(self):
+        """deninfac.m:57-79 on the device: LAD = L \\ Ad(perm,:), smult = d.l(dense.cols), product-form factor, updated d."""
+        if self.dpr1 is None:
+            return
+        L = lib()
+        check(L.sb200_fwblkslv_dev(self.chol, _p(self.Lrect), _p(self.Ad), _p(self.LAD), I64(self.nden)), "sparfwslv")
+        check(L.sb200_gather_dev(I64(self.nden), _p(self.den_idx), _p(self.d_l), _p(self.smult)), "smult")
+        check(L.sb200_dpr1fact_dev(self.dpr1, _p(self.LAD), _p(self.smult), C.c_double(self.maxuden), _p(self.dvec), _p(self.dvec_den)), "dpr1fact")
 
     # ------------------------------------------------------------------ subtree-sharded factor / solve (SURVEY 8e)
     def shard_factor_setup(self, world: int, rank: int):
@@ -367,6 +407,7 @@ class HotPath:
                 self.solve_sharded()
         else:
             self.blkchol()
+            self.deninfac()
             for _ in range(nsolve):
                 self.solve()
         if self.lenud:

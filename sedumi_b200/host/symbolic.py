@@ -166,3 +166,59 @@ def symbolic_factor(ADA: sp.csc_matrix, perm=None) -> dict:
             "L": L,
             "xsuper": (xsuper + 1).astype(np.float64).reshape(-1, 1),
             "tmpsiz": float(tmpsiz_bound(ljc, lir, xsuper))}
+
+
+# --------------------------------------------------------------------------- dense columns (symbcholden.m:45-62)
+def symbfwblk(L: dict, B: sp.csc_matrix) -> sp.csc_matrix:
+    """Pattern of L.L \\ B(L.perm,:) for a sparse B (symbfwblk.c): the nonzeros of every column spread along the
+    elimination tree -- row i reaches its parent, the first off-diagonal row of column i of L.L, and so on."""
+    LL = sp.csc_matrix(L["L"])
+    m = LL.shape[0]
+    perm = np.asarray(L["perm"], dtype=np.int64).ravel() - 1
+    invperm = np.empty(m, dtype=np.int64)
+    invperm[perm] = np.arange(m)
+    ip, ind = LL.indptr, LL.indices
+    parent = np.full(m, -1, dtype=np.int64)
+    for j in range(m):
+        if ip[j + 1] - ip[j] > 1:
+            parent[j] = ind[ip[j] + 1]
+    B = sp.csc_matrix(B)
+    cols, jc = [], [0]
+    for c in range(B.shape[1]):
+        mark = np.zeros(m, dtype=bool)
+        for r in B.indices[B.indptr[c]:B.indptr[c + 1]]:
+            j = int(invperm[r])
+            while j != -1 and not mark[j]:
+                mark[j] = True
+                j = int(parent[j])
+        rows = np.flatnonzero(mark)
+        cols.append(rows)
+        jc.append(jc[-1] + rows.size)
+    ir = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+    return sp.csc_matrix((np.ones(ir.size), ir, np.asarray(jc)), shape=(m, B.shape[1]))
+
+
+def symbcholden(L: dict, dense, DAt_denq=None) -> dict:
+    """Symbolic product-form structure of the dense columns (symbcholden.m:45-62 with finsymbden.c:57-84,155-175) for
+    LP dense columns (no dense Lorentz blocks): Lden = {LAD (pattern of L\\Ad), perm, dz, first}."""
+    from . import setup as hsetup
+    assert len(dense.q) == 0, "dense Lorentz blocks: use the reference's symbcholden"
+    nden = len(dense.cols)
+    LAD = symbfwblk(L, sp.csc_matrix(dense.A[:, :nden]))
+    perm, dz = hsetup.incorder(LAD)                       # incremental ordering of the columns (incorder.c)
+    m = LAD.shape[0]
+    dz = sp.csc_matrix(dz)
+    # first affecting pivot of each column (getfirstpiv): position of its earliest row in the dz order, then the
+    # first dz column whose cumulative count covers it
+    invdz = np.zeros(m, dtype=np.int64)
+    invdz[dz.indices] = np.arange(dz.nnz)
+    first = np.empty(nden)
+    for j in range(nden):
+        rows = LAD.indices[LAD.indptr[j]:LAD.indptr[j + 1]]
+        if rows.size == 0:
+            first[j] = nden + 1.0
+            continue
+        fj = int(invdz[rows].min())
+        y = int(np.searchsorted(dz.indptr[1:], fj + 1, side="left"))
+        first[j] = y + 1.0
+    return {"LAD": LAD, "perm": np.asarray(perm, dtype=np.float64).reshape(-1, 1), "dz": dz, "first": first.reshape(-1, 1)}

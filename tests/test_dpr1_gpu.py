@@ -75,3 +75,32 @@ def test_no_dense_columns_is_identity():
     b = np.arange(12.0).reshape(6, 2)
     Lden = {"betajc": 0.0}
     assert np.array_equal(gpu.fwdpr1(Lden, b), b) and np.array_equal(gpu.bwdpr1(Lden, b), b)
+
+
+@pytest.mark.parametrize("seed,ndense", [(4, 3), (9, 5)])
+def test_device_chain_with_dense_columns(seed, ndense):
+    """The device-resident chain with dense columns (HotPath: blkchol -> L\\Ad -> dpr1fact_dev -> fwblkslv, fwdpr1, ./d,
+    bwdpr1, bwblkslv) against the reference's deninfac.m:57-79 + wrapPcg.m:56-59 sequence on its own MEX files."""
+    import torch
+    from sedumi_b200 import device
+    S, d, L, DC = _dense_problem(seed=seed, ndense=ndense)
+    LAD, Ld, sym, smult = DC.inputs(d, L["d"].copy())
+    Lr, dr = ref.dpr1fact(LAD, Ld, sym, smult, 5e2, nlhs=2)
+    Lr.update(dz=sym["dz"], first=sym["first"], perm=sym["perm"])
+    rng = np.random.default_rng(seed)
+    rhs = rng.standard_normal((S.m, 2))
+    Lm = setup.L_for_mex({k: L[k] for k in ("perm", "L", "xsuper", "tmpsiz")})
+    yref = ref.bwblkslv(Lm, ref.bwdpr1(Lr, ref.fwdpr1(Lr, ref.fwblkslv(Lm, rhs)) / dr.reshape(-1, 1)))
+    hp = device.HotPath(S)
+    assert hp.nden == ndense
+    # the host restatement of symbcholden agrees with the reference's symbolic MEX chain
+    assert np.array_equal(hp.symLden["dz"].indptr, sym["dz"].indptr) and np.array_equal(hp.symLden["dz"].indices, sym["dz"].indices)
+    assert np.array_equal(hp.symLden["perm"].ravel(), np.asarray(sym["perm"]).ravel())
+    assert np.array_equal(hp.symLden["first"].ravel(), np.asarray(sym["first"]).ravel())
+    with torch.cuda.stream(hp.stream()):
+        hp.set_scaling(d)
+        hp.set_rhs(rhs)
+        hp.iteration(1, 0)
+        hp.sync()
+        assert relerr(hp.dvec_den.cpu().numpy()[:S.m], dr.ravel()) <= 1e-10
+        assert relerr(hp.y.cpu().numpy().T, yref) <= 1e-8

@@ -101,3 +101,27 @@ def test_scaling_generators_are_interior():
         U = np.triu(d["u"][off:off + n * n].reshape(n, n, order="F"))
         assert np.all(np.diag(U) > 0)
         off += n * n
+
+
+def test_symbcholden_restatement_matches_reference_symbolic_chain():
+    """host.symbolic.symbcholden (symbfwblk + incorder + finsymbden restated for LP dense columns) against the reference's
+    own symbolic MEX files (symbcholden.m:45-62)."""
+    import os
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refpath
+    from sedumi_b200.host import symbolic
+    for seed, nd in ((4, 3), (8, 4)):
+        raw = problems.synth_blockdiag_sdp(nblk=4, n=10, m=48, nlink=6, density=0.08, dense_lp=nd, seed=seed)
+        At, b, c, K = cones.pretransfo(*raw)[:4]
+        S = setup.build_setup(At, b, c, K, denf=0.3, perm=np.arange(At.shape[1]))
+        assert len(S.dense.cols) == nd
+        DC = refpath.DenseColumnRef(S, dict(S.L))
+        mine = symbolic.symbcholden(S.L, S.dense)
+        for k in ("LAD", "dz"):
+            a, r = sp.csc_matrix(mine[k]), sp.csc_matrix(DC.sym[k])
+            a.sort_indices()
+            assert np.array_equal(a.indptr, r.indptr) and np.array_equal(a.indices, r.indices), k
+        assert np.array_equal(mine["perm"].ravel(), np.asarray(DC.sym["perm"]).ravel())
+        assert np.array_equal(mine["first"].ravel(), np.asarray(DC.sym["first"]).ravel())
