@@ -274,6 +274,12 @@ int sb200_ada_plan_csr(sb200_ada_plan *plan, const long long **Ajc, const int **
                        sb_idx *lpN, sb_idx *nq);
 int sb200_psd_plan_blocks(sb200_psd_plan *plan, const int **n_dev, const long long **off_dev, int *nblk, int *maxn);
 
+/* ------------------------------------------------------------------ PSD algebra of the scaling update
+ * vecsym.c:139-175, sqrtinv.c:86-148, qrK.c:239-297.  x/y/q/r are the lenud-long PSD parts; blocks [nreal, nblk) Hermitian. */
+int sb200_vecsym(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *x, double *y);
+int sb200_sqrtinv(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *q, const double *v, double *y);
+int sb200_qrK(sb_idx nblk, const sb_idx *n, const double *x, double *q, double *r);      /* real blocks */
+
 /* ------------------------------------------------------------------ Lorentz streams
  * ddot.c:165-308, qblkmul.c:57-116, quadadd.c:89-130.
  * Dense ddot / qblkmul: bs[0..nblk] are block starts relative to the first norm-bound row. */

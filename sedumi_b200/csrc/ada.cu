@@ -56,6 +56,10 @@ ata_pattern_kernel(int m, const long long *adajc, const int *adair, const long l
   const long long clo = lo[c], chi = hi[c];
   const int ipc = invperm[c];
   const bool empty_c = skip_empty && (clo >= chi);
+  if (empty_c) {                                     // nothing to add in this column: a coalesced copy / clear
+    for (long long inz = adajc[c] + threadIdx.x; inz < adajc[c + 1]; inz += blockDim.x) out[inz] = accumulate ? in[inz] : 0.0;
+    return;
+  }
   for (long long inz = adajc[c] + warp; inz < adajc[c + 1]; inz += nw) {
     const int i = adair[inz];
     double base = accumulate ? in[inz] : 0.0;

@@ -129,31 +129,48 @@ update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pa
   Sn sj = sn[tl.J];
   double *PJ = rect + sj.poff;
   int r0 = tl.r0, r1 = min(tl.r0 + UT_R, sj.m), c0 = tl.c0, c1 = min(tl.c0 + UT_C, sj.n);
-  // Every thread OWNS entries (r, c) of the tile and walks the descendants in list order (deterministic sums, no
-  // barrier between descendants: the 63 subtrees that feed the border supernode of the arrow used to cost 63 block
-  // barriers and as many dependent descriptor loads per tile).  The position of (r, c) inside a descendant's row list is
-  // found by bisection of its (ascending) relative-index list.
+  // The sub-range of every descendant that falls into this tile is found first, one descendant per thread (the
+  // bisections are chains of dependent global loads: done one descendant at a time by a single thread they cost more
+  // than the update itself); then the descendants are applied in list order, one block barrier each (two descendants
+  // may hit the same entry from different threads).
+  __shared__ int4 s_rng[256];
   const int pb = pair_beg[tl.J], pe = pair_beg[tl.J + 1];
-  const int nr = r1 - r0, nc = c1 - c0;
-  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
-    const int r = r0 + idx % nr, c = c0 + idx / nr;
-    if (r < c) continue;                               // strictly above the diagonal of J
-    double acc = 0.0;
-    for (int e = pb; e < pe; e++) {
-      const Pair p = pairs[e];
+  for (int e0 = pb; e0 < pe; e0 += 256) {
+    const int ne = min(256, pe - e0);
+    __syncthreads();
+    if (threadIdx.x < ne) {
+      const Pair p = pairs[e0 + threadIdx.x];
       const int *rl = rel + p.rel;
-      int lo = 0, hi = p.ncolup;                       // column position t2: rl[t2] == c, t2 < ncolup
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c) lo = mid + 1; else hi = mid; }
-      if (lo >= p.ncolup || rl[lo] != c) continue;
-      const int t2 = lo;
-      hi = p.mk;                                       // row position t1 >= t2: rl[t1] == r
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < r) lo = mid + 1; else hi = mid; }
-      if (lo >= p.mk || rl[lo] != r) continue;
+      int4 g;
+      int lo = 0, hi = p.mk;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r0) lo = mid + 1; else hi = mid; }
+      g.x = lo; hi = p.mk;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < r1) lo = mid + 1; else hi = mid; }
+      g.y = lo;
+      lo = 0; hi = p.ncolup;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c0) lo = mid + 1; else hi = mid; }
+      g.z = lo; hi = p.ncolup;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (rl[mid] < c1) lo = mid + 1; else hi = mid; }
+      g.w = lo;
+      s_rng[threadIdx.x] = g;
+    }
+    __syncthreads();
+    for (int i = 0; i < ne; i++) {
+      const int4 g = s_rng[i];
+      const int nr = g.y - g.x, nc = g.w - g.z;
+      if (nr <= 0 || nc <= 0) continue;                // uniform
+      const Pair p = pairs[e0 + i];
+      const int *rl = rel + p.rel;
       const Sn sk = sn[p.K];
       const int mk = sk.m - sk.n, u0 = p.koff - sk.n;  // U_K is indexed by K's rows below its diagonal block
-      acc += U[sk.uoff + (u0 + lo) + (long long)(u0 + t2) * mk];
+      const double *UK = U + sk.uoff;
+      for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+        const int t1 = g.x + idx % nr, t2 = g.z + idx / nr;
+        if (t1 < t2) continue;                         // strictly above the diagonal of J
+        PJ[rl[t1] + (long long)rl[t2] * sj.m] -= UK[(u0 + t1) + (long long)(u0 + t2) * mk];
+      }
+      __syncthreads();
     }
-    PJ[r + (long long)c * sj.m] -= acc;
   }
 }
 
@@ -589,21 +606,27 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
   for (int c = threadIdx.x; c < n; c += blockDim.x) s[c] = yy[sj.first + c];
   __syncthreads();
   // pull the contributions c_K = L21_K y_K of the descendants, in list order:  s[col] -= c_K[row]
-  // (thread c owns s[c] and walks the descendants itself: no barrier per descendant)
+  // (the descriptors of the descendants are fetched together first -- one round of global latency instead of one per
+  // descendant -- then applied in list order)
   {
+    __shared__ int s_off[256], s_rel[256], s_ncu[256];
     const int pb = pair_beg[list[blockIdx.x]], pe = pair_beg[list[blockIdx.x] + 1];
-    for (int c = threadIdx.x; c < n && pb < pe; c += blockDim.x) {
-      double acc = 0.0;
-      for (int e = pb; e < pe; e++) {
-        const Pair p = pairs[e];
-        const int *rl = rel + p.rel;
-        int lo = 0, hi = p.ncolup;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rl[mid] < c) lo = mid + 1; else hi = mid; }
-        if (lo < p.ncolup && rl[lo] == c) { const Sn sk = sn[p.K]; acc += cv[sk.cvoff + (p.koff - sk.n) + lo]; }
+    for (int e0 = pb; e0 < pe; e0 += 256) {
+      const int ne = min(256, pe - e0);
+      __syncthreads();
+      if (threadIdx.x < ne) {
+        const Pair p = pairs[e0 + threadIdx.x];
+        const Sn sk = sn[p.K];
+        s_off[threadIdx.x] = sk.cvoff + (p.koff - sk.n); s_rel[threadIdx.x] = p.rel; s_ncu[threadIdx.x] = p.ncolup;
       }
-      s[c] -= acc;
+      __syncthreads();
+      for (int i = 0; i < ne; i++) {
+        const double *ck = cv + s_off[i];
+        const int *rl = rel + s_rel[i];
+        for (int t = threadIdx.x; t < s_ncu[i]; t += blockDim.x) s[rl[t]] -= ck[t];       // rl[t] < n: distinct per t inside one descendant
+        __syncthreads();
+      }
     }
-    __syncthreads();
   }
   // dense unit-lower solve of the n x n diagonal block, 32 columns at a time (solve = 0: pull only, used by the
   // sharded forward pass to collect the contributions of a rank's subtrees in the replicated top rows)

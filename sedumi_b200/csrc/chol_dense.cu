@@ -21,7 +21,6 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "chol_plan.h"
-#include "ldl_block.cuh"
 
 namespace sb {
 
@@ -107,13 +106,40 @@ dense_ldl_kernel(int m, double *W, double *Lo, double *d, const double *lb, cons
       if (tid < PB) s_lb[tid] = (tid < w) ? lb[p0 + tid] : 0.0;
       __syncthreads();
       int k_resume = 0, resolved_k = -1;
-      // The 32 pivots of the block are a dependent chain; with the block spread over 8 warps every step paid two block
-      // barriers and shared-memory round trips (670 cycles per pivot, profiles/ncu_r01_top_kernels.txt): one warp does
-      // it in registers instead (warp_factor_block).
+      // All 8 warps cooperate on each pivot step: the lower triangle below/right of the pivot is at most 31*32/2
+      // elements, one per thread.  (Round 2 tried one warp holding the block in registers with the pivot column moved
+      // by shuffles -- ldl_block.cuh, used by the supernodal kernel: as part of THIS kernel it measured 1.8x slower,
+      // the single warp is issue-bound on 31 shuffle/multiply/FMA triples per pivot.)
       while (true) {
-        if (warp == 0) {
-          const int kstop = warp_factor_block(A, s_lb, dloc, skipped, flag, sval, p0, w, m, ub, k_resume, resolved_k, s_x);
-          if (lane == 0) s_state = kstop;
+        {
+        int k = k_resume;
+        for (; k < w; k++) {
+          const int gk = p0 + k;
+          double xkk = A[k][k];
+          const bool resolved = (k == resolved_k);
+          if (resolved) xkk = s_x;
+          const bool skip = !(xkk > s_lb[k]);
+          if (!skip && !resolved && (m - gk > 1) && (xkk < ub)) break;          // stability test needed (uniform)
+          if (skip) {
+            if (tid == 0) { flag[gk] = 1; sval[gk] = xkk; skipped[k] = 1; dloc[k] = 0.0; }
+            continue;
+          }
+          const double rinv = 1.0 / xkk;
+          // element (r,c), k < c <= r < w: A[r][c] -= (A[c][k]/xkk) * A[r][k]
+          {
+            const int r = lane;                                   // warp wq handles columns k+1+wq, +8, ...
+            const double xr = (r > k && r < w) ? A[r][k] : 0.0;
+            for (int c = k + 1 + warp; c < w; c += 8)
+              if (r >= c && r < w) A[r][c] -= (A[c][k] * rinv) * xr;
+          }
+          __syncthreads();
+          // (scaling the column one step later, in the shadow of the next update, saves a barrier but
+          // measured 17 % slower: the extra loop-carried state lengthens the dependent chain)
+          if (tid > k && tid < w) A[tid][k] *= rinv;
+          if (tid == 0) { dloc[k] = xkk; A[k][k] = 1.0; }
+          __syncthreads();
+        }
+        if (tid == 0) s_state = k;
         }
         __syncthreads();
         const int k = s_state;

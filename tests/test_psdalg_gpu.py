@@ -1,0 +1,69 @@
+"""SURVEY 8f row 2 (first part): vecsym, sqrtinv and qrK plugins against the reference's own MEX files.
+Gates: vecsym exact, sqrtinv 1e-14, qrK 1e-10 (q in product form and triu(r); the reference documents tril(r,-1)
+as undefined, qrK.c:80-82)."""
+import numpy as np
+import pytest
+
+from helpers import gpu, ref, relerr
+from sedumi_b200.host import cones
+
+pytestmark = pytest.mark.gpu
+
+
+def _K(l, q, sreal, sherm=()):
+    K = cones.finish_K({"l": float(l), "q": np.array(q, dtype=float), "s": np.array(list(sreal) + list(sherm), dtype=float),
+                        "rsdpN": len(sreal)})
+    return K, cones.K_for_mex(K)
+
+
+@pytest.mark.parametrize("sreal,sherm", [((5, 3), ()), ((40,), ()), ((4,), (3, 6)), ((), (5,))])
+def test_vecsym(sreal, sherm):
+    K, Km = _K(3, (4,), sreal, sherm)
+    rng = np.random.default_rng(1)
+    n = 3 + 4 + sum(k * k for k in sreal) + 2 * sum(k * k for k in sherm)
+    x = rng.standard_normal(n)
+    assert np.array_equal(gpu.vecsym(x, Km), ref.vecsym(x, Km))
+
+
+@pytest.mark.parametrize("sreal,sherm", [((5, 3), ()), ((70, 35), ()), ((4,), (3, 6))])
+def test_sqrtinv(sreal, sherm):
+    K, Km = _K(2, (3,), sreal, sherm)
+    rng = np.random.default_rng(2)
+    lenud = sum(k * k for k in sreal) + 2 * sum(k * k for k in sherm)
+    q = rng.standard_normal(lenud)
+    v = np.exp(rng.standard_normal(2 + 2 * 1 + sum(sreal) + sum(sherm)))
+    assert relerr(gpu.sqrtinv(q, v, Km), ref.sqrtinv(q, v, Km)) <= 1e-14
+
+
+@pytest.mark.parametrize("s", [(1,), (2,), (7, 4), (33, 64, 5), (200,)])
+def test_qrK(s):
+    K, Km = _K(1, (), s)
+    rng = np.random.default_rng(sum(s))
+    x = rng.standard_normal(sum(k * k for k in s))
+    if len(s) > 1:
+        x[:s[0] * s[0]].reshape(s[0], s[0], order="F")[:, 1] = 0.0         # an all-zero column: beta = 1 (qrK.c:103-104)
+    qg, rg = gpu.qrK(x, Km, nlhs=2)
+    qr_, rr = ref.qrK(x, Km, nlhs=2)
+    assert relerr(qg, qr_) <= 1e-10
+    off = 0
+    for n in s:
+        Rg = np.triu(rg.ravel()[off:off + n * n].reshape(n, n, order="F"))
+        Rr = np.triu(rr.ravel()[off:off + n * n].reshape(n, n, order="F"))
+        assert relerr(Rg, Rr) <= 1e-10
+        # and it is a QR factorisation: |R'R - X'X| small
+        X = x[off:off + n * n].reshape(n, n, order="F")
+        assert relerr(Rg.T @ Rg, X.T @ X) <= 1e-10
+        off += n * n
+
+
+def test_qrK_frames_feed_psdframeit():
+    """qrK's q is the product form psdframeit consumes (wregion.m / frameit.m): Q diag(lab) Q' from our qrK through our
+    psdframeit equals the same through the reference's."""
+    s = (12, 9)
+    K, Km = _K(1, (), s)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(sum(k * k for k in s))
+    lab = np.exp(rng.standard_normal(sum(s)))
+    qg, _ = gpu.qrK(x, Km, nlhs=2)
+    qr_, _ = ref.qrK(x, Km, nlhs=2)
+    assert relerr(gpu.psdframeit(lab, qg, Km), ref.psdframeit(lab, qr_, Km)) <= 1e-10
