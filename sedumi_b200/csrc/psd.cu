@@ -45,7 +45,9 @@ struct sb200_psd_plan {
   sb::DevBuf<sb::GemmTile> d_wy_tiles;
   sb::DevBuf<int> d_wy_pblk, d_wy_pidx;          // per panel: block, panel index
   sb::DevBuf<long long> d_wy_toff;               // per block: offset of its first T (32x32 each)
-  sb::DevBuf<double> d_wy_T, d_wy_Y, d_wy_Y2;
+  sb::DevBuf<double> d_wy_T, d_wy_Y, d_wy_Y2, d_wy_G;
+  int wyb = 32;                                     // reflectors per panel: 32 (row kernel) or 128 (GEMM path)
+  int wy_gd = 0, wy_gt = 0, wy_gn = 0;              // descriptors / tiles of the Gram products V_p' V_p (GEMM path)
   // workspaces (lenud doubles each)
   sb::DevBuf<double> d_Tt, d_Wt, d_Xp, d_Y;
   sb::DevBuf<int> d_perm;
@@ -209,6 +211,36 @@ wy_t_kernel(const int *pblk, const int *pidx, const int *ns, const long long *of
     }
 #pragma unroll
     for (int i = 0; i < WYB; i++) T[i + j * WYB] = t[i];     // column-major 32x32, zero padded
+  }
+}
+
+// Wide panels (GEMM path, WYBIG reflectors): G = V_p' V_p comes from the tile-GEMM engine; this kernel forms
+// U = striu(G) + diag(beta_p) in shared memory and inverts it, one thread per column of T = inv(U) (back substitution).
+static const int WYBIG = 128;
+__global__ void __launch_bounds__(WYBIG)
+wy_tinv_big_kernel(const int *pblk, const int *pidx, const int *ns, const long long *offs, const long long *toff,
+                   const double *frms, const double *Gall, double *Tall) {
+  extern __shared__ double Ubig[];                   // WYBIG x (WYBIG + 1)
+  const int k = pblk[blockIdx.x], p = pidx[blockIdx.x];
+  const int n = ns[k];
+  const double *beta = frms + offs[k] + (long long)n * n - n;
+  const int c0 = p * WYBIG, bp = min(WYBIG, n - 1 - c0);
+  const double *G = Gall + (toff[k] + p) * WYBIG * WYBIG;
+  double *T = Tall + (toff[k] + p) * WYBIG * WYBIG;
+  const int j = threadIdx.x, ldu = WYBIG + 1;
+  for (int i = 0; i < WYBIG; i++)                    // column j of U (coalesced over j)
+    Ubig[i * ldu + j] = (i < bp && j < bp) ? (i < j ? G[i + (long long)j * WYBIG] : (i == j ? beta[c0 + i] : 0.0)) : (i == j ? 1.0 : 0.0);
+  __syncthreads();
+  // U t = e_j from the bottom up; t is written straight into T(:, j) and read back from there (own column only)
+  double *t = T + (long long)j * WYBIG;
+  for (int i = WYBIG - 1; i >= 0; i--) {
+    double acc = 0.0;
+    if (j < bp && i <= j) {
+      acc = (i == j) ? 1.0 : 0.0;
+      for (int q = i + 1; q <= j; q++) acc -= Ubig[i * ldu + q] * t[q];
+      acc /= Ubig[i * ldu + i];
+    }
+    t[i] = acc;
   }
 }
 
@@ -700,9 +732,12 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
     // small blocks: the one-warp-per-column kernel is a single short launch (47 us at n=70 against 65 us
     // for T factors + row kernel)
     pl->wy_rows = pl->maxn > 96 && pl->wy_rows_smem <= 220 * 1024;
+    if (const char *e = getenv("SB200_WY_GEMM_MIN_N")) if (pl->maxn >= atoi(e)) pl->wy_rows = false;     // tests: force the GEMM path
     pl->wy = pl->maxn > 96 && !pl->wy_rows;
   }
   if (pl->wy || pl->wy_rows) {
+    const int wyb = pl->wy ? WYBIG : WYB;          // the GEMM path uses wide panels: its products need N, K >> 32 to be efficient
+    pl->wyb = wyb;
     std::vector<GemmDesc> wd;
     std::vector<GemmTile> wt;
     std::vector<int> pblk, pidx;
@@ -710,10 +745,10 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
     long long tcount = 0, ycount = 0;
     int maxP = 0;
     for (int k = 0; k < pl->nblk; k++) {
-      const int nk = pl->n[k], P = (nk - 1 + WYB - 1) / WYB;
+      const int nk = pl->n[k], P = (nk - 1 + wyb - 1) / wyb;
       toff[k] = tcount; yoff[k] = ycount;
       for (int p2 = 0; p2 < P; p2++) { pblk.push_back(k); pidx.push_back(p2); }
-      tcount += P; ycount += (long long)nk * WYB;
+      tcount += P; ycount += (long long)nk * wyb;
       maxP = std::max(maxP, P);
     }
     pl->wy_npanels = (int)pblk.size(); pl->wy_steps = maxP;
@@ -722,10 +757,10 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
       std::vector<GemmDesc> g1, g2, g3;
       std::vector<GemmTile> t1, t2, t3;
       for (int k = 0; k < pl->nblk; k++) {
-        const int nk = pl->n[k], P = (nk - 1 + WYB - 1) / WYB;
+        const int nk = pl->n[k], P = (nk - 1 + wyb - 1) / wyb;
         const int p2 = P - 1 - st;
         if (p2 < 0) continue;
-        const int c0 = p2 * WYB, bp = std::min(WYB, nk - 1 - c0), np = nk - c0;
+        const int c0 = p2 * wyb, bp = std::min(wyb, nk - 1 - c0), np = nk - c0;
         const long long sub = pl->off[k] + c0 + (long long)c0 * nk;      // (c0, c0) corner inside the block
         GemmDesc a{}; a.gatherOff = -1; a.alpha = 1.0;
         // Y(i,c) = sum_r R(i,r) V(r,c):  A = R sub-block, B = F' rows c (k >= row mask)
@@ -736,7 +771,7 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
         // Y2 = Y T'
         GemmDesc b{}; b.gatherOff = -1; b.alpha = 1.0;
         b.offA = yoff[k]; b.lda = nk; b.a_tri = TRI_NONE;
-        b.offB = (toff[k] + p2) * WYB * WYB; b.ldb = WYB; b.b_tri = TRI_NONE;
+        b.offB = (toff[k] + p2) * (long long)wyb * wyb; b.ldb = wyb; b.b_tri = TRI_NONE;
         b.offC = yoff[k]; b.ldc = nk; b.M = np; b.N = bp; b.K = bp; b.lower = 0; b.accumulate = 0;
         gemm_add_tiles(t2, (int)g2.size(), np, bp, false); g2.push_back(b);
         // R(i,r) -= sum_c Y2(i,c) V(r,c):  B = F rows r (k <= row mask)
@@ -754,9 +789,28 @@ static int psd_build(sb200_psd_plan *pl, sb_idx nblk, const sb_idx *n) {
       push(g1, t1, W.d1, W.t1, W.n1); push(g2, t2, W.d2, W.t2, W.n2); push(g3, t3, W.d3, W.t3, W.n3);
       pl->wy_sched.push_back(W);
     }
+    if (pl->wy) {                                    // G_p = V_p' V_p for every panel of every block, one launch
+      std::vector<GemmDesc> gg; std::vector<GemmTile> gt;
+      for (int k = 0; k < pl->nblk; k++) {
+        const int nk = pl->n[k], P = (nk - 1 + wyb - 1) / wyb;
+        for (int p2 = 0; p2 < P; p2++) {
+          const int c0 = p2 * wyb, bp = std::min(wyb, nk - 1 - c0), np = nk - c0;
+          const long long sub = pl->off[k] + c0 + (long long)c0 * nk;
+          GemmDesc g{}; g.gatherOff = -1; g.alpha = 1.0;
+          g.offA = sub; g.lda = nk; g.a_tri = TRI_K_GE_ROW;          // F' rows = reflectors, k = matrix row >= reflector index
+          g.offB = sub; g.ldb = nk; g.b_tri = TRI_K_GE_ROW;
+          g.offC = (toff[k] + p2) * (long long)wyb * wyb; g.ldc = wyb; g.M = bp; g.N = bp; g.K = np; g.lower = 0; g.accumulate = 0;
+          gemm_add_tiles(gt, (int)gg.size(), bp, bp, false); gg.push_back(g);
+        }
+      }
+      pl->wy_gd = (int)wd.size(); pl->wy_gt = (int)wt.size(); pl->wy_gn = (int)gt.size();
+      for (auto &x : gt) x.prob += pl->wy_gd;
+      wd.insert(wd.end(), gg.begin(), gg.end()); wt.insert(wt.end(), gt.begin(), gt.end());
+      SB_TRY(pl->d_wy_G.alloc((size_t)tcount * wyb * wyb));
+    }
     SB_TRY(pl->d_wy_desc.upload(wd)); SB_TRY(pl->d_wy_tiles.upload(wt));
     SB_TRY(pl->d_wy_pblk.upload(pblk)); SB_TRY(pl->d_wy_pidx.upload(pidx)); SB_TRY(pl->d_wy_toff.upload(toff));
-    SB_TRY(pl->d_wy_T.alloc((size_t)tcount * WYB * WYB));
+    SB_TRY(pl->d_wy_T.alloc((size_t)tcount * wyb * wyb));
     SB_TRY(pl->d_wy_Y.alloc((size_t)ycount)); SB_TRY(pl->d_wy_Y2.alloc((size_t)ycount));
   }
   SB_TRY(pl->d_n.upload(pl->n)); SB_TRY(pl->d_off.upload(pl->off)); SB_TRY(pl->d_poff.upload(pl->poff));
@@ -956,10 +1010,20 @@ static int build_q(sb200_psd_plan *pl, const double *frms_dev, bool need_transpo
   }
   if (pl->wy) {
     // R = Q' accumulated right to left, panel by panel:  R <- R (I - V_p T_p V_p')' = R - (R V_p) T_p' V_p'
-    wy_t_kernel<<<pl->wy_npanels, 256, 0, st>>>(pl->d_wy_pblk.p, pl->d_wy_pidx.p, pl->d_n.p, pl->d_off.p, pl->d_wy_toff.p, frms_dev, pl->d_wy_T.p);
-    SB_LAUNCH_CHECK_N("wy_t_kernel");
+    // with panels of 128 reflectors, so that every product of the loop has N or K = 128 (with 32-wide panels the
+    // rank-32 updates were 75 of the 150 ms the n = 4000 block spent in the GEMM engine)
     transpose_scale_kernel<<<dim3(std::min(1024, tp * tp), pl->nblk), dim3(32, 8), 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_poff.p, frms_dev, nullptr, pl->d_Xp.p);   // F'
     SB_LAUNCH_CHECK_N("transpose_scale_kernel");
+    gemm_nt_launch(pl->wy_gn, ctx().sm_count, st, pl->d_wy_desc.p, pl->d_wy_tiles.p + pl->wy_gt, pl->d_Xp.p, pl->d_Xp.p, pl->d_wy_G.p, nullptr);
+    SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+    {
+      const size_t shm = sizeof(double) * WYBIG * (WYBIG + 1);
+      static bool attr_done = false;
+      if (!attr_done) { SB_CUDA(cudaFuncSetAttribute(wy_tinv_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); attr_done = true; }
+      wy_tinv_big_kernel<<<pl->wy_npanels, WYBIG, shm, st>>>(pl->d_wy_pblk.p, pl->d_wy_pidx.p, pl->d_n.p, pl->d_off.p, pl->d_wy_toff.p, frms_dev,
+                                                           pl->d_wy_G.p, pl->d_wy_T.p);
+      SB_LAUNCH_CHECK_N("wy_tinv_big_kernel");
+    }
     set_identity_kernel<<<dim3((unsigned)std::min<long long>(((long long)pl->maxn * pl->maxn + 255) / 256, 1024), pl->nblk), 256, 0, st>>>(pl->d_n.p, pl->d_off.p, pl->d_Wt.p);
     SB_LAUNCH_CHECK_N("set_identity_kernel");
     for (auto &W : pl->wy_sched) {

@@ -107,3 +107,22 @@ def test_urotorder_no_rotation_needed():
     assert R[3].size == 0 and G[3].size == 0 and np.array_equal(R[1], G[1]) and np.array_equal(R[0], G[0])
     x = np.arange(144.0)
     assert np.array_equal(gpu.givensrot(G[2], G[3], x, Km), ref.givensrot(R[2], R[3], x, Km))
+
+
+def test_psdframeit_gemm_wy_path_wide_panels(monkeypatch):
+    """Blocks beyond ~2300 accumulate Q through the tile-GEMM engine with 128-reflector panels (compact WY).  The
+    path is forced at a size the reference handles quickly (the plan cache is keyed by the block sizes: 301 and 143
+    appear nowhere else in the suite)."""
+    monkeypatch.setenv("SB200_WY_GEMM_MIN_N", "100")
+    s = (301, 143)
+    K = _K(s)
+    Km = cones.K_for_mex(K)
+    frms = _frames(K, 77)
+    rng = np.random.default_rng(3)
+    lab = rng.uniform(0.1, 3.0, int(sum(s)))
+    assert relerr(gpu.psdframeit(lab, frms, Km), ref.psdframeit(lab, frms, Km)) <= 1e-10
+    ys = []
+    for n in s:
+        Y = rng.standard_normal((n, n)); ys.append((Y + Y.T).ravel(order="F"))
+    y = np.concatenate(ys)
+    assert relerr(gpu.psdinvjmul(lab, frms, y, Km), ref.psdinvjmul(lab, frms, y, Km)) <= 1e-10
