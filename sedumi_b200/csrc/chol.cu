@@ -320,16 +320,22 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
       for (int j = 0; j < LDLB; j++) if (j < w) P[(long long)(p0 + j) * ld + r] = a[j];
     }
     __syncthreads();
-    // rank-w update of the remaining columns of the panel: P(r,c) -= sum_j L(r,j) d_j L(c,j), r >= c > last block column
+    // rank-w update of the remaining columns of the panel: P(r,c) -= sum_j L(r,j) d_j L(c,j), r >= c > last block column.
+    // One warp per column, lanes over rows (no index arithmetic in the loop; the column's 32 scaled entries are
+    // broadcast reads).
     {
-      const int c0 = p0 + w, ncol = n - c0, nrow = m - c0;
-      for (long long idx = threadIdx.x; idx < (long long)ncol * nrow; idx += blockDim.x) {
-        const int r = c0 + (int)(idx % nrow), c = c0 + (int)(idx / nrow);
-        if (r < c) continue;
-        double acc = 0.0;
+      const int c0 = p0 + w, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      for (int c = c0 + warp; c < n; c += nw) {
+        double *cc = P + (long long)c * ld;
+        for (int r = c + lane; r < m; r += 32) {
+          double acc = 0.0;
 #pragma unroll 8
-        for (int j = 0; j < LDLB; j++) acc += P[(long long)(p0 + j) * ld + r] * (b_d[j] * P[(long long)(p0 + j) * ld + c]);
-        P[(long long)c * ld + r] -= acc;
+          for (int j = 0; j < w; j++) {                         // (columns beyond the block do not exist in the panel)
+            const double *pj = P + (long long)(p0 + j) * ld;
+            acc += pj[r] * (b_d[j] * pj[c]);
+          }
+          cc[r] -= acc;
+        }
       }
     }
     __syncthreads();

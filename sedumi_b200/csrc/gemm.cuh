@@ -59,17 +59,17 @@ template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm vol
 // Fast path: 16-byte copies, no predicates (interior tile, k-slab fully inside the nonzero range,
 // even leading dimension and 16-byte aligned base).  General path: 8-byte copies, zero-filled where
 // the element is out of range or structurally zero.
-template <int KG>
+template <int KG, int GKT>
 __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const double *g, int ld, int rows, int r0, int K, int k0,
                                                 int tri, const int *gather, bool vec_ok) {
   const int tid = threadIdx.x;
-  bool fast = vec_ok && (r0 + GT <= rows) && (k0 + GK <= K);
-  if (tri == TRI_K_LE_ROW) fast = fast && (k0 + GK - 1 <= r0);
+  bool fast = vec_ok && (r0 + GT <= rows) && (k0 + GKT <= K);
+  if (tri == TRI_K_LE_ROW) fast = fast && (k0 + GKT - 1 <= r0);
   if (tri == TRI_K_GE_ROW) fast = fast && (k0 >= r0 + GT - 1);
   if (fast) {
     const int i = (tid & 31) * 2;
 #pragma unroll
-    for (int r = 0; r < GK / (4 * KG); r++) {
+    for (int r = 0; r < GKT / (4 * KG); r++) {
       const int kk = (tid >> 5) + 4 * KG * r, k = k0 + kk;
       const long long col = gather ? gather[k] : k;
       cp_async_16(&S[kk][i], g + r0 + i + col * ld);
@@ -77,7 +77,7 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
   } else {
     const int i = tid & 63, gi = r0 + i;
 #pragma unroll
-    for (int r = 0; r < GK / (2 * KG); r++) {
+    for (int r = 0; r < GKT / (2 * KG); r++) {
       const int kk = (tid >> 6) + 2 * KG * r, k = k0 + kk;
       bool nz = (k < K) && (gi < rows);
       if (tri == TRI_K_LE_ROW) nz = nz && (k <= gi);
@@ -98,7 +98,7 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
 // GST-stage cp.async pipeline: slabs s+1..s+GST-1 are in flight while the DMMAs of slab s run (with two
 // stages the copy of the next slab was issued one slab-time (~250 cycles at full DMMA rate) before it was
 // needed, less than the L2 latency).
-template <int KG>
+template <int KG, int GKT>
 static __global__ void __launch_bounds__(128 * KG)
 gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA, const double *baseB,
                double *baseC, const int *gatherBase) {
@@ -109,15 +109,15 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   const int *gather = (g.gatherOff >= 0) ? gatherBase + g.gatherOff : nullptr;
   const int i0 = tl.ti * GT, c0 = tl.tj * GT;
   extern __shared__ __align__(16) double gemm_sm[];
-  double (*As)[GK][GT + 4] = (double (*)[GK][GT + 4])gemm_sm;                       // [GST][GK][GT+4]
-  double (*Bs)[GK][GT + 4] = (double (*)[GK][GT + 4])(gemm_sm + GST * GK * (GT + 4));
+  double (*As)[GKT][GT + 4] = (double (*)[GKT][GT + 4])gemm_sm;                       // [GST][GKT][GT+4]
+  double (*Bs)[GKT][GT + 4] = (double (*)[GKT][GT + 4])(gemm_sm + GST * GKT * (GT + 4));
   // k-range that can be nonzero for this tile
   int klo = 0, khi = g.K;
   if (g.a_tri == TRI_K_LE_ROW) khi = min(khi, i0 + GT);
   if (g.a_tri == TRI_K_GE_ROW) klo = max(klo, i0);
   if (g.b_tri == TRI_K_LE_ROW) khi = min(khi, c0 + GT);
   if (g.b_tri == TRI_K_GE_ROW) klo = max(klo, c0);
-  klo = (klo / GK) * GK;
+  klo = (klo / GKT) * GKT;
   const bool vecA = ((((unsigned long long)gA) & 15) == 0) && ((g.lda & 1) == 0);
   const bool vecB = ((((unsigned long long)gB) & 15) == 0) && ((g.ldb & 1) == 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,13 +128,13 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-  const int nslab = khi > klo ? (khi - klo + GK - 1) / GK : 0;
+  const int nslab = khi > klo ? (khi - klo + GKT - 1) / GKT : 0;
   // prologue: GST-1 slabs in flight (a group is committed per slot even when empty, so the wait counts stay uniform)
 #pragma unroll
   for (int s = 0; s < GST - 1; s++) {
     if (s < nslab) {
-      gemm_stage_slab<KG>(As[s], gA, g.lda, g.M, i0, g.K, klo + s * GK, g.a_tri, gather, vecA);
-      gemm_stage_slab<KG>(Bs[s], gB, g.ldb, g.N, c0, g.K, klo + s * GK, g.b_tri, nullptr, vecB);
+      gemm_stage_slab<KG, GKT>(As[s], gA, g.lda, g.M, i0, g.K, klo + s * GKT, g.a_tri, gather, vecA);
+      gemm_stage_slab<KG, GKT>(Bs[s], gB, g.ldb, g.N, c0, g.K, klo + s * GKT, g.b_tri, nullptr, vecB);
     }
     cp_async_commit();
   }
@@ -145,14 +145,14 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
     {
       const int sn = s + GST - 1;                  // refill the buffer slab s-1 just released
       if (sn < nslab) {
-        const int k0 = klo + sn * GK;
-        gemm_stage_slab<KG>(As[sn % GST], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
-        gemm_stage_slab<KG>(Bs[sn % GST], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
+        const int k0 = klo + sn * GKT;
+        gemm_stage_slab<KG, GKT>(As[sn % GST], gA, g.lda, g.M, i0, g.K, k0, g.a_tri, gather, vecA);
+        gemm_stage_slab<KG, GKT>(Bs[sn % GST], gB, g.ldb, g.N, c0, g.K, k0, g.b_tri, nullptr, vecB);
       }
       cp_async_commit();
     }
 #pragma unroll
-    for (int kq = 0; kq < GK; kq += 4 * KG) {
+    for (int kq = 0; kq < GKT; kq += 4 * KG) {
       const int k4 = kq + 4 * kgrp;
       double af[4], bf[4];
 #pragma unroll
@@ -169,7 +169,7 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   cp_async_wait_all();
   if (KG == 2) {
     __syncthreads();
-    double *red = &As[0][0][0];                      // 2*GK*(GT+4) doubles >= 4 warps x 32 lanes x 16 values
+    double *red = &As[0][0][0];                      // 2*GKT*(GT+4) doubles >= 4 warps x 32 lanes x 16 values
     const int slot = (warp & 3) * 32 + lane;          // value v of thread t lives at [v*128 + t]: conflict-free
     if (kgrp == 1) {
 #pragma unroll
@@ -217,18 +217,24 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
       }
 }
 
-// Launch: one CTA per tile; the k-split variant when the launch cannot fill the GPU otherwise.
+// Launch: one CTA per tile.  With tiles to spare: 128 threads, no k-split (more CTAs per SM).  With few tiles: the
+// k-split variant; with less than two waves of tiles (small batches, e.g. one rank's share of a sharded problem) the
+// k-split variant with 32-deep slabs -- a launch is then a chain of slab hand-overs (wait, barrier, refill), and
+// halving their number matters more than occupancy (3 x 2 x 32 x 68 doubles = 102 KB per CTA).
+static const int GEMM_SMEM_DEEP = GST * 2 * 32 * (GT + 4) * 8;
 static inline void gemm_nt_launch(int ntiles, int sm_count, cudaStream_t st, const GemmDesc *descs, const GemmTile *tiles,
                                   const double *baseA, const double *baseB, double *baseC, const int *gatherBase) {
   if (ntiles <= 0) return;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(gemm_nt_kernel<1, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(gemm_nt_kernel<2, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    cudaFuncSetAttribute(gemm_nt_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_DEEP);
     attr_done = true;
   }
-  if (ntiles >= 6 * sm_count) gemm_nt_kernel<1><<<ntiles, 128, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
-  else gemm_nt_kernel<2><<<ntiles, 256, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  if (ntiles >= 6 * sm_count) gemm_nt_kernel<1, GK><<<ntiles, 128, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  else if (ntiles >= 2 * sm_count) gemm_nt_kernel<2, GK><<<ntiles, 256, GEMM_SMEM, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
+  else gemm_nt_kernel<2, 32><<<ntiles, 256, GEMM_SMEM_DEEP, st>>>(descs, tiles, baseA, baseB, baseC, gatherBase);
 }
 
 // Host helper: append the tiles of one problem to a tile list.
