@@ -279,6 +279,11 @@ int sb200_psd_plan_blocks(sb200_psd_plan *plan, const int **n_dev, const long lo
 int sb200_vecsym(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *x, double *y);
 int sb200_sqrtinv(sb_idx nblk, sb_idx nreal, const sb_idx *n, const double *q, const double *v, double *y);
 int sb200_qrK(sb_idx nblk, const sb_idx *n, const double *x, double *q, double *r);      /* real blocks */
+/* M-only in the reference (the plugins shadow the .m files); real blocks.  psdmul: mode 0 = psdjmul.m:38-74, mode 1 =
+ * triumtriu.m:38-73; psdfactor.m:37-82 (*ispos = 0: not positive definite); psdinvscale.m:37-83. */
+int sb200_psdmul(int mode, sb_idx nblk, const sb_idx *n, const double *x, const double *y, double *z);
+int sb200_psdfactor(sb_idx nblk, const sb_idx *n, const double *x, double *ux, int *ispos);
+int sb200_psdinvscale(sb_idx nblk, const sb_idx *n, const double *u, const double *x, double *y);
 
 /* ------------------------------------------------------------------ Lorentz streams
  * ddot.c:165-308, qblkmul.c:57-116, quadadd.c:89-130.

@@ -158,3 +158,56 @@ def getada_m(At, K, d, DAtq, pattern=None):
     rows = P.indices
     cols = np.repeat(np.arange(P.shape[1]), np.diff(P.indptr))
     return sp.csc_matrix((ADA[rows, cols], P.indices.copy(), P.indptr.copy()), shape=P.shape), absd
+
+
+# --------------------------------------------------------------------------- PSD algebra that is M code in the reference
+def _blocks(x, K):
+    Ks = np.asarray(K["s"], dtype=np.int64).ravel()
+    N = int((Ks ** 2).sum())
+    x = np.asarray(x, dtype=float).ravel()
+    off = x.size - N
+    out = []
+    for n in Ks:
+        n = int(n)
+        out.append(x[off:off + n * n].reshape(n, n, order="F"))
+        off += n * n
+    return out
+
+
+def psdjmul(x, y, K):
+    """psdjmul.m:38-74 (real blocks): Z_k = (X_k Y_k + (X_k Y_k)')/2."""
+    return np.concatenate([(0.5 * (X @ Y + (X @ Y).T)).ravel(order="F") for X, Y in zip(_blocks(x, K), _blocks(y, K))])
+
+
+def triumtriu(x, y, K):
+    """triumtriu.m:38-73 (real blocks): Z_k = triu(X_k) triu(Y_k), upper triangle mirrored below."""
+    out = []
+    for X, Y in zip(_blocks(x, K), _blocks(y, K)):
+        Z = np.triu(X) @ np.triu(Y)
+        out.append((Z + np.triu(Z, 1).T).ravel(order="F"))
+    return np.concatenate(out)
+
+
+def psdfactor(x, K):
+    """psdfactor.m:37-82 (real blocks): (ux, ispos); ux = L + tril(L,-1)' per block, zeros from the first block that is
+    not positive definite on."""
+    blocks = _blocks(x, K)
+    out = [np.zeros(B.size) for B in blocks]
+    for i, X in enumerate(blocks):
+        try:
+            L = np.linalg.cholesky(np.tril(X) + np.tril(X, -1).T)      # chol(.,'lower') reads the lower triangle
+        except np.linalg.LinAlgError:
+            return np.concatenate(out), False
+        out[i] = (L + np.tril(L, -1).T).ravel(order="F")
+    return np.concatenate(out), True
+
+
+def psdinvscale(ud, x, K):
+    """psdinvscale.m:37-83 (real blocks): Y_k = T \\ (X_k / T'), T = triu(U_k)."""
+    import scipy.linalg as sla
+    out = []
+    for U, X in zip(_blocks(ud, K), _blocks(x, K)):
+        T = np.triu(U)
+        W = sla.solve_triangular(T, X.T, lower=False).T                 # X / T'
+        out.append(sla.solve_triangular(T, W, lower=False).ravel(order="F"))
+    return np.concatenate(out)

@@ -174,6 +174,25 @@ update_kernel(const UTile *tiles, const Sn *sn, const Pair *pairs, const int *pa
   }
 }
 
+// The same update through the plan's gather lists: a thread owns an entry of the ancestor panel and sums the entries of
+// the contribution blocks that reach it, in descendant order (deterministic; no barrier, no search).
+__global__ void __launch_bounds__(256)
+update_gather_kernel(const UTile *tiles, const Sn *sn, const int *uptr, const long long *usrc, const int *uK,
+                     const unsigned char *kmask, const double *U, double *rect) {
+  const UTile tl = tiles[blockIdx.x];
+  const Sn sj = sn[tl.J];
+  const int r0 = tl.r0, r1 = min(tl.r0 + UT_R, sj.m), c0 = tl.c0, c1 = min(tl.c0 + UT_C, sj.n);
+  const int nr = r1 - r0, nc = c1 - c0;
+  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+    const int r = r0 + idx % nr, c = c0 + idx / nr;
+    if (r < c) continue;
+    const long long e = sj.poff + r + (long long)c * sj.m;
+    double acc = 0.0;
+    for (int q = uptr[e]; q < uptr[e + 1]; q++) if (!kmask || kmask[uK[q]]) acc += U[usrc[q]];
+    rect[e] -= acc;
+  }
+}
+
 // ======================================================================= Schur contributions
 // U_K = L21 D L21' (lower triangle) for every supernode of a list: blockIdx.x = supernode, blockIdx.y = lower 64x64
 // tile.  Skipped pivots have d = 0 and drop out (blkchol2.c:375,389).
@@ -264,26 +283,26 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
   const double ub = scal[0];
   __shared__ ArgMax sh_am[32];
   __shared__ double s_x;
-  // ---- blocked pass: 32 columns at a time.  The diagonal block is factored by one warp in registers (ldl_block.cuh),
-  // every row below it is brought up to date by its own thread (a 32-step substitution in registers) and the rest of
-  // the panel takes the rank-32 update.  A pivot that needs the reference's stability test (rare) ends the blocked
-  // pass: the remaining columns, starting with this block, go through the column-by-column code below, which
-  // evaluates the test on the fully updated column exactly like cholonBlk.
-  __shared__ double Ab[LDLB][LDLB + 1];
-  __shared__ double b_lb[LDLB], b_d[LDLB], b_rd[LDLB];
-  __shared__ int b_skip[LDLB], b_stop;
+  // ---- blocked pass: 8 columns at a time.  The diagonal block is factored by one warp in registers (ldl_block.cuh),
+  // every row below it is brought up to date by its own thread (an 8-step substitution in registers) and the rest of
+  // the panel takes the rank-8 update, one warp per column.  A pivot that needs the reference's stability test (rare)
+  // ends the blocked pass: the remaining columns, starting with this block, go through the column-by-column code
+  // below, which evaluates the test on the fully updated column exactly like cholonBlk.
+  __shared__ double Ab[LDLS][LDLS + 1];
+  __shared__ double b_lb[LDLS], b_d[LDLS], b_rd[LDLS];
+  __shared__ int b_skip[LDLS], b_stop;
   int kleg = 0;                                        // first column left to the column-by-column code
-  for (int p0 = 0; p0 < n; p0 += LDLB) {
-    const int w = min(LDLB, n - p0);
-    for (int idx = threadIdx.x; idx < LDLB * LDLB; idx += blockDim.x) {
-      const int r = idx % LDLB, c = idx / LDLB;
+  for (int p0 = 0; p0 < n; p0 += LDLS) {
+    const int w = min(LDLS, n - p0);
+    if (threadIdx.x < LDLS * LDLS) {
+      const int r = threadIdx.x % LDLS, c = threadIdx.x / LDLS;
       Ab[r][c] = (r < w && c < w && r >= c) ? P[(long long)(p0 + c) * ld + p0 + r] : 0.0;
     }
-    if (threadIdx.x < LDLB) { b_skip[threadIdx.x] = 0; b_d[threadIdx.x] = 0.0; b_lb[threadIdx.x] = threadIdx.x < w ? lb[s.first + p0 + threadIdx.x] : 0.0; }
+    if (threadIdx.x < LDLS) { b_skip[threadIdx.x] = 0; b_d[threadIdx.x] = 0.0; b_lb[threadIdx.x] = threadIdx.x < w ? lb[s.first + p0 + threadIdx.x] : 0.0; }
     __syncthreads();
     if (threadIdx.x < 32) {
       // global column = s.first + p0 + k; "column longer than 1" <=> (s.first + m) - (s.first + p0 + k) > 1
-      const int ks = warp_factor_block(Ab, b_lb, b_d, b_skip, flag, sval, s.first + p0, w, s.first + m, ub, 0, -1, 0.0);
+      const int ks = warp_factor_block8(Ab, b_lb, b_d, b_skip, flag, sval, s.first + p0, w, s.first + m, ub);
       if (threadIdx.x == 0) b_stop = ks;
     }
     __syncthreads();
@@ -293,47 +312,46 @@ factor_small_kernel(const int *list, const Sn *sn, double *rect, double *d, cons
       break;
     }
     kleg = p0 + w;
-    if (threadIdx.x < LDLB) b_rd[threadIdx.x] = (threadIdx.x < w && b_d[threadIdx.x] > 0.0) ? 1.0 / b_d[threadIdx.x] : 0.0;
+    if (threadIdx.x < LDLS) b_rd[threadIdx.x] = (threadIdx.x < w && b_d[threadIdx.x] > 0.0) ? 1.0 / b_d[threadIdx.x] : 0.0;
     if (threadIdx.x < w) d[s.first + p0 + threadIdx.x] = b_d[threadIdx.x];
     // L11 back into the panel (unit lower; a skipped column keeps no entries below its diagonal)
-    for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
-      const int r = idx % w, c = idx / w;
+    if (threadIdx.x < w * w) {
+      const int r = threadIdx.x % w, c = threadIdx.x / w;
       if (r >= c) P[(long long)(p0 + c) * ld + p0 + r] = (r == c) ? 1.0 : (b_skip[c] ? 0.0 : Ab[r][c]);
     }
     __syncthreads();
     // rows below the block: L21 = A21 L11^-T D^-1, one thread per row
     for (int r = p0 + w + threadIdx.x; r < m; r += blockDim.x) {
-      double a[LDLB];
+      double a[LDLS];
 #pragma unroll
-      for (int j = 0; j < LDLB; j++) a[j] = (j < w) ? P[(long long)(p0 + j) * ld + r] : 0.0;
+      for (int j = 0; j < LDLS; j++) a[j] = (j < w) ? P[(long long)(p0 + j) * ld + r] : 0.0;
 #pragma unroll
-      for (int j = 0; j < LDLB; j++) {
+      for (int j = 0; j < LDLS; j++) {
         const double rj = b_rd[j];
         const double xj = a[j];
         if (rj > 0.0) {
 #pragma unroll
-          for (int j2 = j + 1; j2 < LDLB; j2++) a[j2] -= xj * Ab[j2][j];
+          for (int j2 = j + 1; j2 < LDLS; j2++) a[j2] -= xj * Ab[j2][j];
           a[j] = xj * rj;
         } else a[j] = 0.0;
       }
 #pragma unroll
-      for (int j = 0; j < LDLB; j++) if (j < w) P[(long long)(p0 + j) * ld + r] = a[j];
+      for (int j = 0; j < LDLS; j++) if (j < w) P[(long long)(p0 + j) * ld + r] = a[j];
     }
     __syncthreads();
     // rank-w update of the remaining columns of the panel: P(r,c) -= sum_j L(r,j) d_j L(c,j), r >= c > last block column.
-    // One warp per column, lanes over rows (no index arithmetic in the loop; the column's 32 scaled entries are
-    // broadcast reads).
+    // One warp per column, lanes over rows; the column's scaled entries are broadcast reads.
     {
       const int c0 = p0 + w, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
       for (int c = c0 + warp; c < n; c += nw) {
         double *cc = P + (long long)c * ld;
+        double lc[LDLS];
+#pragma unroll
+        for (int j = 0; j < LDLS; j++) lc[j] = (j < w) ? b_d[j] * P[(long long)(p0 + j) * ld + c] : 0.0;
         for (int r = c + lane; r < m; r += 32) {
           double acc = 0.0;
-#pragma unroll 8
-          for (int j = 0; j < w; j++) {                         // (columns beyond the block do not exist in the panel)
-            const double *pj = P + (long long)(p0 + j) * ld;
-            acc += pj[r] * (b_d[j] * pj[c]);
-          }
+#pragma unroll
+          for (int j = 0; j < LDLS; j++) if (j < w) acc += P[(long long)(p0 + j) * ld + r] * lc[j];
           cc[r] -= acc;
         }
       }
@@ -601,8 +619,8 @@ __global__ void csc_to_rect_kernel(const Sn *sn, const int *snode, const long lo
 // ======================================================================= solves
 // Forward: one CTA per (supernode of the level, rhs).  y has length m per rhs, already = b(perm).
 __global__ void __launch_bounds__(512)
-fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair_beg, const int *rel,
-               const double *rect, double *y, int m, int solve, double *cvec, long long ctot) {
+fwsolve_kernel(const int *list, const Sn *sn, const int *pull_ptr, const int *pull_src, const int *pull_K,
+               const unsigned char *kmask, const double *rect, double *y, int m, int solve, double *cvec, long long ctot) {
   extern __shared__ double sm[];             // s[n]
   Sn sj = sn[list[blockIdx.x]];
   double *yy = y + (long long)blockIdx.y * m;
@@ -612,28 +630,14 @@ fwsolve_kernel(const int *list, const Sn *sn, const Pair *pairs, const int *pair
   for (int c = threadIdx.x; c < n; c += blockDim.x) s[c] = yy[sj.first + c];
   __syncthreads();
   // pull the contributions c_K = L21_K y_K of the descendants, in list order:  s[col] -= c_K[row]
-  // (the descriptors of the descendants are fetched together first -- one round of global latency instead of one per
-  // descendant -- then applied in list order)
-  {
-    __shared__ int s_off[256], s_rel[256], s_ncu[256];
-    const int pb = pair_beg[list[blockIdx.x]], pe = pair_beg[list[blockIdx.x] + 1];
-    for (int e0 = pb; e0 < pe; e0 += 256) {
-      const int ne = min(256, pe - e0);
-      __syncthreads();
-      if (threadIdx.x < ne) {
-        const Pair p = pairs[e0 + threadIdx.x];
-        const Sn sk = sn[p.K];
-        s_off[threadIdx.x] = sk.cvoff + (p.koff - sk.n); s_rel[threadIdx.x] = p.rel; s_ncu[threadIdx.x] = p.ncolup;
-      }
-      __syncthreads();
-      for (int i = 0; i < ne; i++) {
-        const double *ck = cv + s_off[i];
-        const int *rl = rel + s_rel[i];
-        for (int t = threadIdx.x; t < s_ncu[i]; t += blockDim.x) s[rl[t]] -= ck[t];       // rl[t] < n: distinct per t inside one descendant
-        __syncthreads();
-      }
-    }
+  // (thread c owns s[c]: its contributions are listed in the plan, in descendant order)
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    double acc = 0.0;
+    for (int q = pull_ptr[sj.first + c]; q < pull_ptr[sj.first + c + 1]; q++)
+      if (!kmask || kmask[pull_K[q]]) acc += cv[pull_src[q]];
+    s[c] -= acc;
   }
+  __syncthreads();
   // dense unit-lower solve of the n x n diagonal block, 32 columns at a time (solve = 0: pull only, used by the
   // sharded forward pass to collect the contributions of a rank's subtrees in the replicated top rows)
   const double *P = rect + sj.poff;
@@ -916,6 +920,42 @@ static int build_plan(sb200_chol_plan *pl, sb_idx m64, sb_idx nsuper64, const sb
     for (auto &p : byJ[J]) pairs.push_back(p);
   }
   pl->pair_beg[nsuper] = (int)pairs.size();
+  // gather lists (counting sort by target keeps the descendant order inside each target)
+  {
+    std::vector<int> pptr(m + 1, 0);
+    for (auto &p : pairs) for (int t = 0; t < p.ncolup; t++) pptr[pl->sn[p.J].first + rel[p.rel + t] + 1]++;
+    for (int c = 0; c < m; c++) pptr[c + 1] += pptr[c];
+    std::vector<int> psrc((size_t)std::max(pptr[m], 1)), pK((size_t)std::max(pptr[m], 1)), fill(pptr.begin(), pptr.end() - 1);
+    for (auto &p : pairs) {
+      const Sn &SK = pl->sn[p.K];
+      for (int t = 0; t < p.ncolup; t++) { const int q = fill[pl->sn[p.J].first + rel[p.rel + t]]++; psrc[q] = SK.cvoff + (p.koff - SK.n) + t; pK[q] = p.K; }
+    }
+    SB_TRY(pl->d_pull_ptr.upload(pptr)); SB_TRY(pl->d_pull_src.upload(psrc)); SB_TRY(pl->d_pull_K.upload(pK));
+    long long items = 0;
+    for (auto &p : pairs) items += (long long)p.ncolup * p.mk - (long long)p.ncolup * (p.ncolup - 1) / 2;
+    pl->upd_lists = !pairs.empty() && items < ((long long)1 << 28) && pl->rect < ((long long)1 << 30);
+    if (pl->upd_lists) {
+      std::vector<int> uptr((size_t)pl->rect + 1, 0);
+      for (auto &p : pairs) {
+        const Sn &SJ = pl->sn[p.J];
+        for (int t2 = 0; t2 < p.ncolup; t2++)
+          for (int t1 = t2; t1 < p.mk; t1++) uptr[SJ.poff + rel[p.rel + t1] + (long long)rel[p.rel + t2] * SJ.m + 1]++;
+      }
+      for (long long e = 0; e < pl->rect; e++) uptr[e + 1] += uptr[e];
+      std::vector<long long> usrc((size_t)std::max<long long>(items, 1));
+      std::vector<int> uK((size_t)std::max<long long>(items, 1)), ufill(uptr.begin(), uptr.end() - 1);
+      for (auto &p : pairs) {
+        const Sn &SJ = pl->sn[p.J], &SK = pl->sn[p.K];
+        const long long mk = SK.m - SK.n, u0 = p.koff - SK.n;
+        for (int t2 = 0; t2 < p.ncolup; t2++)
+          for (int t1 = t2; t1 < p.mk; t1++) {
+            const int q = ufill[SJ.poff + rel[p.rel + t1] + (long long)rel[p.rel + t2] * SJ.m]++;
+            usrc[q] = SK.uoff + (u0 + t1) + (u0 + t2) * mk; uK[q] = p.K;
+          }
+      }
+      SB_TRY(pl->d_upd_ptr.upload(uptr)); SB_TRY(pl->d_upd_src.upload(usrc)); SB_TRY(pl->d_upd_K.upload(uK));
+    }
+  }
   int nlev = 0;
   for (int s = 0; s < nsuper; s++) nlev = std::max(nlev, pl->level_of[s] + 1);
   pl->nlevels = nlev;
@@ -1013,8 +1053,12 @@ int sb200_blkchol_dev(sb200_chol_plan *pl, const double *Xpr, const double *absd
   for (int lv = 0; lv < pl->nlevels; lv++) {
     int ntile = (int)pl->level_tiles[lv].size();
     if (ntile) {
-      update_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_pairs.p,
-                                            pl->d_pair_beg.p, pl->d_rel.p, pl->d_U.p, rect);
+      if (pl->upd_lists)
+        update_gather_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_upd_ptr.p, pl->d_upd_src.p,
+                                                    pl->d_upd_K.p, nullptr, pl->d_U.p, rect);
+      else
+        update_kernel<<<ntile, 256, 0, st>>>(pl->d_tiles.p + pl->level_tile_off[lv], pl->d_sn.p, pl->d_pairs.p,
+                                              pl->d_pair_beg.p, pl->d_rel.p, pl->d_U.p, rect);
       SB_LAUNCH_CHECK_N("update_kernel");
     }
     SB_TRY(launch_factor_small(pl, pl->level_small[lv], pl->d_level_list.p + pl->level_small_off[lv], pars, rect, d, flag, sval));
@@ -1073,8 +1117,8 @@ int sb200_fwblkslv_dev(sb200_chol_plan *pl, const double *rect, const double *b,
   SB_TRY(ensure_cvec(pl, (int)nrhs));
   for (int lv = 0; lv < pl->nlevels; lv++) {
     dim3 g((unsigned)pl->level_all[lv].size(), (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pairs.p,
-                                         pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
+    fwsolve_kernel<<<g, 512, shm, st>>>(pl->d_level_all.p + pl->level_all_off[lv], pl->d_sn.p, pl->d_pull_ptr.p, pl->d_pull_src.p,
+                                         pl->d_pull_K.p, nullptr, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
@@ -1261,6 +1305,11 @@ int sb200_chol_shard_create(sb200_chol_plan *pl, sb_idx world64, sb_idx rank64) 
   if (pA.empty()) pA.push_back(Pair{});
   if (pB.empty()) pB.push_back(Pair{});
   SB_TRY(sh->d_lists.upload(lists)); SB_TRY(sh->d_tiles.upload(tiles));
+  {
+    std::vector<unsigned char> kA(ns, 0), kB(ns, 0);
+    for (int K = 0; K < ns; K++) { kA[K] = (K < t0 && sh->owner[K] == rank) ? 1 : 0; kB[K] = K >= t0 ? 1 : 0; }
+    SB_TRY(sh->d_kmaskA.upload(kA)); SB_TRY(sh->d_kmaskB.upload(kB));
+  }
   SB_TRY(sh->d_pairsA.upload(pA)); SB_TRY(sh->d_pairsB.upload(pB));
   SB_TRY(sh->d_pair_begA.upload(begA)); SB_TRY(sh->d_pair_begB.upload(begB));
   SB_TRY(sh->d_colmask.upload(colmask));
@@ -1284,6 +1333,10 @@ static int shard_factor_levels(sb200_chol_plan *pl, bool top, sb200_chol_pars pa
   for (int lv = 0; lv < pl->nlevels; lv++) {
     const int ntile = top ? sh->top_tile_cnt[lv] : sh->own_tile_cnt[lv];
     if (ntile) {
+      if (pl->upd_lists)
+        update_gather_kernel<<<ntile, 256, 0, st>>>(sh->d_tiles.p + (top ? sh->top_tile_off[lv] : sh->own_tile_off[lv]), pl->d_sn.p, pl->d_upd_ptr.p,
+                                                    pl->d_upd_src.p, pl->d_upd_K.p, top ? sh->d_kmaskB.p : nullptr, pl->d_U.p, rect);
+      else
       update_kernel<<<ntile, 256, 0, st>>>(sh->d_tiles.p + (top ? sh->top_tile_off[lv] : sh->own_tile_off[lv]), pl->d_sn.p,
                                             top ? sh->d_pairsB.p : pl->d_pairs.p, top ? sh->d_pair_begB.p : pl->d_pair_beg.p, pl->d_rel.p, pl->d_U.p, rect);
       SB_LAUNCH_CHECK_N("update_kernel");
@@ -1337,6 +1390,10 @@ int sb200_blkchol_shard_local_dev(sb200_chol_plan *pl, const double *Xpr, const 
   if (sh->rank != 0 && sh->top_rect_len) SB_CUDA(cudaMemsetAsync(rect + sh->top_rect_off, 0, sizeof(double) * sh->top_rect_len, st));
   SB_TRY(shard_factor_levels(pl, false, pars, rect, d, flag, sval));
   if (sh->topA_tile_cnt) {
+    if (pl->upd_lists)
+      update_gather_kernel<<<sh->topA_tile_cnt, 256, 0, st>>>(sh->d_tiles.p + sh->topA_tile_off, pl->d_sn.p, pl->d_upd_ptr.p, pl->d_upd_src.p, pl->d_upd_K.p,
+                                                              sh->d_kmaskA.p, pl->d_U.p, rect);
+    else
     update_kernel<<<sh->topA_tile_cnt, 256, 0, st>>>(sh->d_tiles.p + sh->topA_tile_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, pl->d_U.p, rect);
     SB_LAUNCH_CHECK_N("update_kernel");
   }
@@ -1371,12 +1428,12 @@ int sb200_fw_shard_local_dev(sb200_chol_plan *pl, const double *rect, const doub
   for (int lv = 0; lv < pl->nlevels; lv++) {
     if (sh->own_all[lv].empty()) continue;
     dim3 g((unsigned)sh->own_all[lv].size(), (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_pairs.p, pl->d_pair_beg.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->own_all_off[lv], pl->d_sn.p, pl->d_pull_ptr.p, pl->d_pull_src.p, pl->d_pull_K.p, nullptr, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   if (sh->top_list_cnt) {
     dim3 g((unsigned)sh->top_list_cnt, (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_list_off, pl->d_sn.p, sh->d_pairsA.p, sh->d_pair_begA.p, pl->d_rel.p, rect, y, m, 0, pl->d_cvec.p, pl->ctot);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_list_off, pl->d_sn.p, pl->d_pull_ptr.p, pl->d_pull_src.p, pl->d_pull_K.p, sh->d_kmaskA.p, rect, y, m, 0, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   return 0;
@@ -1396,7 +1453,7 @@ int sb200_solve_shard_top_dev(sb200_chol_plan *pl, const double *rect, const dou
   for (int lv = 0; lv < pl->nlevels; lv++) {
     if (sh->top_all[lv].empty()) continue;
     dim3 g((unsigned)sh->top_all[lv].size(), (unsigned)nrhs);
-    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, sh->d_pairsB.p, sh->d_pair_begB.p, pl->d_rel.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
+    fwsolve_kernel<<<g, 512, shm, st>>>(sh->d_lists.p + sh->top_all_off[lv], pl->d_sn.p, pl->d_pull_ptr.p, pl->d_pull_src.p, pl->d_pull_K.p, sh->d_kmaskB.p, rect, y, m, 1, pl->d_cvec.p, pl->ctot);
     SB_LAUNCH_CHECK_N("fwsolve_kernel");
   }
   const long long tot = (long long)m * nrhs;

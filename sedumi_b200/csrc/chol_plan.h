@@ -58,6 +58,11 @@ struct sb200_chol_plan {
   // The forward solve does the same with the vectors c_K = L21 y_K.
   sb::DevBuf<double> d_U, d_cvec;
   long long utot = 0, ctot = 0;
+  // gather lists: for every target (entry of y / entry of an ancestor panel) the contributions that reach it, in
+  // descendant order, with the descendant each comes from (sharded runs filter by descendant)
+  sb::DevBuf<int> d_pull_ptr, d_pull_src, d_pull_K, d_upd_ptr, d_upd_K;
+  sb::DevBuf<long long> d_upd_src;
+  bool upd_lists = false;
   int cvec_nrhs = 0, max_mk = 0;
   size_t small_cap = 0;          // doubles of shared memory a factor CTA may use for its panel
   // dense fast path (one supernode spanning the whole matrix): working copy, inverted diagonal
@@ -78,6 +83,7 @@ struct sb200_chol_plan {
     int topA_tile_off = 0, topA_tile_cnt = 0;                  // partial update of the top by owned descendants
     int top_list_off = 0, top_list_cnt = 0;                    // all top supernodes (pull-only forward pass)
     sb::DevBuf<int> d_lists, d_pair_begA, d_pair_begB, d_colmask;
+    sb::DevBuf<unsigned char> d_kmaskA, d_kmaskB;              // descendants below the top owned by this rank / inside the top
     sb::DevBuf<sb::UTile> d_tiles;
     sb::DevBuf<sb::Pair> d_pairsA, d_pairsB;
   };

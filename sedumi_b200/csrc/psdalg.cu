@@ -10,6 +10,7 @@
 // vecsym and sqrtinv are streams (one thread per entry).  qrK is n-1 dependent reflections per block: one CTA per block,
 // the reflector in shared memory, a block reduction for its norm, then one warp per remaining column (dot + axpy).
 #include <algorithm>
+#include "gemm.cuh"
 #include "sb_internal.h"
 
 namespace sb {
@@ -87,6 +88,95 @@ __global__ void __launch_bounds__(256) qrk_kernel(const AlgBlk *blks, double *q,
   }
 }
 
+// ---- psdjmul.m / triumtriu.m / psdfactor.m / psdinvscale.m (real blocks): transposes, symmetrisations, a per-block
+// Cholesky with MATLAB's "not positive definite" flag and upper-triangular solves with many right-hand sides.
+__global__ void alg_transpose_kernel(const AlgBlk *blks, const double *x, double *y) {
+  __shared__ double tile[32][33];
+  const AlgBlk B = blks[blockIdx.z];
+  const int n = B.n, i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  if (i0 >= n || j0 >= n) return;
+  const double *X = x + B.off; double *Y = y + B.off;
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int i = i0 + threadIdx.x, j = j0 + jj;
+    tile[jj][threadIdx.x] = (i < n && j < n) ? X[i + (long long)j * n] : 0.0;
+  }
+  __syncthreads();
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int i = j0 + threadIdx.x, j = i0 + jj;          // Y(i,j) = X(j,i)
+    if (i < n && j < n) Y[i + (long long)j * n] = tile[threadIdx.x][jj];
+  }
+}
+// mode 0: Z = (P + P')/2 (psdjmul.m:67);  mode 1: Z = P + triu(P,1)' with P upper triangular (triumtriu.m:66);
+// mode 2: Z = L + tril(L,-1)' from the lower triangle (psdfactor.m:74)
+__global__ void alg_sym_kernel(const AlgBlk *blks, const double *p, double *z, int mode) {
+  const AlgBlk B = blks[blockIdx.y];
+  const int n = B.n;
+  const long long tot = (long long)n * n;
+  const double *P = p + B.off; double *Z = z + B.off;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    const long long tr = j + (long long)i * n;
+    if (mode == 0) Z[idx] = 0.5 * (P[idx] + P[tr]);
+    else if (mode == 1) Z[idx] = (i <= j) ? P[idx] : P[tr];
+    else Z[idx] = (i >= j) ? P[idx] : P[tr];
+  }
+}
+// chol(X,'lower') of one block per CTA, left-looking, in place on the lower triangle of W (a copy of X).
+// flag[k] = 0 or the (1-based) column at which the pivot was not positive (MATLAB's second output of chol).
+__global__ void __launch_bounds__(256) alg_chol_kernel(const AlgBlk *blks, double *w, int *flag) {
+  extern __shared__ double rowj[];                   // L(j, 0..j-1)
+  __shared__ double s_piv;
+  const AlgBlk B = blks[blockIdx.x];
+  const int n = B.n;
+  double *L = w + B.off;
+  if (threadIdx.x == 0) flag[blockIdx.x] = 0;
+  for (int j = 0; j < n; j++) {
+    for (int k = threadIdx.x; k < j; k += blockDim.x) rowj[k] = L[j + (long long)k * n];
+    __syncthreads();
+    for (int r = j + threadIdx.x; r < n; r += blockDim.x) {
+      double acc = L[r + (long long)j * n];
+      for (int k = 0; k < j; k++) acc -= L[r + (long long)k * n] * rowj[k];
+      L[r + (long long)j * n] = acc;
+      if (r == j) s_piv = acc;
+    }
+    __syncthreads();
+    const double piv = s_piv;
+    if (!(piv > 0.0)) { if (threadIdx.x == 0) flag[blockIdx.x] = j + 1; return; }
+    const double sq = sqrt(piv);
+    for (int r = j + threadIdx.x; r < n; r += blockDim.x) L[r + (long long)j * n] = (r == j) ? sq : L[r + (long long)j * n] / sq;
+    __syncthreads();
+  }
+}
+// Solve triu(T) Z = B for the columns of B, in place: one warp per column, the column in registers (lanes over rows),
+// column k of T (contiguous) read once per elimination step.
+static const int ALG_SOLVE_MAXCH = 16;               // up to 512 rows per block in registers
+__global__ void __launch_bounds__(256) alg_trsolve_kernel(const AlgBlk *blks, const double *t, double *b) {
+  const AlgBlk B = blks[blockIdx.y];
+  const int n = B.n, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= n) return;
+  const double *T = t + B.off;
+  double *z = b + B.off + (long long)col * n;
+  double v[ALG_SOLVE_MAXCH];
+#pragma unroll
+  for (int c = 0; c < ALG_SOLVE_MAXCH; c++) { const int r = lane + 32 * c; v[c] = r < n ? z[r] : 0.0; }
+  for (int k = n - 1; k >= 0; k--) {
+    const double *Tk = T + (long long)k * n;
+    double zk = 0.0;
+#pragma unroll
+    for (int c = 0; c < ALG_SOLVE_MAXCH; c++) if ((k >> 5) == c) zk = v[c];
+    zk = __shfl_sync(0xffffffffu, zk, k & 31) / Tk[k];
+#pragma unroll
+    for (int c = 0; c < ALG_SOLVE_MAXCH; c++) {
+      const int r = lane + 32 * c;
+      if (r == k) v[c] = zk;
+      else if (r < k) v[c] -= Tk[r] * zk;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < ALG_SOLVE_MAXCH; c++) { const int r = lane + 32 * c; if (r < n) z[r] = v[c]; }
+}
+
 static int alg_blocks(sb_idx nblk, sb_idx nreal, const sb_idx *n, std::vector<AlgBlk> &blks, long long &lenud, long long &sumn, int &maxn) {
   lenud = 0; sumn = 0; maxn = 0;
   for (sb_idx k = 0; k < nblk; k++) {
@@ -162,6 +252,114 @@ int sb200_qrK(sb_idx nblk, const sb_idx *n, const double *x, double *q, double *
   SB_LAUNCH_CHECK_N("qrk_kernel");
   SB_CUDA(cudaMemcpyAsync(q, dq, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaMemcpyAsync(r, dr, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
+// Batched products Z_k = A_k B_k' on the tile-GEMM engine (one launch): descriptors built per call.
+static int alg_gemm(const std::vector<AlgBlk> &blks, int a_tri, int b_tri, const double *dA, const double *dB, double *dC) {
+  std::vector<GemmDesc> descs; std::vector<GemmTile> tiles;
+  for (size_t k = 0; k < blks.size(); k++) {
+    GemmDesc g{}; g.gatherOff = -1; g.alpha = 1.0;
+    g.offA = g.offB = g.offC = blks[k].off; g.lda = g.ldb = g.ldc = blks[k].n; g.a_tri = a_tri; g.b_tri = b_tri;
+    g.M = g.N = g.K = blks[k].n; g.lower = 0; g.accumulate = 0;
+    gemm_add_tiles(tiles, (int)descs.size(), blks[k].n, blks[k].n, false); descs.push_back(g);
+  }
+  GemmDesc *dd = arena<GemmDesc>(descs.size()); GemmTile *dt = arena<GemmTile>(tiles.size());
+  SB_CHECK(dd && dt, "psd algebra: out of device memory");
+  cudaStream_t st = ctx().stream;
+  SB_CUDA(cudaMemcpyAsync(dd, descs.data(), sizeof(GemmDesc) * descs.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dt, tiles.data(), sizeof(GemmTile) * tiles.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaStreamSynchronize(st));                 // host vectors go out of scope
+  gemm_nt_launch((int)tiles.size(), ctx().sm_count, st, dd, dt, dA, dB, dC, nullptr);
+  SB_LAUNCH_CHECK_N("gemm_nt_kernel");
+  return 0;
+}
+
+// z = psdjmul(x,y,K) (mode 0, psdjmul.m:38-74: Z_k = (X_k Y_k + (X_k Y_k)')/2) and z = triumtriu(x,y,K) (mode 1,
+// triumtriu.m:38-73: Z_k = triu(X_k) triu(Y_k), mirrored below the diagonal); real blocks, x/y/z lenud doubles.
+int sb200_psdmul(int mode, sb_idx nblk, const sb_idx *n, const double *x, const double *y, double *z) {
+  SB_TRY(ensure_init());
+  std::vector<AlgBlk> blks; long long lenud, sumn; int maxn;
+  SB_TRY(alg_blocks(nblk, nblk, n, blks, lenud, sumn, maxn));
+  if (lenud == 0) return 0;
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  AlgBlk *db = arena<AlgBlk>(blks.size());
+  double *dx = arena<double>((size_t)lenud), *dy = arena<double>((size_t)lenud), *dyt = arena<double>((size_t)lenud), *dp = arena<double>((size_t)lenud);
+  SB_CHECK(db && dx && dy && dyt && dp, "psdjmul: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(AlgBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  const int tp = (maxn + 31) / 32;
+  alg_transpose_kernel<<<dim3(tp, tp, (unsigned)nblk), dim3(32, 8), 0, st>>>(db, dy, dyt);
+  SB_LAUNCH_CHECK_N("alg_transpose_kernel");
+  // P(i,c) = sum_k X(i,k) Yt(c,k); triumtriu: X(i,k) = 0 for k < i, Y(k,c) = 0 for k > c
+  SB_TRY(alg_gemm(blks, mode == 1 ? TRI_K_GE_ROW : TRI_NONE, mode == 1 ? TRI_K_LE_ROW : TRI_NONE, dx, dyt, dp));
+  alg_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, dp, dx, mode);
+  SB_LAUNCH_CHECK_N("alg_sym_kernel");
+  SB_CUDA(cudaMemcpyAsync(z, dx, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// [ux, ispos] = psdfactor(x,K) (psdfactor.m:37-82): lower Cholesky factor of every real block, mirrored; *ispos = 0 and
+// the blocks from the first failing one on left zero when a block is not positive definite.
+int sb200_psdfactor(sb_idx nblk, const sb_idx *n, const double *x, double *ux, int *ispos) {
+  SB_TRY(ensure_init());
+  std::vector<AlgBlk> blks; long long lenud, sumn; int maxn;
+  SB_TRY(alg_blocks(nblk, nblk, n, blks, lenud, sumn, maxn));
+  *ispos = 1;
+  if (lenud == 0) return 0;
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  AlgBlk *db = arena<AlgBlk>(blks.size());
+  double *dw = arena<double>((size_t)lenud), *du = arena<double>((size_t)lenud);
+  int *dflag = arena<int>(blks.size());
+  SB_CHECK(db && dw && du && dflag, "psdfactor: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(AlgBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dw, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  alg_chol_kernel<<<(unsigned)nblk, 256, sizeof(double) * (size_t)maxn, st>>>(db, dw, dflag);
+  SB_LAUNCH_CHECK_N("alg_chol_kernel");
+  alg_sym_kernel<<<dim3((unsigned)std::min<long long>(((long long)maxn * maxn + 255) / 256, 1024), (unsigned)nblk), 256, 0, st>>>(db, dw, du, 2);
+  SB_LAUNCH_CHECK_N("alg_sym_kernel");
+  std::vector<int> flag(blks.size());
+  SB_CUDA(cudaMemcpyAsync(flag.data(), dflag, sizeof(int) * blks.size(), cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaMemcpyAsync(ux, du, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  for (size_t k = 0; k < blks.size(); k++)
+    if (flag[k]) { *ispos = 0; memset(ux + blks[k].off, 0, sizeof(double) * (size_t)(lenud - blks[k].off)); break; }
+  return 0;
+}
+
+// y = psdinvscale(ud,x,K) (psdinvscale.m:37-83): Y_k = T \ (X_k / T'), T = triu(U_k); real blocks.
+int sb200_psdinvscale(sb_idx nblk, const sb_idx *n, const double *u, const double *x, double *y) {
+  SB_TRY(ensure_init());
+  std::vector<AlgBlk> blks; long long lenud, sumn; int maxn;
+  SB_TRY(alg_blocks(nblk, nblk, n, blks, lenud, sumn, maxn));
+  if (lenud == 0) return 0;
+  SB_CHECK(maxn <= 32 * ALG_SOLVE_MAXCH, "psdinvscale: block order %d beyond the register-resident solve (%d)", maxn, 32 * ALG_SOLVE_MAXCH);
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  AlgBlk *db = arena<AlgBlk>(blks.size());
+  const double *du = (const double *)mirror_input(u, sizeof(double) * lenud);
+  double *dx = arena<double>((size_t)lenud), *dt = arena<double>((size_t)lenud);
+  SB_CHECK(db && du && dx && dt, "psdinvscale: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(AlgBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  const int tp = (maxn + 31) / 32;
+  const dim3 gs((unsigned)((maxn + 7) / 8), (unsigned)nblk);
+  // W' = T \ X'  (= (X / T')'), then Y = T \ W
+  alg_transpose_kernel<<<dim3(tp, tp, (unsigned)nblk), dim3(32, 8), 0, st>>>(db, dx, dt);
+  SB_LAUNCH_CHECK_N("alg_transpose_kernel");
+  alg_trsolve_kernel<<<gs, 256, 0, st>>>(db, du, dt);
+  SB_LAUNCH_CHECK_N("alg_trsolve_kernel");
+  alg_transpose_kernel<<<dim3(tp, tp, (unsigned)nblk), dim3(32, 8), 0, st>>>(db, dt, dx);
+  SB_LAUNCH_CHECK_N("alg_transpose_kernel");
+  alg_trsolve_kernel<<<gs, 256, 0, st>>>(db, du, dx);
+  SB_LAUNCH_CHECK_N("alg_trsolve_kernel");
+  SB_CUDA(cudaMemcpyAsync(y, dx, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
   SB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -67,3 +67,51 @@ def test_qrK_frames_feed_psdframeit():
     qg, _ = gpu.qrK(x, Km, nlhs=2)
     qr_, _ = ref.qrK(x, Km, nlhs=2)
     assert relerr(gpu.psdframeit(lab, qg, Km), ref.psdframeit(lab, qr_, Km)) <= 1e-10
+
+
+# ---- the M-only pieces (psdjmul.m, triumtriu.m, psdfactor.m, psdinvscale.m): numpy restatements as the oracle
+# ("parity unpinned" beyond that: the reference cannot run M code here)
+import os
+import sys
+
+from helpers import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import restate  # noqa: E402
+
+
+@pytest.mark.parametrize("s", [(3,), (40, 7), (130,), (200, 65)])
+def test_psdjmul_triumtriu(s):
+    K, Km = _K(2, (), s)
+    rng = np.random.default_rng(sum(s))
+    lenud = sum(k * k for k in s)
+    x, y = rng.standard_normal(2 + lenud), rng.standard_normal(2 + lenud)        # PSD part = tail
+    assert relerr(gpu.psdjmul(x, y, Km), restate.psdjmul(x, y, K)) <= 1e-12
+    assert relerr(gpu.triumtriu(x, y, Km), restate.triumtriu(x, y, K)) <= 1e-12
+
+
+@pytest.mark.parametrize("s", [(4,), (33, 9), (161,)])
+def test_psdfactor_and_psdinvscale(s):
+    K, Km = _K(1, (), s)
+    rng = np.random.default_rng(7 + sum(s))
+    blocks = []
+    for n in s:
+        G = rng.standard_normal((n, n + 3))
+        blocks.append(G @ G.T / n + 0.1 * np.eye(n))
+    x = np.concatenate([B.ravel(order="F") for B in blocks])
+    ug, pos = gpu.psdfactor(x, Km, nlhs=2)
+    ur, posr = restate.psdfactor(x, K)
+    assert float(np.asarray(pos).ravel()[0]) == 1.0 and posr
+    assert relerr(ug, ur) <= 1e-10
+    # the factor is the `ud` psdinvscale takes (upper triangle = L'): Y = T \ (X / T') with X symmetric
+    X = np.concatenate([(lambda M: (M + M.T).ravel(order="F"))(rng.standard_normal((n, n))) for n in s])
+    assert relerr(gpu.psdinvscale(ug.ravel(), X, Km), restate.psdinvscale(ur, X, K)) <= 1e-9
+    # an indefinite block: flag, and nothing from that block on
+    bad = x.copy()
+    if len(s) > 1:
+        o = s[0] * s[0]
+        bad[o] = -1.0                                       # (1,1) entry of the second block
+        ub, posb = gpu.psdfactor(bad, Km, nlhs=2)
+        urb, posrb = restate.psdfactor(bad, K)
+        assert float(np.asarray(posb).ravel()[0]) == 0.0 and not posrb
+        assert relerr(ub.ravel()[:o], urb[:o]) <= 1e-10 and not np.any(ub.ravel()[o:])
