@@ -22,6 +22,9 @@ CHOL_PARS = {"canceltol": 1e-12, "maxu": 5e5, "abstol": 1e-20}      # checkpars.
 def relerr(a, b):
     a = np.asarray(a.todense() if sp.issparse(a) else a, dtype=float)
     b = np.asarray(b.todense() if sp.issparse(b) else b, dtype=float)
+    if a.shape != b.shape:                       # (N,1) against (N,): compare element by element, never broadcast
+        assert a.size == b.size, (a.shape, b.shape)
+        a, b = a.ravel(), b.ravel()
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
 

@@ -86,8 +86,8 @@ def test_psdjmul_triumtriu(s):
     rng = np.random.default_rng(sum(s))
     lenud = sum(k * k for k in s)
     x, y = rng.standard_normal(2 + lenud), rng.standard_normal(2 + lenud)        # PSD part = tail
-    assert relerr(gpu.psdjmul(x, y, Km), restate.psdjmul(x, y, K)) <= 1e-12
-    assert relerr(gpu.triumtriu(x, y, Km), restate.triumtriu(x, y, K)) <= 1e-12
+    assert relerr(np.ravel(gpu.psdjmul(x, y, Km)), restate.psdjmul(x, y, K)) <= 1e-12
+    assert relerr(np.ravel(gpu.triumtriu(x, y, Km)), restate.triumtriu(x, y, K)) <= 1e-12
 
 
 @pytest.mark.parametrize("s", [(4,), (33, 9), (161,)])
@@ -102,10 +102,10 @@ def test_psdfactor_and_psdinvscale(s):
     ug, pos = gpu.psdfactor(x, Km, nlhs=2)
     ur, posr = restate.psdfactor(x, K)
     assert float(np.asarray(pos).ravel()[0]) == 1.0 and posr
-    assert relerr(ug, ur) <= 1e-10
+    assert relerr(np.ravel(ug), ur) <= 1e-10
     # the factor is the `ud` psdinvscale takes (upper triangle = L'): Y = T \ (X / T') with X symmetric
     X = np.concatenate([(lambda M: (M + M.T).ravel(order="F"))(rng.standard_normal((n, n))) for n in s])
-    assert relerr(gpu.psdinvscale(ug.ravel(), X, Km), restate.psdinvscale(ur, X, K)) <= 1e-9
+    assert relerr(np.ravel(gpu.psdinvscale(ug.ravel(), X, Km)), restate.psdinvscale(ur, X, K)) <= 1e-9
     # an indefinite block: flag, and nothing from that block on
     bad = x.copy()
     if len(s) > 1:

@@ -18,7 +18,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 
 def short(name):
@@ -64,6 +64,7 @@ def main():
             f.write(f"{k},{c},{t:.0f},{t / tot:.4f}\n")
     # ---- shares table: events (bench) vs ncu
     ev = dict(bench["roofline"]["kernel_ms_per_step"])
+    ev.pop("nccl_allreduce", None)
     # psdscale and the psdframeit/psdinvjmul congruences are the same kernel under two profiling labels
     fused = ev.pop("psdscale_small_kernel", 0.0) + ev.pop("small_congruence_kernel", 0.0)
     if fused:
@@ -107,7 +108,7 @@ def main():
             except (KeyError, ValueError):
                 pass
         open(os.path.join(OUT, f"ncu_{TAG}_top_kernels.txt"), "w").write("\n".join(txt) + "\n")
-        json.dump({"control07": traffic}, open(os.path.join(OUT, f"traffic_{TAG}.json"), "w"), indent=1)
+        json.dump({bench["config"]["workload"]: traffic}, open(os.path.join(OUT, f"traffic_{TAG}.json"), "w"), indent=1)
     print("profiles refreshed:", sorted(os.listdir(OUT)))
 
 
