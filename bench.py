@@ -188,7 +188,7 @@ def kernel_work(S, name, key):
     if key not in _WORK_CACHE:
         _WORK_CACHE[key] = getada3_work(S)
     F3, B3 = _WORK_CACHE[key]
-    if name in ("ada3_fused_kernel", "ada3_fused_small_kernel"):
+    if name in ("ada3_fused_kernel", "ada3_fused_small_kernel", "ada3_strip_kernel"):
         return dict(bound="tensor", work=F3, unit="TFLOP/s", bytes=B3, what="getada3 (SURVEY 8d F and B)")
     if name == "gemm_nt_kernel":
         # invcholfac (n^3/3 MACs), psdscale (two triangular products, n^3 flops each), psdinvjmul (two full 2n^3

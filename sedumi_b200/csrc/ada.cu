@@ -451,6 +451,7 @@ __global__ void tt_val_kernel(long long n, const double *tt_w, const int *tt_src
 }  // namespace sb
 
 #include "ada_fused.cuh"
+#include "ada_strip.cuh"
 
 using namespace sb;
 
@@ -513,6 +514,16 @@ struct sb200_ada_plan {
   bool csr_built = false;
   DevBuf<int2> d_fitems;
   long long fused_ndense = 0;
+  // strip path (ada_strip.cuh): blocks too large for two resident CTAs of the fused kernel
+  bool strip_ok = false;
+  int strip_grid = 0, strip_ldA = 0, strip_ldB = 0, strip_nwork = 0;
+  size_t strip_smem = 0;
+  long long strip_scratch_stride = 0, strip_nent = 0;
+  DevBuf<StripGroup> d_sgroups; DevBuf<StripPG> d_spg; DevBuf<StripWork> d_swork;
+  DevBuf<int> d_sblk_grp_beg, d_spair_pg, d_sblk_feoff, d_sfe_ptr, d_sfe_src, d_sneed, d_sblk_lanes;
+  DevBuf<int2> d_sitems;
+  DevBuf<unsigned short> d_sfe_pk;
+  DevBuf<double> d_sfe_val, d_sscratch, d_sws;
 };
 
 static std::map<Hash128, sb200_ada_plan *> g_ada_plans;
@@ -884,6 +895,151 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
       if (need_pq.empty()) need_pq.push_back(0);
       SB_TRY(pl->d_fneed.upload(need_pq)); SB_TRY(pl->d_forder.upload(order));
+      // ---- strips: (pair, column strip) work items for blocks that leave no room for a second resident CTA
+      if (!pl->fused_small && !getenv("SB200_NO_STRIP_ADA3")) {
+        bool sok = true;
+        std::vector<int> bgb(nblk + 1, 0);
+        std::vector<StripGroup> groups;
+        std::vector<int2> sitems;
+        int gwmax = 0;
+        for (sb_idx k = 0; k < nblk && sok; k++) {
+          bgb[k] = (int)groups.size();
+          const int nk = pl->blk_n[k], ns = (nk + 31) / 32, nt = (nk + 7) / 8;
+          int J = 0;
+          while (J < ns) {
+            int J1 = J, nit = 0; long long ent = 0;
+            while (J1 < ns) {
+              long long e2 = 0;
+              for (int cc = 32 * J1; cc < std::min(nk, 32 * J1 + 32); cc++) e2 += nk - cc;
+              const int it = ns - J1;
+              if (J1 > J && (ent + e2 > STRIP_WCAP || nit + it > 8)) break;
+              ent += e2; nit += it; J1++;
+            }
+            if (ent > STRIP_WCAP) { sok = false; break; }
+            StripGroup G{};
+            G.c0 = 32 * J; G.c1 = std::min(nk, 32 * J1);
+            G.base = (int)(((long long)G.c0 * (2 * nk - G.c0 + 1)) / 2);
+            G.gw_al = (G.c1 - G.c0 + 1) & ~1;
+            G.item_beg = (int)sitems.size();
+            std::vector<std::pair<int, int2>> v;
+            for (int Jc = J; Jc < J1; Jc++)
+              for (int I = Jc; I < ns; I++) {
+                const int nra = std::min(4, nt - 4 * I), ncb = std::min(4, nt - 4 * Jc);
+                int cst = 0;
+                for (int a2 = 0; a2 < nra; a2++) for (int b2 = 0; b2 < ncb; b2++) if (I != Jc || a2 >= b2) cst++;
+                v.push_back({-cst, make_int2(I, Jc)});
+              }
+            std::stable_sort(v.begin(), v.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first < y.first; });
+            for (auto &e : v) sitems.push_back(e.second);
+            G.item_end = (int)sitems.size();
+            gwmax = std::max(gwmax, G.c1 - G.c0);
+            groups.push_back(G);
+            J = J1;
+          }
+        }
+        bgb[nblk] = (int)groups.size();
+        if (sok) {
+          auto group_of = [&](int k, int q) {                  // strip of column q in block k
+            for (int g = bgb[k]; g < bgb[k + 1]; g++) if (q < groups[g].c1) return g - bgb[k];
+            return bgb[k + 1] - bgb[k] - 1;
+          };
+          // entries of every partner, strip by strip (At order inside a strip)
+          std::vector<int> feoff(nblk + 1, 0), fe_ptr, fe_src;
+          std::vector<unsigned short> fe_pk;
+          std::vector<int> lanes(std::max<sb_idx>(nblk, 1), 32);
+          std::vector<std::vector<int>> bucket;
+          for (sb_idx k = 0; k < nblk; k++) {
+            feoff[k] = (int)fe_ptr.size();
+            const int ng = bgb[k + 1] - bgb[k];
+            const long long nk = pl->blk_n[k];
+            const size_t ent0 = fe_pk.size();
+            for (int t = blkp_beg[k]; t < blkp_beg[k + 1]; t++) {
+              const AdaPair &P = pl->pairs[blkp_pair[t]];
+              bucket.assign(ng, {});
+              for (int e = P.e0; e < P.e1; e++) bucket[group_of((int)k, (int)(ent_lin[e] / nk))].push_back(e);
+              for (int g = 0; g < ng; g++) {
+                fe_ptr.push_back((int)fe_pk.size());
+                for (int e : bucket[g]) {
+                  const long long pp = ent_lin[e] % nk, qq = ent_lin[e] / nk;
+                  fe_pk.push_back((unsigned short)((qq * (2 * nk - qq + 1)) / 2 - qq + pp - groups[bgb[k] + g].base));
+                  fe_src.push_back(ent_src[e]);
+                }
+              }
+            }
+            const double cnt = (double)(blkp_beg[k + 1] - blkp_beg[k]) * ng;
+            const double a2 = cnt > 0 ? (double)(fe_pk.size() - ent0) / cnt : 0.0;
+            lanes[k] = a2 <= 6.0 ? 4 : (a2 <= 12.0 ? 8 : (a2 <= 24.0 ? 16 : 32));
+          }
+          feoff[nblk] = (int)fe_ptr.size();
+          fe_ptr.push_back((int)fe_pk.size());
+          // per (pair, strip): its share of the needed set, its partial-sum slot; the work list
+          std::vector<int> pair_pg(pl->pairs.size() + 1, 0), sneed;
+          std::vector<StripPG> pgs;
+          std::vector<StripWork> work;
+          std::vector<double> wcost;
+          long long sws = 0, smax_tt = 2;
+          for (size_t pi = 0; pi < pl->pairs.size(); pi++) {
+            const AdaPair &P = pl->pairs[pi];
+            const int k = P.k, ng = bgb[k + 1] - bgb[k];
+            const long long nk = pl->blk_n[k];
+            pair_pg[pi] = (int)pgs.size();
+            bucket.assign(ng, {});
+            if (P.mode != 0)
+              for (int u = 0; u < P.need_cnt; u++) { const int v = need_pq[(size_t)P.need_off + u]; bucket[group_of(k, v >> 16)].push_back(v); }
+            for (int g = 0; g < ng; g++) {
+              const StripGroup &G = groups[bgb[k] + g];
+              StripPG X{};
+              X.need_beg = (int)sneed.size(); X.need_cnt = (int)bucket[g].size();
+              for (int v : bucket[g]) sneed.push_back(v);
+              if (P.mode != 0 && X.need_cnt == 0) { X.part_off = -1; pgs.push_back(X); continue; }
+              X.part_off = sws; sws += P.rank + 2;
+              pgs.push_back(X);
+              double cst;
+              if (P.mode == 0) {
+                double fr = 0;
+                const int nt = (int)((nk + 7) / 8);
+                for (int it = G.item_beg; it < G.item_end; it++) {
+                  const int I = sitems[it].x, Jc = sitems[it].y;
+                  const int nra = std::min(4, nt - 4 * I), ncb = std::min(4, nt - 4 * Jc);
+                  for (int a2 = 0; a2 < nra; a2++) for (int b2 = 0; b2 < ncb; b2++) if (I != Jc || a2 >= b2) fr += 1.0;
+                }
+                cst = fr * 64.0 * P.r + (double)(G.c1 - G.c0) * P.r * 4.0;
+              } else {
+                long long nfull = tt_ptr[P.r0 + P.r] - tt_ptr[P.r0];
+                cst = (double)X.need_cnt * (P.mode == 2 ? (double)nfull : (double)P.r) * 8.0 + (P.mode == 1 ? (double)(G.c1 - G.c0) * P.r * 4.0 : 0.0);
+              }
+              work.push_back(StripWork{(int)pi, g}); wcost.push_back(cst);
+              if (P.mode != 2) smax_tt = std::max(smax_tt, (long long)G.gw_al * P.r);
+            }
+          }
+          pair_pg[pl->pairs.size()] = (int)pgs.size();
+          std::vector<int> ord(work.size());
+          for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+          std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return wcost[a] > wcost[b]; });
+          std::vector<StripWork> work2(work.size());
+          for (size_t i = 0; i < ord.size(); i++) work2[i] = work[ord[i]];
+          if (sneed.empty()) sneed.push_back(0);
+          if (fe_src.empty()) { fe_src.push_back(0); fe_pk.push_back(0); }
+          pl->strip_ldA = ((maxn + 7) & ~7) + 4;
+          pl->strip_ldB = ((gwmax + 7) & ~7) + 4;
+          pl->strip_smem = sizeof(double) * ((size_t)STRIP_WCAP + STRIP_STAGES * FKC * (size_t)(pl->strip_ldA + pl->strip_ldB));
+          const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (226 * 1024) / (pl->strip_smem + 1024)));
+          pl->strip_nwork = (int)work2.size();
+          pl->strip_grid = (int)std::min<long long>((long long)work2.size(), (long long)ctx().sm_count * per_sm);
+          pl->strip_scratch_stride = (smax_tt + 1) & ~1LL;
+          pl->strip_nent = (long long)fe_src.size();
+          if (pl->strip_nwork > 0 && per_sm >= 2) {
+            SB_TRY(pl->d_sgroups.upload(groups)); SB_TRY(pl->d_spg.upload(pgs)); SB_TRY(pl->d_swork.upload(work2));
+            SB_TRY(pl->d_sblk_grp_beg.upload(bgb)); SB_TRY(pl->d_spair_pg.upload(pair_pg)); SB_TRY(pl->d_sblk_feoff.upload(feoff));
+            SB_TRY(pl->d_sfe_ptr.upload(fe_ptr)); SB_TRY(pl->d_sfe_src.upload(fe_src)); SB_TRY(pl->d_sfe_pk.upload(fe_pk));
+            SB_TRY(pl->d_sneed.upload(sneed)); SB_TRY(pl->d_sblk_lanes.upload(lanes)); SB_TRY(pl->d_sitems.upload(sitems));
+            SB_TRY(pl->d_sfe_val.alloc((size_t)pl->strip_nent));
+            SB_TRY(pl->d_sscratch.alloc((size_t)(pl->strip_scratch_stride * std::max(pl->strip_grid, 1))));
+            SB_TRY(pl->d_sws.alloc((size_t)std::max<long long>(sws, 1)));
+            pl->strip_ok = true;
+          }
+        }
+      }
       pl->fused_wcap = (maxn * (maxn + 1) / 2 + 1) & ~1;
       pl->fused_ldmax = ((maxn + 7) & ~7) + 4;
       pl->fused_smem = sizeof(double) * ((size_t)pl->fused_wcap + 4 * FKC * pl->fused_ldmax);
@@ -1155,12 +1311,38 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     udsqr_dev = pl->d_De.p;
   }
   if (pl->fused_ok) {
+    const bool refresh_vals = !pl->tt_val_valid;
     if (!pl->tt_val_valid) {
       tt_val_kernel<<<(unsigned)std::min<long long>((pl->n_tt + 255) / 256, 2048), 256, 0, st>>>(pl->n_tt, pl->d_tt_w.p, pl->d_tt_src.p, pl->d_Atpr.p, pl->d_tt_val.p);
       SB_LAUNCH_CHECK_N("tt_val_kernel");
       if (!ctx().capturing) pl->tt_val_valid = true;      // inside a graph capture the launch must stay part of every replay
     }
     SB_CUDA(cudaMemsetAsync(pl->d_fcounter.p, 0, sizeof(int), st));
+    if (pl->strip_ok) {
+      if (refresh_vals) {
+        gather_val_kernel<<<(unsigned)std::min<long long>((pl->strip_nent + 255) / 256, 2048), 256, 0, st>>>(pl->strip_nent, pl->d_sfe_src.p, pl->d_Atpr.p, pl->d_sfe_val.p);
+        SB_LAUNCH_CHECK_N("gather_val_kernel");
+      }
+      StripArgs SA;
+      SA.pairs = pl->d_pairs.p; SA.work = pl->d_swork.p; SA.nwork = pl->strip_nwork; SA.counter = pl->d_fcounter.p;
+      SA.blk_n = pl->d_blk_n.p; SA.blk_off = pl->d_blk_off.p; SA.blk_grp_beg = pl->d_sblk_grp_beg.p; SA.groups = pl->d_sgroups.p; SA.items = pl->d_sitems.p;
+      SA.pair_pg = pl->d_spair_pg.p; SA.pg = pl->d_spg.p;
+      SA.tt_ptr = pl->d_tt_ptr.p; SA.tt_col = pl->d_tt_col.p; SA.tt_row = pl->d_tt_row.p; SA.tt_val = pl->d_tt_val.p; SA.Rlist = pl->d_Rlist.p; SA.udsqr = udsqr_dev;
+      SA.scratch = pl->d_sscratch.p; SA.scratch_stride = pl->strip_scratch_stride;
+      SA.blk_feoff = pl->d_sblk_feoff.p; SA.fe_ptr = pl->d_sfe_ptr.p; SA.fe_pk = pl->d_sfe_pk.p; SA.fe_val = pl->d_sfe_val.p;
+      SA.need_pq = pl->d_sneed.p; SA.ws = pl->d_sws.p; SA.blk_lanes = pl->d_sblk_lanes.p; SA.ldA = pl->strip_ldA; SA.ldB = pl->strip_ldB;
+      static bool sattr_done = false;
+      if (!sattr_done) {
+        SB_CUDA(cudaFuncSetAttribute(ada3_strip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        sattr_done = true;
+      }
+      ada3_strip_kernel<2><<<pl->strip_grid, STRIP_THREADS, pl->strip_smem, st>>>(SA);
+      SB_LAUNCH_CHECK_N("ada3_strip_kernel");
+      ada3_strip_reduce_kernel<<<pl->m, 256, pl->use_map ? (size_t)pl->m * 4 : 0, st>>>(pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
+          pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_sblk_grp_beg.p, pl->d_spair_pg.p, pl->d_spg.p,
+          pl->d_sws.p, ada_dev, absd_dev, pl->use_map, pl->m);
+      SB_LAUNCH_CHECK_N("ada3_strip_reduce_kernel");
+    } else {
     FusedArgs FA;
     FA.pairs = pl->d_pairs.p; FA.npairs = (int)pl->pairs.size(); FA.counter = pl->d_fcounter.p;
     FA.blk_n = pl->d_blk_n.p; FA.blk_off = pl->d_blk_off.p; FA.tt_ptr = pl->d_tt_ptr.p; FA.tt_col = pl->d_tt_col.p; FA.tt_row = pl->d_tt_row.p; FA.tt_val = pl->d_tt_val.p;
@@ -1181,6 +1363,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
       ada3_reduce_kernel<<<pl->m, 256, pl->use_map ? (size_t)pl->m * 4 : 0, st>>>(0, pl->d_adajc.p, pl->d_adair.p, ip, (int)first,
           pl->d_cpair_beg.p, pl->d_pairs.p, pl->d_blkp_beg.p, pl->d_blkp.p, pl->d_fws.p, ada_dev, absd_dev, pl->use_map, pl->m, 1);
       SB_LAUNCH_CHECK_N("ada3_reduce_kernel");
+    }
     }
   } else
   for (auto &B : pl->batches) {

@@ -96,24 +96,20 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++) acc[ch] = make_double2(0.0, 0.0);
           const int t0 = ptr[rho], t1 = ptr[rho + 1];
-          // four entries per trip: their (column, value) loads go out together, then the 4 x NCH loads of D
-          for (int t = t0; t < t1; t += 4) {
-            double v[4]; const double2 *Dc[4];
+          // eight entries per trip: lanes 0..7 fetch their (column, value), shuffles hand them round, and the 8 x NCH
+          // loads of D they lead to are in flight together (this loop is L2 latency, not bandwidth)
+          for (int t = t0; t < t1; t += 8) {
+            int mycol = 0; double myv = 0.0;
+            if (lane < 8 && t + lane < t1) { mycol = A.tt_col[t + lane]; myv = A.tt_val[t + lane]; }
+#pragma unroll 4
+            for (int u = 0; u < 8; u++) {
+              const int col = __shfl_sync(0xffffffffu, mycol, u);
+              const double v = __shfl_sync(0xffffffffu, myv, u);         // 0 beyond the row's entries (column 0: a valid address)
+              const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)col * n);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const bool ok = t + u < t1;
-              v[u] = ok ? A.tt_val[t + u] : 0.0;
-              Dc[u] = reinterpret_cast<const double2 *>(D + (long long)A.tt_col[ok ? t + u : t0] * n);
-            }
-#pragma unroll
-            for (int ch = 0; ch < NCH; ch++) {
-              const int c = lane + 32 * ch;
-              if (c < half) {
-                const double2 x0 = Dc[0][c], x1 = Dc[1][c], x2 = Dc[2][c], x3 = Dc[3][c];
-                acc[ch].x += v[0] * x0.x; acc[ch].y += v[0] * x0.y;
-                acc[ch].x += v[1] * x1.x; acc[ch].y += v[1] * x1.y;
-                acc[ch].x += v[2] * x2.x; acc[ch].y += v[2] * x2.y;
-                acc[ch].x += v[3] * x3.x; acc[ch].y += v[3] * x3.y;
+              for (int ch = 0; ch < NCH; ch++) {
+                const int c = lane + 32 * ch;
+                if (c < half) { const double2 x = Dc[c]; acc[ch].x += v * x.x; acc[ch].y += v * x.y; }
               }
             }
           }

@@ -15,7 +15,8 @@ from sedumi_b200.mx import MexError
 
 PLUGINS = ["blkchol", "fwblkslv", "bwblkslv", "getada1", "getada2", "getada3", "invcholfac", "psdscale",
            "ddot", "qblkmul", "quadadd", "psdframeit", "psdinvjmul", "urotorder", "givensrot",
-           "dpr1fact", "fwdpr1", "bwdpr1", "adendotd", "adenscale"]
+           "dpr1fact", "fwdpr1", "bwdpr1", "adendotd", "adenscale",
+           "vecsym", "sqrtinv", "qrK", "psdjmul", "triumtriu", "psdfactor", "psdinvscale"]
 
 
 def test_library_exports_every_declared_symbol():

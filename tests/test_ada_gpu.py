@@ -49,6 +49,12 @@ def _problem(name):
         raw = problems.synth_maxcut(n=48, p=0.2, seed=2)
     elif name == "blockdiag_sparse":                  # very sparse coefficients in larger blocks (sparse mode)
         raw = problems.synth_blockdiag_sdp(nblk=3, n=40, m=30, nlink=4, density=0.004, seed=6)
+    elif name == "strip_even":                        # blocks of order 97..208: (pair, column strip) work items (ada_strip.cuh)
+        raw = problems.synth_blockdiag_sdp(nblk=2, n=168, m=70, nlink=5, density=0.02, seed=12)
+    elif name == "strip_odd":                         # odd order: the scalar (unvectorised) staging paths
+        raw = problems.synth_blockdiag_sdp(nblk=3, n=141, m=60, nlink=6, density=0.01, seed=13)
+    elif name == "strip_mixed":                       # a large and a small block in every constraint, plus LP / Lorentz
+        raw = problems.synth_small_mixed(seed=14, m=36, l=2, q=(3,), s=(130, 40), density=0.02)
     elif name == "blockdiag_small":
         raw = problems.synth_blockdiag_sdp(nblk=4, n=20, m=60, nlink=6, density=0.05, seed=5)
     else:
@@ -58,7 +64,7 @@ def _problem(name):
 
 
 @pytest.mark.parametrize("name", ["small_mixed", "small_sdp", "small_free_rot", "blockdiag_small", "maxcut_small",
-                                  "blockdiag_sparse", "arch0", "control07"])
+                                  "blockdiag_sparse", "arch0", "control07", "strip_even", "strip_odd", "strip_mixed"])
 @pytest.mark.parametrize("kind", ["S0", "S1"])
 def test_ada_chain(name, kind):
     S = _problem(name)
