@@ -4,7 +4,7 @@
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CXX      ?= g++
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Isedumi_b200/csrc --fmad=true
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Isedumi_b200/csrc --fmad=true $(if $(FUSED_PROF),-DSB200_FUSED_PROF)
 CSRC     := $(wildcard sedumi_b200/csrc/*.cu)
 COBJ     := $(CSRC:.cu=.o)
 LIB      := sedumi_b200/libsedumi_b200.so

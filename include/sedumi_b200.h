@@ -236,6 +236,9 @@ sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *plan);
 /* sb200_ada_plan_get hands out plans of a bounded cache; a caller that keeps the pointer beyond one call (device-resident
  * chains, captured CUDA graphs) retains it, which exempts it from eviction until the matching release. */
 int sb200_ada_plan_retain(sb200_ada_plan *plan);
+/* Diagnostics (no reference counterpart): cycles per phase of the fused getada3 kernel, see ada.cu. enable=1 arms and
+ * zeroes the counters, enable=0 copies out[0..7]. */
+int sb200_ada_fused_profile(sb200_ada_plan *plan, int enable, unsigned long long *out);
 int sb200_ada_plan_release(sb200_ada_plan *plan);
 int sb200_ada_set_At_values(sb200_ada_plan *plan, const double *Atpr);
 /* device-resident variants: invperm_dev = inverse of the ordering (int32) or NULL = natural */

@@ -295,19 +295,22 @@ __device__ __forceinline__ void dots_partners(const DotsCtx &X) {
         aabs += fabs(term);
       }
     }
-    for (; e + 3 * G < Q.e1; e += 4 * G) {
-      const double a0 = av[e], a1 = av[e + G], a2 = av[e + 2 * G], a3 = av[e + 3 * G];
-      const int i0 = eidx[e], i1 = eidx[e + G], i2 = eidx[e + 2 * G], i3 = eidx[e + 3 * G];
-      const double t0 = a0 * Wp[i0], t1 = a1 * Wp[i1], t2 = a2 * Wp[i2], t3 = a3 * Wp[i3];
-      acc += t0; aabs += fabs(t0);
-      acc += t1; aabs += fabs(t1);
-      acc += t2; aabs += fabs(t2);
-      acc += t3; aabs += fabs(t3);
-    }
-    for (; e < Q.e1; e += G) {
-      const double term = av[e] * Wp[eidx[e]];
-      acc += term;
-      aabs += fabs(term);
+    // trips of 8 entries per lane, all 16 loads of a trip issued before the first product (a partner with up to 8 G
+    // entries costs one L2 round trip); lanes beyond the end contribute an explicit zero -- W may hold entries that were
+    // never written (entry-wise pairs), so 0 * W is not safe
+    for (; e < Q.e1; e += 8 * G) {
+      double a[8]; int ix[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const bool ok = e + u * G < Q.e1;
+        a[u] = ok ? av[e + u * G] : 0.0;
+        ix[u] = ok ? eidx[e + u * G] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double term = ix[u] >= 0 ? a[u] * Wp[ix[u]] : 0.0;
+        acc += term; aabs += fabs(term);
+      }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -514,6 +517,7 @@ struct sb200_ada_plan {
   bool csr_built = false;
   DevBuf<int2> d_fitems;
   long long fused_ndense = 0;
+  DevBuf<unsigned long long> d_fprof; bool fprof_on = false;
   // strip path (ada_strip.cuh): blocks too large for two resident CTAs of the fused kernel
   bool strip_ok = false;
   int strip_grid = 0, strip_ldA = 0, strip_ldB = 0, strip_nwork = 0;
@@ -823,7 +827,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
     for (auto &P : pl->pairs) {
       if (P.sparse || pl->blk_n[P.k] > FUSED_MAX_N) ok = false;
       maxn = std::max(maxn, pl->blk_n[P.k]);
-      max_tt = std::max(max_tt, (long long)pl->blk_n[P.k] * P.r);
+      max_tt = std::max(max_tt, (long long)pl->blk_n[P.k] * (P.r + FKC - 1));   // T rows padded to whole k-slabs
     }
     long long fws = 0;
     for (sb_idx c2 = 0; c2 < m; c2++) {
@@ -896,7 +900,7 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
       if (need_pq.empty()) need_pq.push_back(0);
       SB_TRY(pl->d_fneed.upload(need_pq)); SB_TRY(pl->d_forder.upload(order));
       // ---- strips: (pair, column strip) work items for blocks that leave no room for a second resident CTA
-      if (!pl->fused_small && !getenv("SB200_NO_STRIP_ADA3")) {
+      if (!pl->fused_small && getenv("SB200_STRIP_ADA3")) {         // opt-in: measured slower than the whole-pair kernel
         bool sok = true;
         std::vector<int> bgb(nblk + 1, 0);
         std::vector<StripGroup> groups;
@@ -1149,6 +1153,23 @@ int sb200_ada_plan_csr(sb200_ada_plan *pl, const long long **Ajc, const int **Ai
   *N = pl->N; *m = pl->m; *lpN = pl->lpN; *nq = pl->nq;
   return 0;
 }
+// Diagnostics: per-phase cycle counts of the fused getada3 kernel (thread 0 of every CTA, summed over CTAs and launches
+// since the call that enabled them): out[0..4] = prologue, T, dense product, entry-wise W, inner products; out[5..6] =
+// dense / entry-wise pairs processed; out[7..10] = dense product split: wait for a slab, issue of the next slab's copies,
+// DMMAs, accumulator write-back.  enable = 1 switches the counters on (and zeroes them), 0 reads them.  The kernel only
+// carries the counters when the library is built with `make FUSED_PROF=1` (they cost 22 registers); otherwise zeros.
+int sb200_ada_fused_profile(sb200_ada_plan *pl, int enable, unsigned long long *out) {
+  if (enable) {
+    if (!pl->d_fprof.p) SB_TRY(pl->d_fprof.alloc(16));
+    SB_CUDA(cudaMemsetAsync(pl->d_fprof.p, 0, 16 * sizeof(unsigned long long), ctx().stream));
+    pl->fprof_on = true;
+    return 0;
+  }
+  SB_CHECK(pl->fprof_on, "fused profile counters were not enabled");
+  SB_CUDA(cudaMemcpyAsync(out, pl->d_fprof.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx().stream));
+  SB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
 // Ownership for device-resident callers: a retained plan is exempt from cache eviction until released.
 int sb200_ada_plan_retain(sb200_ada_plan *pl) { if (pl) pl->pins++; return 0; }
 int sb200_ada_plan_release(sb200_ada_plan *pl) { if (pl && pl->pins > 0) pl->pins--; return 0; }
@@ -1349,11 +1370,11 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     FA.Rlist = pl->d_Rlist.p; FA.udsqr = udsqr_dev; FA.scratch = pl->d_fscratch.p; FA.scratch_stride = pl->fused_scratch_stride;
     FA.adajc = pl->d_adajc.p; FA.adair = pl->d_adair.p; FA.invperm = ip; FA.first = (int)first; FA.cpair_beg = pl->d_cpair_beg.p;
     FA.blkp_beg = pl->d_blkp_beg.p; FA.blkp = pl->d_blkp.p; FA.ent_pk = pl->d_ent_pk.p; FA.ent_src = pl->d_ent_src.p; FA.Atpr = pl->d_Atpr.p;
-    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.need_pq = pl->d_fneed.p; FA.order = pl->d_forder.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax;
+    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.need_pq = pl->d_fneed.p; FA.order = pl->d_forder.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax; FA.prof = pl->fprof_on ? pl->d_fprof.p : nullptr;
     static bool attr_done = false;
     if (!attr_done) {
-      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));   // + static
-      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));   // + 1.7 KB static
+      SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
       attr_done = true;
     }
     if (pl->fused_small) ada3_fused_kernel<256, 2><<<pl->fused_grid, pl->fused_threads, pl->fused_smem, st>>>(FA);

@@ -36,6 +36,7 @@ struct FusedArgs {
   const int *blk_item_beg; const int2 *items;        // per block: its lower supertiles (I, J), most expensive first
   const int *need_pq; const int *order;              // entry-wise pairs: their (p | q << 16) lists; processing order of the pairs
   int wcap, ldmax;
+  unsigned long long *prof;                          // optional: cycles per phase summed over CTAs (thread 0's clock), 8 slots
 };
 
 __device__ __forceinline__ int fused_ld(int n) { return ((n + 7) & ~7) + 4; }   // == 4 (mod 8): conflict-free fragment loads
@@ -65,60 +66,163 @@ __device__ __forceinline__ void fused_stage(double *As, double *Bs, int ld, cons
   }
 }
 
+// ---- mbarrier / TMA (1-D bulk copy) helpers of the operand ring
+__device__ __forceinline__ unsigned f_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void f_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }\n"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void f_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// the DMMAs of one k-slab on a warp's supertile
+__device__ __forceinline__ void fused_slab_mma(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc,
+                                               bool full, bool have, int nra, int ncb, unsigned tmask) {
+  if (full) {                                             // interior supertile: no predicates in the inner loop
+#pragma unroll
+    for (int k4 = 0; k4 < FKC; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bf[b] = Bs[(k4 + qc) * ld + 8 * b];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  } else if (have) {
+#pragma unroll
+    for (int k4 = 0; k4 < FKC; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (tmask & (1u << (a * 4 + b))) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+}
+
 template <int NTHREADS, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedArgs A) {
   extern __shared__ __align__(16) double fsm[];
   double *Wp = fsm;                                             // packed lower triangle of W, wcap doubles
   double *stA = fsm + A.wcap;                                   // [2][FKC][ldmax]
   double *stB = stA + 2 * FKC * A.ldmax;
-  __shared__ int s_pair;
+  __shared__ int s_pair[2];
+  __shared__ int sR[FUSED_MAX_N], sPtr[FUSED_MAX_N + 1];       // the pair's row list and row pointers (staging and the T
+                                                                // loop would otherwise start every step with a global load)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int qr = lane >> 2, qc = lane & 3;
   double *Tt = A.scratch + (long long)blockIdx.x * A.scratch_stride;
-  for (;;) {
-    if (tid == 0) s_pair = atomicAdd(A.counter, 1);
-    __syncthreads();
-    if (s_pair >= A.npairs) break;
-    const int pi = A.order[s_pair];
+  // operand ring of the dense products: two stages, each filled by 16 TMA bulk copies (8 columns of D, 8 rows of T)
+  // that complete on the stage's `full` mbarrier; a stage is handed back through its `empty` mbarrier (one arrival per
+  // warp).  No block-wide barrier inside the k loop: a warp only waits for data, the producer only for a free stage.
+  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  if (tid == 0) {
+    s_pair[0] = atomicAdd(A.counter, 1);
+    for (int i = 0; i < 2; i++) { f_mbar_init(f_smem_u32(&s_full[i]), 1); f_mbar_init(f_smem_u32(&s_empty[i]), nw); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  unsigned gslab = 0;                                           // slabs that went through the ring so far (same in every thread)
+#ifdef SB200_FUSED_PROF
+  long long pc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};         // cycles per phase (thread 0), see sb200_ada_fused_profile
+#define FPROF(...) __VA_ARGS__
+#else
+#define FPROF(...)
+#endif
+  for (int turn = 0;; turn ^= 1) {
+    const int cur = s_pair[turn];
+    if (cur >= A.npairs) break;
+    FPROF(long long c0k = clock64();)
+    int nxt = 0;
+    if (tid == 0) nxt = atomicAdd(A.counter, 1);               // the next pair's ticket travels while this one is worked on
+    const int pi = A.order[cur];
     const AdaPair P = A.pairs[pi];
     const int n = A.blk_n[P.k], r = P.r, ld = fused_ld(n);
     const double *D = A.udsqr + A.blk_off[P.k];
-    const int *R = A.Rlist + P.r0;
+    const int *R = sR;
+    const int r8 = (r + FKC - 1) & ~(FKC - 1);                  // the ring moves whole slabs: rows r..r8 of T are zero,
+    for (int i = tid; i < r8; i += blockDim.x) sR[i] = A.Rlist[P.r0 + (i < r ? i : 0)];     // paired with any valid column of D
+    for (int i = tid; i <= r; i += blockDim.x) sPtr[i] = A.tt_ptr[P.r0 + i];
+    __syncthreads();
+    FPROF(if (tid == 0) { const long long c = clock64(); pc[0] += c - c0k; c0k = c; })
     // ---------------- 1. T (as Tt: n x r, column rho = row R[rho] of sym(A) D): one warp per row, lanes over columns
     if (P.mode != 2) {
-      const int *ptr = A.tt_ptr + P.r0;
+      const int *ptr = sPtr;
       const bool vec2 = ((n & 1) == 0) && ((((unsigned long long)D) & 15) == 0) && ((((unsigned long long)Tt) & 15) == 0);
       if (vec2) {                                                // two columns per lane and load
         constexpr int NCH = (FUSED_MAX_N / 2 + 31) / 32;
         const int half = n >> 1;
-        for (int rho = warp; rho < r; rho += nw) {
-          double2 acc[NCH];
+        // the warp walks its rows as ONE stream of 4-entry trips; the (column, value) of the next trip -- of this row
+        // or of the warp's next row -- are fetched before the loads of D of the current trip are consumed, so a trip
+        // exposes one L2 round trip instead of two
+        int rho = warp;
+        int t = rho < r ? ptr[rho] : 0, te = rho < r ? ptr[rho + 1] : 0;
+        int col[4]; double v[4];
 #pragma unroll
-          for (int ch = 0; ch < NCH; ch++) acc[ch] = make_double2(0.0, 0.0);
-          const int t0 = ptr[rho], t1 = ptr[rho + 1];
-          // eight entries per trip: lanes 0..7 fetch their (column, value), shuffles hand them round, and the 8 x NCH
-          // loads of D they lead to are in flight together (this loop is L2 latency, not bandwidth)
-          for (int t = t0; t < t1; t += 8) {
-            int mycol = 0; double myv = 0.0;
-            if (lane < 8 && t + lane < t1) { mycol = A.tt_col[t + lane]; myv = A.tt_val[t + lane]; }
-#pragma unroll 4
-            for (int u = 0; u < 8; u++) {
-              const int col = __shfl_sync(0xffffffffu, mycol, u);
-              const double v = __shfl_sync(0xffffffffu, myv, u);         // 0 beyond the row's entries (column 0: a valid address)
-              const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)col * n);
+        for (int u = 0; u < 4; u++) {
+          const bool ok = t + u < te;
+          v[u] = ok ? A.tt_val[t + u] : 0.0;
+          col[u] = ok ? A.tt_col[t + u] : 0;
+        }
+        double2 acc[NCH];
 #pragma unroll
-              for (int ch = 0; ch < NCH; ch++) {
-                const int c = lane + 32 * ch;
-                if (c < half) { const double2 x = Dc[c]; acc[ch].x += v * x.x; acc[ch].y += v * x.y; }
-              }
-            }
+        for (int ch = 0; ch < NCH; ch++) acc[ch] = make_double2(0.0, 0.0);
+        while (rho < r) {
+          int nrho = rho, nt = t + 4, nte = te;
+          if (nt >= te) { nrho = rho + nw; nt = nrho < r ? ptr[nrho] : 0; nte = nrho < r ? ptr[nrho + 1] : 0; }
+          int ncol[4]; double nv[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const bool ok = nt + u < nte;
+            nv[u] = ok ? A.tt_val[nt + u] : 0.0;
+            ncol[u] = ok ? A.tt_col[nt + u] : 0;
           }
-          double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * n);
+          const double2 *Dc0 = reinterpret_cast<const double2 *>(D + (long long)col[0] * n);
+          const double2 *Dc1 = reinterpret_cast<const double2 *>(D + (long long)col[1] * n);
+          const double2 *Dc2 = reinterpret_cast<const double2 *>(D + (long long)col[2] * n);
+          const double2 *Dc3 = reinterpret_cast<const double2 *>(D + (long long)col[3] * n);
 #pragma unroll
           for (int ch = 0; ch < NCH; ch++) {
             const int c = lane + 32 * ch;
-            if (c < half) dst[c] = acc[ch];
+            if (c < half) {
+              const double2 x0 = Dc0[c], x1 = Dc1[c], x2 = Dc2[c], x3 = Dc3[c];
+              acc[ch].x += v[0] * x0.x; acc[ch].y += v[0] * x0.y;
+              acc[ch].x += v[1] * x1.x; acc[ch].y += v[1] * x1.y;
+              acc[ch].x += v[2] * x2.x; acc[ch].y += v[2] * x2.y;
+              acc[ch].x += v[3] * x3.x; acc[ch].y += v[3] * x3.y;
+            }
           }
+          if (nrho != rho) {
+            double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * n);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+              const int c = lane + 32 * ch;
+              if (c < half) dst[c] = acc[ch];
+              acc[ch] = make_double2(0.0, 0.0);
+            }
+          }
+          rho = nrho; t = nt; te = nte;
+#pragma unroll
+          for (int u = 0; u < 4; u++) { col[u] = ncol[u]; v[u] = nv[u]; }
         }
       } else {
         constexpr int NCH = (FUSED_MAX_N + 31) / 32;
@@ -145,7 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         }
       }
     }
+    if (P.mode == 0) {
+      for (int rho = r + warp; rho < r8; rho += nw)
+        for (int c = lane; c < n; c += 32) Tt[(long long)rho * n + c] = 0.0;
+      asm volatile("fence.proxy.async;\n" ::: "memory");       // T was written through the generic proxy, TMA reads it
+    }
     __syncthreads();
+    FPROF(if (tid == 0) { const long long c = clock64(); pc[1] += c - c0k; c0k = c; })
     // ---------------- 2a. entry-wise evaluation on the needed set (pairs early in their block's list)
     if (P.mode != 0) {
       // four lanes share one needed entry (p, q) and split the sum; eight terms per lane are in flight at a time
@@ -200,6 +310,38 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         for (int a = 0; a < 4; a++)
 #pragma unroll
           for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        if (vec) {
+          // ---- TMA ring
+          const unsigned row_bytes = 8u * (unsigned)n;
+          const int nslab8 = r8 / FKC;
+          auto issue = [&](int sl) {                              // slab sl of this round (warp 0 only)
+            const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
+            if (use > 0) f_mbar_wait(f_smem_u32(&s_empty[st]), (use - 1u) & 1u);      // every warp is done with the stage
+            if (lane == 0) f_mbar_expect_tx(f_smem_u32(&s_full[st]), 2u * FKC * row_bytes);
+            __syncwarp();
+            if (lane < 2 * FKC) {
+              const int kk = lane & (FKC - 1), k = sl * FKC + kk;
+              const double *src = lane < FKC ? D + (long long)sR[k] * n : Tt + (long long)k * n;
+              double *dst = (lane < FKC ? stA : stB) + (st * FKC + kk) * A.ldmax;
+              f_bulk_g2s(f_smem_u32(dst), src, row_bytes, f_smem_u32(&s_full[st]));
+            }
+          };
+          if (warp == 0 && nslab8 > 0) issue(0);
+          for (int sl = 0; sl < nslab8; sl++) {
+            FPROF(long long q0 = clock64();)
+            if (warp == 0 && sl + 1 < nslab8) issue(sl + 1);
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[8] += c - q0; q0 = c; })
+            const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
+            f_mbar_wait(f_smem_u32(&s_full[st]), use & 1u);
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[7] += c - q0; q0 = c; })
+            const double *As = stA + st * FKC * A.ldmax + rb + qr, *Bs = stB + st * FKC * A.ldmax + cb + qr;
+            fused_slab_mma(acc, As, Bs, A.ldmax, qc, full, have, nra, ncb, tmask);
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(f_smem_u32(&s_empty[st]));
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[9] += c - q0; })
+          }
+          gslab += (unsigned)nslab8;
+        } else {
         constexpr int TPR_LOG2 = (NTHREADS == 512) ? 6 : 5;       // 8 k-rows x TPR threads = blockDim
         if (nslab > 0) fused_stage<TPR_LOG2>(stA, stB, ld, D, Tt, R, n, r, 0, vec);
         cp_async_commit();
@@ -210,35 +352,10 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
           if (s + 1 < nslab) fused_stage<TPR_LOG2>(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
           cp_async_commit();
           const double *As = stA + buf * FKC * A.ldmax + rb + qr, *Bs = stB + buf * FKC * A.ldmax + cb + qr;
-          if (full) {                                             // interior supertile: no predicates in the inner loop
-#pragma unroll
-            for (int k4 = 0; k4 < FKC; k4 += 4) {
-              double af[4], bf[4];
-#pragma unroll
-              for (int a = 0; a < 4; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
-#pragma unroll
-              for (int b = 0; b < 4; b++) bf[b] = Bs[(k4 + qc) * ld + 8 * b];
-#pragma unroll
-              for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-            }
-          } else if (have) {
-#pragma unroll
-            for (int k4 = 0; k4 < FKC; k4 += 4) {
-              double af[4], bf[4];
-#pragma unroll
-              for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
-#pragma unroll
-              for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
-#pragma unroll
-              for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                  if (tmask & (1u << (a * 4 + b))) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-            }
-          }
+          fused_slab_mma(acc, As, Bs, ld, qc, full, have, nra, ncb, tmask);
         }
+        }
+        FPROF(long long q1 = clock64();)
         cp_async_wait_all();
         // accumulators -> packed lower triangle: (p, q), p >= q, at q (2n - q + 1)/2 - q + p
 #pragma unroll
@@ -251,9 +368,11 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
               if (a < nra && b < ncb && p < n && q < n && p >= q) Wp[(q * (2 * n - q + 1)) / 2 - q + p] = acc[a][b][e];
             }
         __syncthreads();                                          // the ring is re-used by the next round
+        FPROF(if (tid == 0) pc[10] += clock64() - q1;)
       }
     }
     __syncthreads();
+    FPROF(if (tid == 0) { const long long c = clock64(); pc[P.mode == 0 ? 2 : 3] += c - c0k; c0k = c; if (P.mode == 0) pc[5]++; else pc[6]++; })
     // ---------------- 3. inner products with the partners of block k
     {
       const int c = P.j;
@@ -281,8 +400,11 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         default: dots_partners<32>(X); break;
       }
     }
-    __syncthreads();                                            // Wp, s_pair and the scratch slot are re-used by the next pair
+    if (tid == 0) s_pair[turn ^ 1] = nxt;
+    __syncthreads();                                            // Wp, sR / sPtr and the scratch slot are re-used by the next pair
+    FPROF(if (tid == 0) { const long long c = clock64(); pc[4] += c - c0k; })
   }
+  FPROF(if (tid == 0 && A.prof) for (int i = 0; i < 11; i++) atomicAdd(A.prof + i, (unsigned long long)pc[i]);)
 }
 
 }  // namespace sb

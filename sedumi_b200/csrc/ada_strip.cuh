@@ -84,19 +84,19 @@ __device__ __forceinline__ void strip_dots(const StripArgs &A, const AdaPair &P,
     }
     double acc = 0.0, aabs = 0.0;
     int e = e0 + gl;
-    for (; e + 3 * G < e1; e += 4 * G) {
-      const double a0 = A.fe_val[e], a1 = A.fe_val[e + G], a2 = A.fe_val[e + 2 * G], a3 = A.fe_val[e + 3 * G];
-      const int i0 = A.fe_pk[e], i1 = A.fe_pk[e + G], i2 = A.fe_pk[e + 2 * G], i3 = A.fe_pk[e + 3 * G];
-      const double t0 = a0 * Wg[i0], t1 = a1 * Wg[i1], t2 = a2 * Wg[i2], t3 = a3 * Wg[i3];
-      acc += t0; aabs += fabs(t0);
-      acc += t1; aabs += fabs(t1);
-      acc += t2; aabs += fabs(t2);
-      acc += t3; aabs += fabs(t3);
-    }
-    for (; e < e1; e += G) {
-      const double term = A.fe_val[e] * Wg[A.fe_pk[e]];
-      acc += term;
-      aabs += fabs(term);
+    for (; e < e1; e += 8 * G) {                              // 8 entries per lane and trip, 16 loads in flight (see dots_partners)
+      double a[8]; int ix[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const bool ok = e + u * G < e1;
+        a[u] = ok ? A.fe_val[e + u * G] : 0.0;
+        ix[u] = ok ? (int)A.fe_pk[e + u * G] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double term = ix[u] >= 0 ? a[u] * Wg[ix[u]] : 0.0;
+        acc += term; aabs += fabs(term);
+      }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
@@ -116,16 +116,20 @@ __global__ void __launch_bounds__(STRIP_THREADS, MINB) ada3_strip_kernel(const S
   double *Wg = ssm;                                             // STRIP_WCAP
   double *stA = ssm + STRIP_WCAP;                               // [STRIP_STAGES][FKC][ldA]
   double *stB = stA + STRIP_STAGES * FKC * A.ldA;               // [STRIP_STAGES][FKC][ldB]
-  __shared__ int s_w;
+  __shared__ int s_w[2];
+  __shared__ int sR[FUSED_MAX_N], sPtr[FUSED_MAX_N + 1];       // the pair's row list and row pointers
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int nw = STRIP_THREADS / 32;
   const int qr = lane >> 2, qc = lane & 3;
   double *Tt = A.scratch + (long long)blockIdx.x * A.scratch_stride;
-  for (;;) {
-    if (tid == 0) s_w = atomicAdd(A.counter, 1);
-    __syncthreads();
-    if (s_w >= A.nwork) break;
-    const StripWork Wk = A.work[s_w];
+  if (tid == 0) s_w[0] = atomicAdd(A.counter, 1);
+  __syncthreads();
+  for (int turn = 0;; turn ^= 1) {
+    const int cur = s_w[turn];
+    if (cur >= A.nwork) break;
+    int nxt = 0;
+    if (tid == 0) nxt = atomicAdd(A.counter, 1);               // the next ticket travels while this item is worked on
+    const StripWork Wk = A.work[cur];
     const AdaPair P = A.pairs[Wk.pair];
     const int n = A.blk_n[P.k], r = P.r;
     const int gb = A.blk_grp_beg[P.k], ng = A.blk_grp_beg[P.k + 1] - gb;
@@ -133,64 +137,86 @@ __global__ void __launch_bounds__(STRIP_THREADS, MINB) ada3_strip_kernel(const S
     const StripPG PG = A.pg[A.pair_pg[Wk.pair] + Wk.g];
     const int c0 = Gp.c0, gw = Gp.c1 - Gp.c0, gwa = Gp.gw_al;
     const double *D = A.udsqr + A.blk_off[P.k];
-    const int *R = A.Rlist + P.r0;
+    const int *R = sR;
+    for (int i = tid; i < r; i += STRIP_THREADS) sR[i] = A.Rlist[P.r0 + i];
+    for (int i = tid; i <= r; i += STRIP_THREADS) sPtr[i] = A.tt_ptr[P.r0 + i];
+    __syncthreads();
     const bool vec = ((n & 1) == 0) && ((c0 & 1) == 0) && ((gw & 1) == 0) && ((((unsigned long long)D) & 15) == 0) &&
                      ((((unsigned long long)Tt) & 15) == 0);
     // ---------------- 1. the strip's columns of T: Tt[(q - c0) + rho gwa] = sum_t v_t D(q, col_t), q in [c0, c1)
     if (P.mode != 2) {
-      // a row of T takes 4 columns per lane: LPR = 8 / 16 / 32 lanes per row, 32 / LPR rows per warp at a time; the
-      // (column, value) of up to 8 entries are fetched by the first lanes of the row's group and handed round by
-      // shuffles, so the 8 (x2) loads of D they lead to are all in flight together (this loop is pure L2 latency:
-      // one row at a time with 4 entries per trip cost 5 x what the whole-pair kernel paid)
-      const int *ptr = A.tt_ptr + P.r0;
+      // a row of T takes 4 columns per lane: LPR = 8 / 16 / 32 lanes per row, 32 / LPR rows per warp at a time.  Each
+      // lane group walks its rows as one stream of 4-entry trips and fetches the (column, value) of the next trip -- of
+      // this row or of the group's next row -- before the loads of D of the current trip are consumed: one L2 round
+      // trip per trip.  (One row per warp cost 5 x what the whole-pair kernel paid: this loop is pure latency.)
+      const int *ptr = sPtr;
       const int lpr_log2 = gw <= 32 ? 3 : (gw <= 64 ? 4 : 5);
       const int LPR = 1 << lpr_log2, RPW = 32 >> lpr_log2;
-      const int sub = lane >> lpr_log2, l = lane & (LPR - 1), lead = sub << lpr_log2;
-      const unsigned smask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << lead);
-      for (int rho0 = warp * RPW; rho0 < r; rho0 += nw * RPW) {
-        const int rho = rho0 + sub;
-        const bool rl = rho < r;
-        const int t0 = rl ? ptr[rho] : 0, t1 = rl ? ptr[rho + 1] : 0;
-        if (vec) {
-          const int half = gw >> 1;
-          double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-          for (int t = t0; t < t1; t += 8) {
-            int mycol = 0; double myv = 0.0;
-            if (l < 8 && t + l < t1) { mycol = A.tt_col[t + l]; myv = A.tt_val[t + l]; }
+      const int sub = lane >> lpr_log2, l = lane & (LPR - 1);
+      const int stride = nw * RPW;
+      int rho = warp * RPW + sub;
+      int t = rho < r ? ptr[rho] : 0, te = rho < r ? ptr[rho + 1] : 0;
+      int col[4]; double v[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const int col = __shfl_sync(smask, mycol, lead + u);
-              const double v = __shfl_sync(smask, myv, lead + u);      // 0 beyond the row's entries (column 0: a valid address)
-              const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)col * n + c0);
-              if (l < half) { const double2 x = Dc[l]; acc0.x += v * x.x; acc0.y += v * x.y; }
-              if (l + LPR < half) { const double2 x = Dc[l + LPR]; acc1.x += v * x.x; acc1.y += v * x.y; }
-            }
+      for (int u = 0; u < 4; u++) {
+        const bool ok = t + u < te;
+        v[u] = ok ? A.tt_val[t + u] : 0.0;
+        col[u] = ok ? A.tt_col[t + u] : 0;
+      }
+      const int half = gw >> 1;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};                      // vec: two double2 (chunks l, l + LPR); else 4 columns
+      while (rho < r) {
+        int nrho = rho, nt = t + 4, nte = te;
+        if (nt >= te) { nrho = rho + stride; nt = nrho < r ? ptr[nrho] : 0; nte = nrho < r ? ptr[nrho + 1] : 0; }
+        int ncol[4]; double nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const bool ok = nt + u < nte;
+          nv[u] = ok ? A.tt_val[nt + u] : 0.0;
+          ncol[u] = ok ? A.tt_col[nt + u] : 0;
+        }
+        if (vec) {
+          double2 x[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const double2 *Dc = reinterpret_cast<const double2 *>(D + (long long)col[u] * n + c0);
+            x[u][0] = l < half ? Dc[l] : make_double2(0.0, 0.0);
+            x[u][1] = l + LPR < half ? Dc[l + LPR] : make_double2(0.0, 0.0);
           }
-          if (rl) {
-            double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * gwa);
-            if (l < half) dst[l] = acc0;
-            if (l + LPR < half) dst[l + LPR] = acc1;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            acc[0] += v[u] * x[u][0].x; acc[1] += v[u] * x[u][0].y;
+            acc[2] += v[u] * x[u][1].x; acc[3] += v[u] * x[u][1].y;
           }
         } else {
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int t = t0; t < t1; t += 8) {
-            int mycol = 0; double myv = 0.0;
-            if (l < 8 && t + l < t1) { mycol = A.tt_col[t + l]; myv = A.tt_val[t + l]; }
+          double x[4][4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const int col = __shfl_sync(smask, mycol, lead + u);
-              const double v = __shfl_sync(smask, myv, lead + u);
-              const double *Dc = D + (long long)col * n + c0;
+          for (int u = 0; u < 4; u++) {
+            const double *Dc = D + (long long)col[u] * n + c0;
 #pragma unroll
-              for (int ch = 0; ch < 4; ch++) { const int c = l + LPR * ch; if (c < gw) acc[ch] += v * Dc[c]; }
-            }
+            for (int ch = 0; ch < 4; ch++) { const int c = l + LPR * ch; x[u][ch] = c < gw ? Dc[c] : 0.0; }
           }
-          if (rl) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) acc[ch] += v[u] * x[u][ch];
+        }
+        if (nrho != rho) {
+          if (vec) {
+            double2 *dst = reinterpret_cast<double2 *>(Tt + (long long)rho * gwa);
+            if (l < half) dst[l] = make_double2(acc[0], acc[1]);
+            if (l + LPR < half) dst[l + LPR] = make_double2(acc[2], acc[3]);
+          } else {
             double *dst = Tt + (long long)rho * gwa;
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) { const int c = l + LPR * ch; if (c < gw) dst[c] = acc[ch]; }
           }
+#pragma unroll
+          for (int ch = 0; ch < 4; ch++) acc[ch] = 0.0;
         }
+        rho = nrho; t = nt; te = nte;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { col[u] = ncol[u]; v[u] = nv[u]; }
       }
     }
     __syncthreads();
@@ -313,7 +339,8 @@ __global__ void __launch_bounds__(STRIP_THREADS, MINB) ada3_strip_kernel(const S
         default: strip_dots<32>(A, P, Wk.g, ng, Wg, part, warp, lane, nw); break;
       }
     }
-    __syncthreads();                                            // Wg, s_w and the scratch slot are re-used
+    if (tid == 0) s_w[turn ^ 1] = nxt;
+    __syncthreads();                                            // Wg, sR / sPtr and the scratch slot are re-used
   }
 }
 

@@ -49,6 +49,12 @@ def _problem(name):
         raw = problems.synth_maxcut(n=48, p=0.2, seed=2)
     elif name == "blockdiag_sparse":                  # very sparse coefficients in larger blocks (sparse mode)
         raw = problems.synth_blockdiag_sdp(nblk=3, n=40, m=30, nlink=4, density=0.004, seed=6)
+    elif name == "strip_even_optin":                  # different seeds: a plan of their own (the switch is read at plan build)
+        raw = problems.synth_blockdiag_sdp(nblk=2, n=168, m=70, nlink=5, density=0.02, seed=22)
+    elif name == "strip_odd_optin":
+        raw = problems.synth_blockdiag_sdp(nblk=3, n=141, m=60, nlink=6, density=0.01, seed=23)
+    elif name == "strip_mixed_optin":
+        raw = problems.synth_small_mixed(seed=24, m=36, l=2, q=(3,), s=(130, 40), density=0.02)
     elif name == "strip_even":                        # blocks of order 97..208: (pair, column strip) work items (ada_strip.cuh)
         raw = problems.synth_blockdiag_sdp(nblk=2, n=168, m=70, nlink=5, density=0.02, seed=12)
     elif name == "strip_odd":                         # odd order: the scalar (unvectorised) staging paths
@@ -80,6 +86,17 @@ def test_ada_chain(name, kind):
         assert relerr(a.data, b_.data) <= 1e-10, nm
     assert relerr(G[3], R[3]) <= 1e-10
     assert abs(G[2] - G[2].T).max() == 0.0            # spmakesym gives exact symmetry
+
+
+@pytest.mark.parametrize("name", ["strip_even", "strip_odd", "strip_mixed"])
+def test_ada_strip_path(name, monkeypatch):
+    """The opt-in (pair, column strip) kernel of ada_strip.cuh (SB200_STRIP_ADA3=1, read when the plan is built)."""
+    monkeypatch.setenv("SB200_STRIP_ADA3", "1")
+    S = _problem(name + "_optin")
+    d = problems.scaling(S.K, "S1", seed=21)
+    ur = ref.invcholfac(d["u"], S.Kmex(), d["perm"])
+    R, G = _chain(ref, S, d, ur), _chain(gpu, S, d, ur)
+    assert relerr(G[2].data, R[2].data) <= 1e-10 and relerr(G[3], R[3]) <= 1e-10
 
 
 def test_ada_late_scaling():
