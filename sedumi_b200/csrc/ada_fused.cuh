@@ -86,36 +86,39 @@ __device__ __forceinline__ void f_bulk_g2s(unsigned dst, const void *src, unsign
                :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// the DMMAs of one k-slab on a warp's supertile
-__device__ __forceinline__ void fused_slab_mma(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc,
-                                               bool full, bool have, int nra, int ncb, unsigned tmask) {
-  if (full) {                                             // interior supertile: no predicates in the inner loop
+// The DMMAs of one k-slab on a warp's supertile.  The supertile shapes that occur are known when the plan is built:
+// interior (4 x 4 fragments), diagonal (lower triangle of NRA x NRA) and row-clipped (NRA x 4, the last supertile row);
+// each gets straight-line code.  (A run-time fragment mask compiled to one predicated DMMA + WARPSYNC per fragment slot:
+// the second round of n = 200 -- a quarter of the first round's DMMAs -- took 30 % longer than the first.)
+template <int NRA, bool DIAG>
+__device__ __forceinline__ void fused_slab_mma_static(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc) {
+  constexpr int NCB = DIAG ? NRA : 4;
 #pragma unroll
-    for (int k4 = 0; k4 < FKC; k4 += 4) {
-      double af[4], bf[4];
+  for (int k4 = 0; k4 < FKC; k4 += 4) {
+    double af[4], bf[4];
 #pragma unroll
-      for (int a = 0; a < 4; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
+    for (int a = 0; a < NRA; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
 #pragma unroll
-      for (int b = 0; b < 4; b++) bf[b] = Bs[(k4 + qc) * ld + 8 * b];
+    for (int b = 0; b < NCB; b++) bf[b] = Bs[(k4 + qc) * ld + 8 * b];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+    for (int a = 0; a < NRA; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-    }
-  } else if (have) {
-#pragma unroll
-    for (int k4 = 0; k4 < FKC; k4 += 4) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int a = 0; a < 4; a++) af[a] = (a < nra) ? As[(k4 + qc) * ld + 8 * a] : 0.0;
-#pragma unroll
-      for (int b = 0; b < 4; b++) bf[b] = (b < ncb) ? Bs[(k4 + qc) * ld + 8 * b] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-          if (tmask & (1u << (a * 4 + b))) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-    }
+      for (int b = 0; b < NCB; b++)
+        if (!DIAG || a >= b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+  }
+}
+// variant = NRA - 1 (row-clipped or interior), 4 + NRA - 1 (diagonal), -1: nothing to do
+__device__ __forceinline__ void fused_slab_mma(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc, int variant) {
+  switch (variant) {
+    case 3: fused_slab_mma_static<4, false>(acc, As, Bs, ld, qc); break;
+    case 7: fused_slab_mma_static<4, true>(acc, As, Bs, ld, qc); break;
+    case 0: fused_slab_mma_static<1, false>(acc, As, Bs, ld, qc); break;
+    case 1: fused_slab_mma_static<2, false>(acc, As, Bs, ld, qc); break;
+    case 2: fused_slab_mma_static<3, false>(acc, As, Bs, ld, qc); break;
+    case 4: fused_slab_mma_static<1, true>(acc, As, Bs, ld, qc); break;
+    case 5: fused_slab_mma_static<2, true>(acc, As, Bs, ld, qc); break;
+    case 6: fused_slab_mma_static<3, true>(acc, As, Bs, ld, qc); break;
+    default: break;
   }
 }
 
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
   __syncthreads();
   unsigned gslab = 0;                                           // slabs that went through the ring so far (same in every thread)
 #ifdef SB200_FUSED_PROF
-  long long pc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};         // cycles per phase (thread 0), see sb200_ada_fused_profile
+  long long pc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};         // cycles per phase (thread 0), see sb200_ada_fused_profile
 #define FPROF(...) __VA_ARGS__
 #else
 #define FPROF(...)
@@ -299,12 +302,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         const int nra = have ? min(4, (n - rb + 7) >> 3) : 0;       // fragment rows / columns inside n
         const int ncb = have ? min(4, (n - cb + 7) >> 3) : 0;
         const bool diag = (IJ.x == IJ.y);
-        const bool full = have && !diag && nra == 4 && ncb == 4;
-        unsigned tmask = 0;                                         // fragments of a clipped / diagonal supertile
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b = 0; b < 4; b++) if (a < nra && b < ncb && (!diag || a >= b)) tmask |= 1u << (a * 4 + b);
+        // a non-diagonal supertile of the lower triangle lies strictly left of the last supertile column: ncb == 4
+        const int variant = have ? (diag ? 4 : 0) + nra - 1 : -1;
         double acc[4][4][2];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -314,7 +313,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
           // ---- TMA ring
           const unsigned row_bytes = 8u * (unsigned)n;
           const int nslab8 = r8 / FKC;
-          auto issue = [&](int sl) {                              // slab sl of this round (warp 0 only)
+          // the producer is the LAST warp: the planner sorts a round's supertiles by cost, so it holds the cheapest one
+          // (or none) and its wait for a free stage is off the critical path
+          auto issue = [&](int sl) {                              // slab sl of this round (producer warp only)
             const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
             if (use > 0) f_mbar_wait(f_smem_u32(&s_empty[st]), (use - 1u) & 1u);      // every warp is done with the stage
             if (lane == 0) f_mbar_expect_tx(f_smem_u32(&s_full[st]), 2u * FKC * row_bytes);
@@ -326,19 +327,19 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
               f_bulk_g2s(f_smem_u32(dst), src, row_bytes, f_smem_u32(&s_full[st]));
             }
           };
-          if (warp == 0 && nslab8 > 0) issue(0);
+          if (warp == nw - 1 && nslab8 > 0) issue(0);
           for (int sl = 0; sl < nslab8; sl++) {
             FPROF(long long q0 = clock64();)
-            if (warp == 0 && sl + 1 < nslab8) issue(sl + 1);
-            FPROF(if (tid == 0) { const long long c = clock64(); pc[8] += c - q0; q0 = c; })
+            if (warp == nw - 1 && sl + 1 < nslab8) issue(sl + 1);
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 8 : 12] += c - q0; q0 = c; })
             const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
             f_mbar_wait(f_smem_u32(&s_full[st]), use & 1u);
-            FPROF(if (tid == 0) { const long long c = clock64(); pc[7] += c - q0; q0 = c; })
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 7 : 11] += c - q0; q0 = c; })
             const double *As = stA + st * FKC * A.ldmax + rb + qr, *Bs = stB + st * FKC * A.ldmax + cb + qr;
-            fused_slab_mma(acc, As, Bs, A.ldmax, qc, full, have, nra, ncb, tmask);
+            fused_slab_mma(acc, As, Bs, A.ldmax, qc, variant);
             __syncwarp();
             if (lane == 0) f_mbar_arrive(f_smem_u32(&s_empty[st]));
-            FPROF(if (tid == 0) { const long long c = clock64(); pc[9] += c - q0; })
+            FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 9 : 13] += c - q0; })
           }
           gslab += (unsigned)nslab8;
         } else {
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
           if (s + 1 < nslab) fused_stage<TPR_LOG2>(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
           cp_async_commit();
           const double *As = stA + buf * FKC * A.ldmax + rb + qr, *Bs = stB + buf * FKC * A.ldmax + cb + qr;
-          fused_slab_mma(acc, As, Bs, ld, qc, full, have, nra, ncb, tmask);
+          fused_slab_mma(acc, As, Bs, ld, qc, variant);
         }
         }
         FPROF(long long q1 = clock64();)
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
     __syncthreads();                                            // Wp, sR / sPtr and the scratch slot are re-used by the next pair
     FPROF(if (tid == 0) { const long long c = clock64(); pc[4] += c - c0k; })
   }
-  FPROF(if (tid == 0 && A.prof) for (int i = 0; i < 11; i++) atomicAdd(A.prof + i, (unsigned long long)pc[i]);)
+  FPROF(if (tid == 0 && A.prof) for (int i = 0; i < 14; i++) atomicAdd(A.prof + i, (unsigned long long)pc[i]);)
 }
 
 }  // namespace sb

@@ -34,7 +34,9 @@ def main():
     tot = sum(v[:5])
     print(json.dumps({"cycles_per_launch": {n: v[i] / reps for i, n in enumerate(names)}, "share": {n: v[i] / tot for i, n in enumerate(names)},
                       "dense_pairs": v[5] / reps, "entrywise_pairs": v[6] / reps,
-                      "product_split": {"wait_sync": v[7] / reps, "stage_issue": v[8] / reps, "compute": v[9] / reps, "writeback": v[10] / reps}}))
+                      "product_split": {"round1": {"wait_full": v[7] / reps, "issue_next": v[8] / reps, "mma": v[9] / reps},
+                                        "later_rounds": {"wait_full": v[11] / reps, "issue_next": v[12] / reps, "mma": v[13] / reps},
+                                        "writeback": v[10] / reps}}))
 
 
 if __name__ == "__main__":
