@@ -18,6 +18,8 @@ namespace sb {
 static const int FUSED_MAX_N = 208;                 // 7 x 7 supertiles -> 28 warps; W (packed) + the staging ring fit 227 KB
 static const int FKC = 8;                            // k-slab depth (two DMMA k-steps)
 static const int FUSED_GEMM_WARPS = 16;              // warps that hold a 32x32 accumulator tile in one round
+static const int FTK = 8, FTST = 2;                  // TMA ring: k-depth of a slab, stages (FTK * FTST == 2 * FKC: same shared memory;
+                                                     // 4 x 4 measured 17 % slower: twice the barrier hand-overs per DMMA)
 
 struct FusedArgs {
   const AdaPair *pairs; int npairs;
@@ -90,11 +92,11 @@ __device__ __forceinline__ void f_bulk_g2s(unsigned dst, const void *src, unsign
 // interior (4 x 4 fragments), diagonal (lower triangle of NRA x NRA) and row-clipped (NRA x 4, the last supertile row);
 // each gets straight-line code.  (A run-time fragment mask compiled to one predicated DMMA + WARPSYNC per fragment slot:
 // the second round of n = 200 -- a quarter of the first round's DMMAs -- took 30 % longer than the first.)
-template <int NRA, bool DIAG>
+template <int NRA, bool DIAG, int KD>
 __device__ __forceinline__ void fused_slab_mma_static(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc) {
   constexpr int NCB = DIAG ? NRA : 4;
 #pragma unroll
-  for (int k4 = 0; k4 < FKC; k4 += 4) {
+  for (int k4 = 0; k4 < KD; k4 += 4) {
     double af[4], bf[4];
 #pragma unroll
     for (int a = 0; a < NRA; a++) af[a] = As[(k4 + qc) * ld + 8 * a];
@@ -108,16 +110,17 @@ __device__ __forceinline__ void fused_slab_mma_static(double (&acc)[4][4][2], co
   }
 }
 // variant = NRA - 1 (row-clipped or interior), 4 + NRA - 1 (diagonal), -1: nothing to do
+template <int KD>
 __device__ __forceinline__ void fused_slab_mma(double (&acc)[4][4][2], const double *As, const double *Bs, int ld, int qc, int variant) {
   switch (variant) {
-    case 3: fused_slab_mma_static<4, false>(acc, As, Bs, ld, qc); break;
-    case 7: fused_slab_mma_static<4, true>(acc, As, Bs, ld, qc); break;
-    case 0: fused_slab_mma_static<1, false>(acc, As, Bs, ld, qc); break;
-    case 1: fused_slab_mma_static<2, false>(acc, As, Bs, ld, qc); break;
-    case 2: fused_slab_mma_static<3, false>(acc, As, Bs, ld, qc); break;
-    case 4: fused_slab_mma_static<1, true>(acc, As, Bs, ld, qc); break;
-    case 5: fused_slab_mma_static<2, true>(acc, As, Bs, ld, qc); break;
-    case 6: fused_slab_mma_static<3, true>(acc, As, Bs, ld, qc); break;
+    case 3: fused_slab_mma_static<4, false, KD>(acc, As, Bs, ld, qc); break;
+    case 7: fused_slab_mma_static<4, true, KD>(acc, As, Bs, ld, qc); break;
+    case 0: fused_slab_mma_static<1, false, KD>(acc, As, Bs, ld, qc); break;
+    case 1: fused_slab_mma_static<2, false, KD>(acc, As, Bs, ld, qc); break;
+    case 2: fused_slab_mma_static<3, false, KD>(acc, As, Bs, ld, qc); break;
+    case 4: fused_slab_mma_static<1, true, KD>(acc, As, Bs, ld, qc); break;
+    case 5: fused_slab_mma_static<2, true, KD>(acc, As, Bs, ld, qc); break;
+    case 6: fused_slab_mma_static<3, true, KD>(acc, As, Bs, ld, qc); break;
     default: break;
   }
 }
@@ -134,13 +137,13 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int qr = lane >> 2, qc = lane & 3;
   double *Tt = A.scratch + (long long)blockIdx.x * A.scratch_stride;
-  // operand ring of the dense products: two stages, each filled by 16 TMA bulk copies (8 columns of D, 8 rows of T)
+  // operand ring of the dense products: FTST stages of FTK k-values, each filled by 2 FTK TMA bulk copies (columns of D, rows of T)
   // that complete on the stage's `full` mbarrier; a stage is handed back through its `empty` mbarrier (one arrival per
   // warp).  No block-wide barrier inside the k loop: a warp only waits for data, the producer only for a free stage.
-  __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
+  __shared__ __align__(8) unsigned long long s_full[FTST], s_empty[FTST];
   if (tid == 0) {
     s_pair[0] = atomicAdd(A.counter, 1);
-    for (int i = 0; i < 2; i++) { f_mbar_init(f_smem_u32(&s_full[i]), 1); f_mbar_init(f_smem_u32(&s_empty[i]), nw); }
+    for (int i = 0; i < FTST; i++) { f_mbar_init(f_smem_u32(&s_full[i]), 1); f_mbar_init(f_smem_u32(&s_empty[i]), nw); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -312,31 +315,33 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         if (vec) {
           // ---- TMA ring
           const unsigned row_bytes = 8u * (unsigned)n;
-          const int nslab8 = r8 / FKC;
+          const int nslab8 = r8 / FTK;
           // the producer is the LAST warp: the planner sorts a round's supertiles by cost, so it holds the cheapest one
-          // (or none) and its wait for a free stage is off the critical path
+          // (or none) and its wait for a free stage is off the critical path.  FTST - 1 slabs are in flight ahead of the
+          // one being consumed: a round of cheap supertiles is bound by the copy rate, not by one L2 latency per slab.
           auto issue = [&](int sl) {                              // slab sl of this round (producer warp only)
-            const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
+            const unsigned gs = gslab + (unsigned)sl, st = gs % FTST, use = gs / FTST;
             if (use > 0) f_mbar_wait(f_smem_u32(&s_empty[st]), (use - 1u) & 1u);      // every warp is done with the stage
-            if (lane == 0) f_mbar_expect_tx(f_smem_u32(&s_full[st]), 2u * FKC * row_bytes);
+            if (lane == 0) f_mbar_expect_tx(f_smem_u32(&s_full[st]), 2u * FTK * row_bytes);
             __syncwarp();
-            if (lane < 2 * FKC) {
-              const int kk = lane & (FKC - 1), k = sl * FKC + kk;
-              const double *src = lane < FKC ? D + (long long)sR[k] * n : Tt + (long long)k * n;
-              double *dst = (lane < FKC ? stA : stB) + (st * FKC + kk) * A.ldmax;
+            if (lane < 2 * FTK) {
+              const int kk = lane & (FTK - 1), k = sl * FTK + kk;
+              const double *src = lane < FTK ? D + (long long)sR[k] * n : Tt + (long long)k * n;
+              double *dst = (lane < FTK ? stA : stB) + (st * FTK + kk) * A.ldmax;
               f_bulk_g2s(f_smem_u32(dst), src, row_bytes, f_smem_u32(&s_full[st]));
             }
           };
-          if (warp == nw - 1 && nslab8 > 0) issue(0);
+          if (warp == nw - 1)
+            for (int sl = 0; sl < FTST - 1 && sl < nslab8; sl++) issue(sl);
           for (int sl = 0; sl < nslab8; sl++) {
             FPROF(long long q0 = clock64();)
-            if (warp == nw - 1 && sl + 1 < nslab8) issue(sl + 1);
+            if (warp == nw - 1 && sl + FTST - 1 < nslab8) issue(sl + FTST - 1);
             FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 8 : 12] += c - q0; q0 = c; })
-            const unsigned gs = gslab + (unsigned)sl, st = gs & 1u, use = gs >> 1;
+            const unsigned gs = gslab + (unsigned)sl, st = gs % FTST, use = gs / FTST;
             f_mbar_wait(f_smem_u32(&s_full[st]), use & 1u);
             FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 7 : 11] += c - q0; q0 = c; })
-            const double *As = stA + st * FKC * A.ldmax + rb + qr, *Bs = stB + st * FKC * A.ldmax + cb + qr;
-            fused_slab_mma(acc, As, Bs, A.ldmax, qc, variant);
+            const double *As = stA + st * FTK * A.ldmax + rb + qr, *Bs = stB + st * FTK * A.ldmax + cb + qr;
+            fused_slab_mma<FTK>(acc, As, Bs, A.ldmax, qc, variant);
             __syncwarp();
             if (lane == 0) f_mbar_arrive(f_smem_u32(&s_empty[st]));
             FPROF(if (tid == 0) { const long long c = clock64(); pc[it0 == ib ? 9 : 13] += c - q0; })
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
           if (s + 1 < nslab) fused_stage<TPR_LOG2>(stA + (buf ^ 1) * FKC * A.ldmax, stB + (buf ^ 1) * FKC * A.ldmax, ld, D, Tt, R, n, r, (s + 1) * FKC, vec);
           cp_async_commit();
           const double *As = stA + buf * FKC * A.ldmax + rb + qr, *Bs = stB + buf * FKC * A.ldmax + cb + qr;
-          fused_slab_mma(acc, As, Bs, ld, qc, variant);
+          fused_slab_mma<FKC>(acc, As, Bs, ld, qc, variant);
         }
         }
         FPROF(long long q1 = clock64();)

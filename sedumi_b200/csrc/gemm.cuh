@@ -89,6 +89,41 @@ __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const doubl
   }
 }
 
+// DMMAs of one k-slab on a warp's sub-tile: NRA x NCB fragments (DIAG: the lower triangle of NRA x NRA), straight-line code
+template <int KG, int GKT, int NRA, int NCB, bool DIAG>
+__device__ __forceinline__ void gemm_warp_mma_static(double (&acc)[4][4][2], const double (*As)[GT + 4], const double (*Bs)[GT + 4],
+                                                     int wr, int wc, int qr, int qc, int kgrp) {
+#pragma unroll
+  for (int kq = 0; kq < GKT; kq += 4 * KG) {
+    const int k4 = kq + 4 * kgrp;
+    double af[4], bf[4];
+#pragma unroll
+    for (int a = 0; a < NRA; a++) af[a] = As[k4 + qc][wr + 8 * a + qr];     // A frag: row = lane/4, k = lane%4
+#pragma unroll
+    for (int b = 0; b < NCB; b++) bf[b] = Bs[k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
+#pragma unroll
+    for (int a = 0; a < NRA; a++)
+#pragma unroll
+      for (int b = 0; b < NCB; b++)
+        if (!DIAG || a >= b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+  }
+}
+template <int KG, int GKT>
+__device__ __forceinline__ void gemm_warp_mma(double (&acc)[4][4][2], const double (*As)[GT + 4], const double (*Bs)[GT + 4],
+                                              int wr, int wc, int qr, int qc, int kgrp, int variant) {
+#define SB_GEMM_CASE(v, NRA, NCB, DG) case v: gemm_warp_mma_static<KG, GKT, NRA, NCB, DG>(acc, As, Bs, wr, wc, qr, qc, kgrp); break;
+  switch (variant) {
+    SB_GEMM_CASE(15, 4, 4, false) SB_GEMM_CASE(19, 4, 4, true)
+    SB_GEMM_CASE(0, 1, 1, false) SB_GEMM_CASE(1, 1, 2, false) SB_GEMM_CASE(2, 1, 3, false) SB_GEMM_CASE(3, 1, 4, false)
+    SB_GEMM_CASE(4, 2, 1, false) SB_GEMM_CASE(5, 2, 2, false) SB_GEMM_CASE(6, 2, 3, false) SB_GEMM_CASE(7, 2, 4, false)
+    SB_GEMM_CASE(8, 3, 1, false) SB_GEMM_CASE(9, 3, 2, false) SB_GEMM_CASE(10, 3, 3, false) SB_GEMM_CASE(11, 3, 4, false)
+    SB_GEMM_CASE(12, 4, 1, false) SB_GEMM_CASE(13, 4, 2, false) SB_GEMM_CASE(14, 4, 3, false)
+    SB_GEMM_CASE(16, 1, 1, true) SB_GEMM_CASE(17, 2, 2, true) SB_GEMM_CASE(18, 3, 3, true)
+    default: break;
+  }
+#undef SB_GEMM_CASE
+}
+
 // KG = 2: 256 threads = 2 k-groups x 4 warps; warp w owns rows [32*(w&1), +32) x cols [32*((w>>1)&1), +32) of the
 // tile (16 DMMAs per 8 shared-memory fragment loads) and, inside every k-slab, the k4-steps of its
 // k-group (w>>2); the two partial tiles are added through shared memory at the end.  Splitting k inside
@@ -128,6 +163,14 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  // fragments of this warp's 32x32 sub-tile that hold entries of C (a 200 x 200 block covers 25 x 25 of the 32 x 32
+  // fragments its four 64-tiles span: computing all of them cost 1.64 x the DMMAs)
+  int variant = -1;
+  {
+    const int nra = max(0, min(4, (g.M - (i0 + wr) + 7) >> 3)), ncb = max(0, min(4, (g.N - (c0 + wc) + 7) >> 3));
+    if (nra > 0 && ncb > 0 && !(g.lower && i0 + wr + 31 < c0 + wc))
+      variant = (g.lower && i0 + wr == c0 + wc && nra == ncb) ? 16 + nra - 1 : (nra - 1) * 4 + (ncb - 1);
+  }
   const int nslab = khi > klo ? (khi - klo + GKT - 1) / GKT : 0;
   // prologue: GST-1 slabs in flight (a group is committed per slot even when empty, so the wait counts stay uniform)
 #pragma unroll
@@ -151,19 +194,7 @@ gemm_nt_kernel(const GemmDesc *descs, const GemmTile *tiles, const double *baseA
       }
       cp_async_commit();
     }
-#pragma unroll
-    for (int kq = 0; kq < GKT; kq += 4 * KG) {
-      const int k4 = kq + 4 * kgrp;
-      double af[4], bf[4];
-#pragma unroll
-      for (int a = 0; a < 4; a++) af[a] = As[buf][k4 + qc][wr + 8 * a + qr];     // A frag: row = lane/4, k = lane%4
-#pragma unroll
-      for (int b = 0; b < 4; b++) bf[b] = Bs[buf][k4 + qc][wc + 8 * b + qr];     // B frag: k = lane%4, col = lane/4
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-    }
+    gemm_warp_mma<KG, GKT>(acc, As[buf], Bs[buf], wr, wc, qr, qc, kgrp, variant);
   }
   // add the two k-groups: group 1 parks its partial tile in the (now idle) staging buffers
   cp_async_wait_all();
