@@ -63,28 +63,36 @@ template <int KG, int GKT>
 __device__ __forceinline__ void gemm_stage_slab(double (*S)[GT + 4], const double *g, int ld, int rows, int r0, int K, int k0,
                                                 int tri, const int *gather, bool vec_ok) {
   const int tid = threadIdx.x;
-  bool fast = vec_ok && (r0 + GT <= rows) && (k0 + GKT <= K);
+  // rows of the tile no fragment reads (beyond the last 8-row fragment with entries of C) are not staged at all
+  const int rows8 = min(GT, ((rows - r0 + 7) >> 3) << 3);
+  bool fast = vec_ok && ((rows & 1) == 0) && (k0 + GKT <= K);
   if (tri == TRI_K_LE_ROW) fast = fast && (k0 + GKT - 1 <= r0);
   if (tri == TRI_K_GE_ROW) fast = fast && (k0 >= r0 + GT - 1);
   if (fast) {
     const int i = (tid & 31) * 2;
+    if (i < rows8) {
+      const unsigned nbytes = (r0 + i < rows) ? 16u : 0u;         // rows is even: a 16-byte chunk is inside or outside as a whole
 #pragma unroll
-    for (int r = 0; r < GKT / (4 * KG); r++) {
-      const int kk = (tid >> 5) + 4 * KG * r, k = k0 + kk;
-      const long long col = gather ? gather[k] : k;
-      cp_async_16(&S[kk][i], g + r0 + i + col * ld);
+      for (int r = 0; r < GKT / (4 * KG); r++) {
+        const int kk = (tid >> 5) + 4 * KG * r, k = k0 + kk;
+        const long long col = gather ? gather[k] : k;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&S[kk][i]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sa), "l"(nbytes ? g + r0 + i + col * ld : g), "r"(nbytes) : "memory");
+      }
     }
   } else {
     const int i = tid & 63, gi = r0 + i;
+    if (i < rows8) {
 #pragma unroll
-    for (int r = 0; r < GKT / (2 * KG); r++) {
-      const int kk = (tid >> 6) + 2 * KG * r, k = k0 + kk;
-      bool nz = (k < K) && (gi < rows);
-      if (tri == TRI_K_LE_ROW) nz = nz && (k <= gi);
-      if (tri == TRI_K_GE_ROW) nz = nz && (k >= gi);
-      const double *src = g;
-      if (nz) src = g + gi + (long long)(gather ? gather[k] : k) * ld;
-      cp_async_8(&S[kk][i], src, nz ? 8 : 0);
+      for (int r = 0; r < GKT / (2 * KG); r++) {
+        const int kk = (tid >> 6) + 2 * KG * r, k = k0 + kk;
+        bool nz = (k < K) && (gi < rows);
+        if (tri == TRI_K_LE_ROW) nz = nz && (k <= gi);
+        if (tri == TRI_K_GE_ROW) nz = nz && (k >= gi);
+        const double *src = g;
+        if (nz) src = g + gi + (long long)(gather ? gather[k] : k) * ld;
+        cp_async_8(&S[kk][i], src, nz ? 8 : 0);
+      }
     }
   }
 }
