@@ -76,10 +76,22 @@ def main():
         lines.append(f"| `{k}` | {ms:.3f} | {100 * ms / evtot:.1f}% | {100 * n:.1f}% |")
     open(os.path.join(OUT, f"shares_{TAG}.md"), "w").write("\n".join(lines) + "\n")
     # ---- full capture: raw page -> per-kernel text + DRAM traffic
-    rep = os.path.join(SRC, "top.ncu-rep")
-    if os.path.exists(rep):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(io.StringIO(raw)))
+    reps = [os.path.join(SRC, f) for f in ("top.ncu-rep", "top2.ncu-rep") if os.path.exists(os.path.join(SRC, f))]
+    if reps:
+        rows = []
+        for rep in reps:                      # one table: header + units from the first report, data rows from all
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            rr = list(csv.reader(io.StringIO(raw)))
+            if not rows:
+                rows = rr
+            else:
+                idx0 = {h: i for i, h in enumerate(rows[0])}
+                for r in rr[2:]:
+                    row = [""] * len(rows[0])
+                    for i, h in enumerate(rr[0]):
+                        if h in idx0 and i < len(r):
+                            row[idx0[h]] = r[i]
+                    rows.append(row)
         hdr = rows[0]
         ki = hdr.index("Kernel Name")
         keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
