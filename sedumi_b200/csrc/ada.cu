@@ -41,6 +41,7 @@ struct AdaPair {      // one (constraint, PSD block) with nonzeros
   // A_jk) instead of as a dense DMMA product (mode 0).
   int mode, need_cnt;
   long long need_off;
+  long long slot_off;  // fused path: position in column j of ADA of every partner up to this pair's rank (or -1), looked up at plan time
 };
 
 // --------------------------------------------------------------------- sparse A'WA on a pattern
@@ -251,6 +252,7 @@ struct DotsCtx {
   const int *blkp_beg; const BlkPartner *blkp; const int *invperm;
   const double *Atpr; const int *ent_src; const double *ent_scale;
   double *ws, *ada, *absd;
+  const int *slot_tab;   // by_rank: slot_tab[t - tb] = position of partner t's row in ADA column c (else nullptr: search)
 };
 // The partner loop with G lanes per partner; G is chosen PER BLOCK from the average number of entries of its pairs
 // (control07: 161 entries per pair in the 70x70 block, exactly 1 in the 35x35 block).
@@ -285,6 +287,9 @@ __device__ __forceinline__ void dots_partners(const DotsCtx &X) {
       if (tn < tl) { Qn = blkp[tn]; ipn = by_rank ? 0 : invperm[Qn.j]; }
     }
     if (!by_rank && ipi > ipc) continue;
+    // the partner's position in ADA column c: a table built with the plan (a binary search over a 5000-row column is
+    // 12 dependent L2 round trips on the lane that writes the result: 11 % of the fused kernel's stall samples)
+    const int sl_tab = X.slot_tab ? X.slot_tab[t - tb] : -2;
     const double *av = Atpr + Q.src0 - Q.e0;            // the entries of one pair are consecutive in At.pr ...
     double acc = 0.0, aabs = 0.0;
     int e = Q.e0 + gl;
@@ -322,7 +327,7 @@ __device__ __forceinline__ void dots_partners(const DotsCtx &X) {
         part[t - tb] = acc;
         if (Q.j == c) part[te - tb] = aabs;
       } else {
-        const int sl = cs.find(Q.j);
+        const int sl = sl_tab != -2 ? sl_tab : cs.find(Q.j);
         if (sl >= 0) {
           ada[colbeg + sl] += acc;
           if (Q.j == c && ipc >= first) absd[c] += aabs;
@@ -373,7 +378,7 @@ ada3_dots_kernel(int p0, const long long *adajc, const int *adair, const int *in
   const double *Wp = stage ? Wsm : Wg;
   DotsCtx X;
   X.P = P; X.c = c; X.ipc = ipc; X.first = first; X.multi = multi ? 1 : 0; X.warp = warp; X.lane = lane; X.nw = nw;
-  X.rank_limit = -1;
+  X.rank_limit = -1; X.slot_tab = nullptr;
   X.colbeg = colbeg; X.cs = cs; X.eidx = eidx; X.Wp = Wp; X.blkp_beg = blkp_beg; X.blkp = blkp; X.invperm = invperm;
   X.Atpr = Atpr; X.ent_src = ent_src; X.ent_scale = ent_scale; X.ws = ws; X.ada = ada; X.absd = absd;
   switch (blk_group[P.k]) {
@@ -510,7 +515,7 @@ struct sb200_ada_plan {
   long long fused_scratch_stride = 0, fws = 0, n_tt = 0;
   int any_multi = 0;
   DevBuf<double> d_tt_val, d_fscratch, d_fws;
-  DevBuf<int> d_fcounter, d_fitem_beg, d_fneed, d_forder;
+  DevBuf<int> d_fcounter, d_fitem_beg, d_fneed, d_forder, d_fslot;
   // row-wise (CSR) view of the pattern of At for products At*p without atomics (pcg.cu)
   DevBuf<long long> d_rowptr; DevBuf<int> d_rowcol, d_rowsrc;
   std::vector<long long> h_Ajc; std::vector<int> h_Air;
@@ -893,6 +898,21 @@ static int ada_build(sb200_ada_plan *pl, sb_idx N, sb_idx m, const sb_idx *Ajc, 
         }
       }
       pl->fused_ndense = ndense;
+      {
+        std::vector<int> slots;
+        for (auto &P : pl->pairs) {
+          P.slot_off = (long long)slots.size();
+          const sb_idx *rb = adair + adajc[P.j], *re = adair + adajc[P.j + 1];
+          const int tb = blkp_beg[P.k];
+          for (int t = 0; t <= P.rank; t++) {
+            const sb_idx want = blkp[tb + t].j;
+            const sb_idx *it = std::lower_bound(rb, re, want);
+            slots.push_back((it != re && *it == want) ? (int)(it - rb) : -1);
+          }
+        }
+        if (slots.empty()) slots.push_back(-1);
+        SB_TRY(pl->d_fslot.upload(slots));
+      }
       // pairs are handed out most expensive first (dense products, then the entry-wise ones)
       std::vector<int> order(pl->pairs.size());
       for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
@@ -1379,7 +1399,7 @@ int sb200_getada3_dev(sb200_ada_plan *pl, const double *udsqr_dev, const int *in
     FA.Rlist = pl->d_Rlist.p; FA.udsqr = udsqr_dev; FA.scratch = pl->d_fscratch.p; FA.scratch_stride = pl->fused_scratch_stride;
     FA.adajc = pl->d_adajc.p; FA.adair = pl->d_adair.p; FA.invperm = ip; FA.first = (int)first; FA.cpair_beg = pl->d_cpair_beg.p;
     FA.blkp_beg = pl->d_blkp_beg.p; FA.blkp = pl->d_blkp.p; FA.ent_pk = pl->d_ent_pk.p; FA.ent_src = pl->d_ent_src.p; FA.Atpr = pl->d_Atpr.p;
-    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.need_pq = pl->d_fneed.p; FA.order = pl->d_forder.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax; FA.prof = pl->fprof_on ? pl->d_fprof.p : nullptr;
+    FA.ws = pl->d_fws.p; FA.ada = ada_dev; FA.absd = absd_dev; FA.blk_group = pl->d_blk_group.p; FA.blk_item_beg = pl->d_fitem_beg.p; FA.items = pl->d_fitems.p; FA.need_pq = pl->d_fneed.p; FA.order = pl->d_forder.p; FA.wcap = pl->fused_wcap; FA.ldmax = pl->fused_ldmax; FA.prof = pl->fprof_on ? pl->d_fprof.p : nullptr; FA.slot = pl->d_fslot.p;
     static bool attr_done = false;
     if (!attr_done) {
       SB_CUDA(cudaFuncSetAttribute(ada3_fused_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));   // + 1.7 KB static

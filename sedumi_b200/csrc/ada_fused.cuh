@@ -38,6 +38,7 @@ struct FusedArgs {
   const int *blk_item_beg; const int2 *items;        // per block: its lower supertiles (I, J), most expensive first
   const int *need_pq; const int *order;              // entry-wise pairs: their (p | q << 16) lists; processing order of the pairs
   int wcap, ldmax;
+  const int *slot;                                   // per pair: ADA positions of its partners (AdaPair::slot_off)
   unsigned long long *prof;                          // optional: cycles per phase summed over CTAs (thread 0's clock), 8 slots
 };
 
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
       X.P = P; X.P.part_off = P.fpart_off; X.c = c; X.ipc = ipc; X.first = A.first; X.multi = multi ? 1 : 0;
       X.warp = warp; X.lane = lane; X.nw = nw; X.colbeg = colbeg; X.cs = cs; X.eidx = A.ent_pk; X.Wp = Wp;
       X.blkp_beg = A.blkp_beg; X.blkp = A.blkp; X.invperm = A.invperm; X.Atpr = A.Atpr; X.ent_src = A.ent_src;
-      X.ent_scale = nullptr; X.ws = A.ws; X.ada = A.ada; X.absd = A.absd;
+      X.ent_scale = nullptr; X.ws = A.ws; X.ada = A.ada; X.absd = A.absd; X.slot_tab = A.slot + P.slot_off;
       switch (A.blk_group[P.k]) {
         case 4: dots_partners<4>(X); break;
         case 8: dots_partners<8>(X); break;

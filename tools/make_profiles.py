@@ -78,49 +78,39 @@ def main():
     # ---- full capture: raw page -> per-kernel text + DRAM traffic
     reps = [os.path.join(SRC, f) for f in ("top.ncu-rep", "top2.ncu-rep") if os.path.exists(os.path.join(SRC, f))]
     if reps:
-        rows = []
-        for rep in reps:                      # one table: header + units from the first report, data rows from all
-            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-            rr = list(csv.reader(io.StringIO(raw)))
-            if not rows:
-                rows = rr
-            else:
-                idx0 = {h: i for i, h in enumerate(rows[0])}
-                for r in rr[2:]:
-                    row = [""] * len(rows[0])
-                    for i, h in enumerate(rr[0]):
-                        if h in idx0 and i < len(r):
-                            row[idx0[h]] = r[i]
-                    rows.append(row)
-        hdr = rows[0]
-        ki = hdr.index("Kernel Name")
         keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
                 "launch__registers_per_thread", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
                 "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
                 "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
                 "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
                 "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
-        idx = {h: i for i, h in enumerate(hdr)}
-        seen, traffic, txt = {}, {}, []
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        units = rows[1]
-        for r in rows[2:]:
-            k = short(r[ki])
-            if k in seen:
-                continue
-            seen[k] = 1
-            txt.append(f"== {k}   ({r[ki][:100]})")
-            for h in keep:
-                if h in idx:
-                    txt.append(f"   {h:90s} {r[idx[h]]} {units[idx[h]]}")
-            try:
-                rd = float(r[idx['dram__bytes_read.sum']].replace(",", "")) * unit.get(units[idx['dram__bytes_read.sum']], 1.0)
-                wr = float(r[idx['dram__bytes_write.sum']].replace(",", "")) * unit.get(units[idx['dram__bytes_write.sum']], 1.0)
-                traffic[k] = rd + wr
-            except (KeyError, ValueError):
-                pass
+        seen, traffic, txt = {}, {}, []
+        for rep in reps:                      # every report carries its own units row
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            rows = list(csv.reader(io.StringIO(raw)))
+            hdr, units = rows[0], rows[1]
+            ki = hdr.index("Kernel Name")
+            idx = {h: i for i, h in enumerate(hdr)}
+            for r in rows[2:]:
+                k = short(r[ki])
+                if k in seen:
+                    continue
+                seen[k] = 1
+                txt.append(f"== {k}   ({r[ki][:100]})   [{os.path.basename(rep)}]")
+                for h in keep:
+                    if h in idx:
+                        txt.append(f"   {h:90s} {r[idx[h]]} {units[idx[h]]}")
+                try:
+                    rd = float(r[idx['dram__bytes_read.sum']].replace(",", "")) * unit.get(units[idx['dram__bytes_read.sum']], 1.0)
+                    wr = float(r[idx['dram__bytes_write.sum']].replace(",", "")) * unit.get(units[idx['dram__bytes_write.sum']], 1.0)
+                    traffic[k] = rd + wr
+                except (KeyError, ValueError):
+                    pass
         open(os.path.join(OUT, f"ncu_{TAG}_top_kernels.txt"), "w").write("\n".join(txt) + "\n")
-        json.dump({bench["config"]["workload"]: traffic}, open(os.path.join(OUT, f"traffic_{TAG}.json"), "w"), indent=1)
+        wl = bench["config"]["workload"]
+        key = "blockdiag64" if "64 PSD blocks" in wl else ("control07" if "control07" in wl else wl)      # bench.py's workload name
+        json.dump({key: traffic}, open(os.path.join(OUT, f"traffic_{TAG}.json"), "w"), indent=1)
     print("profiles refreshed:", sorted(os.listdir(OUT)))
 
 
