@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
+#include <string.h>
 #include <mutex>
 #include <thread>
 #include "sb_internal.h"
@@ -105,6 +107,160 @@ Hash128 hash128(const void *data, size_t bytes, Hash128 seed) {
   while (P.done.load(std::memory_order_acquire) < J.nchunks) { }
   Hash128 s2{seed.a ^ (uint64_t)bytes, seed.b + (uint64_t)bytes};
   return hash128_st(J.out, sizeof(Hash128) * J.nchunks, s2);
+}
+
+// ---------------------------------------------------------------- staged copies of pageable host memory
+// H2D: host threads copy chunks of the source into pinned slots (two sets of slots: the DMA of one set overlaps the host
+// copies into the other), each slot goes to the device with an asynchronous copy on the caller's stream.  The call returns
+// when the source has been read completely (the semantics of cudaMemcpyAsync on pageable memory).
+// D2H: the DMAs of one set are enqueued, the previous set is drained to the destination by the host threads; the call
+// returns when the destination is complete (again what the pageable call does).
+namespace {
+struct CopyPool {            // plain mutex / condition-variable fork-join: jobs are 2 MB memcpy's, ~100 us each
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  const std::function<void(size_t)> *fn = nullptr;
+  size_t n = 0, next = 0, done = 0;
+  uint64_t gen = 0;
+  bool stop = false;
+  void loop() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv_job.wait(lk, [&] { return stop || gen != seen; });
+      if (stop) return;
+      seen = gen;
+      while (next < n) {
+        const size_t i = next++;
+        const std::function<void(size_t)> *f = fn;
+        lk.unlock();
+        (*f)(i);
+        lk.lock();
+        if (++done == n) cv_done.notify_all();
+      }
+    }
+  }
+  void run(size_t count, const std::function<void(size_t)> &f) {      // the caller takes its share; returns when all are done
+    std::unique_lock<std::mutex> lk(mu);
+    fn = &f; n = count; next = 0; done = 0; gen++;
+    cv_job.notify_all();
+    while (next < n) {
+      const size_t i = next++;
+      lk.unlock();
+      f(i);
+      lk.lock();
+      ++done;
+    }
+    cv_done.wait(lk, [&] { return done == n; });
+    n = 0; next = 0;                                                   // late wake-ups find nothing to claim
+  }
+  void start() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(7, hc > 1 ? hc - 1 : 0);
+    if (const char *e = getenv("SB200_COPY_THREADS")) nt = std::max(0, std::min(31, atoi(e) - 1));
+    for (int i = 0; i < nt; i++) th.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_job.notify_all();
+    for (auto &t : th) t.join();
+  }
+};
+const size_t STG_CH = (size_t)2 << 20;     // chunk = pinned slot
+const int STG_SLOTS = 8;                   // slots per set, two sets: 32 MB of pinned memory
+struct Staging {
+  char *pin = nullptr;
+  cudaEvent_t ev[2];
+  bool pending[2] = {false, false};
+  CopyPool pool;
+  bool ok = false, tried = false;
+  std::mutex mu;                           // one staged copy at a time
+};
+Staging *g_stg = nullptr;
+}  // namespace
+
+cudaError_t staged_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st, bool *handled) {
+  *handled = false;
+  static const bool off = getenv("SB200_NO_STAGED_COPY") != nullptr;
+  if (off) return cudaSuccess;
+  const void *host = kind == cudaMemcpyHostToDevice ? src : dst;
+  cudaPointerAttributes at;
+  if (::cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+  if (at.type != cudaMemoryTypeUnregistered) return cudaSuccess;      // pinned / managed: the plain asynchronous copy is right
+  if (!g_stg) g_stg = new Staging();
+  Staging &S = *g_stg;
+  std::lock_guard<std::mutex> one(S.mu);
+  if (!S.tried) {
+    S.tried = true;
+    if (::cudaHostAlloc((void **)&S.pin, 2 * STG_SLOTS * STG_CH, cudaHostAllocDefault) == cudaSuccess &&
+        cudaEventCreateWithFlags(&S.ev[0], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&S.ev[1], cudaEventDisableTiming) == cudaSuccess) {
+      S.pool.start();
+      S.ok = true;
+    } else cudaGetLastError();
+  }
+  if (!S.ok) return cudaSuccess;
+  *handled = true;
+  cudaError_t e = cudaSuccess;
+  for (int s = 0; s < 2; s++)                                          // slots may still feed DMAs of an earlier call
+    if (S.pending[s]) { e = cudaEventSynchronize(S.ev[s]); S.pending[s] = false; if (e != cudaSuccess) return e; }
+  const size_t nch = (bytes + STG_CH - 1) / STG_CH;
+  const size_t nwave = (nch + STG_SLOTS - 1) / STG_SLOTS;
+  if (kind == cudaMemcpyHostToDevice) {
+    const char *hs = (const char *)src;
+    for (size_t w = 0; w < nwave; w++) {
+      const int set = (int)(w & 1);
+      if (S.pending[set]) { e = cudaEventSynchronize(S.ev[set]); S.pending[set] = false; if (e != cudaSuccess) return e; }
+      const size_t c0 = w * STG_SLOTS, cnt = std::min<size_t>(STG_SLOTS, nch - c0);
+      char *base = S.pin + (size_t)set * STG_SLOTS * STG_CH;
+      const std::function<void(size_t)> f = [&](size_t i) {
+        const size_t o = (c0 + i) * STG_CH, len = std::min(STG_CH, bytes - o);
+        memcpy(base + i * STG_CH, hs + o, len);
+      };
+      S.pool.run(cnt, f);
+      for (size_t i = 0; i < cnt; i++) {
+        const size_t o = (c0 + i) * STG_CH, len = std::min(STG_CH, bytes - o);
+        e = (::cudaMemcpyAsync)((char *)dst + o, base + i * STG_CH, len, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+      }
+      e = cudaEventRecord(S.ev[set], st);
+      if (e != cudaSuccess) return e;
+      S.pending[set] = true;
+    }
+    return cudaSuccess;
+  }
+  // device -> host
+  char *hd = (char *)dst;
+  auto drain = [&](size_t w) -> cudaError_t {
+    const int set = (int)(w & 1);
+    cudaError_t e2 = cudaEventSynchronize(S.ev[set]);
+    S.pending[set] = false;
+    if (e2 != cudaSuccess) return e2;
+    const size_t c0 = w * STG_SLOTS, cnt = std::min<size_t>(STG_SLOTS, nch - c0);
+    const char *base = S.pin + (size_t)set * STG_SLOTS * STG_CH;
+    const std::function<void(size_t)> f = [&](size_t i) {
+      const size_t o = (c0 + i) * STG_CH, len = std::min(STG_CH, bytes - o);
+      memcpy(hd + o, base + i * STG_CH, len);
+    };
+    S.pool.run(cnt, f);
+    return cudaSuccess;
+  };
+  for (size_t w = 0; w < nwave; w++) {
+    const int set = (int)(w & 1);
+    const size_t c0 = w * STG_SLOTS, cnt = std::min<size_t>(STG_SLOTS, nch - c0);
+    char *base = S.pin + (size_t)set * STG_SLOTS * STG_CH;
+    for (size_t i = 0; i < cnt; i++) {
+      const size_t o = (c0 + i) * STG_CH, len = std::min(STG_CH, bytes - o);
+      e = (::cudaMemcpyAsync)(base + i * STG_CH, (const char *)src + o, len, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+    }
+    e = cudaEventRecord(S.ev[set], st);
+    if (e != cudaSuccess) return e;
+    S.pending[set] = true;
+    if (w > 0) { e = drain(w - 1); if (e != cudaSuccess) return e; }
+  }
+  return drain(nwave - 1);
 }
 
 void set_error(const char *fmt, ...) {

@@ -35,9 +35,17 @@ int  ensure_init();
 
 // Every asynchronous copy of this library goes through here so that the host<->device traffic of a plugin call is
 // COUNTED, not estimated (sb200_xfer_bytes; bench.py prints these as e2e.h2d/d2h_bytes_per_step).
+// Large copies from / to PAGEABLE host memory (what a MEX host hands over) are staged through a ring of pinned buffers
+// by a few host threads (context.cu): the driver's own staging of a pageable cudaMemcpyAsync is single-threaded.
+cudaError_t staged_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st, bool *handled);
 inline cudaError_t counted_memcpy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
   if (kind == cudaMemcpyHostToDevice) ctx().h2d_bytes += (int64_t)bytes;
   else if (kind == cudaMemcpyDeviceToHost) ctx().d2h_bytes += (int64_t)bytes;
+  if (bytes >= ((size_t)4 << 20) && (kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToHost) && !ctx().capturing) {
+    bool handled = false;
+    const cudaError_t e = staged_copy(dst, src, bytes, kind, st, &handled);
+    if (handled) return e;
+  }
   return ::cudaMemcpyAsync(dst, src, bytes, kind, st);
 }
 #define cudaMemcpyAsync(...) sb::counted_memcpy_async(__VA_ARGS__)
