@@ -286,6 +286,10 @@ int sb200_qrK(sb_idx nblk, const sb_idx *n, const double *x, double *q, double *
  * triumtriu.m:38-73; psdfactor.m:37-82 (*ispos = 0: not positive definite); psdinvscale.m:37-83. */
 int sb200_psdmul(int mode, sb_idx nblk, const sb_idx *n, const double *x, const double *y, double *z);
 int sb200_psdfactor(sb_idx nblk, const sb_idx *n, const double *x, double *ux, int *ispos);
+/* [lab,q] = psdeig(x,K) (psdeig.m:40-96; minpsdeig.m:43-68 takes the minimum of lab): eigenvalues of (X_k + X_k')/2 per real
+ * PSD block in ascending order, q (NULL: not wanted) the eigenvectors.  The reference defers to the host's eig(); this is a
+ * cyclic Jacobi method on the device (vectors agree up to sign / rotation inside eigenspaces). */
+int sb200_psdeig(sb_idx nblk, const sb_idx *n, const double *x, double *lab, double *q);
 int sb200_psdinvscale(sb_idx nblk, const sb_idx *n, const double *u, const double *x, double *y);
 
 /* ------------------------------------------------------------------ Lorentz streams

@@ -211,3 +211,21 @@ def psdinvscale(ud, x, K):
         W = sla.solve_triangular(T, X.T, lower=False).T                 # X / T'
         out.append(sla.solve_triangular(T, W, lower=False).ravel(order="F"))
     return np.concatenate(out)
+
+
+def psdeig(x, K, vectors=False):
+    """psdeig.m:40-96 (real blocks): lab = 0.5 eig(XX + XX') per block, ascending; optionally the eigenvectors.
+    The reference calls the host's eig(): LAPACK here (numpy.linalg.eigh) -- parity unpinned beyond that."""
+    labs, qs = [], []
+    for X in _blocks(x, K):
+        w, Q = np.linalg.eigh(X + X.T)
+        labs.append(0.5 * w)
+        qs.append(Q.ravel(order="F"))
+    lab = np.concatenate(labs) if labs else np.zeros(0)
+    return (lab, np.concatenate(qs)) if vectors else lab
+
+
+def minpsdeig(x, K):
+    """minpsdeig.m:43-68: the smallest spectral coefficient over all blocks."""
+    return float(psdeig(x, K).min())
+

@@ -177,6 +177,121 @@ __global__ void __launch_bounds__(256) alg_trsolve_kernel(const AlgBlk *blks, co
   for (int c = 0; c < ALG_SOLVE_MAXCH; c++) { const int r = lane + 32 * c; if (r < n) z[r] = v[c]; }
 }
 
+// Symmetric eigenvalue problem of every block: cyclic two-sided Jacobi in the round-robin (tournament) ordering, one
+// CTA per block.  A step rotates m/2 disjoint index pairs at once: the rotation of pair K = (p,q) is fixed from
+// (a_pp, a_qq, a_pq) at the start of the step, and every 2 x 2 sub-block A([p q],[r s]) of pairs (K, L) becomes
+// J_K' A([p q],[r s]) J_L -- read and written by ONE thread, so the step is in place with two block barriers.  For odd n a
+// dummy index pairs with one real index per step (identity rotation).  V accumulates the rotations column-wise.
+// Stops when the off-diagonal Frobenius norm (summed directly, not as a difference) is below 3e-15 of the matrix's.
+static const int ALG_EIG_MAXN = 2048;
+__device__ __forceinline__ double alg_block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nw; w++) t += red[w];          // same order in every thread: all threads take the same branch later
+  return t;
+}
+__global__ void __launch_bounds__(1024)
+alg_jacobi_kernel(const AlgBlk *blks, const double *x, double *a, double *v, double *lab, double *q, int want_v, int *sweeps) {
+  extern __shared__ double jac_sm[];
+  const AlgBlk B = blks[blockIdx.x];
+  const int n = B.n, tid = threadIdx.x, nt = blockDim.x;
+  const int m = n + (n & 1), hp = m >> 1;
+  double *cs_c = jac_sm, *cs_s = jac_sm + hp;
+  int *pp = (int *)(jac_sm + 2 * hp), *pq = pp + hp;
+  __shared__ double red[32];
+  const double *X = x + B.off;
+  double *A = a + B.off, *V = v + B.off, *Q = q ? q + B.off : nullptr;
+  double *L = lab + B.voff;
+  const long long tot = (long long)n * n;
+  for (long long idx = tid; idx < tot; idx += nt) {
+    const int i = (int)(idx % n), j = (int)(idx / n);
+    A[idx] = 0.5 * (X[idx] + X[j + (long long)i * n]);
+    if (want_v) V[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  int sw = 0;
+  if (n > 1) {
+    double f = 0.0;
+    for (long long idx = tid; idx < tot; idx += nt) f += A[idx] * A[idx];
+    const double fro2 = alg_block_sum(f, red);
+    for (; sw < 30; sw++) {
+      double o = 0.0;
+      for (long long idx = tid; idx < tot; idx += nt) { const int i = (int)(idx % n), j = (int)(idx / n); if (i != j) o += A[idx] * A[idx]; }
+      const double off2 = alg_block_sum(o, red);
+      if (!(off2 > 1e-29 * fro2)) break;                        // uniform: every thread holds the same sums
+      for (int st = 0; st < m - 1; st++) {
+        for (int k = tid; k < hp; k += nt) {
+          int i1, i2;
+          if (k == 0) { i1 = m - 1; i2 = st % (m - 1); }
+          else { i1 = (st + k) % (m - 1); i2 = (st - k + (m - 1)) % (m - 1); }
+          const int p = min(i1, i2), qq = max(i1, i2);
+          double c = 1.0, sn = 0.0;
+          if (qq < n) {
+            const double apq = A[p + (long long)qq * n];
+            if (apq != 0.0) {
+              const double tau = (A[qq + (long long)qq * n] - A[p + (long long)p * n]) / (2.0 * apq);
+              const double t = tau == 0.0 ? 1.0 : copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+              c = 1.0 / sqrt(1.0 + t * t);
+              sn = t * c;
+            }
+          }
+          pp[k] = p; pq[k] = qq; cs_c[k] = c; cs_s[k] = sn;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < hp * hp; idx += nt) {
+          const int K = idx % hp, Lq = idx / hp;
+          const int p = pp[K], q2 = pq[K], r = pp[Lq], s2 = pq[Lq];
+          const double cK = cs_c[K], sK = cs_s[K], cL = cs_c[Lq], sL = cs_s[Lq];
+          const bool vq = q2 < n, vs = s2 < n;
+          const double b00 = A[p + (long long)r * n];
+          const double b10 = vq ? A[q2 + (long long)r * n] : 0.0;
+          const double b01 = vs ? A[p + (long long)s2 * n] : 0.0;
+          const double b11 = (vq && vs) ? A[q2 + (long long)s2 * n] : 0.0;
+          const double t00 = cK * b00 - sK * b10, t10 = sK * b00 + cK * b10;
+          const double t01 = cK * b01 - sK * b11, t11 = sK * b01 + cK * b11;
+          A[p + (long long)r * n] = t00 * cL - t01 * sL;
+          if (vq) A[q2 + (long long)r * n] = t10 * cL - t11 * sL;
+          if (vs) A[p + (long long)s2 * n] = t00 * sL + t01 * cL;
+          if (vq && vs) A[q2 + (long long)s2 * n] = t10 * sL + t11 * cL;
+        }
+        if (want_v)
+          for (int idx = tid; idx < n * hp; idx += nt) {
+            const int i = idx % n, Lq = idx / n;
+            const int r = pp[Lq], s2 = pq[Lq];
+            if (s2 < n) {
+              const double cL = cs_c[Lq], sL = cs_s[Lq];
+              const double vr = V[i + (long long)r * n], vs2 = V[i + (long long)s2 * n];
+              V[i + (long long)r * n] = cL * vr - sL * vs2;
+              V[i + (long long)s2 * n] = sL * vr + cL * vs2;
+            }
+          }
+        __syncthreads();
+      }
+    }
+  }
+  if (tid == 0 && sweeps) sweeps[blockIdx.x] = sw;
+  // ascending order (ties: original index), eigenvectors follow
+  int *rank = pq + hp;                                           // n ints
+  for (int i = tid; i < n; i += nt) {
+    const double li = A[i + (long long)i * n];
+    int rk = 0;
+    for (int j = 0; j < n; j++) { const double lj = A[j + (long long)j * n]; rk += (lj < li) || (lj == li && j < i); }
+    rank[i] = rk;
+    L[rk] = li;
+  }
+  __syncthreads();
+  if (Q)
+    for (long long idx = tid; idx < tot; idx += nt) {
+      const int r = (int)(idx % n), i = (int)(idx / n);
+      Q[r + (long long)rank[i] * n] = V[idx];
+    }
+}
+
 static int alg_blocks(sb_idx nblk, sb_idx nreal, const sb_idx *n, std::vector<AlgBlk> &blks, long long &lenud, long long &sumn, int &maxn) {
   lenud = 0; sumn = 0; maxn = 0;
   for (sb_idx k = 0; k < nblk; k++) {
@@ -364,4 +479,33 @@ int sb200_psdinvscale(sb_idx nblk, const sb_idx *n, const double *u, const doubl
   return 0;
 }
 
+}  // extern "C"
+
+extern "C" {
+// [lab, q] = psdeig(x,K) (psdeig.m:40-96, real blocks): eigenvalues of sym(X_k) = (X_k + X_k')/2 in ascending order
+// (= 0.5 eig(XX + XX')), q (optional, may be NULL) the orthonormal eigenvectors column by column.  The reference calls the
+// host's eig(); here a cyclic Jacobi method (alg_jacobi_kernel), so vectors agree up to sign / rotation inside eigenspaces.
+int sb200_psdeig(sb_idx nblk, const sb_idx *n, const double *x, double *lab, double *q) {
+  SB_TRY(ensure_init());
+  std::vector<AlgBlk> blks; long long lenud, sumn; int maxn;
+  SB_TRY(alg_blocks(nblk, nblk, n, blks, lenud, sumn, maxn));
+  if (lenud == 0) return 0;
+  SB_CHECK(maxn <= ALG_EIG_MAXN, "psdeig: block order %d beyond %d", maxn, ALG_EIG_MAXN);
+  arena_reset();
+  cudaStream_t st = ctx().stream;
+  AlgBlk *db = arena<AlgBlk>(blks.size());
+  double *dx = arena<double>((size_t)lenud), *da = arena<double>((size_t)lenud), *dv = arena<double>((size_t)lenud);
+  double *dq = q ? arena<double>((size_t)lenud) : nullptr, *dl = arena<double>((size_t)sumn);
+  SB_CHECK(db && dx && da && dv && dl && (!q || dq), "psdeig: out of device memory");
+  SB_CUDA(cudaMemcpyAsync(db, blks.data(), sizeof(AlgBlk) * blks.size(), cudaMemcpyHostToDevice, st));
+  SB_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * lenud, cudaMemcpyHostToDevice, st));
+  const int m = maxn + (maxn & 1), hp = m / 2;
+  const size_t shm = sizeof(double) * 2 * hp + sizeof(int) * (2 * (size_t)hp + maxn);
+  alg_jacobi_kernel<<<(unsigned)nblk, 1024, shm, st>>>(db, dx, da, dv, dl, dq, q ? 1 : 0, nullptr);
+  SB_LAUNCH_CHECK_N("alg_jacobi_kernel");
+  SB_CUDA(cudaMemcpyAsync(lab, dl, sizeof(double) * sumn, cudaMemcpyDeviceToHost, st));
+  if (q) SB_CUDA(cudaMemcpyAsync(q, dq, sizeof(double) * lenud, cudaMemcpyDeviceToHost, st));
+  SB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
 }  // extern "C"

@@ -16,7 +16,7 @@ from sedumi_b200.mx import MexError
 PLUGINS = ["blkchol", "fwblkslv", "bwblkslv", "getada1", "getada2", "getada3", "invcholfac", "psdscale",
            "ddot", "qblkmul", "quadadd", "psdframeit", "psdinvjmul", "urotorder", "givensrot",
            "dpr1fact", "fwdpr1", "bwdpr1", "adendotd", "adenscale",
-           "vecsym", "sqrtinv", "qrK", "psdjmul", "triumtriu", "psdfactor", "psdinvscale"]
+           "vecsym", "sqrtinv", "qrK", "psdjmul", "triumtriu", "psdfactor", "psdinvscale", "psdeig", "minpsdeig"]
 
 
 def test_library_exports_every_declared_symbol():

@@ -115,3 +115,43 @@ def test_psdfactor_and_psdinvscale(s):
         urb, posrb = restate.psdfactor(bad, K)
         assert float(np.asarray(posb).ravel()[0]) == 0.0 and not posrb
         assert relerr(ub.ravel()[:o], urb[:o]) <= 1e-10 and not np.any(ub.ravel()[o:])
+
+
+@pytest.mark.parametrize("s", [(1,), (2, 3), (40, 7), (129,), (200, 65)])
+def test_psdeig_minpsdeig(s):
+    """psdeig.m / minpsdeig.m (M-only; the reference calls the host's eig): eigenvalues against LAPACK, eigenvectors through
+    what makes them unique -- orthonormality and Q diag(lab) Q' = (X + X')/2."""
+    K, Km = _K(1, (), s)
+    rng = np.random.default_rng(31 + sum(s))
+    lenud = sum(k * k for k in s)
+    x = rng.standard_normal(1 + lenud)
+    lab_r = restate.psdeig(x, K)
+    lab_g, q_g = gpu.psdeig(x, Km, nlhs=2)
+    lab_g, q_g = np.ravel(lab_g), np.ravel(q_g)
+    scale = max(1.0, np.abs(lab_r).max())
+    assert np.abs(lab_g - lab_r).max() <= 1e-10 * scale
+    assert np.abs(np.ravel(gpu.psdeig(x, Km)) - lab_r).max() <= 1e-10 * scale          # values only
+    o = lo = 0
+    for n, X in zip(s, restate._blocks(x, K)):
+        Q = q_g[o:o + n * n].reshape(n, n, order="F")
+        lam = lab_g[lo:lo + n]
+        assert np.all(np.diff(lam) >= 0)
+        assert np.abs(Q.T @ Q - np.eye(n)).max() <= 1e-12 * n
+        assert np.abs(Q @ np.diag(lam) @ Q.T - 0.5 * (X + X.T)).max() <= 1e-10 * scale
+        o += n * n
+        lo += n
+    assert abs(float(np.ravel(gpu.minpsdeig(x, Km))[0]) - restate.minpsdeig(x, K)) <= 1e-10 * scale
+
+
+def test_psdeig_repeated_and_zero_eigenvalues():
+    s = (6, 5)
+    K, Km = _K(0, (), s)
+    A = np.ones((6, 6))                                    # eigenvalues 0 (x5), 6
+    B = np.diag([1.0, 1.0, 2.0, 2.0, 3.0])
+    x = np.concatenate([A.ravel(order="F"), B.ravel(order="F")])
+    lab, q = gpu.psdeig(x, Km, nlhs=2)
+    lab, q = np.ravel(lab), np.ravel(q)
+    assert np.abs(lab - np.r_[0, 0, 0, 0, 0, 6, 1, 1, 2, 2, 3]).max() <= 1e-12
+    Q = q[:36].reshape(6, 6, order="F")
+    assert np.abs(Q @ np.diag(lab[:6]) @ Q.T - A).max() <= 1e-12
+
