@@ -268,7 +268,17 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
       // four lanes share one needed entry (p, q) and split the sum; eight terms per lane are in flight at a time
       const int *pq = A.need_pq + P.need_off;
       const int g = tid & 3;
-      const int e0 = A.tt_ptr[P.r0], e1 = A.tt_ptr[P.r0 + r];
+      const int e0 = sPtr[0], e1 = sPtr[r];
+      // mode 2: the pair's (value, row, column) list -- at most 2 n entries -- moves into the idle operand ring once, so a
+      // term of the sums below costs the two loads of D and nothing else from global memory
+      double *sval = stA;
+      int *srow = reinterpret_cast<int *>(stA + 2 * FUSED_MAX_N), *scol = srow + 2 * FUSED_MAX_N;
+      const int cnt = e1 - e0;
+      const bool staged = P.mode == 2 && cnt <= 2 * FUSED_MAX_N && 2 * FUSED_MAX_N * 2 <= 2 * FKC * A.ldmax;
+      if (staged) {
+        for (int t = tid; t < cnt; t += blockDim.x) { sval[t] = A.tt_val[e0 + t]; srow[t] = A.tt_row[e0 + t]; scol[t] = A.tt_col[e0 + t]; }
+        __syncthreads();
+      }
       for (int u0 = 0; u0 < P.need_cnt; u0 += (int)(blockDim.x >> 2)) {
         const int u = u0 + (tid >> 2);
         const bool live = u < P.need_cnt;
@@ -280,7 +290,15 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
             for (int rho = g; rho < r; rho += 4) acc += D[pp + (long long)R[rho] * n] * Tt[qq + (long long)rho * n];
           }
         } else {                                                  // few entries in A_jk: sum_t v_t D(p,row_t) D(col_t,q), D symmetric
-          if (live) {
+          if (live && staged) {
+#pragma unroll 8
+            for (int t = g; t < cnt; t += 4) {
+              const int a1 = pp + srow[t] * n, a2 = qq + scol[t] * n;
+              const double d1 = D[a1];
+              const double d2 = a2 == a1 ? d1 : D[a2];            // diagonal entry of W from a diagonal entry of A: one load
+              acc += sval[t] * (d1 * d2);
+            }
+          } else if (live) {
 #pragma unroll 8
             for (int t = e0 + g; t < e1; t += 4)
               acc += A.tt_val[t] * (D[pp + (long long)A.tt_row[t] * n] * D[qq + (long long)A.tt_col[t] * n]);
@@ -290,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) ada3_fused_kernel(const FusedA
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         if (live && g == 0) Wp[(qq * (2 * n - qq + 1)) / 2 - qq + pp] = acc;
       }
+      if (staged) asm volatile("fence.proxy.async;\n" ::: "memory");   // the ring is written by TMA again for the next dense pair
     } else
     // ---------------- 2b. W = D(:,R) T on the lower supertiles, in rounds of at most FUSED_GEMM_WARPS items
     // (the accumulators of the whole lower triangle -- 325 fragments at n = 200 -- do not fit the register file next to
