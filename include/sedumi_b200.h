@@ -235,6 +235,9 @@ int sb200_ada_plan_get_h(sb200_ada_plan **plan, sb_idx N, sb_idx m, const sb_idx
 sb_idx sb200_ada_plan_nnz(const sb200_ada_plan *plan);
 /* sb200_ada_plan_get hands out plans of a bounded cache; a caller that keeps the pointer beyond one call (device-resident
  * chains, captured CUDA graphs) retains it, which exempts it from eviction until the matching release. */
+/* Diagnostics (no reference counterpart): the 128-bit content key under which plans and device mirrors of inputs are
+ * cached; a pure host function of the bytes (independent of SB200_HASH_THREADS). */
+int sb200_content_hash(const void *data, int64_t bytes, uint64_t out[2]);
 int sb200_ada_plan_retain(sb200_ada_plan *plan);
 /* Diagnostics (no reference counterpart): cycles per phase of the fused getada3 kernel, see ada.cu. enable=1 arms and
  * zeroes the counters, enable=0 copies out[0..7]. */

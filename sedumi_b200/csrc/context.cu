@@ -71,7 +71,7 @@ struct HashPool {
   }
   void start() {
     unsigned hc = std::thread::hardware_concurrency();
-    int nt = (int)std::min<unsigned>(3, hc > 1 ? hc - 1 : 0);
+    int nt = (int)std::min<unsigned>(7, hc > 1 ? hc - 1 : 0);     // + the calling thread; the value never depends on the count
     if (const char *e = getenv("SB200_HASH_THREADS")) nt = std::max(0, std::min(15, atoi(e) - 1));
     for (int i = 0; i < nt; i++) th.emplace_back([this] { loop(); });
   }
@@ -500,6 +500,12 @@ int sb200_dev_alloc(void **p, int64_t bytes) {
   return 0;
 }
 int sb200_dev_free(void *p) { SB_CUDA(cudaFree(p)); return 0; }
+// Diagnostics / tests: the 128-bit content key the caches use for `bytes` bytes at `data` (host only, no device needed).
+int sb200_content_hash(const void *data, int64_t bytes, uint64_t out[2]) {
+  const sb::Hash128 h = sb::hash128(data, (size_t)bytes);
+  out[0] = h.a; out[1] = h.b;
+  return 0;
+}
 int sb200_h2d(void *dst, const void *src, int64_t bytes) {
   SB_TRY(sb::ensure_init());
   SB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, sb::ctx().stream));

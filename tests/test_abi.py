@@ -62,3 +62,33 @@ def test_argument_validation_like_the_reference():
         gpu.fwblkslv({"L": L["L"], "xsuper": L["xsuper"]}, np.ones((m, 1)))
     with pytest.raises(MexError, match="P must be square"):
         gpu.blkchol(L, sp.csc_matrix(np.ones((m, m + 1))), CHOL_PARS, nlhs=1)
+
+
+def test_content_hash_does_not_depend_on_the_thread_count():
+    """The 128-bit content key of the plan / mirror caches (context.cu: chunk hashes combined in chunk order): same value with
+    1 and with 8 hashing threads, across the single-/multi-threaded size boundary, and sensitive to one flipped bit."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from sedumi_b200 import device\n"
+        "L = device.lib()\n"
+        "rng = np.random.default_rng(5)\n"
+        "out = []\n"
+        "for nbytes in (0, 17, 512 * 1024, 512 * 1024 + 8, 3 * 1024 * 1024 + 40):\n"
+        "    buf = rng.integers(0, 256, nbytes, dtype=np.uint8)\n"
+        "    h = (C.c_uint64 * 2)()\n"
+        "    L.sb200_content_hash(buf.ctypes.data_as(C.c_void_p), C.c_int64(nbytes), h)\n"
+        "    out.append((h[0], h[1]))\n"
+        "    if nbytes:\n"
+        "        buf[nbytes // 2] ^= 1\n"
+        "        g = (C.c_uint64 * 2)()\n"
+        "        L.sb200_content_hash(buf.ctypes.data_as(C.c_void_p), C.c_int64(nbytes), g)\n"
+        "        assert (g[0], g[1]) != (h[0], h[1])\n"
+        "print(out)\n" % ROOT)
+    res = []
+    for nthreads in ("1", "8"):
+        env = dict(os.environ, SB200_HASH_THREADS=nthreads)
+        res.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
+    assert res[0] == res[1] and len(res[0]) > 20
